@@ -1,0 +1,207 @@
+/*
+ * mpegb200.h -- C-ABI of the B200-native MPEG-1 video / MP2 audio decode hot path.
+ *
+ * This is the drop-in boundary for gen2brain/mpeg's data-parallel kernels.  The host
+ * (the Go package through cgo, or the C++/Python host layer in this repo) keeps the
+ * serial work -- PS demux, bit reader, VLC parse, dequantisation -- and hands packed
+ * arrays to the entry points below; everything behind them is hand-written sm_100a CUDA.
+ *
+ * Reference interfaces replaced (file:line in gen2brain/mpeg @ 27c6f084):
+ *   idct                         video.go:801-928
+ *   copyBlockToDest/addBlockToDest/copyValueToDest/addValueToDest
+ *                                video.go:943-1002 (dispatch video.go:747-798)
+ *   predictMacroblock            video.go:608-637   (decision resolved by the packer)
+ *   copyMacroblock               video_noasm.go:28-80, video_amd64.s:22-595, video_arm64.s:24-319
+ *   Frame.RGBA / Pixels          video.go:31-43     (Go stdlib image/draw YCbCr->RGBA)
+ *   idct36                       audio.go:492-772
+ *   synthWindow                  audio_noasm.go:8-38, audio_amd64.s:33-156, audio_arm64.s:36-85
+ *   synthesis loop + scaling     audio.go:377-422
+ *
+ * Conventions: every function is extern "C", takes plain pointers and sizes, returns
+ * 0 on success or a negative MPEGB200_E* code (never throws, never aborts).  One
+ * context per GPU and per host thread; distinct contexts are fully independent, which
+ * mirrors the reference ("distinct decoders are independent", no shared state).  The
+ * caller owns all host memory; the library owns all device memory.  There is no CPU
+ * fallback: without a CUDA device every entry point fails with MPEGB200_ECUDA.
+ */
+#ifndef MPEGB200_H
+#define MPEGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPEGB200_ABI_VERSION 1
+
+/* error codes */
+#define MPEGB200_OK        0
+#define MPEGB200_EINVAL   -1   /* bad argument (null pointer, stream id out of range, bad geometry ...) */
+#define MPEGB200_ECUDA    -2   /* CUDA runtime error; text via mpegb200_last_error() */
+#define MPEGB200_ENOMEM   -3   /* device or pinned-host allocation failed */
+#define MPEGB200_ESTATE   -4   /* stream not opened / already opened / geometry mismatch */
+#define MPEGB200_ERECORD  -5   /* a packed record failed validation (see mpegb200_video_validate) */
+
+/* picture coding types (video.go:930-933) */
+#define MPEGB200_PIC_I 1
+#define MPEGB200_PIC_P 2
+#define MPEGB200_PIC_B 3
+
+/* macroblock flags */
+#define MPEGB200_MB_INTRA    0x01  /* coded blocks overwrite the destination (video.go:772-784) */
+#define MPEGB200_MB_PREDICT  0x02  /* motion-compensated prediction is written first (video.go:544) */
+#define MPEGB200_MB_REF_BWD  0x04  /* prediction source is the backward reference, else the forward one.
+                                      The packer resolves predictMacroblock (video.go:608-637): for a
+                                      B macroblock with both vectors set the backward copy overwrites the
+                                      forward one, so only the backward prediction is observable. */
+
+/*
+ * One macroblock of work, 16 bytes.  Produced by the host where the reference calls
+ * predictMacroblock (video.go:508,544) and decodeBlock (video.go:556-561).
+ */
+typedef struct mpegb200_mb {
+    uint16_t mb_row;       /* macroblock row    (video.go:514) */
+    uint16_t mb_col;       /* macroblock column (video.go:515) */
+    int16_t  mv_h;         /* half-pel motion vector, FullPx doubling already applied (video.go:612-624) */
+    int16_t  mv_v;
+    uint8_t  flags;        /* MPEGB200_MB_* */
+    uint8_t  cbp;          /* coded block pattern: bit 5 = block 0 (Y top-left) ... bit 0 = block 5 (Cr) */
+    uint16_t pic;          /* index of the owning picture in this call's picture array */
+    uint32_t coeff_block;  /* index, in 64-coefficient blocks, of this macroblock's first coded block.
+                              Blocks of one macroblock are consecutive, in block order 0..5; macroblocks
+                              must be packed in array order: coeff_block[i+1] = coeff_block[i]+popcount(cbp[i]) */
+} mpegb200_mb;
+
+/*
+ * One picture of one stream, 16 bytes.  Buffer indices are the three physical frame
+ * buffers of the stream (frameCurrent / frameForward / frameBackward, video.go:97-99);
+ * the host mirrors the reference's rotation (video.go:406-409, 430-433) and passes
+ * which physical buffer plays which role for this picture.
+ */
+typedef struct mpegb200_picture {
+    int32_t  stream;       /* stream id given to mpegb200_video_open */
+    uint8_t  type;         /* MPEGB200_PIC_* (informational; the kernels only look at macroblock flags) */
+    uint8_t  dst_buf;      /* 0..2: buffer written by this picture (frameCurrent) */
+    uint8_t  fwd_buf;      /* 0..2: forward reference  (frameForward)  */
+    uint8_t  bwd_buf;      /* 0..2: backward reference (frameBackward) */
+    uint32_t first_mb;     /* informational: index of the picture's first record in the mb array */
+    uint32_t n_mb;         /* informational: number of records */
+} mpegb200_picture;
+
+/*
+ * Coefficients: int16_t[64] per coded block, natural (de-zigzagged, row-major) order,
+ * holding the dequantised, oddified and clipped level of video.go:729-741, i.e. the
+ * value just before the premultiply of video.go:744 (the kernel multiplies by
+ * videoPremultiplierMatrix, video.go:1077-1086, on chip).  Intra DC is carried as
+ * dc*8 (so that dc*8*32 == dc<<8, video.go:672); the host must keep |dc| <= 4095.
+ */
+
+/* audio output formats (audio.go:12-23) */
+#define MPEGB200_AUDIO_F32N    0   /* interleaved normalised float32 (Samples.Interleaved) */
+#define MPEGB200_AUDIO_F32NLR  1   /* planar: 1152 left then 1152 right (Samples.Left/Right) */
+#define MPEGB200_AUDIO_F32     2   /* interleaved float32 scaled to int32 range (Samples.F32) */
+#define MPEGB200_AUDIO_S16     3   /* interleaved int16 (Samples.S16) */
+
+#define MPEGB200_SAMPLES_PER_FRAME 1152   /* audio.go:9 */
+
+typedef struct mpegb200_ctx mpegb200_ctx;
+
+/* ---- context ---------------------------------------------------------------------- */
+
+int  mpegb200_abi_version(void);
+/* Create a context on CUDA device `device` able to hold `max_streams` video and
+ * `max_streams` audio streams.  Fails (returns NULL, *err set) when no sm_100 device. */
+mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err);
+void mpegb200_destroy(mpegb200_ctx* ctx);
+const char* mpegb200_last_error(mpegb200_ctx* ctx);
+/* Work is enqueued on the context's stream; by default a private non-blocking stream.
+ * A caller that wants to time with its own events passes its cudaStream_t here. */
+int  mpegb200_set_stream(mpegb200_ctx* ctx, void* cuda_stream);
+void* mpegb200_get_stream(mpegb200_ctx* ctx);
+int  mpegb200_sync(mpegb200_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t mpegb200_launch_count(mpegb200_ctx* ctx);
+
+/* ---- video ------------------------------------------------------------------------ */
+
+/* Allocate and zero the three frame buffers of a stream: each is one allocation
+ * Y | Cb | Cr | pad(lumaWidth*16) exactly as initFrame lays it out (video.go:333-355),
+ * so half-pel reads past a plane's end see the same bytes the reference sees. */
+int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height);
+int mpegb200_video_close(mpegb200_ctx* ctx, int stream);
+/* Geometry queries: luma_width = ((width+15)>>4)<<4 etc. (video.go:314-322). */
+int mpegb200_video_geometry(mpegb200_ctx* ctx, int stream, int* luma_w, int* luma_h,
+                            int* chroma_w, int* chroma_h, size_t* frame_bytes);
+
+/* Check a batch the way the kernels assume it: indices in range, coeff_block packing,
+ * motion windows inside the stream's frame buffer (the reference would panic or read
+ * foreign memory there, video_noasm.go:49-50), no macroblock written twice in a picture,
+ * at most one picture per stream.  Returns 0 or MPEGB200_ERECORD (text in last_error). */
+int mpegb200_video_validate(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics,
+                            size_t n_mb, const mpegb200_mb* mbs, size_t n_blocks);
+
+/* Decode a batch of mutually independent pictures (at most one per stream): fused
+ * motion compensation + 8x8 IDCT + residual add / intra store, one kernel launch.
+ * Host-pointer form: copies the three arrays host->device on the context stream first
+ * (pinned memory makes that asynchronous), then launches. */
+int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics,
+                                   size_t n_mb, const mpegb200_mb* mbs,
+                                   size_t n_blocks, const int16_t* coeffs);
+/* Device-pointer form: the three arrays are already resident in device memory. */
+int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* d_pics,
+                                       size_t n_mb, const mpegb200_mb* d_mbs,
+                                       size_t n_blocks, const int16_t* d_coeffs);
+
+/* Plane read-back for *Frame (Plane.Data, video.go:50-54): copies the macroblock-padded
+ * planes of physical buffer `buf` to host memory.  Any of y/cb/cr may be NULL. */
+int mpegb200_video_read_planes(mpegb200_ctx* ctx, int stream, int buf,
+                               uint8_t* y, uint8_t* cb, uint8_t* cr);
+/* Write planes (test set-up / resume from a checkpointed reference frame). */
+int mpegb200_video_write_planes(mpegb200_ctx* ctx, int stream, int buf,
+                                const uint8_t* y, const uint8_t* cb, const uint8_t* cr);
+/* Whole frame buffer (Y|Cb|Cr|pad) to/from host. */
+int mpegb200_video_read_frame(mpegb200_ctx* ctx, int stream, int buf, uint8_t* dst, size_t dst_bytes);
+int mpegb200_video_write_frame(mpegb200_ctx* ctx, int stream, int buf, const uint8_t* src, size_t src_bytes);
+/* Device address of a frame buffer (Y at +0, Cb at +luma_w*luma_h, Cr after it). */
+void* mpegb200_video_frame_dev(mpegb200_ctx* ctx, int stream, int buf);
+
+/* Frame.RGBA(): YCbCr 4:2:0 -> RGBA8 over the display rectangle width x height,
+ * destination stride 4*width (video.go:31-36, 367-371).  Host form copies the result
+ * into `rgba` (width*height*4 bytes). */
+int mpegb200_video_rgba(mpegb200_ctx* ctx, int stream, int buf, uint8_t* rgba);
+/* Batched device form: frame i = (streams[i], bufs[i]) -> d_rgba + i*rgba_stride_bytes. */
+int mpegb200_video_rgba_batch_dev(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs,
+                                  uint8_t* d_rgba, size_t rgba_stride_bytes);
+
+/* ---- audio ------------------------------------------------------------------------ */
+
+/* Allocate the synthesis state of a stream: V[2][1024] = 0, vPos = 0 (audio.go:77-79). */
+int mpegb200_audio_open(mpegb200_ctx* ctx, int stream);
+int mpegb200_audio_close(mpegb200_ctx* ctx, int stream);
+/* Synthesis of a rectangular batch: each of the n_streams listed streams (distinct ids)
+ * advances by frames_per_stream MP2 frames, in decode order (the V history and vPos carry
+ * from one frame to the next, audio.go:380, and survive across calls like they survive
+ * Rewind, audio.go:149).
+ * samples: int32[n_streams][frames_per_stream][2][36][32] = requantised subband samples
+ * sample[ch][sb][p] of audio.go:72 laid out [ch][3*(4*part+granule)+p][sb] (both channels
+ * always present: mono streams mirror channel 0, audio.go:362-367).
+ * out: per frame 2304 values in `format` (float32, or int16 for MPEGB200_AUDIO_S16),
+ * frames in the same [stream][frame] order.  stream_ids is always a HOST array. */
+int mpegb200_audio_synth(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids,
+                         int frames_per_stream, const int32_t* samples, int format, void* out);
+int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids,
+                             int frames_per_stream, const int32_t* d_samples, int format, void* d_out);
+/* State read-back in the reference's own form: v = float[2][1024], *v_pos (audio.go:63,78). */
+int mpegb200_audio_read_state(mpegb200_ctx* ctx, int stream, float* v, int* v_pos);
+int mpegb200_audio_write_state(mpegb200_ctx* ctx, int stream, const float* v, int v_pos);
+
+/* ---- pinned host memory helpers (for the packer's staging arrays) ------------------- */
+void* mpegb200_host_alloc(size_t bytes);
+void  mpegb200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPEGB200_H */
