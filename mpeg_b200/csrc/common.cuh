@@ -1,0 +1,47 @@
+// common.cuh -- device-side structures shared by the sm_100a kernels and the C-ABI glue.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpegb200.h"
+
+namespace mpegb200 {
+
+// Per-stream video geometry and storage, mirrored in device memory (one entry per stream id).
+// The three physical frame buffers (frameCurrent/Forward/Backward, video.go:97-99) of a stream
+// live in one allocation, `buf_stride` bytes apart; each is Y | Cb | Cr | pad(luma_w*16) exactly
+// as initFrame lays it out (video.go:333-355) followed by >= 64 bytes of slack so that 16-byte
+// aligned super-set loads of a motion window never leave the allocation.
+struct StreamInfo {
+    uint8_t* base;        // buffer b at base + b * buf_stride
+    uint32_t buf_stride;  // multiple of 256
+    uint32_t buf_bytes;   // luma + 2*chroma + luma_w*16 (video.go:340)
+    uint16_t luma_w, luma_h;
+    uint16_t mb_w, mb_h;
+    uint16_t width, height;  // display size (video.go:342-343)
+    uint32_t open;
+};
+static_assert(sizeof(StreamInfo) == 32, "StreamInfo layout");
+
+// Per-stream MP2 synthesis state in the reference's own form (audio.go:63,78).
+struct AudioState {
+    float v[2][1024];
+    int32_t v_pos;
+    int32_t open;
+    int32_t pad[2];
+};
+
+// launch wrappers (video_kernels.cu / audio_kernels.cu); all return cudaGetLastError()
+cudaError_t launch_fused_mc_idct(const StreamInfo* d_streams, int max_streams, const mpegb200_picture* d_pics,
+                                 int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb, const int16_t* d_coeffs,
+                                 uint32_t n_blocks, cudaStream_t stream);
+cudaError_t launch_rgba(const StreamInfo* d_streams, int max_streams, const int32_t* d_stream_ids,
+                        const uint8_t* d_bufs, int n, int max_w, int max_h, uint8_t* d_rgba,
+                        size_t rgba_stride_bytes, cudaStream_t stream);
+cudaError_t launch_audio_synth(AudioState* d_states, int max_streams, const int32_t* d_stream_ids, int n_streams,
+                               int frames_per_stream, const int32_t* d_samples, int format, void* d_out,
+                               const float* d_window, cudaStream_t stream);
+cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
+
+}  // namespace mpegb200

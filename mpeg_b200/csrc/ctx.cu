@@ -1,0 +1,622 @@
+// ctx.cu -- the C-ABI of include/mpegb200.h: context, device memory, transfers, launches.
+// No CPU fallback anywhere: if CUDA is unavailable every entry point reports MPEGB200_ECUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "mp2_window.inc"
+
+namespace mpegb200 {
+cudaError_t configure_audio_kernel();
+}
+using namespace mpegb200;
+
+struct HostStream {
+    bool open = false;
+    int width = 0, height = 0;
+    int luma_w = 0, luma_h = 0, chroma_w = 0, chroma_h = 0;
+    size_t luma_bytes = 0, chroma_bytes = 0, buf_bytes = 0, buf_stride = 0;
+    uint8_t* dev = nullptr;
+};
+
+struct DevBuf {  // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct mpegb200_ctx {
+    int device = 0;
+    int max_streams = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<HostStream> vs;
+    std::vector<StreamInfo> h_info;
+    StreamInfo* d_info = nullptr;
+    bool info_dirty = false;
+    std::vector<uint8_t> audio_open;
+    AudioState* d_audio = nullptr;
+    float* d_window = nullptr;
+    DevBuf s_pics, s_mbs, s_coeffs, s_ids, s_bufs, s_rgba, s_samples, s_out;
+    void* pinned = nullptr;  // small pinned scratch for ids
+    size_t pinned_cap = 0;
+    uint64_t launches = 0;
+    int max_w = 0, max_h = 0;
+    char err[512] = {0};
+};
+
+static int fail(mpegb200_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, MPEGB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                            \
+    } while (0)
+
+static int ensure(mpegb200_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&b.p, cap) != cudaSuccess) {
+        b.p = nullptr;
+        cudaGetLastError();
+        return fail(ctx, MPEGB200_ENOMEM, "device allocation of %zu bytes failed", cap);
+    }
+    b.cap = cap;
+    return 0;
+}
+
+static int ensure_pinned(mpegb200_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return 0;
+    if (ctx->pinned) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+    }
+    if (cudaMallocHost(&ctx->pinned, bytes + 4096) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MPEGB200_ENOMEM, "pinned allocation of %zu bytes failed", bytes);
+    }
+    ctx->pinned_cap = bytes + 4096;
+    return 0;
+}
+
+static int flush_info(mpegb200_ctx* ctx) {
+    if (!ctx->info_dirty) return 0;
+    // stream-ordered so that it lands before any kernel enqueued afterwards; h_info outlives the copy
+    CU(cudaMemcpyAsync(ctx->d_info, ctx->h_info.data(), sizeof(StreamInfo) * ctx->max_streams, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->info_dirty = false;
+    return 0;
+}
+
+extern "C" {
+
+int mpegb200_abi_version(void) { return MPEGB200_ABI_VERSION; }
+
+mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) {
+    auto set = [&](int e) {
+        if (err) *err = e;
+    };
+    if (max_streams <= 0 || max_streams > (1 << 20)) {
+        set(MPEGB200_EINVAL);
+        return nullptr;
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        set(MPEGB200_ECUDA);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        prop.major != 10) {  // the kernels are sm_100a only: no other path exists
+        cudaGetLastError();
+        set(MPEGB200_ECUDA);
+        return nullptr;
+    }
+    mpegb200_ctx* ctx = new (std::nothrow) mpegb200_ctx();
+    if (!ctx) {
+        set(MPEGB200_ENOMEM);
+        return nullptr;
+    }
+    ctx->device = device;
+    ctx->max_streams = max_streams;
+    ctx->vs.resize(max_streams);
+    ctx->h_info.assign(max_streams, StreamInfo{});
+    ctx->audio_open.assign(max_streams, 0);
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->own_stream = ok;
+    ok = ok && cudaMalloc(&ctx->d_info, sizeof(StreamInfo) * max_streams) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_info, 0, sizeof(StreamInfo) * max_streams) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_window, sizeof(float) * 1024) == cudaSuccess;
+    if (ok) {
+        float w[1024];
+        for (int i = 0; i < 512; i++) w[i] = w[i + 512] = (float)kSynthesisWindowX2[i] * 0.5f;  // audio.go:95-98
+        ok = cudaMemcpy(ctx->d_window, w, sizeof(w), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    ok = ok && configure_kernels() == cudaSuccess && configure_audio_kernel() == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        mpegb200_destroy(ctx);
+        set(MPEGB200_ECUDA);
+        return nullptr;
+    }
+    set(MPEGB200_OK);
+    return ctx;
+}
+
+void mpegb200_destroy(mpegb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->vs)
+        if (s.dev) cudaFree(s.dev);
+    for (DevBuf* b : {&ctx->s_pics, &ctx->s_mbs, &ctx->s_coeffs, &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba,
+                      &ctx->s_samples, &ctx->s_out})
+        if (b->p) cudaFree(b->p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->d_info) cudaFree(ctx->d_info);
+    if (ctx->d_audio) cudaFree(ctx->d_audio);
+    if (ctx->d_window) cudaFree(ctx->d_window);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mpegb200_last_error(mpegb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int mpegb200_set_stream(mpegb200_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MPEGB200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return 0;
+}
+
+void* mpegb200_get_stream(mpegb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int mpegb200_sync(mpegb200_ctx* ctx) {
+    if (!ctx) return MPEGB200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+uint64_t mpegb200_launch_count(mpegb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---------------------------------------------------------------------------------------- video */
+
+static HostStream* vstream(mpegb200_ctx* ctx, int stream) {
+    if (!ctx || stream < 0 || stream >= ctx->max_streams) return nullptr;
+    return &ctx->vs[stream];
+}
+
+int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
+    HostStream* s = vstream(ctx, stream);
+    if (!s) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (s->open) return fail(ctx, MPEGB200_ESTATE, "video stream %d already open", stream);
+    if (width <= 0 || height <= 0 || width > 4095 || height > 4095)  // 12-bit fields, video.go:276-277
+        return fail(ctx, MPEGB200_EINVAL, "bad picture size %dx%d", width, height);
+    CU(cudaSetDevice(ctx->device));
+    const int mb_w = (width + 15) >> 4, mb_h = (height + 15) >> 4;  // video.go:314-315
+    s->width = width;
+    s->height = height;
+    s->luma_w = mb_w << 4;
+    s->luma_h = mb_h << 4;
+    s->chroma_w = mb_w << 3;
+    s->chroma_h = mb_h << 3;
+    s->luma_bytes = (size_t)s->luma_w * s->luma_h;
+    s->chroma_bytes = (size_t)s->chroma_w * s->chroma_h;
+    s->buf_bytes = s->luma_bytes + 2 * s->chroma_bytes + (size_t)s->luma_w * 16;  // video.go:340
+    s->buf_stride = (s->buf_bytes + 64 + 255) & ~(size_t)255;
+    if (cudaMalloc(&s->dev, 3 * s->buf_stride) != cudaSuccess) {
+        cudaGetLastError();
+        s->dev = nullptr;
+        return fail(ctx, MPEGB200_ENOMEM, "frame buffers of stream %d (%zu bytes)", stream, 3 * s->buf_stride);
+    }
+    CU(cudaMemsetAsync(s->dev, 0, 3 * s->buf_stride, ctx->stream));  // make([]byte, ...) zeroes, video.go:340
+    StreamInfo& si = ctx->h_info[stream];
+    si.base = s->dev;
+    si.buf_stride = (uint32_t)s->buf_stride;
+    si.buf_bytes = (uint32_t)s->buf_bytes;
+    si.luma_w = (uint16_t)s->luma_w;
+    si.luma_h = (uint16_t)s->luma_h;
+    si.mb_w = (uint16_t)mb_w;
+    si.mb_h = (uint16_t)mb_h;
+    si.width = (uint16_t)width;
+    si.height = (uint16_t)height;
+    si.open = 1;
+    s->open = true;
+    ctx->info_dirty = true;
+    if (width > ctx->max_w) ctx->max_w = width;
+    if (height > ctx->max_h) ctx->max_h = height;
+    return 0;
+}
+
+int mpegb200_video_close(mpegb200_ctx* ctx, int stream) {
+    HostStream* s = vstream(ctx, stream);
+    if (!s) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (!s->open) return fail(ctx, MPEGB200_ESTATE, "video stream %d not open", stream);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->dev);
+    *s = HostStream{};
+    ctx->h_info[stream] = StreamInfo{};
+    ctx->info_dirty = true;
+    return 0;
+}
+
+int mpegb200_video_geometry(mpegb200_ctx* ctx, int stream, int* luma_w, int* luma_h, int* chroma_w, int* chroma_h,
+                            size_t* frame_bytes) {
+    HostStream* s = vstream(ctx, stream);
+    if (!s) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (!s->open) return fail(ctx, MPEGB200_ESTATE, "video stream %d not open", stream);
+    if (luma_w) *luma_w = s->luma_w;
+    if (luma_h) *luma_h = s->luma_h;
+    if (chroma_w) *chroma_w = s->chroma_w;
+    if (chroma_h) *chroma_h = s->chroma_h;
+    if (frame_bytes) *frame_bytes = s->buf_bytes;
+    return 0;
+}
+
+static bool window_inside(long off, int stride, int size, int odd_h, int odd_v, long avail) {
+    const long hi = off + (long)(size - 1 + odd_v) * stride + (size - 1 + odd_h);
+    return off >= 0 && hi < avail;
+}
+
+int mpegb200_video_validate(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics, size_t n_mb,
+                            const mpegb200_mb* mbs, size_t n_blocks) {
+    if (!ctx || n_pictures < 0 || (n_pictures && !pics) || (n_mb && !mbs))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n_pictures > 65536) return fail(ctx, MPEGB200_ERECORD, "at most 65536 pictures per call (16-bit pic index)");
+    std::vector<uint8_t> seen_stream(ctx->max_streams, 0);
+    for (int p = 0; p < n_pictures; p++) {
+        const mpegb200_picture& pic = pics[p];
+        HostStream* s = vstream(ctx, pic.stream);
+        if (!s || !s->open) return fail(ctx, MPEGB200_ERECORD, "picture %d: stream %d not open", p, pic.stream);
+        if (seen_stream[pic.stream]++)
+            return fail(ctx, MPEGB200_ERECORD, "picture %d: second picture of stream %d in one call", p, pic.stream);
+        if (pic.dst_buf > 2 || pic.fwd_buf > 2 || pic.bwd_buf > 2)
+            return fail(ctx, MPEGB200_ERECORD, "picture %d: buffer index out of range", p);
+    }
+    std::vector<std::vector<uint8_t>> written(n_pictures);
+    uint64_t expect_block = n_mb ? mbs[0].coeff_block : 0;
+    for (size_t i = 0; i < n_mb; i++) {
+        const mpegb200_mb& m = mbs[i];
+        if (m.pic >= n_pictures) return fail(ctx, MPEGB200_ERECORD, "mb %zu: picture index %u out of range", i, m.pic);
+        const mpegb200_picture& pic = pics[m.pic];
+        const HostStream& s = ctx->vs[pic.stream];
+        const int mb_w = s.luma_w >> 4, mb_h = s.luma_h >> 4;
+        if (m.mb_row >= mb_h || m.mb_col >= mb_w)
+            return fail(ctx, MPEGB200_ERECORD, "mb %zu: position (%u,%u) outside %dx%d macroblocks", i, m.mb_row,
+                        m.mb_col, mb_h, mb_w);
+        if (m.cbp & ~0x3f) return fail(ctx, MPEGB200_ERECORD, "mb %zu: cbp has more than 6 bits", i);
+        const bool intra = m.flags & MPEGB200_MB_INTRA, pred = m.flags & MPEGB200_MB_PREDICT;
+        if (intra == pred) return fail(ctx, MPEGB200_ERECORD, "mb %zu: exactly one of INTRA / PREDICT must be set", i);
+        if ((m.flags & MPEGB200_MB_REF_BWD) && !pred) return fail(ctx, MPEGB200_ERECORD, "mb %zu: REF_BWD without PREDICT", i);
+        const int ncoded = __builtin_popcount(m.cbp);
+        if (m.coeff_block != expect_block)
+            return fail(ctx, MPEGB200_ERECORD, "mb %zu: coeff_block %u breaks the packing rule (expected %llu)", i,
+                        m.coeff_block, (unsigned long long)expect_block);
+        expect_block += ncoded;
+        if (expect_block > n_blocks) return fail(ctx, MPEGB200_ERECORD, "mb %zu: coefficient blocks run past n_blocks", i);
+        auto& w = written[m.pic];
+        if (w.empty()) w.assign((size_t)mb_w * mb_h, 0);
+        if (w[(size_t)m.mb_row * mb_w + m.mb_col]++)
+            return fail(ctx, MPEGB200_ERECORD, "mb %zu: macroblock (%u,%u) written twice in picture %u", i, m.mb_row,
+                        m.mb_col, m.pic);
+        if (pred) {  // the windows copyMacroblock reads must lie inside the frame buffer (video_noasm.go:49-50)
+            if (((m.flags & MPEGB200_MB_REF_BWD) ? pic.bwd_buf : pic.fwd_buf) == pic.dst_buf)
+                return fail(ctx, MPEGB200_ERECORD, "mb %zu: reference buffer equals destination buffer", i);
+            const long total = (long)s.buf_bytes;
+            const int hp = m.mv_h >> 1, vp = m.mv_v >> 1;
+            const long lsi = (long)((m.mb_row << 4) + vp) * s.luma_w + (m.mb_col << 4) + hp;
+            const int cmh = m.mv_h / 2, cmv = m.mv_v / 2;
+            const long csi = (long)((m.mb_row << 3) + (cmv >> 1)) * s.chroma_w + (m.mb_col << 3) + (cmh >> 1);
+            const long cb0 = (long)s.luma_bytes, cr0 = cb0 + (long)s.chroma_bytes;
+            if (!window_inside(lsi, s.luma_w, 16, m.mv_h & 1, m.mv_v & 1, total) ||
+                !window_inside(csi, s.chroma_w, 8, cmh & 1, cmv & 1, total - cb0) ||
+                !window_inside(csi, s.chroma_w, 8, cmh & 1, cmv & 1, total - cr0))
+                return fail(ctx, MPEGB200_ERECORD, "mb %zu: motion vector (%d,%d) reads outside the frame buffer", i,
+                            m.mv_h, m.mv_v);
+        }
+    }
+    return 0;
+}
+
+int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* d_pics, size_t n_mb,
+                                       const mpegb200_mb* d_mbs, size_t n_blocks, const int16_t* d_coeffs) {
+    if (!ctx || n_pictures < 0 || (n_mb && (!d_pics || !d_mbs)) || (n_blocks && !d_coeffs))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n_mb > 0xffffffffull || n_blocks > 0xffffffffull || n_pictures > 65536)
+        return fail(ctx, MPEGB200_EINVAL, "batch too large");
+    if ((reinterpret_cast<uintptr_t>(d_mbs) & 15) || (reinterpret_cast<uintptr_t>(d_pics) & 15) ||
+        (reinterpret_cast<uintptr_t>(d_coeffs) & 15))
+        return fail(ctx, MPEGB200_EINVAL, "device arrays must be 16-byte aligned");
+    if (n_mb == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = flush_info(ctx)) return rc;
+    CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,
+                            (uint32_t)n_blocks, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics, size_t n_mb,
+                                   const mpegb200_mb* mbs, size_t n_blocks, const int16_t* coeffs) {
+    if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && !coeffs))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n_mb == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure(ctx, ctx->s_pics, sizeof(mpegb200_picture) * (size_t)n_pictures)) return rc;
+    if (int rc = ensure(ctx, ctx->s_mbs, sizeof(mpegb200_mb) * n_mb)) return rc;
+    if (int rc = ensure(ctx, ctx->s_coeffs, 128 * (n_blocks ? n_blocks : 1))) return rc;
+    CU(cudaMemcpyAsync(ctx->s_pics.p, pics, sizeof(mpegb200_picture) * (size_t)n_pictures, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_mbs.p, mbs, sizeof(mpegb200_mb) * n_mb, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_blocks) CU(cudaMemcpyAsync(ctx->s_coeffs.p, coeffs, 128 * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
+    return mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics.p, n_mb,
+                                              (const mpegb200_mb*)ctx->s_mbs.p, n_blocks,
+                                              (const int16_t*)ctx->s_coeffs.p);
+}
+
+static int check_buf(mpegb200_ctx* ctx, int stream, int buf, HostStream** out) {
+    HostStream* s = vstream(ctx, stream);
+    if (!s) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (!s->open) return fail(ctx, MPEGB200_ESTATE, "video stream %d not open", stream);
+    if (buf < 0 || buf > 2) return fail(ctx, MPEGB200_EINVAL, "buffer index %d out of range", buf);
+    *out = s;
+    return 0;
+}
+
+int mpegb200_video_read_planes(mpegb200_ctx* ctx, int stream, int buf, uint8_t* y, uint8_t* cb, uint8_t* cr) {
+    HostStream* s = nullptr;
+    if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const uint8_t* base = s->dev + (size_t)buf * s->buf_stride;
+    if (y) CU(cudaMemcpyAsync(y, base, s->luma_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cb) CU(cudaMemcpyAsync(cb, base + s->luma_bytes, s->chroma_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cr)
+        CU(cudaMemcpyAsync(cr, base + s->luma_bytes + s->chroma_bytes, s->chroma_bytes, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mpegb200_video_write_planes(mpegb200_ctx* ctx, int stream, int buf, const uint8_t* y, const uint8_t* cb,
+                                const uint8_t* cr) {
+    HostStream* s = nullptr;
+    if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* base = s->dev + (size_t)buf * s->buf_stride;
+    if (y) CU(cudaMemcpyAsync(base, y, s->luma_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (cb) CU(cudaMemcpyAsync(base + s->luma_bytes, cb, s->chroma_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (cr)
+        CU(cudaMemcpyAsync(base + s->luma_bytes + s->chroma_bytes, cr, s->chroma_bytes, cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mpegb200_video_read_frame(mpegb200_ctx* ctx, int stream, int buf, uint8_t* dst, size_t dst_bytes) {
+    HostStream* s = nullptr;
+    if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
+    if (!dst || dst_bytes < s->buf_bytes) return fail(ctx, MPEGB200_EINVAL, "destination smaller than %zu bytes", s->buf_bytes);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, s->dev + (size_t)buf * s->buf_stride, s->buf_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mpegb200_video_write_frame(mpegb200_ctx* ctx, int stream, int buf, const uint8_t* src, size_t src_bytes) {
+    HostStream* s = nullptr;
+    if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
+    if (!src || src_bytes != s->buf_bytes) return fail(ctx, MPEGB200_EINVAL, "source must be %zu bytes", s->buf_bytes);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(s->dev + (size_t)buf * s->buf_stride, src, s->buf_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void* mpegb200_video_frame_dev(mpegb200_ctx* ctx, int stream, int buf) {
+    HostStream* s = nullptr;
+    if (check_buf(ctx, stream, buf, &s)) return nullptr;
+    return s->dev + (size_t)buf * s->buf_stride;
+}
+
+int mpegb200_video_rgba_batch_dev(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs,
+                                  uint8_t* d_rgba, size_t rgba_stride_bytes) {
+    if (!ctx || n < 0 || (n && (!streams || !bufs || !d_rgba))) return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n == 0) return 0;
+    int max_w = 0, max_h = 0;
+    for (int i = 0; i < n; i++) {
+        HostStream* s = nullptr;
+        if (int rc = check_buf(ctx, streams[i], bufs[i], &s)) return rc;
+        if ((size_t)s->width * s->height * 4 > rgba_stride_bytes)
+            return fail(ctx, MPEGB200_EINVAL, "rgba stride %zu too small for stream %d", rgba_stride_bytes, streams[i]);
+        if (s->width > max_w) max_w = s->width;
+        if (s->height > max_h) max_h = s->height;
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = flush_info(ctx)) return rc;
+    // ids travel through pinned scratch so the copy is truly asynchronous
+    const size_t id_bytes = sizeof(int32_t) * (size_t)n, need = id_bytes + (size_t)n;
+    if (int rc = ensure_pinned(ctx, need)) return rc;
+    if (int rc = ensure(ctx, ctx->s_ids, id_bytes)) return rc;
+    if (int rc = ensure(ctx, ctx->s_bufs, (size_t)n)) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));  // the pinned scratch may still be in flight from an earlier call
+    memcpy(ctx->pinned, streams, id_bytes);
+    memcpy((uint8_t*)ctx->pinned + id_bytes, bufs, (size_t)n);
+    CU(cudaMemcpyAsync(ctx->s_ids.p, ctx->pinned, id_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_bufs.p, (uint8_t*)ctx->pinned + id_bytes, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_rgba(ctx->d_info, ctx->max_streams, (const int32_t*)ctx->s_ids.p, (const uint8_t*)ctx->s_bufs.p, n, max_w,
+                   max_h, d_rgba, rgba_stride_bytes, ctx->stream));
+    ctx->launches += (uint64_t)((n + 32767) / 32768);
+    return 0;
+}
+
+int mpegb200_video_rgba(mpegb200_ctx* ctx, int stream, int buf, uint8_t* rgba) {
+    HostStream* s = nullptr;
+    if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
+    if (!rgba) return fail(ctx, MPEGB200_EINVAL, "null destination");
+    const size_t bytes = (size_t)s->width * s->height * 4;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure(ctx, ctx->s_rgba, bytes)) return rc;
+    const int32_t id = stream;
+    const uint8_t b = (uint8_t)buf;
+    if (int rc = mpegb200_video_rgba_batch_dev(ctx, 1, &id, &b, (uint8_t*)ctx->s_rgba.p, bytes)) return rc;
+    CU(cudaMemcpyAsync(rgba, ctx->s_rgba.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------- audio */
+
+static int audio_alloc(mpegb200_ctx* ctx) {
+    if (ctx->d_audio) return 0;
+    if (cudaMalloc(&ctx->d_audio, sizeof(AudioState) * (size_t)ctx->max_streams) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->d_audio = nullptr;
+        return fail(ctx, MPEGB200_ENOMEM, "audio state allocation failed");
+    }
+    CU(cudaMemsetAsync(ctx->d_audio, 0, sizeof(AudioState) * (size_t)ctx->max_streams, ctx->stream));
+    return 0;
+}
+
+int mpegb200_audio_open(mpegb200_ctx* ctx, int stream) {
+    if (!ctx || stream < 0 || stream >= ctx->max_streams) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (ctx->audio_open[stream]) return fail(ctx, MPEGB200_ESTATE, "audio stream %d already open", stream);
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = audio_alloc(ctx)) return rc;
+    // V = 0, vPos = 0 (a fresh Audio struct, audio.go:83-84), open = 1
+    CU(cudaMemsetAsync(&ctx->d_audio[stream], 0, sizeof(AudioState), ctx->stream));
+    static const int32_t one = 1;
+    CU(cudaMemcpyAsync(&ctx->d_audio[stream].open, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->audio_open[stream] = 1;
+    return 0;
+}
+
+int mpegb200_audio_close(mpegb200_ctx* ctx, int stream) {
+    if (!ctx || stream < 0 || stream >= ctx->max_streams) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (!ctx->audio_open[stream]) return fail(ctx, MPEGB200_ESTATE, "audio stream %d not open", stream);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(&ctx->d_audio[stream], 0, sizeof(AudioState), ctx->stream));
+    ctx->audio_open[stream] = 0;
+    return 0;
+}
+
+static size_t audio_out_bytes(int format) { return (format == MPEGB200_AUDIO_S16 ? 2 : 4) * (size_t)2 * MPEGB200_SAMPLES_PER_FRAME; }
+
+int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,
+                             const int32_t* d_samples, int format, void* d_out) {
+    if (!ctx || n_streams < 0 || frames_per_stream < 0 || (n_streams && (!stream_ids || !d_samples || !d_out)))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (format < 0 || format > 3) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
+    if (n_streams == 0 || frames_per_stream == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_samples) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail(ctx, MPEGB200_EINVAL, "device arrays must be 16-byte aligned");
+    {
+        std::vector<uint8_t> seen(ctx->max_streams, 0);
+        for (int i = 0; i < n_streams; i++) {
+            const int s = stream_ids[i];
+            if (s < 0 || s >= ctx->max_streams || !ctx->audio_open[s])
+                return fail(ctx, MPEGB200_ESTATE, "audio stream %d not open", s);
+            if (seen[s]++) return fail(ctx, MPEGB200_EINVAL, "audio stream %d listed twice", s);
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t id_bytes = sizeof(int32_t) * (size_t)n_streams;
+    if (int rc = ensure_pinned(ctx, id_bytes)) return rc;
+    if (int rc = ensure(ctx, ctx->s_ids, id_bytes)) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->pinned, stream_ids, id_bytes);
+    CU(cudaMemcpyAsync(ctx->s_ids.p, ctx->pinned, id_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_audio_synth(ctx->d_audio, ctx->max_streams, (const int32_t*)ctx->s_ids.p, n_streams, frames_per_stream,
+                          d_samples, format, d_out, ctx->d_window, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+int mpegb200_audio_synth(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,
+                         const int32_t* samples, int format, void* out) {
+    if (!ctx || n_streams < 0 || frames_per_stream < 0 || (n_streams && (!stream_ids || !samples || !out)))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (format < 0 || format > 3) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
+    if (n_streams == 0 || frames_per_stream == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n_frames = (size_t)n_streams * frames_per_stream;
+    const size_t in_bytes = n_frames * 2 * 36 * 32 * sizeof(int32_t), out_bytes = n_frames * audio_out_bytes(format);
+    if (int rc = ensure(ctx, ctx->s_samples, in_bytes)) return rc;
+    if (int rc = ensure(ctx, ctx->s_out, out_bytes)) return rc;
+    CU(cudaMemcpyAsync(ctx->s_samples.p, samples, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = mpegb200_audio_synth_dev(ctx, n_streams, stream_ids, frames_per_stream, (const int32_t*)ctx->s_samples.p,
+                                          format, ctx->s_out.p))
+        return rc;
+    CU(cudaMemcpyAsync(out, ctx->s_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mpegb200_audio_read_state(mpegb200_ctx* ctx, int stream, float* v, int* v_pos) {
+    if (!ctx || stream < 0 || stream >= ctx->max_streams) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
+    if (!ctx->audio_open[stream]) return fail(ctx, MPEGB200_ESTATE, "audio stream %d not open", stream);
+    CU(cudaSetDevice(ctx->device));
+    AudioState* st = &ctx->d_audio[stream];
+    int32_t vp = 0;
+    if (v) CU(cudaMemcpyAsync(v, st->v, sizeof(float) * 2048, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&vp, &st->v_pos, sizeof(vp), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (v_pos) *v_pos = vp;
+    return 0;
+}
+
+int mpegb200_audio_write_state(mpegb200_ctx* ctx, int stream, const float* v, int v_pos) {
+    if (!ctx || stream < 0 || stream >= ctx->max_streams || !v) return fail(ctx, MPEGB200_EINVAL, "bad argument");
+    if (!ctx->audio_open[stream]) return fail(ctx, MPEGB200_ESTATE, "audio stream %d not open", stream);
+    if (v_pos < 0 || v_pos > 1023 || (v_pos & 63)) return fail(ctx, MPEGB200_EINVAL, "vPos must be a multiple of 64 in 0..960");
+    CU(cudaSetDevice(ctx->device));
+    AudioState* st = &ctx->d_audio[stream];
+    const int32_t vp = v_pos;
+    CU(cudaMemcpyAsync(st->v, v, sizeof(float) * 2048, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(&st->v_pos, &vp, sizeof(vp), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------- host memory */
+
+void* mpegb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void mpegb200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,470 @@
+// video_kernels.cu -- sm_100a kernels for the MPEG-1 video hot path.
+//
+//   fused_mc_idct_kernel : predictMacroblock/copyMacroblock (video.go:608-637, video_noasm.go:28-80)
+//                          + idct (video.go:801-928) + copy/add*ToDest (video.go:943-1002), fused,
+//                          one launch per batch of independent pictures.
+//   rgba_kernel          : Frame.RGBA() (video.go:31-36 -> Go stdlib image/draw YCbCr 4:2:0 -> RGBA).
+//
+// The arithmetic is the reference's integer arithmetic, bit for bit; only the schedule is new.
+#include "common.cuh"
+
+namespace mpegb200 {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 16-byte asynchronous global->shared copy (LDGSTS), L2-only caching: the data is consumed once.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b): two clamps and a pack in one instruction (I2IP).
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// four ints -> four saturated bytes, v0 in the lowest byte (memory order)
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
+    return pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
+}
+
+// videoPremultiplierMatrix, video.go:1077-1086 (folded to immediates by full unrolling)
+__device__ __forceinline__ constexpr int premult(int i) {
+    constexpr int t[64] = {32, 44, 42, 38, 32, 25, 17, 9,  44, 62, 58, 52, 44, 35, 24, 12, 42, 58, 55, 49, 42, 33,
+                           23, 12, 38, 52, 49, 44, 38, 30, 20, 10, 32, 44, 42, 38, 32, 25, 17, 9,  25, 35, 33, 30,
+                           25, 20, 14, 7,  17, 24, 23, 20, 17, 14, 9,  5,  9,  12, 12, 10, 9,  7,  5,  2};
+    return t[i];
+}
+
+// One 8-point pass of the reference transform (video.go:870-895).  int32 is sufficient: with levels
+// clipped to [-2048, 2047] every intermediate stays below 1.9e9 (tests/test_host_logic.py).
+__device__ __forceinline__ void idct_pass8(int& s0, int& s1, int& s2, int& s3, int& s4, int& s5, int& s6, int& s7) {
+    const int b1 = s4;
+    const int b3 = s2 + s6;
+    const int b4 = s5 - s3;
+    const int tmp1 = s1 + s7;
+    const int tmp2 = s3 + s5;
+    const int b6 = s1 - s7;
+    const int b7 = tmp1 + tmp2;
+    const int m0 = s0;
+    const int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
+    const int x0 = x4 - (((tmp1 - tmp2) * 362 + 128) >> 8);
+    const int x1 = m0 - b1;
+    const int x2 = (((s2 - s6) * 362 + 128) >> 8) - b3;
+    const int x3 = m0 + b1;
+    const int y3 = x1 + x2;
+    const int y4 = x3 + b3;
+    const int y5 = x1 - x2;
+    const int y6 = x3 - b3;
+    const int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
+    s0 = b7 + y4;
+    s1 = x4 + y3;
+    s2 = y5 - x0;
+    s3 = y6 - y7;
+    s4 = y6 + y7;
+    s5 = x0 + y5;
+    s6 = y3 - x4;
+    s7 = y4 - b7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused motion compensation + IDCT + residual add / intra store
+//
+// A CTA owns G consecutive macroblock records (any pictures, any streams) and the <= 6G coded
+// blocks that go with them (contiguous in the coefficient array by the packing rule).
+//   phase 0  records -> per-macroblock context in shared memory (pointers, geometry, validity)
+//   phase 1  cp.async: coefficient blocks (padded pitch) and the reference windows of the
+//            predicted macroblocks (16-byte aligned super-sets, 35 rows x 32 B) -> shared memory
+//   phase 2  half-pel interpolation from the staged windows -> 8-bit prediction tile (384 B / MB)
+//   phase 3  one thread per coded block: dp2a unpack+premultiply, two-pass integer IDCT in
+//            registers, add prediction (or not, intra), saturate, write back into the tile
+//   phase 4  tile -> destination frame, 16 B / 8 B per lane, lanes running across adjacent
+//            macroblocks so that horizontally neighbouring records form full 128-byte lines
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoefPitch = 144;   // 128 B of coefficients + 16: LDS.128 by 8 consecutive threads is conflict-free
+constexpr int kWinRow = 32;       // bytes staged per window row (aligned super-set of <= 15 + 17 bytes)
+constexpr int kWinRowsY = 17, kWinRowsC = 9;
+constexpr int kWinBytes = (kWinRowsY + 2 * kWinRowsC) * kWinRow;  // 1120
+constexpr int kPixPitch = 400;    // 384 B tile + 16: LDS.128 across macroblocks is conflict-free
+
+struct MbCtx {            // 32 bytes, one per record of the CTA
+    const uint8_t* ref;   // reference frame buffer (Y at +0), valid if flags & PREDICT
+    uint8_t* dst;         // destination frame buffer
+    uint32_t buf_bytes;
+    uint16_t luma_w, luma_h;
+    int16_t mv_h, mv_v;
+    uint16_t row, col;
+    uint8_t flags, cbp, valid, pad;
+    uint16_t rel_block;   // first coded block relative to the CTA's first block
+};
+static_assert(sizeof(MbCtx) == 40 || sizeof(MbCtx) == 32, "MbCtx size");
+
+template <int G>
+struct FusedSmem {
+    static constexpr int NT = 6 * G;
+    static constexpr int coef_off = 0;
+    static constexpr int win_off = coef_off + NT * kCoefPitch;
+    static constexpr int pix_off = win_off + G * kWinBytes;
+    static constexpr int ctx_off = pix_off + G * kPixPitch;
+    static constexpr int map_off = ctx_off + G * (int)sizeof(MbCtx);
+    static constexpr int total = map_off + NT + 16;
+};
+
+// rounding averages of four packed bytes
+__device__ __forceinline__ uint32_t avg2_u8x4(uint32_t a, uint32_t b) { return __vavgu4(a, b); }  // (a+b+1)>>1
+__device__ __forceinline__ uint32_t avg4_u8x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {  // (a+b+c+d+2)>>2
+    const uint32_t m = 0x00ff00ffu;
+    uint32_t lo = (((a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u) >> 2) & m;
+    uint32_t hi = ((((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u) >> 2) & m;
+    return lo | (hi << 8);
+}
+
+template <int G>
+__global__ void __launch_bounds__(6 * G) fused_mc_idct_kernel(const StreamInfo* __restrict__ streams, int max_streams,
+                                                            const mpegb200_picture* __restrict__ pics, int n_pics,
+                                                            const mpegb200_mb* __restrict__ mbs, uint32_t n_mb,
+                                                            const int16_t* __restrict__ coeffs, uint32_t n_blocks) {
+    using L = FusedSmem<G>;
+    constexpr int NT = L::NT;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_coef = smem + L::coef_off;
+    uint8_t* s_win = smem + L::win_off;
+    uint8_t* s_pix = smem + L::pix_off;
+    MbCtx* s_ctx = reinterpret_cast<MbCtx*>(smem + L::ctx_off);
+    uint8_t* s_map = smem + L::map_off;
+    __shared__ uint32_t s_nb;
+
+    const int tid = threadIdx.x;
+    const uint32_t m0 = blockIdx.x * (uint32_t)G;
+    const int n_here = (int)min((uint32_t)G, n_mb - m0);
+
+    // ---------------- phase 0: records -> context ----------------
+    s_map[tid] = 0xFF;
+    if (tid == 0) s_nb = 0;
+    __syncthreads();
+    const uint32_t block0 = mbs[m0].coeff_block;  // first coded block of the CTA (broadcast load)
+    if (tid < G) {
+        MbCtx c;
+        c.valid = 0;
+        c.flags = 0;
+        c.cbp = 0;
+        if (tid < n_here) {
+            const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + tid];
+            const uint32_t row = raw.x & 0xffffu, col = raw.x >> 16;
+            const int mv_h = (int16_t)(raw.y & 0xffffu), mv_v = (int16_t)(raw.y >> 16);
+            const uint32_t flags = raw.z & 0xffu, cbp = (raw.z >> 8) & 0x3fu, pic_i = raw.z >> 16;
+            const uint32_t cblock = raw.w;
+            const int ncoded = __popc(cbp);
+            bool ok = pic_i < (uint32_t)n_pics;
+            if (ok) {
+                const uint4 praw = reinterpret_cast<const uint4*>(pics)[pic_i];
+                const int stream = (int)praw.x;
+                const uint32_t dst_b = (praw.y >> 8) & 0xffu, fwd_b = (praw.y >> 16) & 0xffu, bwd_b = praw.y >> 24;
+                ok = stream >= 0 && stream < max_streams && dst_b < 3 && fwd_b < 3 && bwd_b < 3;
+                if (ok) {
+                    const StreamInfo si = streams[stream];
+                    ok = si.open && row < si.mb_h && col < si.mb_w;
+                    const uint32_t rel = cblock - block0;
+                    if (ncoded) ok = ok && rel <= (uint32_t)NT && rel + ncoded <= (uint32_t)NT && cblock + ncoded <= n_blocks;
+                    if (ok) {
+                        c.dst = si.base + (size_t)dst_b * si.buf_stride;
+                        c.ref = si.base + (size_t)((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b) * si.buf_stride;
+                        c.buf_bytes = si.buf_bytes;
+                        c.luma_w = si.luma_w;
+                        c.luma_h = si.luma_h;
+                        c.mv_h = (int16_t)mv_h;
+                        c.mv_v = (int16_t)mv_v;
+                        c.row = (uint16_t)row;
+                        c.col = (uint16_t)col;
+                        c.flags = (uint8_t)flags;
+                        c.cbp = (uint8_t)cbp;
+                        c.rel_block = (uint16_t)rel;
+                        c.valid = 1;
+                        int k = 0;
+                        for (int b = 0; b < 6; b++)
+                            if (cbp & (0x20u >> b)) s_map[rel + k++] = (uint8_t)((tid << 3) | b);
+                        if (ncoded) atomicMax(&s_nb, rel + ncoded);
+                    }
+                }
+            }
+        }
+        s_ctx[tid] = c;
+    }
+    __syncthreads();
+
+    // ---------------- phase 1: asynchronous staging ----------------
+    {
+        const uint32_t nb = s_nb;
+        const char* gsrc = reinterpret_cast<const char*>(coeffs) + (size_t)block0 * 128;
+        const uint32_t sdst = smem_u32(s_coef);
+        for (uint32_t ch = tid; ch < nb * 8; ch += NT)
+            cp_async16(sdst + (ch >> 3) * kCoefPitch + (ch & 7) * 16, gsrc + (size_t)ch * 16);
+
+        // reference windows: per predicted macroblock 35 rows x 2 chunks of 16 B
+        constexpr int kChunks = (kWinRowsY + 2 * kWinRowsC) * 2;  // 70
+        const uint32_t swin = smem_u32(s_win);
+        for (int it = tid; it < G * kChunks; it += NT) {
+            const int j = it / kChunks, q = it - j * kChunks;
+            const MbCtx& c = s_ctx[j];
+            if (!c.valid || !(c.flags & MPEGB200_MB_PREDICT)) continue;
+            const int r = q >> 1, half = q & 1;
+            long off;  // byte offset of the row's first needed pixel inside the reference buffer
+            const int lw = c.luma_w, cw = lw >> 1;
+            if (r < kWinRowsY) {  // luma, video_noasm.go:29-33
+                const int hp = c.mv_h >> 1, vp = c.mv_v >> 1;
+                off = (long)((c.row << 4) + vp + r) * lw + (c.col << 4) + hp;
+            } else {  // chroma: vector halved toward zero first, video_noasm.go:35-42
+                const int cmh = c.mv_h / 2, cmv = c.mv_v / 2;
+                const int hp = cmh >> 1, vp = cmv >> 1;
+                const int rr = r < kWinRowsY + kWinRowsC ? r - kWinRowsY : r - kWinRowsY - kWinRowsC;
+                const long plane = (long)lw * c.luma_h + (r < kWinRowsY + kWinRowsC ? 0 : (long)cw * (c.luma_h >> 1));
+                off = plane + (long)((c.row << 3) + vp + rr) * cw + (c.col << 3) + hp;
+            }
+            long a = (off & ~15L) + half * 16;
+            // memory safety only: a validated batch never needs the clamp (mpegb200_video_validate)
+            a = max(0L, min(a, (long)c.buf_bytes + 48 - 16));
+            cp_async16(swin + j * kWinBytes + r * kWinRow + half * 16, c.ref + a);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: half-pel interpolation -> prediction tile ----------------
+    {
+        constexpr int kItems = 48;  // 8-pixel pieces per macroblock: 32 luma, 8 Cb, 8 Cr
+        for (int it = tid; it < G * kItems; it += NT) {
+            const int j = it / kItems, q = it - j * kItems;
+            const MbCtx& c = s_ctx[j];
+            if (!c.valid || !(c.flags & MPEGB200_MB_PREDICT)) continue;
+            int y, x0, wrow0, mh, mv, stride, tile_off;
+            long off;  // same offset as in phase 1, for row 0 of the plane
+            const int lw = c.luma_w, cw = lw >> 1;
+            if (q < 32) {
+                y = q >> 1;
+                x0 = (q & 1) * 8;
+                mh = c.mv_h;
+                mv = c.mv_v;
+                stride = lw;
+                wrow0 = 0;
+                off = (long)((c.row << 4) + (mv >> 1)) * lw + (c.col << 4) + (mh >> 1);
+                tile_off = y * 16 + x0;
+            } else {
+                const int p = (q - 32) >> 3;
+                y = (q - 32) & 7;
+                x0 = 0;
+                mh = c.mv_h / 2;
+                mv = c.mv_v / 2;
+                stride = cw;
+                wrow0 = kWinRowsY + p * kWinRowsC;
+                off = (long)((c.row << 3) + (mv >> 1)) * cw + (c.col << 3) + (mh >> 1);  // plane base is 16-aligned
+                tile_off = 256 + p * 64 + y * 8;
+            }
+            const bool odd_h = mh & 1, odd_v = mv & 1;
+            const uint8_t* wbase = s_win + j * kWinBytes + wrow0 * kWinRow;
+            // byte position of pixel (y, x0) inside its staged row: the row was staged from (off_row & ~15)
+            const int b0 = (int)((off + (long)y * stride) & 15) + x0;
+            const uint32_t* w0p = reinterpret_cast<const uint32_t*>(wbase + y * kWinRow + (b0 & ~3));
+            const int sh = (b0 & 3) * 8;
+            const uint32_t a0 = w0p[0], a1 = w0p[1], a2 = w0p[2];
+            uint32_t lo = __funnelshift_rc(a0, a1, sh), hi = __funnelshift_rc(a1, a2, sh);
+            if (odd_h) {
+                const uint32_t lo1 = __funnelshift_rc(a0, a1, sh + 8), hi1 = __funnelshift_rc(a1, a2, sh + 8);
+                if (odd_v) {
+                    const int b1 = (int)((off + (long)(y + 1) * stride) & 15) + x0;
+                    const uint32_t* w1p = reinterpret_cast<const uint32_t*>(wbase + (y + 1) * kWinRow + (b1 & ~3));
+                    const int sh1 = (b1 & 3) * 8;
+                    const uint32_t c0 = w1p[0], c1 = w1p[1], c2 = w1p[2];
+                    lo = avg4_u8x4(lo, lo1, __funnelshift_rc(c0, c1, sh1), __funnelshift_rc(c0, c1, sh1 + 8));
+                    hi = avg4_u8x4(hi, hi1, __funnelshift_rc(c1, c2, sh1), __funnelshift_rc(c1, c2, sh1 + 8));
+                } else {
+                    lo = avg2_u8x4(lo, lo1);
+                    hi = avg2_u8x4(hi, hi1);
+                }
+            } else if (odd_v) {
+                const int b1 = (int)((off + (long)(y + 1) * stride) & 15) + x0;
+                const uint32_t* w1p = reinterpret_cast<const uint32_t*>(wbase + (y + 1) * kWinRow + (b1 & ~3));
+                const int sh1 = (b1 & 3) * 8;
+                const uint32_t c0 = w1p[0], c1 = w1p[1], c2 = w1p[2];
+                lo = avg2_u8x4(lo, __funnelshift_rc(c0, c1, sh1));
+                hi = avg2_u8x4(hi, __funnelshift_rc(c1, c2, sh1));
+            }
+            *reinterpret_cast<uint2*>(s_pix + j * kPixPitch + tile_off) = make_uint2(lo, hi);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: one thread per coded block ----------------
+    {
+        const uint32_t bm = s_map[tid];
+        if (bm != 0xFF) {
+            const int j = bm >> 3, k = bm & 7;
+            const bool intra = s_ctx[j].flags & MPEGB200_MB_INTRA;
+            int c[64];
+            const uint4* src = reinterpret_cast<const uint4*>(s_coef + tid * kCoefPitch);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const uint4 w = src[r];
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    // level * premultiplier (video.go:744): dp2a multiplies the two int16 halves by bytes
+                    c[r * 8 + 2 * p] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p), 0);
+                    c[r * 8 + 2 * p + 1] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p + 1) << 8, 0);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)  // columns, video.go:869-896
+                idct_pass8(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
+            uint8_t* tile = s_pix + j * kPixPitch + (k < 4 ? (k >> 1) * 128 + (k & 1) * 8 : 256 + (k - 4) * 64);
+            const int tpitch = k < 4 ? 16 : 8;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {  // rows, video.go:899-926, then copy/addBlockToDest
+                idct_pass8(c[r * 8], c[r * 8 + 1], c[r * 8 + 2], c[r * 8 + 3], c[r * 8 + 4], c[r * 8 + 5], c[r * 8 + 6],
+                           c[r * 8 + 7]);
+                int v[8];
+#pragma unroll
+                for (int x = 0; x < 8; x++) v[x] = (c[r * 8 + x] + 128) >> 8;
+                uint2* tp = reinterpret_cast<uint2*>(tile + r * tpitch);
+                if (!intra) {
+                    const uint2 pr = *tp;  // clamp(dest + residual), video.go:958-971
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        v[x] = (int)__dp4a(pr.x, 1u << (8 * x), (uint32_t)v[x]);
+                        v[4 + x] = (int)__dp4a(pr.y, 1u << (8 * x), (uint32_t)v[4 + x]);
+                    }
+                }
+                *tp = make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 4: tile -> destination frame ----------------
+    for (int it = tid; it < 16 * G; it += NT) {  // luma: 16 rows x 16 bytes per macroblock
+        const int r = it / G, j = it - r * G;
+        const MbCtx& c = s_ctx[j];
+        if (!c.valid) continue;
+        const uint32_t mask = (c.flags & MPEGB200_MB_PREDICT) ? 0x3fu : c.cbp;  // blocks with defined pixels
+        const int kl = r < 8 ? 0 : 2;
+        const bool left = mask & (0x20u >> kl), right = mask & (0x10u >> kl);
+        if (!left && !right) continue;
+        const uint8_t* t = s_pix + j * kPixPitch + r * 16;
+        uint8_t* d = c.dst + (size_t)((c.row << 4) + r) * c.luma_w + (c.col << 4);
+        if (left && right) {
+            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(t);
+        } else if (left) {
+            *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(t);
+        } else {
+            *reinterpret_cast<uint2*>(d + 8) = *reinterpret_cast<const uint2*>(t + 8);
+        }
+    }
+    for (int it = tid; it < 16 * G; it += NT) {  // chroma: 2 planes x 8 rows x 8 bytes
+        const int pr = it / G, j = it - pr * G;
+        const int p = pr >> 3, r = pr & 7;
+        const MbCtx& c = s_ctx[j];
+        if (!c.valid) continue;
+        const uint32_t mask = (c.flags & MPEGB200_MB_PREDICT) ? 0x3fu : c.cbp;
+        if (!(mask & (0x02u >> p))) continue;
+        const int cw = c.luma_w >> 1;
+        const size_t plane = (size_t)c.luma_w * c.luma_h + (p ? (size_t)cw * (c.luma_h >> 1) : 0);
+        uint8_t* d = c.dst + plane + (size_t)((c.row << 3) + r) * cw + (c.col << 3);
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(s_pix + j * kPixPitch + 256 + p * 64 + r * 8);
+    }
+}
+
+constexpr int kG = 16;  // macroblock records per CTA (96 threads)
+
+cudaError_t launch_fused_mc_idct(const StreamInfo* d_streams, int max_streams, const mpegb200_picture* d_pics,
+                                 int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb, const int16_t* d_coeffs,
+                                 uint32_t n_blocks, cudaStream_t stream) {
+    if (n_mb == 0) return cudaSuccess;
+    const uint32_t grid = (n_mb + kG - 1) / kG;
+    fused_mc_idct_kernel<kG><<<grid, 6 * kG, FusedSmem<kG>::total, stream>>>(d_streams, max_streams, d_pics, n_pics,
+                                                                            d_mbs, n_mb, d_coeffs, n_blocks);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame.RGBA(): Go 1.23 image/draw -> imageutil.DrawYCbCr, 4:2:0 (restated; parity unpinned):
+//   yy1 = Y*0x10101; cb1 = Cb-128; cr1 = Cr-128
+//   R = sat8((yy1 + 91881*cr1) >> 16), G = sat8((yy1 - 22554*cb1 - 46802*cr1) >> 16),
+//   B = sat8((yy1 + 116130*cb1) >> 16), A = 255; chroma sample (x/2, y/2).
+// One thread converts 4 horizontally adjacent pixels of one row: 4 B of Y + 2 B Cb + 2 B Cr in,
+// one 16-byte store out.  grid = (ceil(ceil(w/4)/64), h, n_frames).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rgba_px(int y, int cb1, int cr1) {
+    const int yy1 = y * 0x10101;
+    const int r = (yy1 + 91881 * cr1) >> 16;
+    const int g = (yy1 - 22554 * cb1 - 46802 * cr1) >> 16;
+    const int b = (yy1 + 116130 * cb1) >> 16;
+    // bytes R,G,B,A in memory order; (v>>16) clamped to 0..255 equals the reference's bit trick
+    return pack_sat_u8(g, r, pack_sat_u8(255, b, 0u));
+}
+
+__global__ void __launch_bounds__(64) rgba_kernel(const StreamInfo* __restrict__ streams, int max_streams,
+                                                  const int32_t* __restrict__ stream_ids,
+                                                  const uint8_t* __restrict__ bufs, uint8_t* __restrict__ out,
+                                                  size_t out_stride) {
+    const int f = blockIdx.z;
+    const int stream = stream_ids[f];
+    if (stream < 0 || stream >= max_streams) return;
+    const StreamInfo si = streams[stream];
+    const uint32_t buf = bufs[f];
+    if (!si.open || buf >= 3) return;
+    const int y = blockIdx.y;
+    const int x = (blockIdx.x * 64 + threadIdx.x) * 4;
+    if (y >= si.height || x >= si.width) return;
+    const uint8_t* base = si.base + (size_t)buf * si.buf_stride;
+    const int cw = si.luma_w >> 1;
+    const uint8_t* yp = base + (size_t)y * si.luma_w + x;
+    const uint8_t* cbp = base + (size_t)si.luma_w * si.luma_h + (size_t)(y >> 1) * cw + (x >> 1);
+    const uint8_t* crp = cbp + (size_t)cw * (si.luma_h >> 1);
+    const uint32_t yy = *reinterpret_cast<const uint32_t*>(yp);  // luma_w is a multiple of 16: always readable
+    const uint32_t cbb = *reinterpret_cast<const uint16_t*>(cbp);
+    const uint32_t crr = *reinterpret_cast<const uint16_t*>(crp);
+    const int cb0 = (int)(cbb & 0xff) - 128, cb1 = (int)(cbb >> 8) - 128;
+    const int cr0 = (int)(crr & 0xff) - 128, cr1 = (int)(crr >> 8) - 128;
+    uint4 o;
+    o.x = rgba_px(yy & 0xff, cb0, cr0);
+    o.y = rgba_px((yy >> 8) & 0xff, cb0, cr0);
+    o.z = rgba_px((yy >> 16) & 0xff, cb1, cr1);
+    o.w = rgba_px(yy >> 24, cb1, cr1);
+    uint8_t* op = out + (size_t)f * out_stride + ((size_t)y * si.width + x) * 4;
+    const int left = si.width - x;
+    if (left >= 4 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+        *reinterpret_cast<uint4*>(op) = o;
+    } else {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(op);
+        o32[0] = o.x;
+        if (left > 1) o32[1] = o.y;
+        if (left > 2) o32[2] = o.z;
+        if (left > 3) o32[3] = o.w;
+    }
+}
+
+cudaError_t launch_rgba(const StreamInfo* d_streams, int max_streams, const int32_t* d_stream_ids,
+                        const uint8_t* d_bufs, int n, int max_w, int max_h, uint8_t* d_rgba,
+                        size_t rgba_stride_bytes, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int per_row = (max_w + 3) / 4;
+    for (int first = 0; first < n; first += 32768) {
+        const int cnt = min(32768, n - first);
+        dim3 grid((per_row + 63) / 64, max_h, cnt);
+        rgba_kernel<<<grid, 64, 0, stream>>>(d_streams, max_streams, d_stream_ids + first, d_bufs + first,
+                                             d_rgba + (size_t)first * rgba_stride_bytes, rgba_stride_bytes);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t configure_kernels() {
+    return cudaFuncSetAttribute(fused_mc_idct_kernel<kG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                FusedSmem<kG>::total);
+}
+
+}  // namespace mpegb200

@@ -1,0 +1,296 @@
+"""Parity of the CUDA video path (through the C-ABI) with the CPU oracle.  Needs a B200.
+
+Bit-exact everywhere: Y/Cb/Cr planes are integer work.  Reads like the reference's own tests:
+TestVideoGolden (mpeg_test.go:203-231), runParitySweep (video_test.go:63-103)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from mpeg_b200 import workload as wl
+
+pytestmark = pytest.mark.gpu
+
+VIDEO_GOLDEN = 0xEA6D7FCB1340BA3F
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import mpeg_b200
+    c = mpeg_b200.Context(device=0, max_streams=64)
+    yield c
+    c.close()
+
+
+def fresh_stream(ctx, sid, w, h):
+    try:
+        ctx.video_close(sid)
+    except Exception:
+        pass
+    ctx.video_open(sid, w, h)
+
+
+def assert_frames_equal(ctx, fs, stream, oracle_stream=None, msg=""):
+    o = stream if oracle_stream is None else oracle_stream
+    for b in range(3):
+        got = ctx.video_read_frame(stream, b)
+        want = fs.whole(o, b)
+        if not np.array_equal(got, want):
+            bad = np.flatnonzero(got != want)
+            raise AssertionError(f"{msg} stream {stream} buf {b}: {len(bad)} bytes differ, first at {bad[0]} "
+                                 f"(got {got[bad[0]]}, want {want[bad[0]]})")
+
+
+def test_golden_clip_through_gpu(ctx, golden_dir):
+    """TestVideoGolden with the kernels swapped in: the oracle's parser emits the packed records,
+    the GPU does MC + IDCT + add, the returned frames hash to the reference's golden value."""
+    data = (golden_dir / "test.mpeg1video").read_bytes()
+    v = ol.VideoOracle(data, tap=True)
+    fresh_stream(ctx, 0, v.width, v.height)
+    h, frames = ol.FNV_OFFSET, 0
+    while True:
+        f = v.decode()
+        pics, mbs, coeffs = v.tap()
+        if len(mbs):
+            ctx.video_validate(pics, mbs, len(coeffs))
+            # one launch per picture: consecutive pictures of a stream depend on each other
+            for i in range(len(pics)):
+                p = pics[i:i + 1].copy()
+                m = mbs[p["first_mb"][0]:p["first_mb"][0] + p["n_mb"][0]].copy()
+                m["pic"] = 0
+                p["first_mb"] = 0
+                ctx.video_decode_pictures(p, m, coeffs_slice(m, coeffs))
+        if f is None:
+            break
+        y, cb, cr = ctx.video_read_planes(0, v.last_buf())
+        assert np.array_equal(y, f.plane("y")), f"frame {frames}"
+        h = ol.fnv(h, y)
+        h = ol.fnv(h, cb)
+        h = ol.fnv(h, cr)
+        frames += 1
+    assert h == VIDEO_GOLDEN, f"{h:#018x} after {frames} frames"
+
+
+def coeffs_slice(m, coeffs):
+    """Coefficient blocks of a record slice, re-based so that coeff_block starts at 0."""
+    if len(m) == 0:
+        return np.zeros((0, 64), np.int16)
+    first = int(m["coeff_block"][0])
+    n = int(sum(bin(int(c)).count("1") for c in m["cbp"]))
+    m["coeff_block"] -= first
+    return coeffs[first:first + n]
+
+
+def test_copy_macroblock_parity_sweep_gpu(ctx):
+    """video_test.go:63-103 on the GPU: every half-pel mode, negative vectors, chroma rounding."""
+    fs = ol.FrameSet(1, 64, 64)
+    fresh_stream(ctx, 1, 64, 64)
+    from test_oracle_golden import fill_test_frame
+    fill_test_frame(fs, 0, 1, 1)  # source = forward buffer 1, fill 1
+    ctx.video_write_frame(1, 1, fs.whole(0, 1))
+    recs, want = [], []
+    for mb_row in (1, 2):
+        for mb_col in (1, 2):
+            for mh in range(-3, 4):
+                for mv in range(-3, 4):
+                    fill_test_frame(fs, 0, 0, 0)
+                    ctx.video_write_frame(1, 0, fs.whole(0, 0))
+                    m = np.zeros(1, wl.MB_DTYPE)
+                    m["mb_row"], m["mb_col"], m["mv_h"], m["mv_v"] = mb_row, mb_col, mh, mv
+                    m["flags"] = wl.MB_PREDICT
+                    p = np.zeros(1, wl.PICTURE_DTYPE)
+                    p[0] = (1, wl.PIC_P, 0, 1, 2, 0, 1)
+                    ctx.video_validate(p, m, 0)
+                    ctx.video_decode_pictures(p, m, np.zeros((0, 64), np.int16))
+                    assert ol.lib().orc_copy_macroblock(mh, mv, mb_row, mb_col, C.byref(fs.frame(0, 1)),
+                                                        C.byref(fs.frame(0, 0))) == 0
+                    got = ctx.video_read_frame(1, 0)
+                    assert np.array_equal(got, fs.whole(0, 0)), (mb_row, mb_col, mh, mv)
+
+
+@pytest.mark.parametrize("geometry,n_pictures", [(wl.CIF, 30), (wl.Geometry(176, 144), 12), (wl.Geometry(200, 120), 9)])
+def test_synthetic_sequence_bit_exact(ctx, geometry, n_pictures):
+    """BASELINE config 2 (ii): one stream, coding order I P B B P B B ..., natural distributions,
+    all three buffers compared after every picture."""
+    g = geometry
+    rng = wl.stream_rng(2, 0)
+    fs = ol.FrameSet(1, g.width, g.height)
+    fresh_stream(ctx, 2, g.width, g.height)
+    for b in range(3):  # start from arbitrary (stale) buffer contents, SURVEY Q6
+        buf = wl.random_reference_frame(rng, g)
+        fs.whole(0, b)[:] = buf
+        ctx.video_write_frame(2, b, buf)
+    rot = wl.BufferRotation()
+    types = [wl.PIC_I] + [wl.PIC_P, wl.PIC_B, wl.PIC_B] * 20
+    for i in range(n_pictures):
+        t = types[i]
+        dst, fwd, bwd = rot.begin(t)
+        mbs, coeffs = wl.make_picture(rng, g, t, "natural")
+        pics, mbs, coeffs = wl.batch_pictures([(mbs, coeffs)], [2], t, [(dst, fwd, bwd)])
+        ctx.video_validate(pics, mbs, len(coeffs))
+        ctx.video_decode_pictures(pics, mbs, coeffs)
+        opics = pics.copy()
+        opics["stream"] = 0
+        assert fs.exec_pictures(opics, mbs, coeffs) == 0
+        rot.end(t)
+        assert_frames_equal(ctx, fs, 2, 0, msg=f"picture {i} type {t}")
+
+
+def test_dense_720p_batch_bit_exact(ctx):
+    """BASELINE config 3 at reduced stream count: dense-P 720p, several streams in one launch."""
+    g = wl.HD720
+    n = 6
+    fs = ol.FrameSet(n, g.width, g.height)
+    per, bufs = [], []
+    for s in range(n):
+        rng = wl.stream_rng(3, s)
+        fresh_stream(ctx, 10 + s, g.width, g.height)
+        ref = wl.random_reference_frame(rng, g)
+        fs.whole(s, 1)[:] = ref
+        ctx.video_write_frame(10 + s, 1, ref)
+        per.append(wl.make_picture(rng, g, wl.PIC_P, "dense"))
+        bufs.append((0, 1, 2))
+    pics, mbs, coeffs = wl.batch_pictures(per, [10 + s for s in range(n)], wl.PIC_P, bufs)
+    ctx.video_validate(pics, mbs, len(coeffs))
+    ctx.video_decode_pictures(pics, mbs, coeffs)
+    opics = pics.copy()
+    opics["stream"] = np.arange(n)
+    assert fs.exec_pictures(opics, mbs, coeffs, threads=ol.lib().orc_max_threads()) == 0
+    for s in range(n):
+        assert_frames_equal(ctx, fs, 10 + s, s, msg="dense 720p")
+    # size-independent properties on the same batch: idempotence (same inputs -> same output)
+    before = [ctx.video_read_frame(10 + s, 0) for s in range(n)]
+    ctx.video_decode_pictures(pics, mbs, coeffs)
+    for s in range(n):
+        assert np.array_equal(before[s], ctx.video_read_frame(10 + s, 0))
+    for s in range(n):
+        ctx.video_close(10 + s)
+
+
+def test_zero_residual_zero_vector_picture_is_a_copy(ctx):
+    """A P picture whose macroblocks all have a zero vector and no coded blocks reproduces the
+    reference picture byte for byte (skipped macroblocks, video.go:503-510)."""
+    g = wl.CIF
+    rng = wl.stream_rng(2, 7)
+    fresh_stream(ctx, 3, g.width, g.height)
+    ref = wl.random_reference_frame(rng, g)
+    ctx.video_write_frame(3, 1, ref)
+    mbs = np.zeros(g.n_mb, wl.MB_DTYPE)
+    mbs["mb_row"] = np.repeat(np.arange(g.mb_h), g.mb_w)
+    mbs["mb_col"] = np.tile(np.arange(g.mb_w), g.mb_h)
+    mbs["flags"] = wl.MB_PREDICT
+    pics = np.zeros(1, wl.PICTURE_DTYPE)
+    pics[0] = (3, wl.PIC_P, 0, 1, 2, 0, len(mbs))
+    ctx.video_decode_pictures(pics, mbs, np.zeros((0, 64), np.int16))
+    got = ctx.video_read_frame(3, 0)
+    assert np.array_equal(got[:g.picture_bytes], ref[:g.picture_bytes])
+    assert not got[g.picture_bytes:].any()  # the pad is never written
+
+
+def test_ragged_and_edge_batches(ctx):
+    g = wl.Geometry(64, 48)
+    rng = wl.stream_rng(2, 11)
+    fs = ol.FrameSet(2, g.width, g.height)
+    for s in (4, 5):
+        fresh_stream(ctx, s, g.width, g.height)
+        for b in range(3):
+            buf = wl.random_reference_frame(rng, g)
+            fs.whole(s - 4, b)[:] = buf
+            ctx.video_write_frame(s, b, buf)
+    # empty batch: a no-op
+    ctx.video_decode_pictures(np.zeros(0, wl.PICTURE_DTYPE), np.zeros(0, wl.MB_DTYPE), np.zeros((0, 64), np.int16))
+    # ragged: stream 4 gets 5 scattered macroblocks, stream 5 a full B picture; untouched macroblocks keep stale pixels
+    m4, c4 = wl.make_picture(rng, g, wl.PIC_P, "natural")
+    keep = np.array([0, 3, 4, 7, 11])
+    cnt = np.array([bin(int(c)).count("1") for c in m4["cbp"]])
+    sel = np.concatenate([np.arange(m4["coeff_block"][k], m4["coeff_block"][k] + cnt[k]) for k in keep]).astype(int)
+    m4k = m4[keep].copy()
+    m4k["coeff_block"] = np.cumsum(cnt[keep]) - cnt[keep]
+    c4k = c4[sel]
+    m5, c5 = wl.make_picture(rng, g, wl.PIC_B, "natural")
+    pics, mbs, coeffs = wl.batch_pictures([(m4k, c4k), (m5, c5)], [4, 5], wl.PIC_B, [(0, 1, 2), (2, 0, 1)])
+    ctx.video_validate(pics, mbs, len(coeffs))
+    ctx.video_decode_pictures(pics, mbs, coeffs)
+    opics = pics.copy()
+    opics["stream"] = [0, 1]
+    assert fs.exec_pictures(opics, mbs, coeffs) == 0
+    assert_frames_equal(ctx, fs, 4, 0, "ragged")
+    assert_frames_equal(ctx, fs, 5, 1, "full B")
+    # an intra macroblock with a hole in its cbp keeps the old pixels of the missing block (aborted block)
+    m = np.zeros(1, wl.MB_DTYPE)
+    m["mb_row"], m["mb_col"], m["flags"], m["cbp"] = 1, 2, wl.MB_INTRA, 0b101101
+    co = wl._draw_blocks(rng, 4, np.ones(4, bool), dense=False)
+    p = np.zeros(1, wl.PICTURE_DTYPE)
+    p[0] = (4, wl.PIC_I, 1, 0, 2, 0, 1)
+    ctx.video_decode_pictures(p, m, co)
+    op = p.copy()
+    op["stream"] = 0
+    assert fs.exec_pictures(op, m, co) == 0
+    assert_frames_equal(ctx, fs, 4, 0, "intra with holes")
+    # windows running off the bottom of a plane read the next plane (contiguous planes)
+    m = np.zeros(2, wl.MB_DTYPE)
+    m["mb_row"], m["mb_col"] = g.mb_h - 1, [0, 1]
+    m["mv_v"], m["mv_h"], m["flags"] = [9, 15], [1, 0], wl.MB_PREDICT
+    p[0] = (4, wl.PIC_P, 2, 1, 0, 0, 2)
+    ctx.video_validate(p, m, 0)
+    ctx.video_decode_pictures(p, m, np.zeros((0, 64), np.int16))
+    op = p.copy()
+    op["stream"] = 0
+    assert fs.exec_pictures(op, m, np.zeros((0, 64), np.int16)) == 0
+    assert_frames_equal(ctx, fs, 4, 0, "over-read into next plane")
+
+
+def test_validate_rejects_bad_records(ctx):
+    import mpeg_b200
+    g = wl.Geometry(64, 48)
+    fresh_stream(ctx, 6, g.width, g.height)
+    p = np.zeros(1, wl.PICTURE_DTYPE)
+    p[0] = (6, wl.PIC_P, 0, 1, 2, 0, 1)
+    m = np.zeros(1, wl.MB_DTYPE)
+    m["flags"] = wl.MB_PREDICT
+    ctx.video_validate(p, m, 0)
+
+    def bad(**kw):
+        mm, pp, nb = m.copy(), p.copy(), kw.pop("n_blocks", 0)
+        for k, v in kw.items():
+            (pp if k in pp.dtype.names else mm)[k] = v
+        with pytest.raises(mpeg_b200.MpegB200Error) as e:
+            ctx.video_validate(pp, mm, nb)
+        assert e.value.code == -5
+
+    bad(mv_h=-1)                      # reads left of the frame buffer: the Go code would panic
+    bad(mb_row=g.mb_h)                # outside the picture
+    bad(flags=0)                      # neither intra nor predicted
+    bad(flags=wl.MB_INTRA | wl.MB_PREDICT)
+    bad(cbp=1, n_blocks=0)            # coefficient block beyond the array
+    bad(stream=7)                     # stream not open
+    bad(dst_buf=3)
+    bad(fwd_buf=0)                    # reference == destination
+    two = np.concatenate([m, m])
+    with pytest.raises(mpeg_b200.MpegB200Error):
+        ctx.video_validate(p, two, 0)  # same macroblock twice in one picture
+    with pytest.raises(mpeg_b200.MpegB200Error):
+        ctx.video_validate(np.concatenate([p, p]), m, 0)  # two pictures of one stream
+    with pytest.raises(mpeg_b200.MpegB200Error):
+        ctx.video_open(6, 64, 48)      # already open
+    with pytest.raises(mpeg_b200.MpegB200Error):
+        ctx.video_read_frame(9, 0)     # not open
+
+
+def test_rgba_matches_oracle(ctx):
+    """Frame.RGBA(): GPU vs the CPU restatement of Go's image/draw arithmetic (parity unpinned
+    against Go itself), including widths that are not multiples of 4 or 16."""
+    for sid, (w, h) in enumerate([(160, 120), (352, 288), (50, 34), (61, 33)]):
+        g = wl.Geometry(w, h)
+        rng = wl.stream_rng(3, 100 + sid)
+        fs = ol.FrameSet(1, w, h)
+        fresh_stream(ctx, 20 + sid, w, h)
+        buf = wl.random_reference_frame(rng, g)
+        buf[:64] = [0, 255] * 32  # extremes
+        fs.whole(0, 2)[:] = buf
+        ctx.video_write_frame(20 + sid, 2, buf)
+        got = ctx.video_rgba(20 + sid, 2, w, h)
+        want = fs.rgba(0, 2)
+        assert np.array_equal(got, want), (w, h)
+        assert (got[..., 3] == 255).all()

@@ -1,0 +1,137 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, the host-side
+workload generator and buffer-rotation mirror behave, the int32 bound of the IDCT holds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+
+def test_library_exports_every_declared_symbol():
+    from mpeg_b200 import _lib
+    L = _lib.load()
+    names = _lib.exported_symbols()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mpegb200.h but not exported"
+    assert set(L._signatures) == set(names)
+    assert L.mpegb200_abi_version() == 1
+
+
+def test_no_silent_cpu_fallback_without_a_gpu():
+    import torch
+    import mpeg_b200
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mpeg_b200.MpegB200Error):
+        mpeg_b200.Context()
+
+
+def test_product_does_not_import_the_oracle():
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    for p in list((root / "mpeg_b200").rglob("*.py")) + list((root / "mpeg_b200" / "csrc").glob("*.c*")):
+        text = p.read_text()
+        for needle in ("oracle_lib", "liboracle", "import oracle", "from oracle", "oracle/", "mpeg_oracle", "orc_"):
+            assert needle not in text, f"{p} reaches into the oracle ({needle})"
+
+
+def test_record_struct_layouts_match_the_header():
+    from mpeg_b200 import context as cx
+    assert cx.MB_DTYPE.itemsize == 16 and cx.PICTURE_DTYPE.itemsize == 16
+    assert cx.MB_DTYPE.fields["coeff_block"][1] == 12 and cx.MB_DTYPE.fields["pic"][1] == 10
+    assert cx.PICTURE_DTYPE.fields["first_mb"][1] == 8
+    assert cx.MB_DTYPE == ol.MB_DTYPE and cx.PICTURE_DTYPE == ol.PIC_DTYPE
+
+
+def test_zigzag_and_geometry():
+    from mpeg_b200 import workload as wl
+    assert wl.ZIGZAG[:10].tolist() == [0, 1, 8, 16, 9, 2, 3, 10, 17, 24]  # video.go:1044-1046
+    assert sorted(wl.ZIGZAG.tolist()) == list(range(64))
+    g = wl.HD720
+    assert (g.mb_w, g.mb_h, g.n_mb) == (80, 45, 3600)
+    assert g.picture_bytes == 1382400 and g.frame_bytes == 1382400 + 20480
+    assert wl.CIF.n_mb == 396 and wl.CIF.picture_bytes == 152064
+
+
+def test_workload_generator_obeys_the_packing_rules():
+    from mpeg_b200 import workload as wl
+    g = wl.CIF
+    rng = wl.stream_rng(2, 0)
+    for t, mode in [(wl.PIC_I, "natural"), (wl.PIC_P, "natural"), (wl.PIC_B, "natural"), (wl.PIC_P, "dense")]:
+        mbs, coeffs = wl.make_picture(rng, g, t, mode)
+        cnt = np.array([bin(int(c)).count("1") for c in mbs["cbp"]])
+        assert np.array_equal(mbs["coeff_block"], np.cumsum(cnt) - cnt) and cnt.sum() == len(coeffs)
+        intra = (mbs["flags"] & wl.MB_INTRA) != 0
+        assert ((mbs["flags"] & wl.MB_PREDICT) != 0).sum() + intra.sum() == len(mbs)
+        assert (mbs["cbp"][intra] == 63).all()
+        assert np.abs(coeffs.astype(int)).max() <= 2047 * 8
+        if t == wl.PIC_I:
+            assert intra.all()
+        if mode == "dense":
+            assert (mbs["cbp"] == 63).all() and (coeffs != 0).mean() > 0.99
+            total, read = wl.algorithmic_bytes(mbs, len(coeffs))
+            assert total == 1552 * g.n_mb and read == 1168 * g.n_mb   # 1552 B / dense-P macroblock
+        # the oracle accepts every generated record (windows inside the planes)
+        fs = ol.FrameSet(1, g.width, g.height)
+        pics, m, c = wl.batch_pictures([(mbs, coeffs)], [0], t, [(0, 1, 2)])
+        assert fs.exec_pictures(pics, m, c) == 0
+
+
+def test_buffer_rotation_mirrors_the_decoder(golden_dir):
+    """The host-side rotation mirror (video.go:406-409, 430-433) reproduces the buffer roles the
+    oracle's decoder reports for the reference clip."""
+    from mpeg_b200 import workload as wl
+    v = ol.VideoOracle((golden_dir / "test.mpeg1video").read_bytes(), tap=True)
+    rot = wl.BufferRotation()
+    seen = 0
+    while v.decode() is not None and seen < 60:
+        pics, _, _ = v.tap()
+        for p in pics:
+            dst, fwd, bwd = rot.begin(int(p["type"]))
+            assert (dst, fwd, bwd) == (int(p["dst_buf"]), int(p["fwd_buf"]), int(p["bwd_buf"]))
+            rot.end(int(p["type"]))
+            seen += 1
+    assert seen >= 60
+
+
+def test_idct_intermediates_fit_int32():
+    """propagate |.| bounds through both passes of the transform for clipped levels
+    (|level| <= 2048, intra DC <= 2047*8 in level form): every intermediate stays below 2^31, so
+    the kernel's int32 arithmetic is exact.  Triangle-inequality bound, not sampling."""
+    pm = np.array([32, 44, 42, 38, 32, 25, 17, 9, 44, 62, 58, 52, 44, 35, 24, 12, 42, 58, 55, 49, 42, 33, 23, 12,
+                   38, 52, 49, 44, 38, 30, 20, 10, 32, 44, 42, 38, 32, 25, 17, 9, 25, 35, 33, 30, 25, 20, 14, 7,
+                   17, 24, 23, 20, 17, 14, 9, 5, 9, 12, 12, 10, 9, 7, 5, 2], dtype=np.int64).reshape(8, 8)
+    bound = 2048 * pm
+    bound[0, 0] = max(bound[0, 0], 2047 * 8 * 32)
+    worst = 0
+
+    def pass8(s):
+        nonlocal worst
+        s0, s1, s2, s3, s4, s5, s6, s7 = s
+        b1, b3, b4 = s4, s2 + s6, s5 + s3
+        t1, t2, b6 = s1 + s7, s3 + s5, s1 + s7
+        b7 = t1 + t2
+        p1 = b6 * 473 + b4 * 196 + 128
+        x4 = (p1 >> 8) + 1 + b7
+        p2 = (t1 + t2) * 362 + 128
+        x0 = x4 + (p2 >> 8) + 1
+        x1 = s0 + b1
+        p3 = (s2 + s6) * 362 + 128
+        x2 = (p3 >> 8) + 1 + b3
+        x3 = s0 + b1
+        y3, y4, y5, y6 = x1 + x2, x3 + b3, x1 + x2, x3 + b3
+        p4 = b4 * 473 + b6 * 196 + 128
+        y7 = x0 + (p4 >> 8) + 1
+        outs = [b7 + y4, x4 + y3, y5 + x0, y6 + y7, y6 + y7, x0 + y5, y3 + x4, y4 + b7]
+        worst = max(worst, p1, p2, p3, p4, *outs)
+        return outs
+
+    cols = [pass8([int(bound[r, c]) for r in range(8)]) for c in range(8)]
+    after = np.array(cols, dtype=object).T  # after[r][c]
+    for r in range(8):
+        outs = pass8([int(after[r][c]) for c in range(8)])
+        worst = max(worst, *[o + 128 for o in outs])
+    assert worst < 2**31, worst
+    assert worst > 1.5e9  # the bound is tight-ish: int32 has ~12 % headroom (1.897e9)
