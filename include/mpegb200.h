@@ -164,6 +164,15 @@ int mpegb200_video_write_planes(mpegb200_ctx* ctx, int stream, int buf,
 /* Whole frame buffer (Y|Cb|Cr|pad) to/from host. */
 int mpegb200_video_read_frame(mpegb200_ctx* ctx, int stream, int buf, uint8_t* dst, size_t dst_bytes);
 int mpegb200_video_write_frame(mpegb200_ctx* ctx, int stream, int buf, const uint8_t* src, size_t src_bytes);
+/* Batched, asynchronous picture read-back: frame i = (streams[i], bufs[i]); its Y|Cb|Cr bytes
+ * (luma + 2*chroma, without the pad) go to dst + i*dst_stride.  `dst` is host memory (pinned for
+ * true asynchrony) for _host, device memory for _dev.  Enqueued on the context stream: call
+ * mpegb200_sync before touching the bytes.  This is what feeds Plane.Data of many *Frames at once
+ * and, in the multi-GPU layout, the send buffer of the NCCL gather. */
+int mpegb200_video_read_pictures_host(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs,
+                                      uint8_t* dst, size_t dst_stride);
+int mpegb200_video_read_pictures_dev(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs,
+                                     uint8_t* d_dst, size_t dst_stride);
 /* Device address of a frame buffer (Y at +0, Cb at +luma_w*luma_h, Cr after it). */
 void* mpegb200_video_frame_dev(mpegb200_ctx* ctx, int stream, int buf);
 

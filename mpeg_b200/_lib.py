@@ -67,6 +67,8 @@ def load():
         "mpegb200_video_read_frame": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
         "mpegb200_video_write_frame": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
         "mpegb200_video_frame_dev": (vp, [vp, C.c_int, C.c_int]),
+        "mpegb200_video_read_pictures_host": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t]),
+        "mpegb200_video_read_pictures_dev": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t]),
         "mpegb200_video_rgba": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "mpegb200_video_rgba_batch_dev": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t]),
         "mpegb200_audio_open": (C.c_int, [vp, C.c_int]),

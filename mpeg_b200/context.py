@@ -130,6 +130,13 @@ class Context:
         data = np.ascontiguousarray(data, np.uint8).reshape(-1)
         self._ck(self.L.mpegb200_video_write_frame(self.h, stream, buf, _ptr(data), data.nbytes))
 
+    def video_read_pictures(self, streams, bufs, dst: int, stride: int, device: bool = False):
+        """Asynchronous batched read-back of Y|Cb|Cr into host (pinned) or device memory at `dst`."""
+        streams = np.ascontiguousarray(streams, np.int32)
+        bufs = np.ascontiguousarray(bufs, np.uint8)
+        fn = self.L.mpegb200_video_read_pictures_dev if device else self.L.mpegb200_video_read_pictures_host
+        self._ck(fn(self.h, len(streams), _ptr(streams), _ptr(bufs), C.c_void_p(dst), stride))
+
     def video_frame_dev(self, stream: int, buf: int) -> int:
         p = self.L.mpegb200_video_frame_dev(self.h, stream, buf)
         if not p:

@@ -439,6 +439,30 @@ int mpegb200_video_write_frame(mpegb200_ctx* ctx, int stream, int buf, const uin
     return 0;
 }
 
+static int read_pictures(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs, uint8_t* dst,
+                         size_t dst_stride, cudaMemcpyKind kind) {
+    if (!ctx || n < 0 || (n && (!streams || !bufs || !dst))) return fail(ctx, MPEGB200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++) {
+        HostStream* s = nullptr;
+        if (int rc = check_buf(ctx, streams[i], bufs[i], &s)) return rc;
+        const size_t bytes = s->luma_bytes + 2 * s->chroma_bytes;
+        if (bytes > dst_stride) return fail(ctx, MPEGB200_EINVAL, "stride %zu smaller than a picture (%zu)", dst_stride, bytes);
+        CU(cudaMemcpyAsync(dst + (size_t)i * dst_stride, s->dev + (size_t)bufs[i] * s->buf_stride, bytes, kind, ctx->stream));
+    }
+    return 0;
+}
+
+int mpegb200_video_read_pictures_host(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs,
+                                      uint8_t* dst, size_t dst_stride) {
+    return read_pictures(ctx, n, streams, bufs, dst, dst_stride, cudaMemcpyDeviceToHost);
+}
+
+int mpegb200_video_read_pictures_dev(mpegb200_ctx* ctx, int n, const int32_t* streams, const uint8_t* bufs,
+                                     uint8_t* d_dst, size_t dst_stride) {
+    return read_pictures(ctx, n, streams, bufs, d_dst, dst_stride, cudaMemcpyDeviceToDevice);
+}
+
 void* mpegb200_video_frame_dev(mpegb200_ctx* ctx, int stream, int buf) {
     HostStream* s = nullptr;
     if (check_buf(ctx, stream, buf, &s)) return nullptr;
@@ -460,16 +484,12 @@ int mpegb200_video_rgba_batch_dev(mpegb200_ctx* ctx, int n, const int32_t* strea
     }
     CU(cudaSetDevice(ctx->device));
     if (int rc = flush_info(ctx)) return rc;
-    // ids travel through pinned scratch so the copy is truly asynchronous
-    const size_t id_bytes = sizeof(int32_t) * (size_t)n, need = id_bytes + (size_t)n;
-    if (int rc = ensure_pinned(ctx, need)) return rc;
+    // small pageable copies are staged by the driver at call time: asynchronous and safe to reuse
+    const size_t id_bytes = sizeof(int32_t) * (size_t)n;
     if (int rc = ensure(ctx, ctx->s_ids, id_bytes)) return rc;
     if (int rc = ensure(ctx, ctx->s_bufs, (size_t)n)) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));  // the pinned scratch may still be in flight from an earlier call
-    memcpy(ctx->pinned, streams, id_bytes);
-    memcpy((uint8_t*)ctx->pinned + id_bytes, bufs, (size_t)n);
-    CU(cudaMemcpyAsync(ctx->s_ids.p, ctx->pinned, id_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->s_bufs.p, (uint8_t*)ctx->pinned + id_bytes, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_ids.p, streams, id_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_bufs.p, bufs, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CU(launch_rgba(ctx->d_info, ctx->max_streams, (const int32_t*)ctx->s_ids.p, (const uint8_t*)ctx->s_bufs.p, n, max_w,
                    max_h, d_rgba, rgba_stride_bytes, ctx->stream));
     ctx->launches += (uint64_t)((n + 32767) / 32768);
@@ -547,11 +567,8 @@ int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* st
     }
     CU(cudaSetDevice(ctx->device));
     const size_t id_bytes = sizeof(int32_t) * (size_t)n_streams;
-    if (int rc = ensure_pinned(ctx, id_bytes)) return rc;
     if (int rc = ensure(ctx, ctx->s_ids, id_bytes)) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->pinned, stream_ids, id_bytes);
-    CU(cudaMemcpyAsync(ctx->s_ids.p, ctx->pinned, id_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_ids.p, stream_ids, id_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(launch_audio_synth(ctx->d_audio, ctx->max_streams, (const int32_t*)ctx->s_ids.p, n_streams, frames_per_stream,
                           d_samples, format, d_out, ctx->d_window, ctx->stream));
     ctx->launches++;

@@ -120,6 +120,8 @@ def test_audio_argument_errors(ctx):
         ctx.audio_synth([3, 3], 1, np.zeros((2, 2, 36, 32), np.int32))  # listed twice
     with pytest.raises(mpeg_b200.MpegB200Error):
         ctx.audio_open(3)                   # already open
-    out = ctx.audio_synth([3], 1, s)        # all-zero samples -> all-zero (positive zero) output
-    assert not out.view(np.uint32).any()
+    out = ctx.audio_synth([3], 1, s)        # all-zero samples: u = +0, and +0 / -1090519040 = -0 (audio.go:390)
+    assert (out.view(np.uint32) == 0x80000000).all()
+    want = ol.synth_batch(ol.synth_states(1), 1, 1, s)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
     ctx.audio_close(3)

@@ -53,14 +53,15 @@ def test_golden_clip_through_gpu(ctx, golden_dir):
         f = v.decode()
         pics, mbs, coeffs = v.tap()
         if len(mbs):
-            ctx.video_validate(pics, mbs, len(coeffs))
             # one launch per picture: consecutive pictures of a stream depend on each other
             for i in range(len(pics)):
                 p = pics[i:i + 1].copy()
                 m = mbs[p["first_mb"][0]:p["first_mb"][0] + p["n_mb"][0]].copy()
                 m["pic"] = 0
                 p["first_mb"] = 0
-                ctx.video_decode_pictures(p, m, coeffs_slice(m, coeffs))
+                c = coeffs_slice(m, coeffs)
+                ctx.video_validate(p, m, len(c))
+                ctx.video_decode_pictures(p, m, c)
         if f is None:
             break
         y, cb, cr = ctx.video_read_planes(0, v.last_buf())
