@@ -15,14 +15,28 @@ namespace mpegb200 {
 // aligned super-set loads of a motion window never leave the allocation.
 struct StreamInfo {
     uint8_t* base;        // buffer b at base + b * buf_stride
-    uint32_t buf_stride;  // multiple of 256
+    uint32_t buf_stride;  // multiple of luma_w*16 (and of 256)
     uint32_t buf_bytes;   // luma + 2*chroma + luma_w*16 (video.go:340)
     uint16_t luma_w, luma_h;
     uint16_t mb_w, mb_h;
     uint16_t width, height;  // display size (video.go:342-343)
-    uint32_t open;
+    uint16_t slab;           // index into the tensor-map table (TMA kernel)
+    uint16_t slot;           // stream slot inside the slab: buffer b is tensor z = slot*3 + b
+    uint8_t open;
+    uint8_t tma_ok;          // chroma pitch is a multiple of 16 bytes (even mb_w): TMA path usable
+    uint8_t pad[10];
 };
-static_assert(sizeof(StreamInfo) == 32, "StreamInfo layout");
+static_assert(sizeof(StreamInfo) == 48, "StreamInfo layout");
+
+// Tensor maps of one slab (streams of one geometry sharing one allocation), kept in global memory.
+//   luma  : 3-D u8 tensor {luma_w + 32, buf_stride / luma_w, 3 * capacity}, strides {luma_w, buf_stride}:
+//           the whole frame buffer seen as rows of luma_w bytes, rows overlapping by 32 bytes so that a
+//           window crossing the right edge continues on the next row exactly like linear addressing does.
+//   chroma: same over the bytes from the Cb plane on, pitch luma_w / 2, x extent + 32.
+struct alignas(128) SlabMaps {
+    unsigned char luma[128];
+    unsigned char chroma[128];
+};
 
 // Per-stream MP2 synthesis state in the reference's own form (audio.go:63,78).
 struct AudioState {
@@ -42,6 +56,11 @@ cudaError_t launch_rgba(const StreamInfo* d_streams, int max_streams, const int3
 cudaError_t launch_audio_synth(AudioState* d_states, int max_streams, const int32_t* d_stream_ids, int n_streams,
                                int frames_per_stream, const int32_t* d_samples, int format, void* d_out,
                                const float* d_window, cudaStream_t stream);
+// TMA kernel (video_fused_tma.cu).  coef_map: 128-byte CUtensorMap over the coefficient array (host copy,
+// passed by value as a __grid_constant__ parameter); d_maps: per-slab window tensor maps in global memory.
+cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, const StreamInfo* d_streams, int max_streams,
+                             const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb,
+                             uint32_t n_blocks, cudaStream_t stream);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

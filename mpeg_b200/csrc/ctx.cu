@@ -1,6 +1,9 @@
 // ctx.cu -- the C-ABI of include/mpegb200.h: context, device memory, transfers, launches.
 // No CPU fallback anywhere: if CUDA is unavailable every entry point reports MPEGB200_ECUDA.
+#include <cuda.h>
+
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -19,8 +22,22 @@ struct HostStream {
     int width = 0, height = 0;
     int luma_w = 0, luma_h = 0, chroma_w = 0, chroma_h = 0;
     size_t luma_bytes = 0, chroma_bytes = 0, buf_bytes = 0, buf_stride = 0;
-    uint8_t* dev = nullptr;
+    uint8_t* dev = nullptr;  // first of the three buffers (inside the slab)
+    int slab = -1, slot = -1;
 };
+
+// Streams of one geometry share one allocation ("slab") so that a single pair of tensor maps
+// (SlabMaps) addresses every frame buffer of the slab: TMA coordinate z = slot*3 + buffer.
+struct Slab {
+    bool alive = false;
+    int width = 0, height = 0;
+    size_t buf_stride = 0;
+    int capacity = 0, used = 0;
+    std::vector<uint8_t> slot_used;
+    uint8_t* dev = nullptr;
+    bool tma_ok = false;
+};
+static const int kMaxSlabs = 1024;
 
 struct DevBuf {  // grow-only device scratch
     void* p = nullptr;
@@ -40,8 +57,11 @@ struct mpegb200_ctx {
     AudioState* d_audio = nullptr;
     float* d_window = nullptr;
     DevBuf s_pics, s_mbs, s_coeffs, s_ids, s_bufs, s_rgba, s_samples, s_out;
-    void* pinned = nullptr;  // small pinned scratch for ids
-    size_t pinned_cap = 0;
+    std::vector<Slab> slabs;
+    SlabMaps* d_maps = nullptr;   // kMaxSlabs entries
+    int n_generic_streams = 0;    // open streams that cannot use the TMA kernel (odd mb_w or encode failure)
+    bool force_generic = false;   // MPEGB200_FUSED=generic (A/B measurements)
+    void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
     uint64_t launches = 0;
     int max_w = 0, max_h = 0;
     char err[512] = {0};
@@ -80,22 +100,6 @@ static int ensure(mpegb200_ctx* ctx, DevBuf& b, size_t bytes) {
         return fail(ctx, MPEGB200_ENOMEM, "device allocation of %zu bytes failed", cap);
     }
     b.cap = cap;
-    return 0;
-}
-
-static int ensure_pinned(mpegb200_ctx* ctx, size_t bytes) {
-    if (bytes <= ctx->pinned_cap) return 0;
-    if (ctx->pinned) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        cudaFreeHost(ctx->pinned);
-        ctx->pinned = nullptr;
-        ctx->pinned_cap = 0;
-    }
-    if (cudaMallocHost(&ctx->pinned, bytes + 4096) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(ctx, MPEGB200_ENOMEM, "pinned allocation of %zu bytes failed", bytes);
-    }
-    ctx->pinned_cap = bytes + 4096;
     return 0;
 }
 
@@ -154,6 +158,17 @@ mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) {
         for (int i = 0; i < 512; i++) w[i] = w[i + 512] = (float)kSynthesisWindowX2[i] * 0.5f;  // audio.go:95-98
         ok = cudaMemcpy(ctx->d_window, w, sizeof(w), cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    ok = ok && cudaMalloc(&ctx->d_maps, sizeof(SlabMaps) * kMaxSlabs) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_maps, 0, sizeof(SlabMaps) * kMaxSlabs) == cudaSuccess;
+    if (ok) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            ctx->encode_fn = nullptr;
+        cudaGetLastError();
+        const char* sel = getenv("MPEGB200_FUSED");
+        ctx->force_generic = sel && strcmp(sel, "generic") == 0;
+    }
     ok = ok && configure_kernels() == cudaSuccess && configure_audio_kernel() == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
@@ -169,12 +184,12 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (auto& s : ctx->vs)
-        if (s.dev) cudaFree(s.dev);
+    for (auto& sl : ctx->slabs)
+        if (sl.dev) cudaFree(sl.dev);
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
     for (DevBuf* b : {&ctx->s_pics, &ctx->s_mbs, &ctx->s_coeffs, &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba,
                       &ctx->s_samples, &ctx->s_out})
         if (b->p) cudaFree(b->p);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_audio) cudaFree(ctx->d_audio);
     if (ctx->d_window) cudaFree(ctx->d_window);
@@ -212,6 +227,37 @@ static HostStream* vstream(mpegb200_ctx* ctx, int stream) {
     return &ctx->vs[stream];
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Window tensor maps of a slab (see SlabMaps in common.cuh).  Returns false if the driver refuses them.
+static bool encode_slab_maps(mpegb200_ctx* ctx, const Slab& sl, const HostStream& g, SlabMaps* out) {
+    if (!ctx->encode_fn) return false;
+    EncodeTiledFn enc = (EncodeTiledFn)ctx->encode_fn;
+    const cuuint32_t ones[3] = {1, 1, 1};
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.luma_w + 32, sl.buf_stride / g.luma_w, (cuuint64_t)3 * sl.capacity};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.luma_w, sl.buf_stride};
+        const cuuint32_t box[3] = {32, 17, 1};
+        if (enc((CUtensorMap*)out->luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, sl.dev, dims, strides, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.chroma_w + 32, (sl.buf_stride - g.luma_bytes) / g.chroma_w,
+                                    (cuuint64_t)3 * sl.capacity};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.chroma_w, sl.buf_stride};
+        const cuuint32_t box[3] = {32, 9, 1};
+        if (enc((CUtensorMap*)out->chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, sl.dev + g.luma_bytes, dims, strides, box,
+                ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
     HostStream* s = vstream(ctx, stream);
     if (!s) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
@@ -220,34 +266,89 @@ int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
         return fail(ctx, MPEGB200_EINVAL, "bad picture size %dx%d", width, height);
     CU(cudaSetDevice(ctx->device));
     const int mb_w = (width + 15) >> 4, mb_h = (height + 15) >> 4;  // video.go:314-315
-    s->width = width;
-    s->height = height;
-    s->luma_w = mb_w << 4;
-    s->luma_h = mb_h << 4;
-    s->chroma_w = mb_w << 3;
-    s->chroma_h = mb_h << 3;
-    s->luma_bytes = (size_t)s->luma_w * s->luma_h;
-    s->chroma_bytes = (size_t)s->chroma_w * s->chroma_h;
-    s->buf_bytes = s->luma_bytes + 2 * s->chroma_bytes + (size_t)s->luma_w * 16;  // video.go:340
-    s->buf_stride = (s->buf_bytes + 64 + 255) & ~(size_t)255;
-    if (cudaMalloc(&s->dev, 3 * s->buf_stride) != cudaSuccess) {
-        cudaGetLastError();
-        s->dev = nullptr;
-        return fail(ctx, MPEGB200_ENOMEM, "frame buffers of stream %d (%zu bytes)", stream, 3 * s->buf_stride);
+    HostStream g;
+    g.width = width;
+    g.height = height;
+    g.luma_w = mb_w << 4;
+    g.luma_h = mb_h << 4;
+    g.chroma_w = mb_w << 3;
+    g.chroma_h = mb_h << 3;
+    g.luma_bytes = (size_t)g.luma_w * g.luma_h;
+    g.chroma_bytes = (size_t)g.chroma_w * g.chroma_h;
+    g.buf_bytes = g.luma_bytes + 2 * g.chroma_bytes + (size_t)g.luma_w * 16;  // video.go:340
+    const size_t unit = (size_t)g.luma_w * 16;                                  // multiple of 256
+    g.buf_stride = (g.buf_bytes + 64 + unit - 1) / unit * unit;
+
+    // find a slab of this geometry with a free slot, or make one
+    int si = -1;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        const Slab& sl = ctx->slabs[i];
+        if (sl.alive && sl.width == width && sl.height == height && sl.used < sl.capacity) {
+            si = (int)i;
+            break;
+        }
     }
-    CU(cudaMemsetAsync(s->dev, 0, 3 * s->buf_stride, ctx->stream));  // make([]byte, ...) zeroes, video.go:340
-    StreamInfo& si = ctx->h_info[stream];
-    si.base = s->dev;
-    si.buf_stride = (uint32_t)s->buf_stride;
-    si.buf_bytes = (uint32_t)s->buf_bytes;
-    si.luma_w = (uint16_t)s->luma_w;
-    si.luma_h = (uint16_t)s->luma_h;
-    si.mb_w = (uint16_t)mb_w;
-    si.mb_h = (uint16_t)mb_h;
-    si.width = (uint16_t)width;
-    si.height = (uint16_t)height;
-    si.open = 1;
+    if (si < 0) {
+        for (size_t i = 0; i < ctx->slabs.size(); i++)
+            if (!ctx->slabs[i].alive) {
+                si = (int)i;
+                break;
+            }
+        if (si < 0) {
+            if ((int)ctx->slabs.size() >= kMaxSlabs) return fail(ctx, MPEGB200_ENOMEM, "too many geometry slabs");
+            ctx->slabs.emplace_back();
+            si = (int)ctx->slabs.size() - 1;
+        }
+        Slab& sl = ctx->slabs[si];
+        sl = Slab{};
+        const size_t per_stream = 3 * g.buf_stride;
+        size_t cap = ((size_t)1 << 30) / per_stream;
+        if (cap < 1) cap = 1;
+        if (cap > (size_t)ctx->max_streams) cap = (size_t)ctx->max_streams;
+        sl.capacity = (int)cap;
+        sl.width = width;
+        sl.height = height;
+        sl.buf_stride = g.buf_stride;
+        sl.slot_used.assign(cap, 0);
+        if (cudaMalloc(&sl.dev, cap * per_stream + 256) != cudaSuccess) {
+            cudaGetLastError();
+            sl.dev = nullptr;
+            return fail(ctx, MPEGB200_ENOMEM, "frame-buffer slab for %dx%d (%zu bytes)", width, height, cap * per_stream);
+        }
+        CU(cudaMemsetAsync(sl.dev, 0, cap * per_stream + 256, ctx->stream));  // make([]byte, ...) zeroes, video.go:340
+        sl.alive = true;
+        SlabMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        sl.tma_ok = (mb_w % 2 == 0) && encode_slab_maps(ctx, sl, g, &maps);  // chroma pitch must be a multiple of 16 B
+        if (sl.tma_ok) CU(cudaMemcpy(&ctx->d_maps[si], &maps, sizeof(maps), cudaMemcpyHostToDevice));
+    }
+    Slab& sl = ctx->slabs[si];
+    int slot = 0;
+    while (sl.slot_used[slot]) slot++;
+    sl.slot_used[slot] = 1;
+    sl.used++;
+    *s = g;
+    s->slab = si;
+    s->slot = slot;
+    s->dev = sl.dev + (size_t)slot * 3 * g.buf_stride;
+    CU(cudaMemsetAsync(s->dev, 0, 3 * g.buf_stride, ctx->stream));  // a re-used slot starts zeroed like a new one
+    StreamInfo& info = ctx->h_info[stream];
+    memset(&info, 0, sizeof(info));
+    info.base = s->dev;
+    info.buf_stride = (uint32_t)g.buf_stride;
+    info.buf_bytes = (uint32_t)g.buf_bytes;
+    info.luma_w = (uint16_t)g.luma_w;
+    info.luma_h = (uint16_t)g.luma_h;
+    info.mb_w = (uint16_t)mb_w;
+    info.mb_h = (uint16_t)mb_h;
+    info.width = (uint16_t)width;
+    info.height = (uint16_t)height;
+    info.slab = (uint16_t)si;
+    info.slot = (uint16_t)slot;
+    info.open = 1;
+    info.tma_ok = sl.tma_ok ? 1 : 0;
     s->open = true;
+    if (!sl.tma_ok) ctx->n_generic_streams++;
     ctx->info_dirty = true;
     if (width > ctx->max_w) ctx->max_w = width;
     if (height > ctx->max_h) ctx->max_h = height;
@@ -260,7 +361,14 @@ int mpegb200_video_close(mpegb200_ctx* ctx, int stream) {
     if (!s->open) return fail(ctx, MPEGB200_ESTATE, "video stream %d not open", stream);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(s->dev);
+    Slab& sl = ctx->slabs[s->slab];
+    sl.slot_used[s->slot] = 0;
+    sl.used--;
+    if (!sl.tma_ok) ctx->n_generic_streams--;
+    if (sl.used == 0) {
+        cudaFree(sl.dev);
+        sl = Slab{};
+    }
     *s = HostStream{};
     ctx->h_info[stream] = StreamInfo{};
     ctx->info_dirty = true;
@@ -357,8 +465,26 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     if (int rc = flush_info(ctx)) return rc;
-    CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,
-                            (uint32_t)n_blocks, ctx->stream));
+    bool use_tma = !ctx->force_generic && ctx->n_generic_streams == 0 && ctx->encode_fn;
+    CUtensorMap coef_map;
+    if (use_tma) {
+        // 2-D view of the coefficient array: n_blocks rows of 64 int16, boxes of 32 rows, 128-byte swizzle
+        const cuuint64_t dims[2] = {64, n_blocks ? (cuuint64_t)n_blocks : 1};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {64, 32}, ones[2] = {1, 1};
+        void* base = n_blocks ? (void*)d_coeffs : (void*)ctx->d_window;  // any valid 16-byte aligned address when empty
+        use_tma = ((EncodeTiledFn)ctx->encode_fn)(&coef_map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box,
+                                                  ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (use_tma) {
+        CU(launch_fused_tma(&coef_map, ctx->d_maps, ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs,
+                            (uint32_t)n_mb, (uint32_t)n_blocks, ctx->stream));
+    } else {
+        CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,
+                                (uint32_t)n_blocks, ctx->stream));
+    }
     ctx->launches++;
     return 0;
 }

@@ -295,3 +295,30 @@ def test_rgba_matches_oracle(ctx):
         want = fs.rgba(0, 2)
         assert np.array_equal(got, want), (w, h)
         assert (got[..., 3] == 255).all()
+
+
+def test_windows_wrap_across_row_ends_like_linear_indexing(ctx):
+    """copyMacroblock indexes the plane linearly (si = y*stride + x, video_noasm.go:31): a vector that
+    points left of column 0 reads the end of the row above, one that points past the last column reads
+    the start of the next row.  The golden clip contains such vectors; pin the behaviour explicitly."""
+    g = wl.Geometry(96, 64)
+    rng = wl.stream_rng(2, 21)
+    fs = ol.FrameSet(1, g.width, g.height)
+    fresh_stream(ctx, 8, g.width, g.height)
+    for b in range(3):
+        buf = wl.random_reference_frame(rng, g)
+        fs.whole(0, b)[:] = buf
+        ctx.video_write_frame(8, b, buf)
+    cases = [(1, 0, -3, 0), (1, 0, -31, 5), (2, 0, -1, -1), (1, g.mb_w - 1, 5, 0), (2, g.mb_w - 1, 31, 3),
+             (g.mb_h - 1, g.mb_w - 1, 9, 2), (1, 0, -33, -7)]
+    for row, col, mh, mv in cases:
+        m = np.zeros(1, wl.MB_DTYPE)
+        m["mb_row"], m["mb_col"], m["mv_h"], m["mv_v"], m["flags"] = row, col, mh, mv, wl.MB_PREDICT
+        p = np.zeros(1, wl.PICTURE_DTYPE)
+        p[0] = (8, wl.PIC_P, 0, 1, 2, 0, 1)
+        ctx.video_validate(p, m, 0)
+        ctx.video_decode_pictures(p, m, np.zeros((0, 64), np.int16))
+        op = p.copy()
+        op["stream"] = 0
+        assert fs.exec_pictures(op, m, np.zeros((0, 64), np.int16)) == 0
+        assert_frames_equal(ctx, fs, 8, 0, msg=f"wrap case {(row, col, mh, mv)}")
