@@ -148,35 +148,41 @@ __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b, uint32_t c, uin
 }
 
 constexpr int kG = 16;                 // macroblock records per CTA
-constexpr int kNT = 6 * kG;            // one thread per potential coded block
+constexpr int kNT = 6 * kG;            // one thread per output block (8x8)
 constexpr int kCoefBox = 32;           // blocks per coefficient TMA box (32 x 128 B = 4 KiB)
 constexpr int kWinY = 640, kWinC = 384;            // bytes reserved per window (544 / 288 used), 128-aligned
 constexpr int kWinBytes = kWinY + 2 * kWinC;       // 1408 per macroblock
 constexpr int kWinTx = 32 * 17 + 2 * 32 * 9;       // bytes the three boxes deliver: 1120
-constexpr int kBlkPitch = 72;          // prediction/pixel tile: 64 B per 8x8 block + 8: conflict-free for block threads
 
-struct MbCtx {                // 32 bytes
+struct MbCtx {                // 24 bytes
     uint8_t* dst_y;           // destination of the macroblock's luma (row 0, col 0 of the MB)
     uint8_t* dst_c;           // destination of its Cb; Cr at + chroma_bytes
     uint32_t chroma_bytes;
     uint16_t luma_w;
-    uint8_t flags, cbp, valid, mask;  // mask: blocks whose pixels are defined (all six if predicted, else cbp)
-    uint8_t ox_y, ox_c;       // byte offset of pixel (0,0) inside the staged 32-byte rows (x & 15)
-    uint8_t mode_y, mode_c;   // bit 0: horizontal half-pel, bit 1: vertical half-pel (luma / chroma vector)
-    uint16_t rel_block;
+    uint16_t mcw;             // byte 0 luma, byte 1 chroma: (x & 15) | mode << 4 | 0x80 if predicted;
+                              // mode bit 0 = horizontal half-pel, bit 1 = vertical half-pel
 };
-static_assert(sizeof(MbCtx) == 32, "MbCtx size");
+static_assert(sizeof(MbCtx) == 24, "MbCtx size");
+
+struct TmaJob {               // 32 bytes: what the issuing warps need for one predicted macroblock
+    const SlabMaps* maps;
+    int lx, ly, cx, cy, z, chroma_h;
+};
+static_assert(sizeof(TmaJob) == 32, "TmaJob size");
 
 struct Smem {
     static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
-    static constexpr int win = coef + kNT * 128;                 // kG x 1152
-    static constexpr int pix = win + kG * kWinBytes;             // kNT x 72
-    static constexpr int ctx = pix + kNT * kBlkPitch;            // kG x 40
-    static constexpr int map = ctx + kG * (int)sizeof(MbCtx);    // kNT bytes
-    static constexpr int bar = (map + kNT + 7) & ~7;             // 8 bytes
-    static constexpr int mc = bar + 8;                           // kG x 4: interpolation word per macroblock
-    static constexpr int total = mc + kG * 4 + 8;                // + the two CTA counters
+    static constexpr int win = coef + kNT * 128;                 // kG x 1408
+    static constexpr int ctx = win + kG * kWinBytes;             // kG x 24
+    static constexpr int map = ctx + kG * (int)sizeof(MbCtx);    // kNT x 2: output-block list, sorted by interpolation mode
+    static constexpr int bar = (map + kNT * 2 + 7) & ~7;         // 8 bytes
+    static constexpr int cnt = bar + 8;                          // 8 bin counters + nb + npred
+    static constexpr int job = (cnt + 10 * 4 + 15) & ~15;        // kG x 32
+    static constexpr int total = job + kG * (int)sizeof(TmaJob);
 };
+
+// Output-block list entry: [3:0] macroblock in CTA, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
+constexpr uint32_t kNoBlock = 0xFFFFu;
 
 __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
                                                        const SlabMaps* __restrict__ slab_maps,
@@ -187,254 +193,278 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
     uint8_t* s_coef = smem + Smem::coef;
     uint8_t* s_win = smem + Smem::win;
-    uint8_t* s_pix = smem + Smem::pix;
     MbCtx* s_ctx = reinterpret_cast<MbCtx*>(smem + Smem::ctx);
-    uint8_t* s_map = smem + Smem::map;
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(smem + Smem::map);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
-    uint32_t* s_mc = reinterpret_cast<uint32_t*>(smem + Smem::mc);
-    uint32_t& s_nb = s_mc[kG];
-    uint32_t& s_npred = s_mc[kG + 1];
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + Smem::cnt);  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
+    TmaJob* s_job = reinterpret_cast<TmaJob*>(smem + Smem::job);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t m0 = blockIdx.x * (uint32_t)kG;
     const int n_here = (int)min((uint32_t)kG, n_mb - m0);
 
-    s_map[tid] = 0xFF;
+    s_map[tid] = (uint16_t)kNoBlock;
+    if (tid < 10) s_cnt[tid] = 0;
+    if (tid < kG) s_ctx[tid].mcw = 0;
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         mbar_init(s_bar, 1);
         fence_barrier_init();
-        s_nb = 0;
-        s_npred = 0;
     }
     __syncthreads();
 
-    // ---------------- producer: record j is owned by lane j/3 of warp j%3, so that the (per lane
-    // serialised) TMA issue is spread over all three warps ----------------
-    {
-        const int j = lane * 3 + warp;
-        if (lane < (kG + 2) / 3 && j < kG) {
-            const uint32_t block0 = mbs[m0].coeff_block;
-            MbCtx c;
-            c.valid = 0;
-            c.flags = 0;
-            c.cbp = 0;
-            c.mask = 0;
-            c.ox_y = c.ox_c = c.mode_y = c.mode_c = 0;
-            uint32_t mcw = 0;
-            if (j < n_here) {
-                const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + j];
-                const uint32_t row = raw.x & 0xffffu, col = raw.x >> 16;
-                const int mv_h = (int16_t)(raw.y & 0xffffu), mv_v = (int16_t)(raw.y >> 16);
-                const uint32_t flags = raw.z & 0xffu, cbp = (raw.z >> 8) & 0x3fu, pic_i = raw.z >> 16;
-                const uint32_t cblock = raw.w;
-                const int ncoded = __popc(cbp);
-                bool ok = pic_i < (uint32_t)n_pics;
+    // ---------------- producer, part 1 (warp 0, lane j owns record j): context, window coordinates,
+    // bin counting for the mode-sorted block list ----------------
+    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0;
+    if (warp == 0 && lane < n_here) {
+        const int pj = lane;
+        const uint32_t block0 = mbs[m0].coeff_block;
+        const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + pj];
+        const uint32_t row = raw.x & 0xffffu, col = raw.x >> 16;
+        const int mv_h = (int16_t)(raw.y & 0xffffu), mv_v = (int16_t)(raw.y >> 16);
+        const uint32_t flags = raw.z & 0xffu, cbp = (raw.z >> 8) & 0x3fu, pic_i = raw.z >> 16;
+        const uint32_t cblock = raw.w;
+        const int ncoded = __popc(cbp);
+        bool ok = pic_i < (uint32_t)n_pics;
+        if (ok) {
+            const uint4 praw = reinterpret_cast<const uint4*>(pics)[pic_i];
+            const int stream = (int)praw.x;
+            const uint32_t dst_b = (praw.y >> 8) & 0xffu, fwd_b = (praw.y >> 16) & 0xffu, bwd_b = praw.y >> 24;
+            ok = stream >= 0 && stream < max_streams && dst_b < 3 && fwd_b < 3 && bwd_b < 3;
+            if (ok) {
+                const StreamInfo si = streams[stream];
+                ok = si.open && si.tma_ok && row < si.mb_h && col < si.mb_w;
+                const uint32_t rel = cblock - block0;
+                if (ncoded) ok = ok && rel <= (uint32_t)kNT && rel + ncoded <= (uint32_t)kNT && cblock + ncoded <= n_blocks;
                 if (ok) {
-                    const uint4 praw = reinterpret_cast<const uint4*>(pics)[pic_i];
-                    const int stream = (int)praw.x;
-                    const uint32_t dst_b = (praw.y >> 8) & 0xffu, fwd_b = (praw.y >> 16) & 0xffu, bwd_b = praw.y >> 24;
-                    ok = stream >= 0 && stream < max_streams && dst_b < 3 && fwd_b < 3 && bwd_b < 3;
-                    if (ok) {
-                        const StreamInfo si = streams[stream];
-                        ok = si.open && si.tma_ok && row < si.mb_h && col < si.mb_w;
-                        const uint32_t rel = cblock - block0;
-                        if (ncoded) ok = ok && rel <= (uint32_t)kNT && rel + ncoded <= (uint32_t)kNT && cblock + ncoded <= n_blocks;
-                        if (ok) {
-                            const uint32_t lw = si.luma_w, cw = lw >> 1;
-                            const uint32_t luma_bytes = lw * si.luma_h;
-                            uint8_t* dst = si.base + (size_t)dst_b * si.buf_stride;
-                            c.dst_y = dst + (size_t)(row << 4) * lw + (col << 4);
-                            c.dst_c = dst + luma_bytes + (size_t)(row << 3) * cw + (col << 3);
-                            c.chroma_bytes = cw * (si.luma_h >> 1);
-                            c.luma_w = (uint16_t)lw;
-                            c.flags = (uint8_t)flags;
-                            c.cbp = (uint8_t)cbp;
-                            c.rel_block = (uint16_t)rel;
-                            c.valid = 1;
-                            const bool predicted = (flags & MPEGB200_MB_PREDICT) != 0;
-                            c.mask = predicted ? 0x3f : (uint8_t)cbp;
-                            int k = 0;
-                            for (int b = 0; b < 6; b++)
-                                if (cbp & (0x20u >> b)) s_map[rel + k++] = (uint8_t)((j << 3) | b);
-                            if (ncoded) atomicMax(&s_nb, rel + ncoded);
-                            if (predicted) {  // window origins, video_noasm.go:29-42
-                                const SlabMaps* maps = slab_maps + si.slab;
-                                const int z = si.slot * 3 + (int)((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b);
-                                int lx = (int)(col << 4) + (mv_h >> 1);
-                                int ly = (int)(row << 4) + (mv_v >> 1);
-                                const int cmh = mv_h / 2, cmv = mv_v / 2;  // toward zero
-                                int cx = (int)(col << 3) + (cmh >> 1);
-                                int cy = (int)(row << 3) + (cmv >> 1);
-                                // The reference indexes linearly (si = y*stride + x, video_noasm.go:31,39), so a
-                                // window starting left of column 0 really starts near the end of the row above.
-                                // Fold x into [0, pitch): same bytes, and inside the tensor's (overlapping) rows.
-                                {
-                                    int q = lx / (int)lw, r = lx - q * (int)lw;
-                                    if (r < 0) { r += (int)lw; q--; }
-                                    lx = r;
-                                    ly += q;
-                                    q = cx / (int)cw;
-                                    r = cx - q * (int)cw;
-                                    if (r < 0) { r += (int)cw; q--; }
-                                    cx = r;
-                                    cy += q;
-                                }
-                                c.ox_y = (uint8_t)(lx & 15);
-                                c.ox_c = (uint8_t)(cx & 15);
-                                c.mode_y = (uint8_t)((mv_h & 1) | ((mv_v & 1) << 1));
-                                c.mode_c = (uint8_t)((cmh & 1) | ((cmv & 1) << 1));
-                                // interpolation word: byte 0 luma, byte 1 chroma: offset | mode << 4 | 0x80 (predicted)
-                                mcw = (uint32_t)(c.ox_y | (c.mode_y << 4) | 0x80) | ((uint32_t)(c.ox_c | (c.mode_c << 4) | 0x80) << 8);
-                                atomicAdd(&s_npred, 1u);
-                                uint8_t* w = s_win + j * kWinBytes;
-                                const int chroma_h = si.luma_h >> 1;
-                                // the TMA unit needs a 16-byte aligned innermost coordinate
-                                tma_load_3d(w, maps->luma, s_bar, lx & ~15, ly, z);
-                                tma_load_3d(w + kWinY, maps->chroma, s_bar, cx & ~15, cy, z);
-                                tma_load_3d(w + kWinY + kWinC, maps->chroma, s_bar, cx & ~15, cy + chroma_h, z);
-                            }
+                    const uint32_t lw = si.luma_w, cw = lw >> 1;
+                    uint8_t* dst = si.base + (size_t)dst_b * si.buf_stride;
+                    MbCtx c;
+                    c.dst_y = dst + (size_t)(row << 4) * lw + (col << 4);
+                    c.dst_c = dst + (size_t)lw * si.luma_h + (size_t)(row << 3) * cw + (col << 3);
+                    c.chroma_bytes = cw * (si.luma_h >> 1);
+                    c.luma_w = (uint16_t)lw;
+                    c.mcw = 0;
+                    const bool predicted = (flags & MPEGB200_MB_PREDICT) != 0 && !(flags & MPEGB200_MB_INTRA);
+                    uint32_t mode_y = 0, mode_c = 0;
+                    if (predicted) {  // window origins, video_noasm.go:29-42
+                        int lx = (int)(col << 4) + (mv_h >> 1);
+                        int ly = (int)(row << 4) + (mv_v >> 1);
+                        const int cmh = mv_h / 2, cmv = mv_v / 2;  // toward zero
+                        int cx = (int)(col << 3) + (cmh >> 1);
+                        int cy = (int)(row << 3) + (cmv >> 1);
+                        // The reference indexes linearly (si = y*stride + x, video_noasm.go:31,39), so a window
+                        // starting left of column 0 really starts near the end of the row above.  Fold x into
+                        // [0, pitch): same bytes, and inside the tensor's (overlapping) rows.
+                        {
+                            int q = lx / (int)lw, r = lx - q * (int)lw;
+                            if (r < 0) { r += (int)lw; q--; }
+                            lx = r;
+                            ly += q;
+                            q = cx / (int)cw;
+                            r = cx - q * (int)cw;
+                            if (r < 0) { r += (int)cw; q--; }
+                            cx = r;
+                            cy += q;
+                        }
+                        mode_y = (uint32_t)((mv_h & 1) | ((mv_v & 1) << 1));
+                        mode_c = (uint32_t)((cmh & 1) | ((cmv & 1) << 1));
+                        c.mcw = (uint16_t)(((lx & 15) | (mode_y << 4) | 0x80) | (((cx & 15) | (mode_c << 4) | 0x80) << 8));
+                        atomicAdd(&s_cnt[9], 1u);
+                        // box origins for the three issuing warps; the TMA unit needs x on a 16-byte boundary
+                        TmaJob t;
+                        t.maps = slab_maps + si.slab;
+                        t.lx = lx & ~15;
+                        t.ly = ly;
+                        t.cx = cx & ~15;
+                        t.cy = cy;
+                        t.z = si.slot * 3 + (int)((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b);
+                        t.chroma_h = si.luma_h >> 1;
+                        s_job[pj] = t;
+                    }
+                    s_ctx[pj] = c;
+                    if (ncoded) atomicMax(&s_cnt[8], rel + ncoded);
+                    // every 8x8 block whose pixels this record defines goes on the output list, binned by
+                    // (coded?, interpolation mode) so that the threads of a warp take the same code path
+                    out_mask = predicted ? 0x3fu : cbp;
+                    cbp_r = cbp;
+                    rel_r = rel;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        if (out_mask & (0x20u >> k)) {
+                            const uint32_t bin = ((cbp & (0x20u >> k)) ? 0u : 4u) + (predicted ? (k < 4 ? mode_y : mode_c) : 0u);
+                            const uint32_t pp = atomicAdd(&s_cnt[bin], 1u);  // < 96
+                            bins |= bin << (4 * k);
+                            if (k < 4) pos |= pp << (8 * k); else pos_hi |= pp << (8 * (k - 4));
                         }
                     }
                 }
             }
-            s_ctx[j] = c;
-            s_mc[j] = mcw;
         }
     }
-    __syncthreads();       // contexts, block map and totals visible
+    __syncthreads();
+    // ---------------- producer, part 2: warp w issues plane w (Y, Cb, Cr) of every predicted macroblock;
+    // warp 0 also posts the transaction count, fetches the coefficient boxes and writes the block list -------
+    if (lane < kG && (s_ctx[lane].mcw & 0x80u)) {
+        const TmaJob t = s_job[lane];
+        uint8_t* w = s_win + lane * kWinBytes;
+        if (warp == 0)
+            tma_load_3d(w, t.maps->luma, s_bar, t.lx, t.ly, t.z);
+        else
+            tma_load_3d(w + kWinY + (warp - 1) * kWinC, t.maps->chroma, s_bar, t.cx, t.cy + (warp - 1) * t.chroma_h, t.z);
+    }
     if (warp == 0) {
-        const uint32_t n_box = (s_nb + kCoefBox - 1) / kCoefBox;
-        // complete_tx of the window boxes may already have been counted: the phase cannot complete
-        // before this (single) arrival, and the transaction count is allowed to run negative meanwhile
-        if (lane == 0) mbar_arrive_expect_tx(s_bar, n_box * (kCoefBox * 128) + s_npred * kWinTx);
+        const uint32_t n_box = (s_cnt[8] + kCoefBox - 1) / kCoefBox;
+        // complete_tx of the window boxes may already have been counted: the phase cannot complete before
+        // this (single) arrival, and the transaction count is allowed to run negative meanwhile
+        if (lane == 0) mbar_arrive_expect_tx(s_bar, n_box * (kCoefBox * 128) + s_cnt[9] * kWinTx);
         __syncwarp();
         if (lane < (int)n_box)  // rows past n_blocks are zero-filled by the TMA unit
             tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(mbs[m0].coeff_block + lane * kCoefBox));
+        if (out_mask) {
+            uint32_t run = 0, base_of[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                base_of[b] = run;
+                run += s_cnt[b];
+            }
+            uint32_t slot = rel_r;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                if (out_mask & (0x20u >> k)) {
+                    const uint32_t bin = (bins >> (4 * k)) & 15u;
+                    const uint32_t pp = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
+                    const bool coded = cbp_r & (0x20u >> k);
+                    uint32_t bsel = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) bsel = bin == (uint32_t)b ? base_of[b] : bsel;
+                    s_map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
+                    if (coded) slot++;
+                }
+            }
+        }
     }
+    __syncthreads();       // block list visible
     mbar_wait(s_bar, 0);   // all tiles have landed
 
-    // ---------------- interpolation: 8-pixel row pieces; per pass warp 0 / 1 take the luma of two
-    // macroblocks, warp 2 their chroma; a thread's piece geometry is fixed, only the macroblock moves ----
-    {
-        int sub, wrow, pix_off;  // which of the pass's two macroblocks, byte offset of the row in its window, tile offset
-        if (warp < 2) {
-            const int y = lane >> 1, x0 = (lane & 1) * 8;
-            sub = warp;
-            wrow = y * 32 + x0;
-            pix_off = ((y >> 3) * 2 + (x0 >> 3)) * kBlkPitch + (y & 7) * 8;
-        } else {
-            const int p = (lane >> 3) & 1, y = lane & 7;
-            sub = lane >> 4;
-            wrow = kWinY + p * kWinC + y * 32;
-            pix_off = (4 + p) * kBlkPitch + y * 8;
-        }
-        const bool chroma = warp >= 2;
-        const uint32_t win0 = smem_u32(s_win) + wrow;
-        const int mc_shift = chroma ? 8 : 0;
-#pragma unroll 2
-        for (int j = sub; j < kG; j += 2) {
-            const uint32_t mcw = s_mc[j] >> mc_shift;
-            if (!(mcw & 0x80u)) continue;
-            const uint32_t a = win0 + j * kWinBytes + (mcw & 15u);
-            const uint32_t mode = mcw >> 4;
-            const uint32_t aw = a & ~3u, sh = (a & 3u) * 8;
-            uint32_t w0, w1, w2;
-            asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
-                         : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(aw));
-            uint32_t lo = __funnelshift_rc(w0, w1, sh), hi = __funnelshift_rc(w1, w2, sh);
-            if (mode & 1) {
-                const uint32_t lo1 = __funnelshift_rc(w0, w1, sh + 8), hi1 = __funnelshift_rc(w1, w2, sh + 8);
-                if (mode & 2) {
-                    uint32_t v0, v1, v2;
-                    asm volatile("ld.shared.u32 %0, [%3+32];\n\tld.shared.u32 %1, [%3+36];\n\tld.shared.u32 %2, [%3+40];"
-                                 : "=r"(v0), "=r"(v1), "=r"(v2) : "r"(aw));
-                    lo = avg4(lo, lo1, __funnelshift_rc(v0, v1, sh), __funnelshift_rc(v0, v1, sh + 8));
-                    hi = avg4(hi, hi1, __funnelshift_rc(v1, v2, sh), __funnelshift_rc(v1, v2, sh + 8));
-                } else {
-                    lo = avg2(lo, lo1);
-                    hi = avg2(hi, hi1);
-                }
-            } else if (mode & 2) {
-                uint32_t v0, v1, v2;
-                asm volatile("ld.shared.u32 %0, [%3+32];\n\tld.shared.u32 %1, [%3+36];\n\tld.shared.u32 %2, [%3+40];"
-                             : "=r"(v0), "=r"(v1), "=r"(v2) : "r"(aw));
-                lo = avg2(lo, __funnelshift_rc(v0, v1, sh));
-                hi = avg2(hi, __funnelshift_rc(v1, v2, sh));
-            }
-            *reinterpret_cast<uint2*>(s_pix + j * 6 * kBlkPitch + pix_off) = make_uint2(lo, hi);
-        }
-    }
-    __syncthreads();
+    // ---------------- one thread per output block: interpolate, IDCT, add, saturate, store ----------------
+    const uint32_t e = s_map[tid];
+    if (e == kNoBlock) return;
+    const int j = e & 15, k = (e >> 4) & 7;
+    const bool coded = e & 0x80u;
+    const MbCtx& cx = s_ctx[j];
+    const uint32_t mcb = (uint32_t)(cx.mcw >> (k < 4 ? 0 : 8)) & 0xffu;
+    const bool pred = mcb & 0x80u;
 
-    // ---------------- one thread per coded block: premultiply, IDCT, add, saturate ----------------
-    {
-        const uint32_t bm = s_map[tid];
-        if (bm != 0xFF) {
-            const int j = bm >> 3, k = bm & 7;
-            const uint32_t fl = s_ctx[j].flags;
-            const bool add = (fl & MPEGB200_MB_PREDICT) && !(fl & MPEGB200_MB_INTRA);
-            int c[64];
-            const uint8_t* src = s_coef + tid * 128;
-            const int sw = (tid & 7) << 4;  // 128-byte swizzle: 16-byte chunk index ^= row index mod 8
+    // prediction: eight rows of eight bytes, straight from the staged window (video_noasm.go:44-80)
+    uint32_t p0[8], p1[8];
+    if (pred) {
+        // s_win is 128-byte aligned, so the byte offset decides the word alignment
+        const uint32_t a = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + (mcb & 15u);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_win + (a & ~3u));
+        const uint32_t sh = (a & 3u) * 8;
+        const uint32_t mode = (mcb >> 4) & 3u;
+#define LOAD_ROW(R, W0, W1, W2) \
+    do {                        \
+        W0 = wp[(R) * 8];       \
+        W1 = wp[(R) * 8 + 1];   \
+        W2 = wp[(R) * 8 + 2];   \
+    } while (0)
+        if (mode == 0) {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const uint4 w = *reinterpret_cast<const uint4*>(src + ((r << 4) ^ sw));
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int p = 0; p < 4; p++) {  // level * premultiplier (video.go:744) straight from the int16 pairs
-                    c[r * 8 + 2 * p] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p), 0);
-                    c[r * 8 + 2 * p + 1] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p + 1) << 8, 0);
-                }
+                uint32_t w0, w1, w2;
+                LOAD_ROW(r, w0, w1, w2);
+                p0[r] = __funnelshift_rc(w0, w1, sh);
+                p1[r] = __funnelshift_rc(w1, w2, sh);
             }
+        } else if (mode == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; i++)  // columns, video.go:869-896
-                idct_pass8(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
-            uint8_t* tile = s_pix + (j * 6 + k) * kBlkPitch;
+            for (int r = 0; r < 8; r++) {
+                uint32_t w0, w1, w2;
+                LOAD_ROW(r, w0, w1, w2);
+                p0[r] = avg2(__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w0, w1, sh + 8));
+                p1[r] = avg2(__funnelshift_rc(w1, w2, sh), __funnelshift_rc(w1, w2, sh + 8));
+            }
+        } else if (mode == 2) {
+            uint32_t w0, w1, w2;
+            LOAD_ROW(0, w0, w1, w2);
+            uint32_t u0 = __funnelshift_rc(w0, w1, sh), u1 = __funnelshift_rc(w1, w2, sh);
 #pragma unroll
-            for (int r = 0; r < 8; r++) {  // rows, video.go:899-926, then copy/addBlockToDest (:943-971)
-                int v[8];
-                idct_row8(&c[r * 8], v);
-                uint2* tp = reinterpret_cast<uint2*>(tile + r * 8);
-                if (add) {
-                    const uint2 pr = *tp;
+            for (int r = 0; r < 8; r++) {
+                LOAD_ROW(r + 1, w0, w1, w2);
+                const uint32_t n0 = __funnelshift_rc(w0, w1, sh), n1 = __funnelshift_rc(w1, w2, sh);
+                p0[r] = avg2(u0, n0);
+                p1[r] = avg2(u1, n1);
+                u0 = n0;
+                u1 = n1;
+            }
+        } else {
+            uint32_t w0, w1, w2;
+            LOAD_ROW(0, w0, w1, w2);
+            uint32_t u0 = __funnelshift_rc(w0, w1, sh), u1 = __funnelshift_rc(w1, w2, sh);
+            uint32_t s0 = __funnelshift_rc(w0, w1, sh + 8), s1 = __funnelshift_rc(w1, w2, sh + 8);
 #pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        v[x] = (int)__dp4a(pr.x, 1u << (8 * x), (uint32_t)v[x]);
-                        v[4 + x] = (int)__dp4a(pr.y, 1u << (8 * x), (uint32_t)v[4 + x]);
-                    }
-                }
-                *tp = make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
+            for (int r = 0; r < 8; r++) {
+                LOAD_ROW(r + 1, w0, w1, w2);
+                const uint32_t n0 = __funnelshift_rc(w0, w1, sh), n1 = __funnelshift_rc(w1, w2, sh);
+                const uint32_t t0 = __funnelshift_rc(w0, w1, sh + 8), t1 = __funnelshift_rc(w1, w2, sh + 8);
+                p0[r] = avg4(u0, s0, n0, t0);
+                p1[r] = avg4(u1, s1, n1, t1);
+                u0 = n0; u1 = n1; s0 = t0; s1 = t1;
             }
         }
+#undef LOAD_ROW
     }
-    __syncthreads();
 
-    // ---------------- tile -> frame: lanes across neighbouring macroblocks ----------------
-    for (int it = tid; it < 16 * kG; it += kNT) {  // luma rows
-        const int r = it / kG, j = it - r * kG;
-        const MbCtx& c = s_ctx[j];
-        if (!c.valid) continue;
-        const int kl = (r >> 3) * 2;
-        const uint8_t* t = s_pix + (j * 6 + kl) * kBlkPitch + (r & 7) * 8;
-        const uint2 l = *reinterpret_cast<const uint2*>(t), rr = *reinterpret_cast<const uint2*>(t + kBlkPitch);
-        uint8_t* d = c.dst_y + (size_t)r * c.luma_w;
-        const bool left = c.mask & (0x20u >> kl), right = c.mask & (0x10u >> kl);
-        if (left && right) {
-            *reinterpret_cast<uint4*>(d) = make_uint4(l.x, l.y, rr.x, rr.y);
-        } else if (left) {
-            *reinterpret_cast<uint2*>(d) = l;
-        } else if (right) {
-            *reinterpret_cast<uint2*>(d + 8) = rr;
+    uint8_t* dst;
+    uint32_t pitch;
+    if (k < 4) {
+        pitch = cx.luma_w;
+        dst = cx.dst_y + (size_t)((k >> 1) * 8) * pitch + (k & 1) * 8;
+    } else {
+        pitch = cx.luma_w >> 1;
+        dst = cx.dst_c + (k == 5 ? cx.chroma_bytes : 0u);
+    }
+
+    if (!coded) {  // predicted block without residual: the prediction is the result (skipped / cbp bit clear)
+#pragma unroll
+        for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) = make_uint2(p0[r], p1[r]);
+        return;
+    }
+
+    int c[64];
+    {
+        const int slot = e >> 8;
+        const uint8_t* src = s_coef + slot * 128;
+        const int sw = (slot & 7) << 4;  // 128-byte swizzle: 16-byte chunk index ^= row index mod 8
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint4 w = *reinterpret_cast<const uint4*>(src + ((r << 4) ^ sw));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int p = 0; p < 4; p++) {  // level * premultiplier (video.go:744) straight from the int16 pairs
+                c[r * 8 + 2 * p] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p), 0);
+                c[r * 8 + 2 * p + 1] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p + 1) << 8, 0);
+            }
         }
     }
-    for (int it = tid; it < 16 * kG; it += kNT) {  // chroma rows: 2 planes x 8
-        const int pr = it / kG, j = it - pr * kG;
-        const int p = pr >> 3, r = pr & 7;
-        const MbCtx& c = s_ctx[j];
-        if (!c.valid || !(c.mask & (0x02u >> p))) continue;
-        uint8_t* d = c.dst_c + (p ? c.chroma_bytes : 0) + (size_t)r * (c.luma_w >> 1);
-        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(s_pix + (j * 6 + 4 + p) * kBlkPitch + r * 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++)  // columns, video.go:869-896
+        idct_pass8(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {  // rows, video.go:899-926, then copy/addBlockToDest (:943-971)
+        int v[8];
+        idct_row8(&c[r * 8], v);
+        if (pred) {
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                v[x] = (int)__dp4a(p0[r], 1u << (8 * x), (uint32_t)v[x]);
+                v[4 + x] = (int)__dp4a(p1[r], 1u << (8 * x), (uint32_t)v[4 + x]);
+            }
+        }
+        *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) =
+            make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
     }
 }
 
