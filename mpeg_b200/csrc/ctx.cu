@@ -56,7 +56,13 @@ struct mpegb200_ctx {
     std::vector<uint8_t> audio_open;
     AudioState* d_audio = nullptr;
     float* d_window = nullptr;
-    DevBuf s_pics, s_mbs, s_coeffs, s_ids, s_bufs, s_rgba, s_samples, s_out;
+    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_ids, s_bufs, s_rgba, s_samples, s_out;
+    // host-pointer pipeline: uploads and read-backs run on their own streams so that the H2D copy of the
+    // next step overlaps the kernels and the D2H copy of the current one (double-buffered staging)
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_kernel = nullptr, ev_down = nullptr;
+    uint64_t upload_seq = 0;
+    bool down_pending = false;
     std::vector<Slab> slabs;
     SlabMaps* d_maps = nullptr;   // kMaxSlabs entries
     int n_generic_streams = 0;    // open streams that cannot use the TMA kernel (odd mb_w or encode failure)
@@ -89,6 +95,8 @@ static int ensure(mpegb200_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
     if (b.p) {
         CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->up_stream) CU(cudaStreamSynchronize(ctx->up_stream));
+        if (ctx->down_stream) CU(cudaStreamSynchronize(ctx->down_stream));
         CU(cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -100,6 +108,15 @@ static int ensure(mpegb200_ctx* ctx, DevBuf& b, size_t bytes) {
         return fail(ctx, MPEGB200_ENOMEM, "device allocation of %zu bytes failed", cap);
     }
     b.cap = cap;
+    return 0;
+}
+
+// the compute stream must not overwrite a frame buffer that an asynchronous read-back is still copying
+static int join_readback(mpegb200_ctx* ctx) {
+    if (ctx->down_pending) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_down, 0));
+        ctx->down_pending = false;
+    }
     return 0;
 }
 
@@ -150,6 +167,14 @@ mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) {
     ctx->audio_open.assign(max_streams, 0);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->own_stream = ok;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_kernel, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_down, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_info, sizeof(StreamInfo) * max_streams) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_info, 0, sizeof(StreamInfo) * max_streams) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_window, sizeof(float) * 1024) == cudaSuccess;
@@ -187,9 +212,19 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     for (auto& sl : ctx->slabs)
         if (sl.dev) cudaFree(sl.dev);
     if (ctx->d_maps) cudaFree(ctx->d_maps);
-    for (DevBuf* b : {&ctx->s_pics, &ctx->s_mbs, &ctx->s_coeffs, &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba,
-                      &ctx->s_samples, &ctx->s_out})
+    if (ctx->up_stream) cudaStreamSynchronize(ctx->up_stream);
+    if (ctx->down_stream) cudaStreamSynchronize(ctx->down_stream);
+    for (DevBuf* b : {&ctx->s_pics[0], &ctx->s_pics[1], &ctx->s_mbs[0], &ctx->s_mbs[1], &ctx->s_coeffs[0],
+                      &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out})
         if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+        if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+    }
+    if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
+    if (ctx->ev_down) cudaEventDestroy(ctx->ev_down);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_audio) cudaFree(ctx->d_audio);
     if (ctx->d_window) cudaFree(ctx->d_window);
@@ -214,7 +249,10 @@ void* mpegb200_get_stream(mpegb200_ctx* ctx) { return ctx ? (void*)ctx->stream :
 int mpegb200_sync(mpegb200_ctx* ctx) {
     if (!ctx) return MPEGB200_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->up_stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->down_stream));
+    ctx->down_pending = false;
     return 0;
 }
 
@@ -465,6 +503,7 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     if (int rc = flush_info(ctx)) return rc;
+    if (int rc = join_readback(ctx)) return rc;
     bool use_tma = !ctx->force_generic && ctx->n_generic_streams == 0 && ctx->encode_fn;
     CUtensorMap coef_map;
     if (use_tma) {
@@ -495,16 +534,25 @@ int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpeg
         return fail(ctx, MPEGB200_EINVAL, "null argument");
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
-    if (int rc = ensure(ctx, ctx->s_pics, sizeof(mpegb200_picture) * (size_t)n_pictures)) return rc;
-    if (int rc = ensure(ctx, ctx->s_mbs, sizeof(mpegb200_mb) * n_mb)) return rc;
-    if (int rc = ensure(ctx, ctx->s_coeffs, 128 * (n_blocks ? n_blocks : 1))) return rc;
-    CU(cudaMemcpyAsync(ctx->s_pics.p, pics, sizeof(mpegb200_picture) * (size_t)n_pictures, cudaMemcpyHostToDevice,
-                       ctx->stream));
-    CU(cudaMemcpyAsync(ctx->s_mbs.p, mbs, sizeof(mpegb200_mb) * n_mb, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_blocks) CU(cudaMemcpyAsync(ctx->s_coeffs.p, coeffs, 128 * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-    return mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics.p, n_mb,
-                                              (const mpegb200_mb*)ctx->s_mbs.p, n_blocks,
-                                              (const int16_t*)ctx->s_coeffs.p);
+    const int slot = (int)(ctx->upload_seq++ & 1);
+    if (int rc = ensure(ctx, ctx->s_pics[slot], sizeof(mpegb200_picture) * (size_t)n_pictures)) return rc;
+    if (int rc = ensure(ctx, ctx->s_mbs[slot], sizeof(mpegb200_mb) * n_mb)) return rc;
+    if (int rc = ensure(ctx, ctx->s_coeffs[slot], 128 * (n_blocks ? n_blocks : 1))) return rc;
+    // the staging slot is free once the kernel that consumed it two calls ago has finished
+    CU(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_free[slot], 0));
+    CU(cudaMemcpyAsync(ctx->s_pics[slot].p, pics, sizeof(mpegb200_picture) * (size_t)n_pictures, cudaMemcpyHostToDevice,
+                       ctx->up_stream));
+    CU(cudaMemcpyAsync(ctx->s_mbs[slot].p, mbs, sizeof(mpegb200_mb) * n_mb, cudaMemcpyHostToDevice, ctx->up_stream));
+    if (n_blocks)
+        CU(cudaMemcpyAsync(ctx->s_coeffs[slot].p, coeffs, 128 * n_blocks, cudaMemcpyHostToDevice, ctx->up_stream));
+    CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
+    if (int rc = join_readback(ctx)) return rc;
+    int rc = mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
+                                                (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks,
+                                                (const int16_t*)ctx->s_coeffs[slot].p);
+    CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
+    return rc;
 }
 
 static int check_buf(mpegb200_ctx* ctx, int stream, int buf, HostStream** out) {
@@ -535,6 +583,7 @@ int mpegb200_video_write_planes(mpegb200_ctx* ctx, int stream, int buf, const ui
     HostStream* s = nullptr;
     if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
     CU(cudaSetDevice(ctx->device));
+    if (int rc = join_readback(ctx)) return rc;
     uint8_t* base = s->dev + (size_t)buf * s->buf_stride;
     if (y) CU(cudaMemcpyAsync(base, y, s->luma_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (cb) CU(cudaMemcpyAsync(base + s->luma_bytes, cb, s->chroma_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -560,6 +609,7 @@ int mpegb200_video_write_frame(mpegb200_ctx* ctx, int stream, int buf, const uin
     if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
     if (!src || src_bytes != s->buf_bytes) return fail(ctx, MPEGB200_EINVAL, "source must be %zu bytes", s->buf_bytes);
     CU(cudaSetDevice(ctx->device));
+    if (int rc = join_readback(ctx)) return rc;
     CU(cudaMemcpyAsync(s->dev + (size_t)buf * s->buf_stride, src, s->buf_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -569,12 +619,23 @@ static int read_pictures(mpegb200_ctx* ctx, int n, const int32_t* streams, const
                          size_t dst_stride, cudaMemcpyKind kind) {
     if (!ctx || n < 0 || (n && (!streams || !bufs || !dst))) return fail(ctx, MPEGB200_EINVAL, "null argument");
     CU(cudaSetDevice(ctx->device));
+    // host read-backs run on the download stream, behind everything enqueued on the compute stream so far
+    cudaStream_t q = ctx->stream;
+    if (kind == cudaMemcpyDeviceToHost) {
+        CU(cudaEventRecord(ctx->ev_kernel, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->down_stream, ctx->ev_kernel, 0));
+        q = ctx->down_stream;
+    }
     for (int i = 0; i < n; i++) {
         HostStream* s = nullptr;
         if (int rc = check_buf(ctx, streams[i], bufs[i], &s)) return rc;
         const size_t bytes = s->luma_bytes + 2 * s->chroma_bytes;
         if (bytes > dst_stride) return fail(ctx, MPEGB200_EINVAL, "stride %zu smaller than a picture (%zu)", dst_stride, bytes);
-        CU(cudaMemcpyAsync(dst + (size_t)i * dst_stride, s->dev + (size_t)bufs[i] * s->buf_stride, bytes, kind, ctx->stream));
+        CU(cudaMemcpyAsync(dst + (size_t)i * dst_stride, s->dev + (size_t)bufs[i] * s->buf_stride, bytes, kind, q));
+    }
+    if (kind == cudaMemcpyDeviceToHost) {
+        CU(cudaEventRecord(ctx->ev_down, ctx->down_stream));
+        ctx->down_pending = true;
     }
     return 0;
 }
@@ -618,7 +679,7 @@ int mpegb200_video_rgba_batch_dev(mpegb200_ctx* ctx, int n, const int32_t* strea
     CU(cudaMemcpyAsync(ctx->s_bufs.p, bufs, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CU(launch_rgba(ctx->d_info, ctx->max_streams, (const int32_t*)ctx->s_ids.p, (const uint8_t*)ctx->s_bufs.p, n, max_w,
                    max_h, d_rgba, rgba_stride_bytes, ctx->stream));
-    ctx->launches += (uint64_t)((n + 32767) / 32768);
+    ctx->launches += 1;
     return 0;
 }
 

@@ -170,60 +170,60 @@ struct TmaJob {               // 32 bytes: what the issuing warps need for one p
 };
 static_assert(sizeof(TmaJob) == 32, "TmaJob size");
 
-// One pipeline stage = everything a group of kG records needs: tiles written by TMA, and the context,
-// job and block-list arrays written by the producer warp.
-struct Stage {
+struct Smem {
     static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
     static constexpr int win = coef + kNT * 128;                 // kG x 1408
     static constexpr int ctx = win + kG * kWinBytes;             // kG x 24
     static constexpr int map = ctx + kG * (int)sizeof(MbCtx);    // kNT x 2: output-block list, sorted by interpolation mode
-    static constexpr int cnt = (map + kNT * 2 + 3) & ~3;         // 8 bin counters + nb + npred
+    static constexpr int bar = (map + kNT * 2 + 7) & ~7;         // 8 bytes
+    static constexpr int cnt = bar + 8;                          // 8 bin counters + nb + npred
     static constexpr int job = (cnt + 10 * 4 + 15) & ~15;        // kG x 32
-    static constexpr int bytes = (job + kG * (int)sizeof(TmaJob) + 1023) & ~1023;
-};
-constexpr int kStages = 3;
-constexpr int kProducers = 2;          // producer warps; warp p fills the groups with iteration index = p (mod kProducers)
-constexpr int kThreads = 32 * kProducers + kNT;  // warps 0..kProducers-1 produce, the next three consume
-
-struct Smem {
-    static constexpr int bars = kStages * Stage::bytes;          // full[kStages], empty[kStages]
-    static constexpr int total = bars + 2 * kStages * 8;
+    static constexpr int total = job + kG * (int)sizeof(TmaJob);
 };
 
-// Output-block list entry: [3:0] macroblock in group, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
+// Output-block list entry: [3:0] macroblock in CTA, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
 constexpr uint32_t kNoBlock = 0xFFFFu;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+__global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                       const SlabMaps* __restrict__ slab_maps,
+                                                       const StreamInfo* __restrict__ streams, int max_streams,
+                                                       const mpegb200_picture* __restrict__ pics, int n_pics,
+                                                       const mpegb200_mb* __restrict__ mbs, uint32_t n_mb,
+                                                       uint32_t n_blocks) {
+    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
+    uint8_t* s_coef = smem + Smem::coef;
+    uint8_t* s_win = smem + Smem::win;
+    MbCtx* s_ctx = reinterpret_cast<MbCtx*>(smem + Smem::ctx);
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(smem + Smem::map);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + Smem::cnt);  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
+    TmaJob* s_job = reinterpret_cast<TmaJob*>(smem + Smem::job);
 
-// ------------------------------------------------------------------------------------------------
-// Producer (one warp): decode the group's records, sort its output blocks by code path, post the
-// transaction count and issue every TMA box of the group into `stage`.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void produce_group(uint8_t* stage, uint64_t* full, const CUtensorMap* coef_map,
-                                              const SlabMaps* __restrict__ slab_maps,
-                                              const StreamInfo* __restrict__ streams, int max_streams,
-                                              const mpegb200_picture* __restrict__ pics, int n_pics,
-                                              uint4 raw, uint32_t n_mb, uint32_t n_blocks, uint32_t group, int lane) {
-    uint8_t* s_coef = stage + Stage::coef;
-    uint8_t* s_win = stage + Stage::win;
-    MbCtx* s_ctx = reinterpret_cast<MbCtx*>(stage + Stage::ctx);
-    uint16_t* s_map = reinterpret_cast<uint16_t*>(stage + Stage::map);
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(stage + Stage::cnt);  // [0..7] bins, [8] coded blocks, [9] predicted MBs
-    TmaJob* s_job = reinterpret_cast<TmaJob*>(stage + Stage::job);
-
-    const uint32_t m0 = group * (uint32_t)kG;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t m0 = blockIdx.x * (uint32_t)kG;
     const int n_here = (int)min((uint32_t)kG, n_mb - m0);
-    for (int i = lane; i < kNT; i += 32) s_map[i] = (uint16_t)kNoBlock;
-    if (lane < 10) s_cnt[lane] = 0;
-    if (lane < kG) s_ctx[lane].mcw = 0;
-    __syncwarp();
 
-    const uint32_t block0 = __shfl_sync(0xffffffffu, raw.w, 0);  // first coded block of the group
+    s_map[tid] = (uint16_t)kNoBlock;
+    if (tid < 10) s_cnt[tid] = 0;
+    if (tid < kG) s_ctx[tid].mcw = 0;
+    if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // ---------------- producer, part 1 (warp 0, lane j owns record j): context, window coordinates,
+    // bin counting for the mode-sorted block list ----------------
     uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0;
-    bool predicted = false;
-    if (lane < n_here) {
+    if (tid == 32) {  // pull the records of the CTA that will run about one wave later into L2
+        const uint32_t ahead = m0 + (uint32_t)kG * 1024u;
+        if (ahead < n_mb) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(mbs) + ahead));
+    }
+    if (warp == 0 && lane < n_here) {
+        const int pj = lane;
+        const uint32_t block0 = mbs[m0].coeff_block;
+        const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + pj];
         const uint32_t row = raw.x & 0xffffu, col = raw.x >> 16;
         const int mv_h = (int16_t)(raw.y & 0xffffu), mv_v = (int16_t)(raw.y >> 16);
         const uint32_t flags = raw.z & 0xffu, cbp = (raw.z >> 8) & 0x3fu, pic_i = raw.z >> 16;
@@ -249,7 +249,7 @@ __device__ __forceinline__ void produce_group(uint8_t* stage, uint64_t* full, co
                     c.chroma_bytes = cw * (si.luma_h >> 1);
                     c.luma_w = (uint16_t)lw;
                     c.mcw = 0;
-                    predicted = (flags & MPEGB200_MB_PREDICT) != 0 && !(flags & MPEGB200_MB_INTRA);
+                    const bool predicted = (flags & MPEGB200_MB_PREDICT) != 0 && !(flags & MPEGB200_MB_INTRA);
                     uint32_t mode_y = 0, mode_c = 0;
                     if (predicted) {  // window origins, video_noasm.go:29-42
                         int lx = (int)(col << 4) + (mv_h >> 1);
@@ -274,7 +274,9 @@ __device__ __forceinline__ void produce_group(uint8_t* stage, uint64_t* full, co
                         mode_y = (uint32_t)((mv_h & 1) | ((mv_v & 1) << 1));
                         mode_c = (uint32_t)((cmh & 1) | ((cmv & 1) << 1));
                         c.mcw = (uint16_t)(((lx & 15) | (mode_y << 4) | 0x80) | (((cx & 15) | (mode_c << 4) | 0x80) << 8));
-                        TmaJob t;  // the TMA unit needs x on a 16-byte boundary
+                        atomicAdd(&s_cnt[9], 1u);
+                        // box origins for the three issuing warps; the TMA unit needs x on a 16-byte boundary
+                        TmaJob t;
                         t.maps = slab_maps + si.slab;
                         t.lx = lx & ~15;
                         t.ly = ly;
@@ -282,9 +284,9 @@ __device__ __forceinline__ void produce_group(uint8_t* stage, uint64_t* full, co
                         t.cy = cy;
                         t.z = si.slot * 3 + (int)((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b);
                         t.chroma_h = si.luma_h >> 1;
-                        s_job[lane] = t;
+                        s_job[pj] = t;
                     }
-                    s_ctx[lane] = c;
+                    s_ctx[pj] = c;
                     if (ncoded) atomicMax(&s_cnt[8], rel + ncoded);
                     // every 8x8 block whose pixels this record defines goes on the output list, binned by
                     // (coded?, interpolation mode) so that the threads of a warp take the same code path
@@ -304,55 +306,53 @@ __device__ __forceinline__ void produce_group(uint8_t* stage, uint64_t* full, co
             }
         }
     }
-    const uint32_t n_pred = __popc(__ballot_sync(0xffffffffu, predicted));
-    __syncwarp();
-    const uint32_t n_box = (s_cnt[8] + kCoefBox - 1) / kCoefBox;
-    if (out_mask) {
-        uint32_t run = 0, base_of[8];
+    __syncthreads();
+    // ---------------- producer, part 2: warp w issues plane w (Y, Cb, Cr) of every predicted macroblock;
+    // warp 0 also posts the transaction count, fetches the coefficient boxes and writes the block list -------
+    if (lane < kG && (s_ctx[lane].mcw & 0x80u)) {
+        const TmaJob t = s_job[lane];
+        uint8_t* w = s_win + lane * kWinBytes;
+        if (warp == 0)
+            tma_load_3d(w, t.maps->luma, s_bar, t.lx, t.ly, t.z);
+        else
+            tma_load_3d(w + kWinY + (warp - 1) * kWinC, t.maps->chroma, s_bar, t.cx, t.cy + (warp - 1) * t.chroma_h, t.z);
+    }
+    if (warp == 0) {
+        const uint32_t n_box = (s_cnt[8] + kCoefBox - 1) / kCoefBox;
+        // complete_tx of the window boxes may already have been counted: the phase cannot complete before
+        // this (single) arrival, and the transaction count is allowed to run negative meanwhile
+        if (lane == 0) mbar_arrive_expect_tx(s_bar, n_box * (kCoefBox * 128) + s_cnt[9] * kWinTx);
+        __syncwarp();
+        if (lane < (int)n_box)  // rows past n_blocks are zero-filled by the TMA unit
+            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(mbs[m0].coeff_block + lane * kCoefBox));
+        if (out_mask) {
+            uint32_t run = 0, base_of[8];
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            base_of[b] = run;
-            run += s_cnt[b];
-        }
-        uint32_t slot = rel_r;
+            for (int b = 0; b < 8; b++) {
+                base_of[b] = run;
+                run += s_cnt[b];
+            }
+            uint32_t slot = rel_r;
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            if (out_mask & (0x20u >> k)) {
-                const uint32_t bin = (bins >> (4 * k)) & 15u;
-                const uint32_t pp = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
-                const bool coded = cbp_r & (0x20u >> k);
-                uint32_t bsel = 0;
+            for (int k = 0; k < 6; k++) {
+                if (out_mask & (0x20u >> k)) {
+                    const uint32_t bin = (bins >> (4 * k)) & 15u;
+                    const uint32_t pp = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
+                    const bool coded = cbp_r & (0x20u >> k);
+                    uint32_t bsel = 0;
 #pragma unroll
-                for (int b = 0; b < 8; b++) bsel = bin == (uint32_t)b ? base_of[b] : bsel;
-                s_map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
-                if (coded) slot++;
+                    for (int b = 0; b < 8; b++) bsel = bin == (uint32_t)b ? base_of[b] : bsel;
+                    s_map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
+                    if (coded) slot++;
+                }
             }
         }
     }
-    __syncwarp();
-    // the arrive releases the generic-proxy writes above (context, list) to the consumers' acquire
-    if (lane == 0) mbar_arrive_expect_tx(full, n_box * (kCoefBox * 128) + n_pred * kWinTx);
-    if (lane < (int)n_box)  // rows past n_blocks are zero-filled by the TMA unit
-        tma_load_2d(s_coef + lane * (kCoefBox * 128), coef_map, full, 0, (int)(block0 + lane * kCoefBox));
-    if (predicted) {
-        const TmaJob t = s_job[lane];
-        uint8_t* w = s_win + lane * kWinBytes;
-        tma_load_3d(w, t.maps->luma, full, t.lx, t.ly, t.z);
-        tma_load_3d(w + kWinY, t.maps->chroma, full, t.cx, t.cy, t.z);
-        tma_load_3d(w + kWinY + kWinC, t.maps->chroma, full, t.cx, t.cy + t.chroma_h, t.z);
-    }
-}
+    __syncthreads();       // block list visible
+    mbar_wait(s_bar, 0);   // all tiles have landed
 
-// ------------------------------------------------------------------------------------------------
-// Consumer: one thread per output block -- interpolate, IDCT, add, saturate, store.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void consume_block(const uint8_t* stage, int t) {
-    const uint8_t* s_coef = stage + Stage::coef;
-    const uint8_t* s_win = stage + Stage::win;
-    const MbCtx* s_ctx = reinterpret_cast<const MbCtx*>(stage + Stage::ctx);
-    const uint16_t* s_map = reinterpret_cast<const uint16_t*>(stage + Stage::map);
-
-    const uint32_t e = s_map[t];
+    // ---------------- one thread per output block: interpolate, IDCT, add, saturate, store ----------------
+    const uint32_t e = s_map[tid];
     if (e == kNoBlock) return;
     const int j = e & 15, k = (e >> 4) & 7;
     const bool coded = e & 0x80u;
@@ -363,7 +363,7 @@ __device__ __forceinline__ void consume_block(const uint8_t* stage, int t) {
     // prediction: eight rows of eight bytes, straight from the staged window (video_noasm.go:44-80)
     uint32_t p0[8], p1[8];
     if (pred) {
-        // the window area is 128-byte aligned, so the byte offset decides the word alignment
+        // s_win is 128-byte aligned, so the byte offset decides the word alignment
         const uint32_t a = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + (mcb & 15u);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_win + (a & ~3u));
         const uint32_t sh = (a & 3u) * 8;
@@ -472,83 +472,21 @@ __device__ __forceinline__ void consume_block(const uint8_t* stage, int t) {
     }
 }
 
-// Persistent, warp-specialised: CTA c works on groups c, c + gridDim.x, ...  Warp 0 runs ahead through a
-// ring of kStages stages (wait empty -> decode, sort, expect_tx, TMA); warps 1..3 follow (wait full ->
-// one block per thread -> arrive empty).  The record -> picture -> stream pointer chase and the DRAM
-// latency of the tiles are thus overlapped with the arithmetic of the previous group.
-__global__ void __launch_bounds__(kThreads) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                           const SlabMaps* __restrict__ slab_maps,
-                                                           const StreamInfo* __restrict__ streams, int max_streams,
-                                                           const mpegb200_picture* __restrict__ pics, int n_pics,
-                                                           const mpegb200_mb* __restrict__ mbs, uint32_t n_mb,
-                                                           uint32_t n_blocks) {
-    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tiles need 1024-byte alignment
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Smem::bars);
-    uint64_t* empty = full + kStages;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_groups = (n_mb + kG - 1) / kG;
-
-    if (tid == 0) {
-        if (smem_u32(smem) & 1023u) __trap();
-        for (int s = 0; s < kStages; s++) {
-            mbar_init(&full[s], 1);           // the producer's expect_tx arrival (+ the TMA bytes)
-            mbar_init(&empty[s], kNT / 32);   // one arrival per consumer warp
-        }
-        fence_barrier_init();
-    }
-    __syncthreads();
-
-    if (warp < kProducers) {
-        // records of the producer's next group are fetched one iteration ahead, so that their DRAM
-        // latency is not on the path between "stage released" and "TMA issued"
-        const uint4* rec = reinterpret_cast<const uint4*>(mbs);
-        uint32_t it = warp;
-        uint32_t g = blockIdx.x + warp * gridDim.x;
-        uint4 next = make_uint4(0, 0, 0, 0);
-        if (g < n_groups && g * kG + lane < n_mb && lane < kG) next = rec[g * kG + lane];
-        for (; g < n_groups; g += kProducers * gridDim.x, it += kProducers) {
-            const uint4 raw = next;
-            const uint32_t gn = g + kProducers * gridDim.x;
-            if (gn < n_groups && gn * kG + lane < n_mb && lane < kG) next = rec[gn * kG + lane];
-            const uint32_t s = it % kStages, use = it / kStages;
-            if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);  // consumers have released the stage's previous group
-            produce_group(smem + s * Stage::bytes, &full[s], &coef_map, slab_maps, streams, max_streams, pics, n_pics, raw,
-                          n_mb, n_blocks, g, lane);
-        }
-    } else {
-        const int t = tid - 32 * kProducers;
-        uint32_t it = 0;
-        for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
-            const uint32_t s = it % kStages, use = it / kStages;
-            mbar_wait(&full[s], use & 1);
-            consume_block(smem + s * Stage::bytes, t);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-    }
-}
-
 }  // namespace
 
 cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, const StreamInfo* d_streams, int max_streams,
                              const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb,
                              uint32_t n_blocks, cudaStream_t stream) {
     if (n_mb == 0) return cudaSuccess;
-    static int resident = 0;  // CTAs that fit the device at once (persistent grid)
-    if (!resident) {
+    static bool configured = false;
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_tma_kernel, kThreads, Smem::total);
-        if (e != cudaSuccess) return e;
-        resident = sms * (per_sm > 0 ? per_sm : 1);
+        configured = true;
     }
-    const uint32_t n_groups = (n_mb + kG - 1) / kG;
-    const uint32_t grid = n_groups < (uint32_t)resident ? n_groups : (uint32_t)resident;
-    fused_tma_kernel<<<grid, kThreads, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps,
-                                                              d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
+    const uint32_t grid = (n_mb + kG - 1) / kG;
+    fused_tma_kernel<<<grid, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps,
+                                                         d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
     return cudaGetLastError();
 }
 

@@ -395,8 +395,6 @@ cudaError_t launch_fused_mc_idct(const StreamInfo* d_streams, int max_streams, c
 //   yy1 = Y*0x10101; cb1 = Cb-128; cr1 = Cr-128
 //   R = sat8((yy1 + 91881*cr1) >> 16), G = sat8((yy1 - 22554*cb1 - 46802*cr1) >> 16),
 //   B = sat8((yy1 + 116130*cb1) >> 16), A = 255; chroma sample (x/2, y/2).
-// One thread converts 4 horizontally adjacent pixels of one row: 4 B of Y + 2 B Cb + 2 B Cr in,
-// one 16-byte store out.  grid = (ceil(ceil(w/4)/64), h, n_frames).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rgba_px(int y, int cb1, int cr1) {
     const int yy1 = y * 0x10101;
@@ -407,44 +405,61 @@ __device__ __forceinline__ uint32_t rgba_px(int y, int cb1, int cr1) {
     return pack_sat_u8(g, r, pack_sat_u8(255, b, 0u));
 }
 
-__global__ void __launch_bounds__(64) rgba_kernel(const StreamInfo* __restrict__ streams, int max_streams,
-                                                  const int32_t* __restrict__ stream_ids,
-                                                  const uint8_t* __restrict__ bufs, uint8_t* __restrict__ out,
-                                                  size_t out_stride) {
-    const int f = blockIdx.z;
+// One thread converts an 8 x 2 pixel patch (two luma rows share one chroma row): 16 B of Y, 4 B of Cb and
+// 4 B of Cr in, four 16-byte stores out.  Work items are flattened over (frame, row pair, 8-pixel column);
+// `cols`/`pairs` are the launch-wide maxima, frames with a smaller display rectangle exit early.
+__global__ void __launch_bounds__(256) rgba_kernel(const StreamInfo* __restrict__ streams, int max_streams,
+                                                   const int32_t* __restrict__ stream_ids,
+                                                   const uint8_t* __restrict__ bufs, uint8_t* __restrict__ out,
+                                                   size_t out_stride, uint32_t cols, uint32_t pairs, uint32_t total) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= total) return;
+    const uint32_t per_frame = cols * pairs;
+    const uint32_t f = idx / per_frame, rem = idx - f * per_frame;
+    const uint32_t pr = rem / cols, col = rem - pr * cols;
     const int stream = stream_ids[f];
     if (stream < 0 || stream >= max_streams) return;
     const StreamInfo si = streams[stream];
     const uint32_t buf = bufs[f];
     if (!si.open || buf >= 3) return;
-    const int y = blockIdx.y;
-    const int x = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int x = (int)col * 8, y = (int)pr * 2;
     if (y >= si.height || x >= si.width) return;
     const uint8_t* base = si.base + (size_t)buf * si.buf_stride;
-    const int cw = si.luma_w >> 1;
-    const uint8_t* yp = base + (size_t)y * si.luma_w + x;
-    const uint8_t* cbp = base + (size_t)si.luma_w * si.luma_h + (size_t)(y >> 1) * cw + (x >> 1);
+    const int lw = si.luma_w, cw = lw >> 1;
+    const uint8_t* yp = base + (size_t)y * lw + x;           // luma_w is a multiple of 16 and x of 8: aligned, readable
+    const uint8_t* cbp = base + (size_t)lw * si.luma_h + (size_t)(y >> 1) * cw + (x >> 1);
     const uint8_t* crp = cbp + (size_t)cw * (si.luma_h >> 1);
-    const uint32_t yy = *reinterpret_cast<const uint32_t*>(yp);  // luma_w is a multiple of 16: always readable
-    const uint32_t cbb = *reinterpret_cast<const uint16_t*>(cbp);
-    const uint32_t crr = *reinterpret_cast<const uint16_t*>(crp);
-    const int cb0 = (int)(cbb & 0xff) - 128, cb1 = (int)(cbb >> 8) - 128;
-    const int cr0 = (int)(crr & 0xff) - 128, cr1 = (int)(crr >> 8) - 128;
-    uint4 o;
-    o.x = rgba_px(yy & 0xff, cb0, cr0);
-    o.y = rgba_px((yy >> 8) & 0xff, cb0, cr0);
-    o.z = rgba_px((yy >> 16) & 0xff, cb1, cr1);
-    o.w = rgba_px(yy >> 24, cb1, cr1);
-    uint8_t* op = out + (size_t)f * out_stride + ((size_t)y * si.width + x) * 4;
-    const int left = si.width - x;
-    if (left >= 4 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-        *reinterpret_cast<uint4*>(op) = o;
-    } else {
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(op);
-        o32[0] = o.x;
-        if (left > 1) o32[1] = o.y;
-        if (left > 2) o32[2] = o.z;
-        if (left > 3) o32[3] = o.w;
+    const uint2 y0 = *reinterpret_cast<const uint2*>(yp);
+    const bool row1 = y + 1 < si.height;
+    const uint2 y1 = row1 ? *reinterpret_cast<const uint2*>(yp + lw) : make_uint2(0, 0);
+    const uint32_t cbw = *reinterpret_cast<const uint32_t*>(cbp), crw = *reinterpret_cast<const uint32_t*>(crp);
+    int cb[4], cr[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        cb[i] = (int)((cbw >> (8 * i)) & 0xff) - 128;
+        cr[i] = (int)((crw >> (8 * i)) & 0xff) - 128;
+    }
+    const int left = si.width - x;  // pixels of this patch inside the display rectangle
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        if (r == 1 && !row1) break;
+        const uint2 yy = r ? y1 : y0;
+        uint32_t px[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            px[i] = rgba_px((yy.x >> (8 * i)) & 0xff, cb[i >> 1], cr[i >> 1]);
+            px[4 + i] = rgba_px((yy.y >> (8 * i)) & 0xff, cb[2 + (i >> 1)], cr[2 + (i >> 1)]);
+        }
+        uint8_t* op = out + (size_t)f * out_stride + ((size_t)(y + r) * si.width + x) * 4;
+        if (left >= 8 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            reinterpret_cast<uint4*>(op)[0] = make_uint4(px[0], px[1], px[2], px[3]);
+            reinterpret_cast<uint4*>(op)[1] = make_uint4(px[4], px[5], px[6], px[7]);
+        } else {
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(op);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < left) o32[i] = px[i];
+        }
     }
 }
 
@@ -452,12 +467,15 @@ cudaError_t launch_rgba(const StreamInfo* d_streams, int max_streams, const int3
                         const uint8_t* d_bufs, int n, int max_w, int max_h, uint8_t* d_rgba,
                         size_t rgba_stride_bytes, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    const int per_row = (max_w + 3) / 4;
-    for (int first = 0; first < n; first += 32768) {
-        const int cnt = min(32768, n - first);
-        dim3 grid((per_row + 63) / 64, max_h, cnt);
-        rgba_kernel<<<grid, 64, 0, stream>>>(d_streams, max_streams, d_stream_ids + first, d_bufs + first,
-                                             d_rgba + (size_t)first * rgba_stride_bytes, rgba_stride_bytes);
+    const uint32_t cols = (uint32_t)(max_w + 7) / 8, pairs = (uint32_t)(max_h + 1) / 2;
+    const uint64_t per_frame = (uint64_t)cols * pairs;
+    const int chunk = (int)((0x7fffffffull / per_frame) < (uint64_t)n ? (0x7fffffffull / per_frame) : (uint64_t)n);
+    for (int first = 0; first < n; first += chunk) {
+        const int cnt = min(chunk, n - first);
+        const uint32_t total = (uint32_t)(per_frame * cnt);
+        rgba_kernel<<<(total + 255) / 256, 256, 0, stream>>>(d_streams, max_streams, d_stream_ids + first, d_bufs + first,
+                                                             d_rgba + (size_t)first * rgba_stride_bytes, rgba_stride_bytes,
+                                                             cols, pairs, total);
     }
     return cudaGetLastError();
 }
