@@ -252,7 +252,8 @@ def main():
 
     S = args.streams
     t0 = time.time()
-    g, refs, pics, mbs, coeffs = build_batch(S, rank * S, args.mode, log)
+    from mpeg_b200.sharding import stream_range
+    g, refs, pics, mbs, coeffs = build_batch(S, stream_range(rank, world, S)[0], args.mode, log)
     log(f"workload built in {time.time() - t0:.1f} s: {S} streams, {len(mbs)} macroblocks, {len(coeffs)} blocks")
     alg_total, alg_read = wl.algorithmic_bytes(mbs, len(coeffs))
 
@@ -354,16 +355,16 @@ def main():
     # ---- NCCL gather of the decoded frames (the only collective of the path), timed on its own
     gather = None
     if dist is not None:
-        send = torch.empty(S * g.picture_bytes, dtype=torch.uint8, device="cuda")
+        from mpeg_b200.sharding import gather_frames
+        send = torch.empty((S, g.picture_bytes), dtype=torch.uint8, device="cuda")
         with torch.cuda.stream(stream):
             ctx.video_read_pictures(ids, np.full(S, variants[0][1], np.uint8), send.data_ptr(), g.picture_bytes, device=True)
         stream.synchronize()
-        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-        dist.gather(send, recv, dst=0)  # warm-up
+        gather_frames(send, dst=0)  # warm-up
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        dist.gather(send, recv, dst=0)
+        gather_frames(send, dst=0)
         b.record()
         barrier()
         t = torch.tensor([a.elapsed_time(b)], device="cuda")

@@ -1,0 +1,92 @@
+/*
+ * mpegb200_host.h -- host half of the drop-in: the serial work gen2brain/mpeg keeps on the CPU
+ * (bit reader, VLC parse, dequantisation, PS demux), emitting the packed records of mpegb200.h.
+ *
+ * In the reference these are the Go functions around the kernels (file:line @ 27c6f084):
+ *   Video:  NewVideo video.go:110, HasHeader :130, Decode :209-268 (display order, end flush),
+ *           decodeSequenceHeader :270-331, decodePicture :374-434, decodeSlice :436-460,
+ *           decodeMacroblock :462-562, decodeMotionVector(s) :564-606, predictMacroblock :608-637
+ *           (decision only), decodeBlock :639-746 (parse + dequantise + oddify + clip)
+ *   Audio:  NewAudio audio.go:83, Decode :163-182, decodeHeader :184-272, decodeFrame :274-375
+ *           (allocation, scale factors, readSamples :440-490 requantisation)
+ *   Demux:  demux.go:85-138 (headers), :473-568 (packet walk)
+ * A Go build keeps using its own Go code for this half; this C++ restatement exists
+ * because no Go toolchain is available here, and it is what the Python mirror (mpeg_b200.Video /
+ * Audio / MPEG) drives.  It is product code: written independently of oracle/ and cross-checked
+ * against it record for record in tests/test_host_parser.py.
+ *
+ * All functions are plain C; parsers are CPU-only objects and need no GPU.
+ */
+#ifndef MPEGB200_HOST_H
+#define MPEGB200_HOST_H
+
+#include "mpegb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- video elementary stream ------------------------------------------------------------------ */
+
+typedef struct mpegb200_video_parser mpegb200_video_parser;
+
+/* One kernel launch worth of records: a picture, or one wave of a picture that rewrites macroblocks
+ * (a later record that defines all six blocks replaces the earlier one; one that defines only some
+ * blocks goes into the next wave -- the reference decodes serially, video.go:454-459). */
+typedef struct mpegb200_launch {
+    mpegb200_picture picture;   /* stream = 0; the caller patches its own stream id in */
+    uint32_t first_mb, n_mb;    /* slice of the step's mb array; coeff_block is relative to first_block */
+    uint32_t first_block, n_blocks;
+} mpegb200_launch;
+
+/* What one Video.Decode() call amounts to (video.go:209-268). */
+typedef struct mpegb200_video_step {
+    int has_frame;              /* 0: end of stream (Decode() == nil) */
+    int frame_buf;              /* physical buffer 0..2 holding the frame to return */
+    double time;                /* Frame.Time (video.go:263) */
+    int n_launches;             /* pictures decoded on the way (0 for the end-of-stream flush, video.go:223-229) */
+    const mpegb200_launch* launches;
+    const mpegb200_mb* mbs;
+    const int16_t* coeffs;      /* 64 per block */
+} mpegb200_video_step;
+
+mpegb200_video_parser* mpegb200_video_parser_new(const uint8_t* data, size_t len);   /* NewVideo; copies data */
+void   mpegb200_video_parser_free(mpegb200_video_parser* v);
+int    mpegb200_video_parser_has_header(mpegb200_video_parser* v);
+int    mpegb200_video_parser_width(mpegb200_video_parser* v);
+int    mpegb200_video_parser_height(mpegb200_video_parser* v);
+double mpegb200_video_parser_framerate(mpegb200_video_parser* v);
+void   mpegb200_video_parser_set_no_delay(mpegb200_video_parser* v, int no_delay);   /* video.go:178 */
+void   mpegb200_video_parser_rewind(mpegb200_video_parser* v);                       /* video.go:195 */
+int    mpegb200_video_parser_has_ended(mpegb200_video_parser* v);
+/* Parse up to and including the picture that makes a frame due.  Pointers in *out stay valid until
+ * the next call on the same parser.  Returns 0, or MPEGB200_EINVAL. */
+int    mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* out);
+
+/* ---- MP2 elementary stream --------------------------------------------------------------------- */
+
+typedef struct mpegb200_audio_parser mpegb200_audio_parser;
+
+mpegb200_audio_parser* mpegb200_audio_parser_new(const uint8_t* data, size_t len);   /* NewAudio */
+void   mpegb200_audio_parser_free(mpegb200_audio_parser* a);
+int    mpegb200_audio_parser_has_header(mpegb200_audio_parser* a);
+int    mpegb200_audio_parser_samplerate(mpegb200_audio_parser* a);
+int    mpegb200_audio_parser_channels(mpegb200_audio_parser* a);
+void   mpegb200_audio_parser_rewind(mpegb200_audio_parser* a);                       /* audio.go:149 */
+/* Parse one frame: fills samples[2][36][32] (layout of mpegb200_audio_synth) and *time.
+ * Returns 1 if a frame was parsed, 0 at the end (Decode() == nil). */
+int    mpegb200_audio_parser_next(mpegb200_audio_parser* a, int32_t* samples, double* time);
+
+/* ---- MPEG program stream ----------------------------------------------------------------------- */
+
+/* Split a program stream into its video (0xE0) and first audio (0xC0) elementary streams.  The
+ * buffers are malloc'ed; release with mpegb200_buffer_free.  Returns 0 or MPEGB200_EINVAL
+ * (no pack / system header: ErrInvalidHeader, demux.go:32). */
+int  mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_t* video_len, uint8_t** audio,
+                          size_t* audio_len, int* n_video_packets, int* n_audio_packets);
+void mpegb200_buffer_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPEGB200_HOST_H */

@@ -79,6 +79,26 @@ def load():
         "mpegb200_audio_write_state": (C.c_int, [vp, C.c_int, vp, C.c_int]),
         "mpegb200_host_alloc": (vp, [C.c_size_t]),
         "mpegb200_host_free": (None, [vp]),
+        # host half (include/mpegb200_host.h)
+        "mpegb200_video_parser_new": (vp, [C.c_char_p, C.c_size_t]),
+        "mpegb200_video_parser_free": (None, [vp]),
+        "mpegb200_video_parser_has_header": (C.c_int, [vp]),
+        "mpegb200_video_parser_width": (C.c_int, [vp]),
+        "mpegb200_video_parser_height": (C.c_int, [vp]),
+        "mpegb200_video_parser_framerate": (C.c_double, [vp]),
+        "mpegb200_video_parser_set_no_delay": (None, [vp, C.c_int]),
+        "mpegb200_video_parser_rewind": (None, [vp]),
+        "mpegb200_video_parser_has_ended": (C.c_int, [vp]),
+        "mpegb200_video_parser_next": (C.c_int, [vp, vp]),
+        "mpegb200_audio_parser_new": (vp, [C.c_char_p, C.c_size_t]),
+        "mpegb200_audio_parser_free": (None, [vp]),
+        "mpegb200_audio_parser_has_header": (C.c_int, [vp]),
+        "mpegb200_audio_parser_samplerate": (C.c_int, [vp]),
+        "mpegb200_audio_parser_channels": (C.c_int, [vp]),
+        "mpegb200_audio_parser_rewind": (None, [vp]),
+        "mpegb200_audio_parser_next": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
+        "mpegb200_demux_split": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(vp), szp, C.POINTER(vp), szp, ip, ip]),
+        "mpegb200_buffer_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
@@ -95,5 +115,8 @@ EXPORTED_SYMBOLS = None
 def exported_symbols():
     """Names include/mpegb200.h declares (parsed from the header), for the no-GPU ABI test."""
     import re
-    hdr = (PKG.parent / "include" / "mpegb200.h").read_text()
-    return sorted(set(re.findall(r"\b(mpegb200_[a-z0-9_]+)\s*\(", hdr)))
+    names = set()
+    for h in ("mpegb200.h", "mpegb200_host.h"):
+        hdr = (PKG.parent / "include" / h).read_text()
+        names |= set(re.findall(r"\b(mpegb200_[a-z0-9_]+)\s*\(", hdr))
+    return sorted(names)

@@ -1,0 +1,968 @@
+// host_parser.cpp -- the host half of the drop-in (include/mpegb200_host.h): MPEG-1 video and MP2
+// bitstream parsing, dequantisation / requantisation and PS demux on the CPU, producing the packed
+// records the sm_100a kernels consume.  CPU only; no CUDA in this file.
+//
+// Behaviour follows the reference's serial half (citations in mpegb200_host.h and below); the
+// machinery is its own: a 64-bit window bit reader and table-driven multi-bit VLC decoding instead of
+// the reference's one-bit-per-step tree walk (buffer.go:352-376), records instead of pixels.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/mpegb200_host.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// bit reader (most significant bit first, buffer.go:223-255), zero bits past the end
+// ------------------------------------------------------------------------------------------------
+struct BitReader {
+    const uint8_t* p = nullptr;  // has >= 8 readable zero bytes after len
+    size_t len = 0;
+    uint64_t pos = 0;  // in bits
+    bool ended = false;
+
+    int64_t left() const { return (int64_t)(len * 8) - (int64_t)pos; }
+    bool has(int64_t n) {  // buffer.go:203-221 for a fully resident source
+        if (left() >= n) return true;
+        ended = true;
+        return false;
+    }
+    uint32_t peek(int n) const {  // n <= 32
+        const size_t b = (size_t)(pos >> 3);
+        if (b >= len) return 0;
+        uint64_t w = 0;
+        for (int i = 0; i < 8; i++) w = (w << 8) | p[b + i];
+        w <<= (pos & 7);
+        return n ? (uint32_t)(w >> (64 - n)) : 0;
+    }
+    void skip_bits(int n) { pos += (uint64_t)n; }
+    uint32_t read(int n) {
+        const uint32_t v = peek(n);
+        pos += (uint64_t)n;
+        return v;
+    }
+    int read1() { return (int)read(1); }
+    void align() { pos = (pos + 7) & ~(uint64_t)7; }                // buffer.go:257
+    void skip(int n) { if (has(n)) pos += (uint64_t)n; }            // buffer.go:261
+    int skip_bytes(uint8_t v) {                                     // buffer.go:267
+        align();
+        int n = 0;
+        while (has(8) && p[pos >> 3] == v) {
+            pos += 8;
+            n++;
+        }
+        return n;
+    }
+    int next_start_code() {  // buffer.go:279-302
+        align();
+        size_t i = (size_t)(pos >> 3);
+        while (i + 5 <= len) {
+            if (p[i] == 0 && p[i + 1] == 0 && p[i + 2] == 1) {
+                pos = (uint64_t)(i + 4) << 3;
+                return p[i + 3];
+            }
+            i++;
+        }
+        pos = (uint64_t)i << 3;
+        ended = true;
+        return -1;
+    }
+    int find_start_code(int code) {  // buffer.go:304-311
+        for (;;) {
+            const int c = next_start_code();
+            if (c == code || c == -1) return c;
+        }
+    }
+    int has_start_code(int code) {  // buffer.go:313-324
+        const uint64_t save = pos;
+        const int c = find_start_code(code);
+        pos = save;
+        return c;
+    }
+    bool peek_non_zero(int n) { return has(n) && peek(n) != 0; }   // buffer.go:341-350
+};
+
+// ------------------------------------------------------------------------------------------------
+// variable-length codes: prefix rows -> direct lookup tables
+// ------------------------------------------------------------------------------------------------
+#define VLC_INVALID (-32768)
+struct vlc_code {
+    const char* bits;
+    int value;
+};
+#include "mpeg1_vlc_codes.inc"
+
+struct VlcTable {
+    struct Entry {
+        int32_t value;
+        uint8_t len;  // 0 = continue in a second-level table (value = its index)
+    };
+    int first_bits = 0, max_bits = 0;
+    std::vector<Entry> first;
+    std::vector<std::vector<Entry>> second;
+
+    void build(const vlc_code* rows, size_t n, int first_level_bits) {
+        max_bits = 0;
+        for (size_t i = 0; i < n; i++) max_bits = std::max(max_bits, (int)strlen(rows[i].bits));
+        first_bits = std::min(first_level_bits, max_bits);
+        first.assign((size_t)1 << first_bits, Entry{0, 0xff});
+        for (size_t i = 0; i < n; i++) {
+            const int len = (int)strlen(rows[i].bits);
+            uint32_t code = 0;
+            for (int b = 0; b < len; b++) code = (code << 1) | (uint32_t)(rows[i].bits[b] == '1');
+            const int32_t value = rows[i].value == VLC_INVALID ? 0 : rows[i].value;  // unassigned prefix -> 0
+            if (len <= first_bits) {
+                const uint32_t lo = code << (first_bits - len);
+                for (uint32_t f = 0; f < (1u << (first_bits - len)); f++) first[lo + f] = Entry{value, (uint8_t)len};
+            } else {
+                const uint32_t head = code >> (len - first_bits);
+                if (first[head].len != 0) {
+                    first[head] = Entry{(int32_t)second.size(), 0};
+                    second.emplace_back((size_t)1 << (max_bits - first_bits), Entry{0, 0xff});
+                }
+                auto& sub = second[(size_t)first[head].value];
+                const int rest = len - first_bits, sub_bits = max_bits - first_bits;
+                const uint32_t lo = (code & ((1u << rest) - 1)) << (sub_bits - rest);
+                for (uint32_t f = 0; f < (1u << (sub_bits - rest)); f++) sub[lo + f] = Entry{value, (uint8_t)len};
+            }
+        }
+    }
+    int read(BitReader& br) const {
+        const uint32_t bits = br.peek(max_bits);
+        Entry e = first[bits >> (max_bits - first_bits)];
+        if (e.len == 0) e = second[(size_t)e.value][bits & ((1u << (max_bits - first_bits)) - 1)];
+        if (e.len == 0xff) {  // not reachable with the complete tables of the standard
+            br.skip_bits(max_bits);
+            return 0;
+        }
+        br.skip_bits(e.len);
+        return e.value;
+    }
+};
+
+struct Tables {
+    VlcTable addr_inc, type_i, type_p, type_b, cbp, motion, dc_luma, dc_chroma, coeff;
+    uint8_t zigzag[64];
+    Tables() {
+#define BUILD(t, rows, fb) t.build(rows, sizeof(rows) / sizeof(rows[0]), fb)
+        BUILD(addr_inc, VLC_MB_ADDR_INC, 11);
+        BUILD(type_i, VLC_MB_TYPE_I, 8);
+        BUILD(type_p, VLC_MB_TYPE_P, 8);
+        BUILD(type_b, VLC_MB_TYPE_B, 8);
+        BUILD(cbp, VLC_CBP, 9);
+        BUILD(motion, VLC_MOTION, 11);
+        BUILD(dc_luma, VLC_DC_SIZE_LUMA, 8);
+        BUILD(dc_chroma, VLC_DC_SIZE_CHROMA, 8);
+        BUILD(coeff, VLC_DCT_COEFF, 9);
+#undef BUILD
+        // zig-zag scan (video.go:1044-1053): walk the anti-diagonals
+        int i = 0;
+        for (int d = 0; d < 15; d++) {
+            const int lo = d < 8 ? 0 : d - 7, hi = d < 8 ? d : 7;
+            for (int t = lo; t <= hi; t++) {
+                const int r = (d & 1) ? t : d - t, c = d - r;  // odd diagonals run downwards
+                zigzag[i++] = (uint8_t)(r * 8 + c);
+            }
+        }
+    }
+};
+const Tables& tables() {
+    static const Tables t;
+    return t;
+}
+
+const uint8_t kIntraQuant[64] = {  // ISO 11172-2 default intra matrix (video.go:1055-1064)
+    8,  16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37, 19, 22, 26, 27, 29, 34, 34, 38, 22, 22, 26, 27, 29, 34, 37, 40,
+    22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32, 35, 40, 48, 58, 26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
+const double kPictureRate[16] = {0.000, 23.976, 24.000, 25.000, 29.970, 30.000, 50.000, 59.940,
+                                 60.000, 0.000,  0.000,  0.000,  0.000,  0.000,  0.000,  0.000};
+
+enum { kPicI = 1, kPicP = 2, kPicB = 3 };
+enum { kStartPicture = 0x00, kSliceFirst = 0x01, kSliceLast = 0xAF, kUserData = 0xB2, kSequence = 0xB3, kExtension = 0xB5 };
+
+struct Motion {
+    int full_px = 0, r_size = 0, h = 0, v = 0;
+    bool is_set = false;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// video
+// ------------------------------------------------------------------------------------------------
+struct mpegb200_video_parser {
+    std::vector<uint8_t> data;
+    BitReader br;
+    double frame_rate = 0, time = 0;
+    int frames_decoded = 0;
+    int width = 0, height = 0, mb_w = 0, mb_h = 0, mb_size = 0;
+    int start_code = -1, picture_type = 0;
+    Motion fwd, bwd;
+    bool has_header = false, has_reference = false, no_delay = false;
+    int quantizer_scale = 0, mb_addr = 0, mb_row = 0, mb_col = 0;
+    bool slice_begin = false, intra = false;
+    int dc_pred[3] = {128, 128, 128};
+    int cur = 0, fwd_buf = 1, bwd_buf = 2;  // physical buffers playing frameCurrent / Forward / Backward
+    uint8_t intra_q[64], non_intra_q[64];
+    int32_t level[64];  // the reference's blockData before the premultiply; persists like it (video.go:101)
+
+    // records of the step being built
+    std::vector<mpegb200_launch> launches;
+    std::vector<mpegb200_mb> mbs;
+    std::vector<int16_t> coeffs;
+    // picture under construction
+    std::vector<mpegb200_mb> pic_mbs;
+    std::vector<int16_t> pic_coeffs;
+    std::vector<int32_t> last_writer;  // per macroblock address: index into pic_mbs, -1 = none
+    bool pic_has_rewrites = false;
+    int rec = -1;
+
+    void reset_levels() { memset(level, 0, sizeof(level)); }
+};
+
+namespace {
+
+using VP = mpegb200_video_parser;
+
+bool decode_sequence_header(VP* v) {  // video.go:270-331
+    BitReader& br = v->br;
+    if (!br.has(64 + 2 * 64 * 8)) return false;
+    v->width = (int)br.read(12);
+    v->height = (int)br.read(12);
+    if (v->width <= 0 || v->height <= 0) return false;
+    br.read(4);  // aspect ratio
+    v->frame_rate = kPictureRate[br.read(4)];
+    br.read(18);  // bit rate
+    br.skip(1 + 10 + 1);
+    const Tables& t = tables();
+    if (br.read1()) {
+        for (int i = 0; i < 64; i++) v->intra_q[t.zigzag[i]] = (uint8_t)br.read(8);
+    } else {
+        memcpy(v->intra_q, kIntraQuant, 64);
+    }
+    if (br.read1()) {
+        for (int i = 0; i < 64; i++) v->non_intra_q[t.zigzag[i]] = (uint8_t)br.read(8);
+    } else {
+        memset(v->non_intra_q, 16, 64);
+    }
+    v->mb_w = (v->width + 15) >> 4;
+    v->mb_h = (v->height + 15) >> 4;
+    v->mb_size = v->mb_w * v->mb_h;
+    v->cur = 0;      // initFrame x3 (video.go:324-326): current, forward, backward = buffers 0, 1, 2
+    v->fwd_buf = 1;
+    v->bwd_buf = 2;
+    v->has_header = true;
+    return true;
+}
+
+bool ensure_header(VP* v) {  // video.go:130-147
+    if (v->has_header) return true;
+    if (v->start_code != kSequence) v->start_code = v->br.find_start_code(kSequence);
+    if (v->start_code == -1) return false;
+    return decode_sequence_header(v);
+}
+
+int decode_motion_vector(VP* v, int r_size, int motion) {  // video.go:583-606
+    const int fscale = 1 << r_size;
+    const int m_code = tables().motion.read(v->br);
+    int d;
+    if (m_code != 0 && fscale != 1) {
+        const int r = (int)v->br.read(r_size);
+        d = ((abs(m_code) - 1) << r_size) + r + 1;
+        if (m_code < 0) d = -d;
+    } else {
+        d = m_code;
+    }
+    motion += d;
+    if (motion > (fscale << 4) - 1)
+        motion -= fscale << 5;
+    else if (motion < -(fscale << 4))
+        motion += fscale << 5;
+    return motion;
+}
+
+// A new record for the macroblock at (mb_row, mb_col); remembers rewrites (SURVEY: serial semantics).
+mpegb200_mb& new_record(VP* v) {
+    mpegb200_mb m;
+    memset(&m, 0, sizeof(m));
+    m.mb_row = (uint16_t)v->mb_row;
+    m.mb_col = (uint16_t)v->mb_col;
+    m.coeff_block = (uint32_t)(v->pic_coeffs.size() / 64);
+    v->rec = (int)v->pic_mbs.size();
+    v->pic_mbs.push_back(m);
+    const int addr = v->mb_row * v->mb_w + v->mb_col;
+    if (v->last_writer[addr] >= 0) v->pic_has_rewrites = true;
+    v->last_writer[addr] = v->rec;
+    return v->pic_mbs.back();
+}
+
+// predictMacroblock (video.go:608-637), decision only: which reference, which vector.
+void pack_prediction(VP* v, mpegb200_mb& m) {
+    int h = v->fwd.h, w = v->fwd.v;
+    if (v->fwd.full_px) {
+        h <<= 1;
+        w <<= 1;
+    }
+    bool use_bwd = false;
+    if (v->picture_type == kPicB) {
+        // forward copy, then -- if set -- the backward copy on top of it: only the latter is observable
+        if (!v->fwd.is_set || v->bwd.is_set) {
+            use_bwd = true;
+            h = v->bwd.h;
+            w = v->bwd.v;
+            if (v->bwd.full_px) {
+                h <<= 1;
+                w <<= 1;
+            }
+        }
+    }
+    m.flags |= MPEGB200_MB_PREDICT | (use_bwd ? MPEGB200_MB_REF_BWD : 0);
+    m.mv_h = (int16_t)h;
+    m.mv_v = (int16_t)w;
+}
+
+void decode_block(VP* v, int block) {  // video.go:639-799, up to the hand-over to the kernels
+    BitReader& br = v->br;
+    const Tables& t = tables();
+    int n = 0;
+    const uint8_t* q;
+    if (v->intra) {
+        const int plane = block > 3 ? block - 3 : 0;
+        const int size = (plane == 0 ? t.dc_luma : t.dc_chroma).read(br);
+        int dc = v->dc_pred[plane];
+        if (size > 0) {
+            const int diff = (int)br.read(size);
+            dc += (diff & (1 << (size - 1))) ? diff : (-(1 << size) | (diff + 1));
+        }
+        v->dc_pred[plane] = dc;
+        v->level[0] = dc * 8;  // dc << 8 == (dc * 8) * premultiplier[0] (32), video.go:672
+        q = v->intra_q;
+        n = 1;
+    } else {
+        q = v->non_intra_q;
+    }
+    for (;;) {
+        const int c = t.coeff.read(br);
+        if (c == 0x0001 && n > 0 && br.read1() == 0) break;  // end_of_block
+        int run, lv;
+        if (c == 0xffff) {  // escape
+            run = (int)br.read(6);
+            lv = (int)br.read(8);
+            if (lv == 0)
+                lv = (int)br.read(8);
+            else if (lv == 128)
+                lv = (int)br.read(8) - 256;
+            else if (lv > 128)
+                lv -= 256;
+        } else {
+            run = c >> 8;
+            lv = c & 0xff;
+            if (br.read1()) lv = -lv;
+        }
+        n += run;
+        if (n < 0 || n >= 64) return;  // invalid run: the block is dropped, its coefficients stay (video.go:712-714)
+        const int dz = t.zigzag[n++];
+        lv *= 2;  // dequantise, oddify, clip: video.go:719-741
+        if (!v->intra) lv += lv < 0 ? -1 : 1;
+        lv = (lv * v->quantizer_scale * (int)q[dz]) >> 4;
+        if ((lv & 1) == 0) lv -= lv > 0 ? 1 : -1;
+        if (lv > 2047) lv = 2047;
+        if (lv < -2048) lv = -2048;
+        v->level[dz] = lv;
+    }
+    // hand-over: what idct + copy/add*ToDest would consume (video.go:772-798)
+    const size_t at = v->pic_coeffs.size();
+    v->pic_coeffs.resize(at + 64, 0);
+    int16_t* out = &v->pic_coeffs[at];
+    auto put = [&](int i) {
+        const int32_t l = v->level[i];
+        out[i] = (int16_t)(l > 32767 ? 32767 : (l < -32768 ? -32768 : l));
+    };
+    if (n == 1) {  // DC only: the rest of the array is ignored and survives (video.go:774-777)
+        put(0);
+        v->level[0] = 0;
+    } else {
+        if (n < 10) {  // sparse transform: rows/cols 0..3 only (video.go:807-866)
+            for (int r = 0; r < 4; r++)
+                for (int c2 = 0; c2 < 4; c2++) put(r * 8 + c2);
+        } else {
+            for (int i = 0; i < 64; i++) put(i);
+        }
+        v->reset_levels();
+    }
+    v->pic_mbs[(size_t)v->rec].cbp |= (uint8_t)(0x20 >> block);
+}
+
+void decode_macroblock(VP* v) {  // video.go:462-562
+    BitReader& br = v->br;
+    const Tables& t = tables();
+    int inc = 0, code = t.addr_inc.read(br);
+    while (code == 34) code = t.addr_inc.read(br);  // stuffing
+    while (code == 35) {                            // escape
+        inc += 33;
+        code = t.addr_inc.read(br);
+    }
+    inc += code;
+    if (v->slice_begin) {
+        v->slice_begin = false;
+        v->mb_addr += inc;
+    } else {
+        if (v->mb_addr + inc >= v->mb_size) return;
+        if (inc > 1) {
+            v->dc_pred[0] = v->dc_pred[1] = v->dc_pred[2] = 128;
+            if (v->picture_type == kPicP) v->fwd.h = v->fwd.v = 0;
+        }
+        while (inc > 1) {  // skipped macroblocks are pure predictions
+            v->mb_addr++;
+            v->mb_row = v->mb_addr / v->mb_w;
+            v->mb_col = v->mb_addr % v->mb_w;
+            pack_prediction(v, new_record(v));
+            inc--;
+        }
+        v->mb_addr++;
+    }
+    v->mb_row = v->mb_addr / v->mb_w;
+    v->mb_col = v->mb_addr % v->mb_w;
+    if (v->mb_col >= v->mb_w || v->mb_row >= v->mb_h) return;
+
+    const VlcTable& tt = v->picture_type == kPicI ? t.type_i : (v->picture_type == kPicP ? t.type_p : t.type_b);
+    const int type = tt.read(br);
+    v->intra = type & 0x01;
+    v->fwd.is_set = type & 0x08;
+    v->bwd.is_set = type & 0x04;
+    if (type & 0x10) v->quantizer_scale = (int)br.read(5);
+
+    mpegb200_mb& m = new_record(v);
+    if (v->intra) {
+        v->fwd.h = v->fwd.v = v->bwd.h = v->bwd.v = 0;
+        m.flags |= MPEGB200_MB_INTRA;
+    } else {
+        v->dc_pred[0] = v->dc_pred[1] = v->dc_pred[2] = 128;
+        if (v->fwd.is_set) {  // decodeMotionVectors, video.go:564-581
+            v->fwd.h = decode_motion_vector(v, v->fwd.r_size, v->fwd.h);
+            v->fwd.v = decode_motion_vector(v, v->fwd.r_size, v->fwd.v);
+        } else if (v->picture_type == kPicP) {
+            v->fwd.h = v->fwd.v = 0;
+        }
+        if (v->bwd.is_set) {
+            v->bwd.h = decode_motion_vector(v, v->bwd.r_size, v->bwd.h);
+            v->bwd.v = decode_motion_vector(v, v->bwd.r_size, v->bwd.v);
+        }
+        pack_prediction(v, m);
+    }
+    int cbp = 0;
+    if (type & 0x02)
+        cbp = t.cbp.read(br);
+    else if (v->intra)
+        cbp = 0x3f;
+    for (int block = 0; block < 6; block++)
+        if (cbp & (0x20 >> block)) decode_block(v, block);
+}
+
+void decode_slice(VP* v, int slice) {  // video.go:436-460
+    BitReader& br = v->br;
+    v->slice_begin = true;
+    v->mb_addr = (slice - 1) * v->mb_w - 1;
+    v->fwd.h = v->fwd.v = v->bwd.h = v->bwd.v = 0;
+    v->dc_pred[0] = v->dc_pred[1] = v->dc_pred[2] = 128;
+    v->quantizer_scale = (int)br.read(5);
+    while (br.read1()) br.skip(8);
+    do {
+        decode_macroblock(v);
+    } while (v->mb_addr < v->mb_size - 1 && br.peek_non_zero(23));
+}
+
+// Close the picture: split it into launches without double writes and append them to the step.
+void emit_picture(VP* v, int type, int dst, int fwd, int bwd) {
+    const size_t n = v->pic_mbs.size();
+    std::vector<uint8_t> dead(n, 0);
+    std::vector<size_t> cuts;  // record indices where a new wave starts
+    if (v->pic_has_rewrites) {
+        std::vector<int32_t> seen((size_t)v->mb_size, -1);
+        for (size_t i = 0; i < n; i++) {
+            const mpegb200_mb& m = v->pic_mbs[i];
+            const size_t addr = (size_t)m.mb_row * v->mb_w + m.mb_col;
+            if (seen[addr] >= 0) {
+                const bool complete = (m.flags & MPEGB200_MB_PREDICT) || ((m.flags & MPEGB200_MB_INTRA) && m.cbp == 0x3f);
+                if (complete) {
+                    dead[(size_t)seen[addr]] = 1;  // the later record defines every pixel: it simply wins
+                } else {
+                    cuts.push_back(i);  // partial rewrite must see the earlier result: next launch
+                    std::fill(seen.begin(), seen.end(), -1);
+                }
+            }
+            seen[addr] = (int32_t)i;
+        }
+    }
+    cuts.push_back(n);
+    size_t begin = 0;
+    for (size_t cut : cuts) {
+        mpegb200_launch L;
+        memset(&L, 0, sizeof(L));
+        L.picture.stream = 0;
+        L.picture.type = (uint8_t)type;
+        L.picture.dst_buf = (uint8_t)dst;
+        L.picture.fwd_buf = (uint8_t)fwd;
+        L.picture.bwd_buf = (uint8_t)bwd;
+        L.first_mb = (uint32_t)v->mbs.size();
+        L.first_block = (uint32_t)(v->coeffs.size() / 64);
+        uint32_t blocks = 0;
+        for (size_t i = begin; i < cut; i++) {
+            if (dead[i]) continue;
+            mpegb200_mb m = v->pic_mbs[i];
+            const int nc = __builtin_popcount(m.cbp);
+            const int16_t* src = &v->pic_coeffs[(size_t)m.coeff_block * 64];
+            m.coeff_block = blocks;
+            m.pic = 0;
+            v->mbs.push_back(m);
+            v->coeffs.insert(v->coeffs.end(), src, src + (size_t)nc * 64);
+            blocks += (uint32_t)nc;
+        }
+        L.n_mb = (uint32_t)v->mbs.size() - L.first_mb;
+        L.n_blocks = blocks;
+        L.picture.first_mb = 0;
+        L.picture.n_mb = L.n_mb;
+        if (L.n_mb || cut == n) v->launches.push_back(L);
+        begin = cut;
+    }
+}
+
+void decode_picture(VP* v) {  // video.go:374-434
+    BitReader& br = v->br;
+    br.skip(10);
+    v->picture_type = (int)br.read(3);
+    br.skip(16);
+    if (v->picture_type <= 0 || v->picture_type > kPicB) return;
+    if (v->picture_type == kPicP || v->picture_type == kPicB) {
+        v->fwd.full_px = br.read1();
+        const int f = (int)br.read(3);
+        if (f == 0) return;
+        v->fwd.r_size = f - 1;
+    }
+    if (v->picture_type == kPicB) {
+        v->bwd.full_px = br.read1();
+        const int f = (int)br.read(3);
+        if (f == 0) return;
+        v->bwd.r_size = f - 1;
+    }
+    const int temp = v->fwd_buf;  // rotation by index instead of by struct copy (video.go:406-409)
+    if (v->picture_type == kPicI || v->picture_type == kPicP) v->fwd_buf = v->bwd_buf;
+
+    v->pic_mbs.clear();
+    v->pic_coeffs.clear();
+    v->last_writer.assign((size_t)v->mb_size, -1);
+    v->pic_has_rewrites = false;
+    v->rec = -1;
+
+    do {
+        v->start_code = br.next_start_code();
+    } while (v->start_code == kExtension || v->start_code == kUserData);
+    while (v->start_code >= kSliceFirst && v->start_code <= kSliceLast) {
+        decode_slice(v, v->start_code & 0xff);
+        if (v->mb_addr >= v->mb_size - 2) break;
+        v->start_code = br.next_start_code();
+    }
+    emit_picture(v, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf);
+
+    if (v->picture_type == kPicI || v->picture_type == kPicP) {  // video.go:430-433
+        v->bwd_buf = v->cur;
+        v->cur = temp;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+mpegb200_video_parser* mpegb200_video_parser_new(const uint8_t* data, size_t len) {
+    if (!data && len) return nullptr;
+    auto* v = new (std::nothrow) mpegb200_video_parser();
+    if (!v) return nullptr;
+    v->data.assign(data, data + len);
+    v->data.resize(len + 16, 0);
+    v->br.p = v->data.data();
+    v->br.len = len;
+    v->reset_levels();
+    v->start_code = v->br.find_start_code(kSequence);  // NewVideo, video.go:114-118
+    if (v->start_code != -1) decode_sequence_header(v);
+    return v;
+}
+
+void mpegb200_video_parser_free(mpegb200_video_parser* v) { delete v; }
+int mpegb200_video_parser_has_header(mpegb200_video_parser* v) { return v && ensure_header(v); }
+int mpegb200_video_parser_width(mpegb200_video_parser* v) { return v && ensure_header(v) ? v->width : 0; }
+int mpegb200_video_parser_height(mpegb200_video_parser* v) { return v && ensure_header(v) ? v->height : 0; }
+double mpegb200_video_parser_framerate(mpegb200_video_parser* v) { return v && ensure_header(v) ? v->frame_rate : 0; }
+void mpegb200_video_parser_set_no_delay(mpegb200_video_parser* v, int no_delay) {
+    if (v) v->no_delay = no_delay != 0;
+}
+int mpegb200_video_parser_has_ended(mpegb200_video_parser* v) { return v ? v->br.ended : 1; }
+
+void mpegb200_video_parser_rewind(mpegb200_video_parser* v) {  // video.go:195-201
+    if (!v) return;
+    v->br.pos = 0;
+    v->br.ended = false;
+    v->time = 0;
+    v->frames_decoded = 0;
+    v->has_reference = false;
+    v->start_code = -1;
+}
+
+int mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* out) {  // Video.Decode, video.go:209-268
+    if (!v || !out) return MPEGB200_EINVAL;
+    memset(out, 0, sizeof(*out));
+    v->launches.clear();
+    v->mbs.clear();
+    v->coeffs.clear();
+    if (!ensure_header(v)) return 0;
+    int frame = -1;
+    for (;;) {
+        if (v->start_code != kStartPicture) {
+            v->start_code = v->br.find_start_code(kStartPicture);
+            if (v->start_code == -1) {
+                if (v->has_reference && !v->no_delay && v->br.ended && (v->picture_type == kPicI || v->picture_type == kPicP)) {
+                    v->has_reference = false;  // flush the last reference frame (video.go:223-229)
+                    frame = v->bwd_buf;
+                    break;
+                }
+                return 0;
+            }
+        }
+        if (v->br.has_start_code(kStartPicture) == -1 && !v->br.ended) return 0;
+        decode_picture(v);
+        if (v->no_delay)
+            frame = v->bwd_buf;
+        else if (v->picture_type == kPicB)
+            frame = v->cur;
+        else if (v->has_reference)
+            frame = v->fwd_buf;
+        else
+            v->has_reference = true;
+        if (frame >= 0) break;
+    }
+    out->has_frame = 1;
+    out->frame_buf = frame;
+    out->time = v->time;
+    v->frames_decoded++;
+    v->time = (double)v->frames_decoded / v->frame_rate;
+    out->n_launches = (int)v->launches.size();
+    out->launches = v->launches.data();
+    out->mbs = v->mbs.data();
+    out->coeffs = v->coeffs.data();
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// MP2 (audio.go:184-490): header, allocation, scale factors, requantised samples
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Quantizer {
+    uint16_t levels;
+    uint8_t group, bits;
+};
+// ISO 11172-3 Annex B tables 3-B.2a-d in kjmp2's compact form (audio.go:901-973)
+const Quantizer kQuant[17] = {{3, 1, 5},     {5, 1, 7},     {7, 0, 3},      {9, 1, 10},     {15, 0, 4},     {31, 0, 5},
+                              {63, 0, 6},    {127, 0, 7},   {255, 0, 8},    {511, 0, 9},    {1023, 0, 10},  {2047, 0, 11},
+                              {4095, 0, 12}, {8191, 0, 13}, {16383, 0, 14}, {32767, 0, 15}, {65535, 0, 16}};
+const uint8_t kRateClass[2][14] = {{0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2}, {0, 0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2}};
+const uint8_t kTablePick[3][3] = {{8, 8, 12}, {27 | 64, 27 | 64, 27 | 64}, {30 | 64, 27 | 64, 30 | 64}};
+const uint8_t kSbAlloc[2][30] = {
+    {0x44, 0x44, 0x34, 0x34, 0x34, 0x34, 0x34, 0x34, 0x34, 0x34, 0x34, 0x34},
+    {0x43, 0x43, 0x43, 0x42, 0x42, 0x42, 0x42, 0x42, 0x42, 0x42, 0x42, 0x31, 0x31, 0x31, 0x31,
+     0x31, 0x31, 0x31, 0x31, 0x31, 0x31, 0x31, 0x31, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20}};
+const uint8_t kAllocRows[6][16] = {{0, 1, 2, 17},
+                                   {0, 1, 2, 3, 4, 5, 6, 17},
+                                   {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 17},
+                                   {0, 1, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17},
+                                   {0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16},
+                                   {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}};
+const int kSampleRate[4] = {44100, 48000, 32000, 0};
+const int kBitRate[14] = {32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384};
+const int64_t kScaleBase[3] = {0x02000000, 0x01965FEA, 0x01428A30};
+enum { kModeStereo = 0, kModeJoint = 1, kModeDual = 2, kModeMono = 3 };
+
+}  // namespace
+
+struct mpegb200_audio_parser {
+    std::vector<uint8_t> data;
+    BitReader br;
+    double time = 0;
+    int samples_decoded = 0, samplerate_index = 3, bitrate_index = 0, mode = 0, channels = 0, bound = 0;
+    int next_frame_data_size = 0;
+    bool has_header = false;
+    const Quantizer* alloc[2][32] = {};
+    uint8_t scfsi[2][32] = {};
+    int64_t scale[2][32][3] = {};
+};
+
+namespace {
+
+using AP = mpegb200_audio_parser;
+
+bool find_frame_sync(BitReader& br) {  // buffer.go:326-339
+    size_t i;
+    for (i = (size_t)(br.pos >> 3); i + 1 < br.len; i++)
+        if (br.p[i] == 0xFF && (br.p[i + 1] & 0xFE) == 0xFC) {
+            br.pos = ((uint64_t)(i + 1) << 3) + 3;
+            return true;
+        }
+    br.pos = (uint64_t)(i + 1) << 3;
+    return false;
+}
+
+int decode_header(AP* a) {  // audio.go:184-272
+    BitReader& br = a->br;
+    if (!br.has(48)) return 0;
+    br.skip_bytes(0x00);
+    const int sync = (int)br.read(11);
+    if (sync != 0x7ff && !find_frame_sync(br)) return 0;
+    const int version = (int)br.read(2), layer = (int)br.read(2);
+    const bool has_crc = br.read1() == 0;
+    if (version != 3 || layer != 2) return 0;  // MPEG-1, layer II
+    const int bitrate_index = (int)br.read(4) - 1;
+    if (bitrate_index > 13) return 0;
+    const int samplerate_index = (int)br.read(2);
+    if (samplerate_index == 3) return 0;
+    const int padding = br.read1();
+    br.skip(1);
+    const int mode = (int)br.read(2);
+    if (a->has_header && (a->bitrate_index != bitrate_index || a->samplerate_index != samplerate_index || a->mode != mode))
+        return 0;
+    a->bitrate_index = bitrate_index;
+    a->samplerate_index = samplerate_index;
+    a->mode = mode;
+    a->has_header = true;
+    if (mode == kModeStereo || mode == kModeJoint)
+        a->channels = 2;
+    else if (mode == kModeMono)
+        a->channels = 1;
+    if (mode == kModeJoint) {
+        a->bound = ((int)br.read(2) + 1) << 2;
+    } else {
+        br.skip(2);
+        a->bound = mode == kModeMono ? 0 : 32;
+    }
+    br.skip(4);
+    if (has_crc) br.skip(16);
+    if (bitrate_index < 0) return 0;  // "free format": the Go code would index out of range
+    const int frame_size = 144000 * kBitRate[bitrate_index] / kSampleRate[samplerate_index] + padding;
+    return frame_size - (has_crc ? 6 : 4);
+}
+
+const Quantizer* read_allocation(AP* a, int sb, int tab3) {  // audio.go:429-438
+    const int tab4 = kSbAlloc[tab3][sb];
+    const int qtab = kAllocRows[tab4 & 15][a->br.read(tab4 >> 4)];
+    return qtab ? &kQuant[qtab - 1] : nullptr;
+}
+
+// readSamples (audio.go:440-490): three requantised samples of one subband
+void read_samples(AP* a, int ch, int sb, int part, int64_t out[3]) {
+    const Quantizer* q = a->alloc[ch][sb];
+    if (!q) {
+        out[0] = out[1] = out[2] = 0;
+        return;
+    }
+    int64_t sf = a->scale[ch][sb][part];
+    if (sf == 63) {
+        sf = 0;
+    } else {
+        const int shift = (int)(sf / 3);
+        sf = (kScaleBase[sf % 3] + (((int64_t)1 << shift) >> 1)) >> shift;
+    }
+    int64_t adj = q->levels;
+    if (q->group) {
+        int64_t val = a->br.read(q->bits);
+        out[0] = val % adj;
+        val /= adj;
+        out[1] = val % adj;
+        out[2] = val / adj;
+    } else {
+        out[0] = a->br.read(q->bits);
+        out[1] = a->br.read(q->bits);
+        out[2] = a->br.read(q->bits);
+    }
+    const int64_t scale = 65536 / (adj + 1);
+    adj = ((adj + 1) >> 1) - 1;
+    for (int i = 0; i < 3; i++) {
+        const int64_t val = (adj - out[i]) * scale;
+        out[i] = (val * (sf >> 12) + ((val * (sf & 4095) + 2048) >> 12)) >> 12;
+    }
+}
+
+void decode_frame(AP* a, int32_t* samples) {  // audio.go:274-375 + the sample layout of mpegb200_audio_synth
+    BitReader& br = a->br;
+    const int tab2 = kRateClass[a->mode == kModeMono ? 0 : 1][a->bitrate_index];
+    int tab3 = kTablePick[tab2][a->samplerate_index];
+    const int sblimit = tab3 & 63;
+    tab3 >>= 6;
+    if (a->bound > sblimit) a->bound = sblimit;
+    for (int sb = 0; sb < a->bound; sb++) {
+        a->alloc[0][sb] = read_allocation(a, sb, tab3);
+        a->alloc[1][sb] = read_allocation(a, sb, tab3);
+    }
+    for (int sb = a->bound; sb < sblimit; sb++) a->alloc[1][sb] = a->alloc[0][sb] = read_allocation(a, sb, tab3);
+    const int channels = a->mode == kModeMono ? 1 : 2;
+    for (int sb = 0; sb < sblimit; sb++) {
+        for (int ch = 0; ch < channels; ch++)
+            if (a->alloc[ch][sb]) a->scfsi[ch][sb] = (uint8_t)br.read(2);
+        if (a->mode == kModeMono) a->scfsi[1][sb] = a->scfsi[0][sb];
+    }
+    for (int sb = 0; sb < sblimit; sb++) {
+        for (int ch = 0; ch < channels; ch++) {
+            if (!a->alloc[ch][sb]) continue;
+            int64_t* s = a->scale[ch][sb];
+            switch (a->scfsi[ch][sb]) {  // audio.go:322-342
+                case 0: s[0] = br.read(6); s[1] = br.read(6); s[2] = br.read(6); break;
+                case 1: s[0] = s[1] = br.read(6); s[2] = br.read(6); break;
+                case 2: s[0] = s[1] = s[2] = br.read(6); break;
+                default: s[0] = br.read(6); s[1] = s[2] = br.read(6); break;
+            }
+        }
+        if (a->mode == kModeMono)
+            for (int i = 0; i < 3; i++) a->scale[1][sb][i] = a->scale[0][sb][i];
+    }
+    memset(samples, 0, sizeof(int32_t) * 2 * 36 * 32);  // subbands >= sblimit stay zero (audio.go:368-375)
+    for (int part = 0; part < 3; part++)
+        for (int granule = 0; granule < 4; granule++) {
+            const int step0 = 3 * (4 * part + granule);
+            int64_t s0[3], s1[3];
+            for (int sb = 0; sb < sblimit; sb++) {
+                read_samples(a, 0, sb, part, s0);
+                if (sb < a->bound)
+                    read_samples(a, 1, sb, part, s1);
+                else
+                    memcpy(s1, s0, sizeof(s0));  // joint/mono: channel 1 mirrors channel 0 (audio.go:362-367)
+                for (int p = 0; p < 3; p++) {
+                    samples[(0 * 36 + step0 + p) * 32 + sb] = (int32_t)s0[p];
+                    samples[(1 * 36 + step0 + p) * 32 + sb] = (int32_t)s1[p];
+                }
+            }
+        }
+    br.align();
+}
+
+}  // namespace
+
+extern "C" {
+
+mpegb200_audio_parser* mpegb200_audio_parser_new(const uint8_t* data, size_t len) {
+    if (!data && len) return nullptr;
+    auto* a = new (std::nothrow) mpegb200_audio_parser();
+    if (!a) return nullptr;
+    a->data.assign(data, data + len);
+    a->data.resize(len + 16, 0);
+    a->br.p = a->data.data();
+    a->br.len = len;
+    a->next_frame_data_size = decode_header(a);
+    return a;
+}
+void mpegb200_audio_parser_free(mpegb200_audio_parser* a) { delete a; }
+int mpegb200_audio_parser_has_header(mpegb200_audio_parser* a) {
+    if (!a) return 0;
+    if (a->has_header) return 1;
+    a->next_frame_data_size = decode_header(a);
+    return a->has_header;
+}
+int mpegb200_audio_parser_samplerate(mpegb200_audio_parser* a) {
+    return mpegb200_audio_parser_has_header(a) ? kSampleRate[a->samplerate_index] : 0;
+}
+int mpegb200_audio_parser_channels(mpegb200_audio_parser* a) { return a ? a->channels : 0; }
+void mpegb200_audio_parser_rewind(mpegb200_audio_parser* a) {  // audio.go:149-154
+    if (!a) return;
+    a->br.pos = 0;
+    a->br.ended = false;
+    a->time = 0;
+    a->samples_decoded = 0;
+    a->next_frame_data_size = 0;
+}
+int mpegb200_audio_parser_next(mpegb200_audio_parser* a, int32_t* samples, double* time) {  // audio.go:163-182
+    if (!a || !samples) return 0;
+    if (a->next_frame_data_size == 0) a->next_frame_data_size = decode_header(a);
+    if (a->next_frame_data_size == 0 || !a->br.has((int64_t)a->next_frame_data_size << 3)) return 0;
+    decode_frame(a, samples);
+    a->next_frame_data_size = 0;
+    if (time) *time = a->time;
+    a->samples_decoded += MPEGB200_SAMPLES_PER_FRAME;
+    a->time = (double)a->samples_decoded / (double)kSampleRate[a->samplerate_index];
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// program stream (demux.go): pack + system header, then PES packets of the wanted ids
+// ------------------------------------------------------------------------------------------------
+int mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_t* video_len, uint8_t** audio,
+                         size_t* audio_len, int* n_video_packets, int* n_audio_packets) {
+    if (!data || !video || !video_len || !audio || !audio_len) return MPEGB200_EINVAL;
+    std::vector<uint8_t> padded(data, data + len);
+    padded.resize(len + 16, 0);
+    BitReader br;
+    br.p = padded.data();
+    br.len = len;
+    auto skip_clock = [&]() {  // decodeTime, demux.go:520-529
+        br.read(3); br.skip(1); br.read(15); br.skip(1); br.read(15); br.skip(1);
+    };
+    if (br.find_start_code(0xBA) == -1 || !br.has(64) || br.read(4) != 0x02) return MPEGB200_EINVAL;  // demux.go:91-113
+    skip_clock();
+    br.skip(1); br.skip(22); br.skip(1);
+    if (br.find_start_code(0xBB) == -1 || !br.has(56)) return MPEGB200_EINVAL;                        // demux.go:116-133
+    br.skip(16); br.skip(24); br.read(6); br.skip(5); br.read(5);
+    std::vector<uint8_t> v, a;
+    int nv = 0, na = 0;
+    for (;;) {  // demux.go:500-510
+        const int code = br.next_start_code();
+        if (code == -1) break;
+        if (!(code == 0xE0 || code == 0xBD || (code >= 0xC0 && code <= 0xC3))) continue;
+        if (!br.has(16 << 3)) break;  // decodePacket, demux.go:531-568
+        int64_t length = br.read(16);
+        length -= br.skip_bytes(0xff);
+        if (br.read(2) == 0x01) {
+            br.skip(16);
+            length -= 2;
+        }
+        const int marker = (int)br.read(2);
+        if (marker == 0x03) {
+            skip_clock();
+            br.skip(40);
+            length -= 10;
+        } else if (marker == 0x02) {
+            skip_clock();
+            length -= 5;
+        } else if (marker == 0x00) {
+            br.skip(4);
+            length -= 1;
+        } else {
+            continue;
+        }
+        if (length < 0 || !br.has(length << 3)) break;
+        const uint8_t* payload = padded.data() + (br.pos >> 3);
+        if (code == 0xE0) {
+            v.insert(v.end(), payload, payload + length);
+            nv++;
+        } else if (code == 0xC0) {
+            a.insert(a.end(), payload, payload + length);
+            na++;
+        }
+        br.pos += (uint64_t)length << 3;
+    }
+    *video = (uint8_t*)malloc(v.size() ? v.size() : 1);
+    *audio = (uint8_t*)malloc(a.size() ? a.size() : 1);
+    if (!*video || !*audio) return MPEGB200_ENOMEM;
+    memcpy(*video, v.data(), v.size());
+    memcpy(*audio, a.data(), a.size());
+    *video_len = v.size();
+    *audio_len = a.size();
+    if (n_video_packets) *n_video_packets = nv;
+    if (n_audio_packets) *n_audio_packets = na;
+    return 0;
+}
+
+void mpegb200_buffer_free(void* p) { free(p); }
+
+}  // extern "C"

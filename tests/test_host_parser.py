@@ -1,0 +1,189 @@
+"""The product's host half (mpeg_b200/csrc/host_parser.cpp, include/mpegb200_host.h) against the oracle's
+restatement of the reference parser: record for record, sample for sample.  CPU only.
+
+The two parsers are written independently (table-driven multi-bit VLC vs bit-serial tree walk), so equality
+on the reference's clips checks the product's tables, dequantisation, motion-vector reconstruction, skipped
+macroblock handling, buffer rotation, display order and the rewrite resolution."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from mpeg_b200 import _lib
+from mpeg_b200.mpeg import Launch, VideoStep, demux_split
+from mpeg_b200.packing import resolve_rewrites
+
+
+def parser_steps(data):
+    L = _lib.load()
+    h = L.mpegb200_video_parser_new(data, len(data))
+    assert h
+    try:
+        while True:
+            st = VideoStep()
+            assert L.mpegb200_video_parser_next(h, C.byref(st)) == 0
+            if not st.has_frame:
+                return
+            launches = []
+            for i in range(st.n_launches):
+                ln = st.launches[i]
+                mbs = np.frombuffer(C.string_at(st.mbs + 16 * ln.first_mb, 16 * ln.n_mb), dtype=ol.MB_DTYPE).copy()
+                co = np.frombuffer(C.string_at(st.coeffs + 128 * ln.first_block, 128 * ln.n_blocks), dtype=np.int16).reshape(-1, 64).copy()
+                launches.append(((ln.type, ln.dst_buf, ln.fwd_buf, ln.bwd_buf, ln.n_mb), mbs, co))
+            yield st.frame_buf, st.time, launches
+    finally:
+        L.mpegb200_video_parser_free(h)
+
+
+def oracle_steps(data):
+    v = ol.VideoOracle(data, tap=True)
+    while True:
+        f = v.decode()
+        if f is None:
+            return
+        pics, mbs, coeffs = v.tap()
+        launches = []
+        for i in range(len(pics)):
+            p = pics[i:i + 1].copy()
+            m = mbs[p["first_mb"][0]:p["first_mb"][0] + p["n_mb"][0]].copy()
+            m["pic"] = 0
+            p["first_mb"] = 0
+            first = int(m["coeff_block"][0]) if len(m) else 0
+            n = int(sum(bin(int(c)).count("1") for c in m["cbp"]))
+            m["coeff_block"] -= first
+            for wp, wm, wc in resolve_rewrites(p, m, coeffs[first:first + n]):
+                launches.append(((int(p["type"][0]), int(p["dst_buf"][0]), int(p["fwd_buf"][0]), int(p["bwd_buf"][0]), len(wm)), wm, wc))
+        yield v.last_buf(), f.time, launches
+
+
+def video_streams(golden_dir):
+    es = (golden_dir / "test.mpeg1video").read_bytes()
+    ps_video = ol.demux_split((golden_dir / "test.mpg").read_bytes())[0]
+    return {"test.mpeg1video": es, "test.mpg video": ps_video}
+
+
+@pytest.mark.parametrize("which", ["test.mpeg1video", "test.mpg video"])
+def test_video_parser_emits_the_same_records_as_the_oracle(golden_dir, which):
+    data = video_streams(golden_dir)[which]
+    n_steps = n_launch = n_mb = n_blocks = 0
+    got_iter, want_iter = parser_steps(data), oracle_steps(data)
+    for want in want_iter:
+        got = next(got_iter)
+        assert got[0] == want[0], f"step {n_steps}: returned buffer"
+        assert got[1] == want[1], f"step {n_steps}: frame time"
+        assert len(got[2]) == len(want[2]), f"step {n_steps}: number of launches"
+        for (gh, gm, gc), (wh, wm, wc) in zip(got[2], want[2]):
+            assert gh == wh, f"step {n_steps}: picture header {gh} != {wh}"
+            assert np.array_equal(gm, wm), f"step {n_steps}: macroblock records differ"
+            assert np.array_equal(gc, wc), f"step {n_steps}: coefficient blocks differ"
+            n_launch += 1
+            n_mb += len(gm)
+            n_blocks += len(gc)
+        n_steps += 1
+    assert next(got_iter, None) is None      # both report the end of the stream at the same point
+    assert n_steps > 200 and n_mb > 20000 and n_blocks > 20000
+
+
+def test_video_parser_header_and_controls(golden_dir):
+    # mpeg_test.go:233-274 on the host half alone
+    L = _lib.load()
+    data = (golden_dir / "test.mpeg1video").read_bytes()
+    h = L.mpegb200_video_parser_new(data, len(data))
+    assert L.mpegb200_video_parser_has_header(h)
+    assert (L.mpegb200_video_parser_width(h), L.mpegb200_video_parser_height(h)) == (160, 120)
+    assert L.mpegb200_video_parser_framerate(h) == 30.0
+    st = VideoStep()
+    first = []
+    for _ in range(5):
+        assert L.mpegb200_video_parser_next(h, C.byref(st)) == 0 and st.has_frame
+        first.append((st.frame_buf, st.time, st.n_launches))
+    L.mpegb200_video_parser_rewind(h)       # video.go:195-201: time and reference state restart
+    again = []
+    for _ in range(5):
+        assert L.mpegb200_video_parser_next(h, C.byref(st)) == 0 and st.has_frame
+        again.append((st.frame_buf, st.time, st.n_launches))
+    assert [a[1] for a in again] == [f[1] for f in first] and [a[2] for a in again] == [f[2] for f in first]
+    L.mpegb200_video_parser_free(h)
+    # garbage in: no header, Decode() == nil
+    junk = bytes(range(256)) * 4
+    h = L.mpegb200_video_parser_new(junk, len(junk))
+    assert not L.mpegb200_video_parser_has_header(h)
+    assert L.mpegb200_video_parser_next(h, C.byref(st)) == 0 and not st.has_frame
+    L.mpegb200_video_parser_free(h)
+
+
+def test_no_delay_mode_matches_the_oracle(golden_dir):
+    # SetNoDelay (video.go:176-180): every picture returns frameBackward
+    data = (golden_dir / "test.mpeg1video").read_bytes()
+    L = _lib.load()
+    h = L.mpegb200_video_parser_new(data, len(data))
+    L.mpegb200_video_parser_set_no_delay(h, 1)
+    v = ol.VideoOracle(data)
+    v.set_no_delay(True)
+    st = VideoStep()
+    for _ in range(40):
+        f = v.decode()
+        assert L.mpegb200_video_parser_next(h, C.byref(st)) == 0
+        assert bool(st.has_frame) == (f is not None)
+        if f is None:
+            break
+        assert st.frame_buf == v.last_buf() and st.time == f.time
+    L.mpegb200_video_parser_free(h)
+
+
+def test_corrupted_streams_do_not_crash_the_parser(golden_dir):
+    # flipped bits and truncation: the reference tolerates these with early-outs;
+    # the product parser must stay memory safe and terminate (contents are not compared)
+    data = bytearray((golden_dir / "test.mpeg1video").read_bytes()[:60000])
+    rng = np.random.default_rng(7)
+    L = _lib.load()
+    for trial in range(6):
+        d = bytearray(data)
+        for pos in rng.integers(200, len(d), 40):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        d = bytes(d[: len(d) - int(rng.integers(0, 5000))])
+        h = L.mpegb200_video_parser_new(d, len(d))
+        st = VideoStep()
+        steps = 0
+        while L.mpegb200_video_parser_next(h, C.byref(st)) == 0 and st.has_frame and steps < 500:
+            for i in range(st.n_launches):
+                ln = st.launches[i]
+                mbs = np.frombuffer(C.string_at(st.mbs + 16 * ln.first_mb, 16 * ln.n_mb), dtype=ol.MB_DTYPE)
+                assert (mbs["mb_row"] < 8).all() and (mbs["mb_col"] < 10).all()
+                cnt = np.array([bin(int(c)).count("1") for c in mbs["cbp"]], dtype=np.int64)
+                assert np.array_equal(mbs["coeff_block"], np.cumsum(cnt) - cnt) and cnt.sum() == ln.n_blocks
+            steps += 1
+        L.mpegb200_video_parser_free(h)
+
+
+@pytest.mark.parametrize("which", ["test.mp2", "test.mpg audio"])
+def test_audio_parser_emits_the_same_samples_as_the_oracle(golden_dir, which):
+    data = (golden_dir / "test.mp2").read_bytes() if which == "test.mp2" else ol.demux_split((golden_dir / "test.mpg").read_bytes())[1]
+    L = _lib.load()
+    h = L.mpegb200_audio_parser_new(data, len(data))
+    a = ol.AudioOracle(data)
+    assert L.mpegb200_audio_parser_has_header(h) and a.has_header()
+    assert L.mpegb200_audio_parser_samplerate(h) == a.samplerate and L.mpegb200_audio_parser_channels(h) == a.channels
+    s = np.zeros((2, 36, 32), np.int32)
+    t = C.c_double()
+    frames = 0
+    while True:
+        want = a.decode()
+        got = L.mpegb200_audio_parser_next(h, C.c_void_p(s.ctypes.data), C.byref(t))
+        assert bool(got) == (want is not None)
+        if want is None:
+            break
+        assert np.array_equal(s, a.last_samples()), f"frame {frames}"
+        frames += 1
+    assert frames > 30
+    L.mpegb200_audio_parser_free(h)
+
+
+def test_demux_matches_the_oracle(golden_dir):
+    data = (golden_dir / "test.mpg").read_bytes()
+    assert demux_split(data) == ol.demux_split(data)
+    assert demux_split(data)[2:] == (143, 37)
+    from mpeg_b200.mpeg import ErrInvalidMPEG
+    with pytest.raises(ErrInvalidMPEG):
+        demux_split(b"\x00" * 100)
