@@ -58,9 +58,11 @@ cudaError_t launch_audio_synth(AudioState* d_states, int max_streams, const int3
                                const float* d_window, cudaStream_t stream);
 // TMA kernel (video_fused_tma.cu).  coef_map: 128-byte CUtensorMap over the coefficient array (host copy,
 // passed by value as a __grid_constant__ parameter); d_maps: per-slab window tensor maps in global memory.
-cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, const StreamInfo* d_streams, int max_streams,
-                             const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb,
-                             uint32_t n_blocks, cudaStream_t stream);
+// d_plans: scratch of fused_plan_bytes(n_mb) bytes, 16-byte aligned (one 768-byte plan per 16 records).
+cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void* d_plans, const StreamInfo* d_streams,
+                             int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
+                             uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream);
+size_t fused_plan_bytes(uint32_t n_mb);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

@@ -56,7 +56,7 @@ struct mpegb200_ctx {
     std::vector<uint8_t> audio_open;
     AudioState* d_audio = nullptr;
     float* d_window = nullptr;
-    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_ids, s_bufs, s_rgba, s_samples, s_out;
+    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans;
     // host-pointer pipeline: uploads and read-backs run on their own streams so that the H2D copy of the
     // next step overlaps the kernels and the D2H copy of the current one (double-buffered staging)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
@@ -215,7 +215,8 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     if (ctx->up_stream) cudaStreamSynchronize(ctx->up_stream);
     if (ctx->down_stream) cudaStreamSynchronize(ctx->down_stream);
     for (DevBuf* b : {&ctx->s_pics[0], &ctx->s_pics[1], &ctx->s_mbs[0], &ctx->s_mbs[1], &ctx->s_coeffs[0],
-                      &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out})
+                      &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out,
+                      &ctx->s_plans})
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
@@ -518,8 +519,10 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
     if (use_tma) {
-        CU(launch_fused_tma(&coef_map, ctx->d_maps, ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs,
-                            (uint32_t)n_mb, (uint32_t)n_blocks, ctx->stream));
+        if (int rc = ensure(ctx, ctx->s_plans, fused_plan_bytes((uint32_t)n_mb))) return rc;
+        CU(launch_fused_tma(&coef_map, ctx->d_maps, ctx->s_plans.p, ctx->d_info, ctx->max_streams, d_pics, n_pictures,
+                            d_mbs, (uint32_t)n_mb, (uint32_t)n_blocks, ctx->stream));
+        ctx->launches++;  // the plan pre-pass
     } else {
         CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,
                                 (uint32_t)n_blocks, ctx->stream));

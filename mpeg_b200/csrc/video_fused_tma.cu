@@ -154,76 +154,65 @@ constexpr int kWinY = 640, kWinC = 384;            // bytes reserved per window 
 constexpr int kWinBytes = kWinY + 2 * kWinC;       // 1408 per macroblock
 constexpr int kWinTx = 32 * 17 + 2 * 32 * 9;       // bytes the three boxes deliver: 1120
 
-struct MbCtx {                // 24 bytes
+// ------------------------------------------------------------------------------------------------
+// Group plan: everything a CTA needs to know about its kG records, computed once by a pre-pass
+// (plan_kernel) so that the decode, the record -> picture -> stream pointer chase and the sorting of
+// the output blocks are neither repeated nor serialised inside the arithmetic kernel.
+// ------------------------------------------------------------------------------------------------
+struct PlanMb {               // 32 bytes
     uint8_t* dst_y;           // destination of the macroblock's luma (row 0, col 0 of the MB)
-    uint8_t* dst_c;           // destination of its Cb; Cr at + chroma_bytes
-    uint32_t chroma_bytes;
-    uint16_t luma_w;
+    uint32_t dst_c_off;       // Cb destination = dst_y + dst_c_off; Cr at + (luma_w/2) * chroma_h
+    uint16_t luma_w, chroma_h;
     uint16_t mcw;             // byte 0 luma, byte 1 chroma: (x & 15) | mode << 4 | 0x80 if predicted;
                               // mode bit 0 = horizontal half-pel, bit 1 = vertical half-pel
+    uint16_t slab;            // tensor-map pair of the stream's slab
+    int16_t lx, ly, cx, cy;   // box origins (x folded into [0, pitch) and aligned down to 16)
+    uint16_t z;               // 3 * slot + reference buffer
+    uint16_t pad;
 };
-static_assert(sizeof(MbCtx) == 24, "MbCtx size");
+static_assert(sizeof(PlanMb) == 32, "PlanMb size");
 
-struct TmaJob {               // 32 bytes: what the issuing warps need for one predicted macroblock
-    const SlabMaps* maps;
-    int lx, ly, cx, cy, z, chroma_h;
+struct GroupPlan {            // 768 bytes = 48 x 16
+    uint32_t n_box, n_pred, block0, pad0;
+    uint16_t map[kNT];        // output-block list, sorted by (coded?, interpolation mode)
+    PlanMb mb[kG];
+    uint8_t pad1[768 - 16 - 2 * kNT - 32 * kG];
 };
-static_assert(sizeof(TmaJob) == 32, "TmaJob size");
+static_assert(sizeof(GroupPlan) == 768, "GroupPlan size");
 
-struct Smem {
-    static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
-    static constexpr int win = coef + kNT * 128;                 // kG x 1408
-    static constexpr int ctx = win + kG * kWinBytes;             // kG x 24
-    static constexpr int map = ctx + kG * (int)sizeof(MbCtx);    // kNT x 2: output-block list, sorted by interpolation mode
-    static constexpr int bar = (map + kNT * 2 + 7) & ~7;         // 8 bytes
-    static constexpr int cnt = bar + 8;                          // 8 bin counters + nb + npred
-    static constexpr int job = (cnt + 10 * 4 + 15) & ~15;        // kG x 32
-    static constexpr int total = job + kG * (int)sizeof(TmaJob);
-};
-
-// Output-block list entry: [3:0] macroblock in CTA, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
+// Output-block list entry: [3:0] macroblock in group, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
 constexpr uint32_t kNoBlock = 0xFFFFu;
 
-__global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                       const SlabMaps* __restrict__ slab_maps,
-                                                       const StreamInfo* __restrict__ streams, int max_streams,
-                                                       const mpegb200_picture* __restrict__ pics, int n_pics,
-                                                       const mpegb200_mb* __restrict__ mbs, uint32_t n_mb,
-                                                       uint32_t n_blocks) {
-    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
-    uint8_t* s_coef = smem + Smem::coef;
-    uint8_t* s_win = smem + Smem::win;
-    MbCtx* s_ctx = reinterpret_cast<MbCtx*>(smem + Smem::ctx);
-    uint16_t* s_map = reinterpret_cast<uint16_t*>(smem + Smem::map);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + Smem::cnt);  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
-    TmaJob* s_job = reinterpret_cast<TmaJob*>(smem + Smem::job);
+constexpr int kPlanGroupsPerCta = 8;   // 16 lanes per group
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t m0 = blockIdx.x * (uint32_t)kG;
-    const int n_here = (int)min((uint32_t)kG, n_mb - m0);
-
-    s_map[tid] = (uint16_t)kNoBlock;
-    if (tid < 10) s_cnt[tid] = 0;
-    if (tid < kG) s_ctx[tid].mcw = 0;
-    if (tid == 0) {
-        if (smem_u32(smem) & 1023u) __trap();
-        mbar_init(s_bar, 1);
-        fence_barrier_init();
+__global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan* __restrict__ plans,
+                                                                     const StreamInfo* __restrict__ streams,
+                                                                     int max_streams,
+                                                                     const mpegb200_picture* __restrict__ pics,
+                                                                     int n_pics, const mpegb200_mb* __restrict__ mbs,
+                                                                     uint32_t n_mb, uint32_t n_blocks) {
+    __shared__ __align__(16) GroupPlan s_plan[kPlanGroupsPerCta];
+    __shared__ uint32_t s_cnt[kPlanGroupsPerCta][10];  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
+    const int tid = threadIdx.x, gl = tid >> 4, lane = tid & 15;
+    const uint32_t n_groups = (n_mb + kG - 1) / kG;
+    const uint32_t group = blockIdx.x * kPlanGroupsPerCta + gl;
+    GroupPlan& P = s_plan[gl];
+    for (int i = lane; i < kNT; i += 16) P.map[i] = (uint16_t)kNoBlock;
+    if (lane < 10) s_cnt[gl][lane] = 0;
+    {
+        PlanMb z;
+        memset(&z, 0, sizeof(z));
+        P.mb[lane] = z;
     }
     __syncthreads();
 
-    // ---------------- producer, part 1 (warp 0, lane j owns record j): context, window coordinates,
-    // bin counting for the mode-sorted block list ----------------
+    const uint32_t m0 = group * (uint32_t)kG;
+    const bool have = group < n_groups && m0 + lane < n_mb;
     uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0;
-    if (tid == 32) {  // pull the records of the CTA that will run about one wave later into L2
-        const uint32_t ahead = m0 + (uint32_t)kG * 1024u;
-        if (ahead < n_mb) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(mbs) + ahead));
-    }
-    if (warp == 0 && lane < n_here) {
-        const int pj = lane;
-        const uint32_t block0 = mbs[m0].coeff_block;
-        const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + pj];
+    uint32_t block0 = 0;
+    if (group < n_groups) block0 = mbs[m0].coeff_block;
+    if (have) {
+        const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + lane];
         const uint32_t row = raw.x & 0xffffu, col = raw.x >> 16;
         const int mv_h = (int16_t)(raw.y & 0xffffu), mv_v = (int16_t)(raw.y >> 16);
         const uint32_t flags = raw.z & 0xffu, cbp = (raw.z >> 8) & 0x3fu, pic_i = raw.z >> 16;
@@ -243,12 +232,14 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
                 if (ok) {
                     const uint32_t lw = si.luma_w, cw = lw >> 1;
                     uint8_t* dst = si.base + (size_t)dst_b * si.buf_stride;
-                    MbCtx c;
+                    PlanMb c;
+                    memset(&c, 0, sizeof(c));
                     c.dst_y = dst + (size_t)(row << 4) * lw + (col << 4);
-                    c.dst_c = dst + (size_t)lw * si.luma_h + (size_t)(row << 3) * cw + (col << 3);
-                    c.chroma_bytes = cw * (si.luma_h >> 1);
+                    c.dst_c_off = (uint32_t)((size_t)lw * si.luma_h + (size_t)(row << 3) * cw + (col << 3) -
+                                             ((size_t)(row << 4) * lw + (col << 4)));
                     c.luma_w = (uint16_t)lw;
-                    c.mcw = 0;
+                    c.chroma_h = (uint16_t)(si.luma_h >> 1);
+                    c.slab = si.slab;
                     const bool predicted = (flags & MPEGB200_MB_PREDICT) != 0 && !(flags & MPEGB200_MB_INTRA);
                     uint32_t mode_y = 0, mode_c = 0;
                     if (predicted) {  // window origins, video_noasm.go:29-42
@@ -274,20 +265,15 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
                         mode_y = (uint32_t)((mv_h & 1) | ((mv_v & 1) << 1));
                         mode_c = (uint32_t)((cmh & 1) | ((cmv & 1) << 1));
                         c.mcw = (uint16_t)(((lx & 15) | (mode_y << 4) | 0x80) | (((cx & 15) | (mode_c << 4) | 0x80) << 8));
-                        atomicAdd(&s_cnt[9], 1u);
-                        // box origins for the three issuing warps; the TMA unit needs x on a 16-byte boundary
-                        TmaJob t;
-                        t.maps = slab_maps + si.slab;
-                        t.lx = lx & ~15;
-                        t.ly = ly;
-                        t.cx = cx & ~15;
-                        t.cy = cy;
-                        t.z = si.slot * 3 + (int)((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b);
-                        t.chroma_h = si.luma_h >> 1;
-                        s_job[pj] = t;
+                        c.lx = (int16_t)(lx & ~15);  // the TMA unit needs x on a 16-byte boundary
+                        c.ly = (int16_t)ly;
+                        c.cx = (int16_t)(cx & ~15);
+                        c.cy = (int16_t)cy;
+                        c.z = (uint16_t)(si.slot * 3 + ((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b));
+                        atomicAdd(&s_cnt[gl][9], 1u);
                     }
-                    s_ctx[pj] = c;
-                    if (ncoded) atomicMax(&s_cnt[8], rel + ncoded);
+                    P.mb[lane] = c;
+                    if (ncoded) atomicMax(&s_cnt[gl][8], rel + ncoded);
                     // every 8x8 block whose pixels this record defines goes on the output list, binned by
                     // (coded?, interpolation mode) so that the threads of a warp take the same code path
                     out_mask = predicted ? 0x3fu : cbp;
@@ -297,7 +283,7 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
                     for (int k = 0; k < 6; k++) {
                         if (out_mask & (0x20u >> k)) {
                             const uint32_t bin = ((cbp & (0x20u >> k)) ? 0u : 4u) + (predicted ? (k < 4 ? mode_y : mode_c) : 0u);
-                            const uint32_t pp = atomicAdd(&s_cnt[bin], 1u);  // < 96
+                            const uint32_t pp = atomicAdd(&s_cnt[gl][bin], 1u);  // < 96
                             bins |= bin << (4 * k);
                             if (k < 4) pos |= pp << (8 * k); else pos_hi |= pp << (8 * (k - 4));
                         }
@@ -307,58 +293,108 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
         }
     }
     __syncthreads();
-    // ---------------- producer, part 2: warp w issues plane w (Y, Cb, Cr) of every predicted macroblock;
-    // warp 0 also posts the transaction count, fetches the coefficient boxes and writes the block list -------
-    if (lane < kG && (s_ctx[lane].mcw & 0x80u)) {
-        const TmaJob t = s_job[lane];
-        uint8_t* w = s_win + lane * kWinBytes;
-        if (warp == 0)
-            tma_load_3d(w, t.maps->luma, s_bar, t.lx, t.ly, t.z);
-        else
-            tma_load_3d(w + kWinY + (warp - 1) * kWinC, t.maps->chroma, s_bar, t.cx, t.cy + (warp - 1) * t.chroma_h, t.z);
-    }
-    if (warp == 0) {
-        const uint32_t n_box = (s_cnt[8] + kCoefBox - 1) / kCoefBox;
-        // complete_tx of the window boxes may already have been counted: the phase cannot complete before
-        // this (single) arrival, and the transaction count is allowed to run negative meanwhile
-        if (lane == 0) mbar_arrive_expect_tx(s_bar, n_box * (kCoefBox * 128) + s_cnt[9] * kWinTx);
-        __syncwarp();
-        if (lane < (int)n_box)  // rows past n_blocks are zero-filled by the TMA unit
-            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(mbs[m0].coeff_block + lane * kCoefBox));
-        if (out_mask) {
-            uint32_t run = 0, base_of[8];
+    if (out_mask) {
+        uint32_t run = 0, base_of[8];
 #pragma unroll
-            for (int b = 0; b < 8; b++) {
-                base_of[b] = run;
-                run += s_cnt[b];
-            }
-            uint32_t slot = rel_r;
+        for (int b = 0; b < 8; b++) {
+            base_of[b] = run;
+            run += s_cnt[gl][b];
+        }
+        uint32_t slot = rel_r;
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                if (out_mask & (0x20u >> k)) {
-                    const uint32_t bin = (bins >> (4 * k)) & 15u;
-                    const uint32_t pp = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
-                    const bool coded = cbp_r & (0x20u >> k);
-                    uint32_t bsel = 0;
+        for (int k = 0; k < 6; k++) {
+            if (out_mask & (0x20u >> k)) {
+                const uint32_t bin = (bins >> (4 * k)) & 15u;
+                const uint32_t pp = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
+                const bool coded = cbp_r & (0x20u >> k);
+                uint32_t bsel = 0;
 #pragma unroll
-                    for (int b = 0; b < 8; b++) bsel = bin == (uint32_t)b ? base_of[b] : bsel;
-                    s_map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
-                    if (coded) slot++;
-                }
+                for (int b = 0; b < 8; b++) bsel = bin == (uint32_t)b ? base_of[b] : bsel;
+                P.map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
+                if (coded) slot++;
             }
         }
     }
-    __syncthreads();       // block list visible
-    mbar_wait(s_bar, 0);   // all tiles have landed
+    if (lane == 0) {
+        P.n_box = (s_cnt[gl][8] + kCoefBox - 1) / kCoefBox;
+        P.n_pred = s_cnt[gl][9];
+        P.block0 = block0;
+        P.pad0 = 0;
+    }
+    __syncthreads();
+    if (group < n_groups) {  // 768 bytes out, 16 bytes per lane per step
+        const uint4* src = reinterpret_cast<const uint4*>(&P);
+        uint4* dstp = reinterpret_cast<uint4*>(plans + group);
+#pragma unroll
+        for (int i = 0; i < 3; i++) dstp[lane + 16 * i] = src[lane + 16 * i];
+    }
+}
 
-    // ---------------- one thread per output block: interpolate, IDCT, add, saturate, store ----------------
-    const uint32_t e = s_map[tid];
+struct Smem {
+    static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
+    static constexpr int win = coef + kNT * 128;                 // kG x 1408
+    static constexpr int plan = win + kG * kWinBytes;            // 768: the group's plan
+    static constexpr int bar = plan + (int)sizeof(GroupPlan);    // 8 bytes
+    static constexpr int total = bar + 16;
+};
+
+// ------------------------------------------------------------------------------------------------
+// The arithmetic kernel: one CTA = one group plan = kG records.  Load the plan (48 x 16 bytes), issue
+// every TMA box (warp w: plane w of each predicted macroblock; warp 0 also the coefficient boxes), wait on
+// the one mbarrier, then one thread per output block: interpolate, IDCT, add, saturate, store.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                       const SlabMaps* __restrict__ slab_maps,
+                                                       const GroupPlan* __restrict__ plans) {
+    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
+    uint8_t* s_coef = smem + Smem::coef;
+    uint8_t* s_win = smem + Smem::win;
+    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid < 48) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
+    if (tid == 64) {
+        if (smem_u32(smem) & 1023u) __trap();
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
+        const PlanMb& t = P.mb[lane];
+        const SlabMaps* maps = slab_maps + t.slab;
+        uint8_t* w = s_win + lane * kWinBytes;
+        if (warp == 0)
+            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly, t.z);
+        else
+            tma_load_3d(w + kWinY + (warp - 1) * kWinC, maps->chroma, s_bar, t.cx, t.cy + (warp - 1) * (int)t.chroma_h, t.z);
+    }
+    if (warp == 0) {
+        // complete_tx of boxes issued before this arrival is fine: the phase cannot complete before the
+        // (single) arrival, and the transaction count is allowed to run negative meanwhile
+        if (lane == 0) mbar_arrive_expect_tx(s_bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
+        if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
+            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(P.block0 + lane * kCoefBox));
+    }
+
+    const uint32_t e = P.map[tid];
     if (e == kNoBlock) return;
     const int j = e & 15, k = (e >> 4) & 7;
     const bool coded = e & 0x80u;
-    const MbCtx& cx = s_ctx[j];
+    const PlanMb& cx = P.mb[j];
     const uint32_t mcb = (uint32_t)(cx.mcw >> (k < 4 ? 0 : 8)) & 0xffu;
     const bool pred = mcb & 0x80u;
+    uint8_t* dst;
+    uint32_t pitch;
+    if (k < 4) {
+        pitch = cx.luma_w;
+        dst = cx.dst_y + (size_t)((k >> 1) * 8) * pitch + (k & 1) * 8;
+    } else {
+        pitch = cx.luma_w >> 1;
+        dst = cx.dst_y + cx.dst_c_off + (k == 5 ? pitch * (uint32_t)cx.chroma_h : 0u);
+    }
+    mbar_wait(s_bar, 0);   // all tiles have landed
 
     // prediction: eight rows of eight bytes, straight from the staged window (video_noasm.go:44-80)
     uint32_t p0[8], p1[8];
@@ -421,16 +457,6 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
 #undef LOAD_ROW
     }
 
-    uint8_t* dst;
-    uint32_t pitch;
-    if (k < 4) {
-        pitch = cx.luma_w;
-        dst = cx.dst_y + (size_t)((k >> 1) * 8) * pitch + (k & 1) * 8;
-    } else {
-        pitch = cx.luma_w >> 1;
-        dst = cx.dst_c + (k == 5 ? cx.chroma_bytes : 0u);
-    }
-
     if (!coded) {  // predicted block without residual: the prediction is the result (skipped / cbp bit clear)
 #pragma unroll
         for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) = make_uint2(p0[r], p1[r]);
@@ -474,9 +500,11 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
 
 }  // namespace
 
-cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, const StreamInfo* d_streams, int max_streams,
-                             const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb,
-                             uint32_t n_blocks, cudaStream_t stream) {
+size_t fused_plan_bytes(uint32_t n_mb) { return (size_t)((n_mb + kG - 1) / kG) * sizeof(GroupPlan); }
+
+cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void* d_plans, const StreamInfo* d_streams,
+                             int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
+                             uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream) {
     if (n_mb == 0) return cudaSuccess;
     static bool configured = false;
     if (!configured) {
@@ -484,9 +512,11 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, const
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const uint32_t grid = (n_mb + kG - 1) / kG;
-    fused_tma_kernel<<<grid, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps,
-                                                         d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
+    const uint32_t n_groups = (n_mb + kG - 1) / kG;
+    GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
+    plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
+        plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
+    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
     return cudaGetLastError();
 }
 
