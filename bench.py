@@ -401,7 +401,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
-                         "kernel": "fused_mc_idct_kernel", "algorithmic_bytes_per_launch": int(alg_total),
+                         "kernel": "plan_kernel + fused_tma_kernel (one mpegb200_video_decode_pictures_dev call)", "algorithmic_bytes_per_launch": int(alg_total),
                          "algorithmic_read_bytes_per_launch": int(alg_read), "read_only_frac": alg_read / (fused_ms * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src, "launch_ms": fused_ms},
             "cpu_baseline": cpu,
