@@ -32,7 +32,8 @@ static_assert(sizeof(StreamInfo) == 48, "StreamInfo layout");
 //   luma  : 3-D u8 tensor {luma_w + 32, buf_stride / luma_w, 3 * capacity}, strides {luma_w, buf_stride}:
 //           the whole frame buffer seen as rows of luma_w bytes, rows overlapping by 32 bytes so that a
 //           window crossing the right edge continues on the next row exactly like linear addressing does.
-//   chroma: same over the bytes from the Cb plane on, pitch luma_w / 2, x extent + 32.
+//   chroma: 4-D {chroma_w + 32, rows to the end of the buffer, plane (Cb, Cr: chroma_bytes apart), 3 * capacity}:
+//           one box fetches the Cb and the Cr window of a macroblock together.
 struct alignas(128) SlabMaps {
     unsigned char luma[128];
     unsigned char chroma[128];

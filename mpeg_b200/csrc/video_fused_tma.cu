@@ -6,8 +6,9 @@
 // re-aligning unaligned windows (profiles/r1_v1_fused_summary.md).  Here:
 //   * coefficients: one cp.async.bulk.tensor per 32 blocks, 128-byte swizzle, so that one thread per
 //     block reads its eight 16-byte rows bank-conflict free;
-//   * reference windows: three cp.async.bulk.tensor per predicted macroblock (32x17 luma, 32x9 Cb,
-//     32x9 Cr).  The TMA unit wants the innermost start coordinate on a 16-byte boundary (measured:
+//   * reference windows: two cp.async.bulk.tensor per predicted macroblock (32x17 luma; one rank-4 box
+//     for 32x9 Cb + 32x9 Cr -- the TMA unit serves about one box per 46 cycles per SM however small, and that
+//     rate, not bytes or instructions, bounded the three-box version).  The TMA unit wants the innermost start coordinate on a 16-byte boundary (measured:
 //     tools/tma_probe.cu, an unaligned x raises "illegal instruction"), so the box starts at x & ~15
 //     and pixel (0,0) sits at byte x & 15 of every staged row -- one offset per macroblock instead of
 //     per-row address arithmetic.  Rows past a plane continue into the next plane and columns past the
@@ -17,6 +18,9 @@
 //   * one mbarrier per CTA collects all of it (expect_tx = sum of box bytes).
 // The arithmetic is the reference's, bit for bit.
 #include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -58,6 +62,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* map, uint64_t
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 
@@ -150,9 +161,9 @@ __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b, uint32_t c, uin
 constexpr int kG = 16;                 // macroblock records per CTA
 constexpr int kNT = 6 * kG;            // one thread per output block (8x8)
 constexpr int kCoefBox = 32;           // blocks per coefficient TMA box (32 x 128 B = 4 KiB)
-constexpr int kWinY = 640, kWinC = 384;            // bytes reserved per window (544 / 288 used), 128-aligned
-constexpr int kWinBytes = kWinY + 2 * kWinC;       // 1408 per macroblock
-constexpr int kWinTx = 32 * 17 + 2 * 32 * 9;       // bytes the three boxes deliver: 1120
+constexpr int kWinY = 640, kWinC = 288;            // luma box: 32x17 = 544 B in 640; chroma box: Cb 32x9 then Cr 32x9 = 576 B in 640
+constexpr int kWinBytes = kWinY + 640;             // 1280 per macroblock, both boxes 128-byte aligned
+constexpr int kWinTx = 32 * 17 + 2 * 32 * 9;       // bytes the two boxes deliver: 1120
 
 // ------------------------------------------------------------------------------------------------
 // Group plan: everything a CTA needs to know about its kG records, computed once by a pre-pass
@@ -338,47 +349,10 @@ struct Smem {
     static constexpr int total = bar + 16;
 };
 
-// ------------------------------------------------------------------------------------------------
-// The arithmetic kernel: one CTA = one group plan = kG records.  Load the plan (48 x 16 bytes), issue
-// every TMA box (warp w: plane w of each predicted macroblock; warp 0 also the coefficient boxes), wait on
-// the one mbarrier, then one thread per output block: interpolate, IDCT, add, saturate, store.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                       const SlabMaps* __restrict__ slab_maps,
-                                                       const GroupPlan* __restrict__ plans) {
-    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
-    uint8_t* s_coef = smem + Smem::coef;
-    uint8_t* s_win = smem + Smem::win;
-    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid < 48) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
-    if (tid == 64) {
-        if (smem_u32(smem) & 1023u) __trap();
-        mbar_init(s_bar, 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-
-    if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
-        const PlanMb& t = P.mb[lane];
-        const SlabMaps* maps = slab_maps + t.slab;
-        uint8_t* w = s_win + lane * kWinBytes;
-        if (warp == 0)
-            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly, t.z);
-        else
-            tma_load_3d(w + kWinY + (warp - 1) * kWinC, maps->chroma, s_bar, t.cx, t.cy + (warp - 1) * (int)t.chroma_h, t.z);
-    }
-    if (warp == 0) {
-        // complete_tx of boxes issued before this arrival is fine: the phase cannot complete before the
-        // (single) arrival, and the transaction count is allowed to run negative meanwhile
-        if (lane == 0) mbar_arrive_expect_tx(s_bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
-        if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
-            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(P.block0 + lane * kCoefBox));
-    }
-
-    const uint32_t e = P.map[tid];
+// One output block: interpolate, IDCT, add, saturate, store.  `t` = index into the plan's block list.
+__device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t* s_coef, const uint8_t* s_win, int t,
+                                              uint64_t* bar, uint32_t parity) {
+    const uint32_t e = P.map[t];
     if (e == kNoBlock) return;
     const int j = e & 15, k = (e >> 4) & 7;
     const bool coded = e & 0x80u;
@@ -394,7 +368,7 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
         pitch = cx.luma_w >> 1;
         dst = cx.dst_y + cx.dst_c_off + (k == 5 ? pitch * (uint32_t)cx.chroma_h : 0u);
     }
-    mbar_wait(s_bar, 0);   // all tiles have landed
+    mbar_wait(bar, parity);   // all tiles of the group have landed
 
     // prediction: eight rows of eight bytes, straight from the staged window (video_noasm.go:44-80)
     uint32_t p0[8], p1[8];
@@ -498,6 +472,132 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The arithmetic kernel: one CTA = one group plan = kG records.  Load the plan (48 x 16 bytes), issue
+// every TMA box (warp w: plane w of each predicted macroblock; warp 0 also the coefficient boxes), wait on
+// the one mbarrier, then one thread per output block: interpolate, IDCT, add, saturate, store.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                       const SlabMaps* __restrict__ slab_maps,
+                                                       const GroupPlan* __restrict__ plans) {
+    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
+    uint8_t* s_coef = smem + Smem::coef;
+    uint8_t* s_win = smem + Smem::win;
+    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid < 48) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
+    if (tid == 64) {
+        if (smem_u32(smem) & 1023u) __trap();
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
+        const PlanMb& t = P.mb[lane];
+        const SlabMaps* maps = slab_maps + t.slab;
+        uint8_t* w = s_win + lane * kWinBytes;
+        if (warp == 0)
+            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly, t.z);
+        else if (warp == 1)  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
+            tma_load_4d(w + kWinY, maps->chroma, s_bar, t.cx, t.cy, 0, t.z);
+    }
+    if (warp == 0) {
+        // complete_tx of boxes issued before this arrival is fine: the phase cannot complete before the
+        // (single) arrival, and the transaction count is allowed to run negative meanwhile
+        if (lane == 0) mbar_arrive_expect_tx(s_bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
+        if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
+            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(P.block0 + lane * kCoefBox));
+    }
+
+    process_block(P, s_coef, s_win, tid, s_bar, 0);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Experimental variant (MPEGB200_FUSED=ring): persistent CTAs, warp 0 streams plans and TMA boxes through a
+// ring of kRingStages stages, warps 1..3 consume.  Same arithmetic (process_block).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRingStages = 2;
+constexpr int kRingThreads = 32 + kNT;
+struct Ring {
+    static constexpr int stage_bytes = (Smem::plan + (int)sizeof(GroupPlan) + 1023) & ~1023;
+    static constexpr int bars = kRingStages * stage_bytes;
+    static constexpr int total = bars + 2 * kRingStages * 8;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kRingThreads) fused_ring_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                                 const SlabMaps* __restrict__ slab_maps,
+                                                                 const GroupPlan* __restrict__ plans, uint32_t n_groups) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Ring::bars);
+    uint64_t* empty = full + kRingStages;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        for (int s = 0; s < kRingStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kNT / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // plans are fetched one iteration ahead: lane l holds uint4 #l and (l < 16) #32+l of the next plan
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        uint32_t g = blockIdx.x;
+        if (g < n_groups) {
+            const uint4* src = reinterpret_cast<const uint4*>(plans + g);
+            n0 = src[lane];
+            if (lane < 16) n1 = src[32 + lane];
+        }
+        for (uint32_t it = 0; g < n_groups; g += gridDim.x, it++) {
+            const uint4 c0 = n0, c1 = n1;
+            const uint32_t gn = g + gridDim.x;
+            if (gn < n_groups) {
+                const uint4* src = reinterpret_cast<const uint4*>(plans + gn);
+                n0 = src[lane];
+                if (lane < 16) n1 = src[32 + lane];
+            }
+            const uint32_t s = it % kRingStages, use = it / kRingStages;
+            if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+            uint8_t* st = smem + s * Ring::stage_bytes;
+            GroupPlan& P = *reinterpret_cast<GroupPlan*>(st + Smem::plan);
+            reinterpret_cast<uint4*>(&P)[lane] = c0;
+            if (lane < 16) reinterpret_cast<uint4*>(&P)[32 + lane] = c1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
+            if (lane < (int)P.n_box)
+                tma_load_2d(st + Smem::coef + lane * (kCoefBox * 128), &coef_map, &full[s], 0, (int)(P.block0 + lane * kCoefBox));
+            if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
+                const PlanMb& t = P.mb[lane];
+                const SlabMaps* maps = slab_maps + t.slab;
+                uint8_t* w = st + Smem::win + lane * kWinBytes;
+                tma_load_3d(w, maps->luma, &full[s], t.lx, t.ly, t.z);
+                tma_load_4d(w + kWinY, maps->chroma, &full[s], t.cx, t.cy, 0, t.z);
+            }
+        }
+    } else {
+        const int t = tid - 32;
+        uint32_t it = 0;
+        for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
+            const uint32_t s = it % kRingStages, use = it / kRingStages;
+            const uint8_t* st = smem + s * Ring::stage_bytes;
+            // the plan itself is written by the producer before its (releasing) arrival on full[s]
+            mbar_wait(&full[s], use & 1);
+            process_block(*reinterpret_cast<const GroupPlan*>(st + Smem::plan), st + Smem::coef, st + Smem::win, t, &full[s], use & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    }
+}
+
 }  // namespace
 
 size_t fused_plan_bytes(uint32_t n_mb) { return (size_t)((n_mb + kG - 1) / kG) * sizeof(GroupPlan); }
@@ -516,7 +616,28 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
-    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
+    static int ring = -1, resident = 0;
+    if (ring < 0) {
+        const char* sel = getenv("MPEGB200_FUSED");
+        ring = sel && strcmp(sel, "ring") == 0;
+        if (ring) {
+            cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring::total);
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_ring_kernel, kRingThreads, Ring::total);
+            if (e != cudaSuccess) return e;
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
+    }
+    if (ring) {
+        const uint32_t grid = n_groups < (uint32_t)resident ? n_groups : (uint32_t)resident;
+        fused_ring_kernel<<<grid, kRingThreads, Ring::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps,
+                                                                     plans, n_groups);
+    } else {
+        fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
+    }
     return cudaGetLastError();
 }
 

@@ -326,3 +326,53 @@ def test_windows_wrap_across_row_ends_like_linear_indexing(ctx):
         op["stream"] = 0
         assert fs.exec_pictures(op, m, np.zeros((0, 64), np.int16)) == 0
         assert_frames_equal(ctx, fs, 8, 0, msg=f"wrap case {(row, col, mh, mv)}")
+
+
+def test_mixed_geometries_slabs_and_kernel_selection(ctx):
+    """Streams of different sizes live in different slabs (own tensor maps); a stream whose chroma pitch is not
+    a multiple of 16 bytes (odd macroblock width) forces the generic kernel for the launch.  Either way the
+    output is the oracle's."""
+    geos = [wl.Geometry(64, 48), wl.Geometry(96, 64), wl.Geometry(64, 48)]
+    sids = [30, 31, 32]
+    rng = wl.stream_rng(2, 77)
+    oracles = []
+    for sid, g in zip(sids, geos):
+        fresh_stream(ctx, sid, g.width, g.height)
+        fs = ol.FrameSet(1, g.width, g.height)
+        for b in range(3):
+            buf = wl.random_reference_frame(rng, g)
+            fs.whole(0, b)[:] = buf
+            ctx.video_write_frame(sid, b, buf)
+        oracles.append(fs)
+
+    def run_batch():
+        per = [wl.make_picture(rng, g, wl.PIC_B, "natural") for g in geos]
+        pics, mbs, coeffs = wl.batch_pictures(per, sids, wl.PIC_B, [(0, 1, 2)] * len(geos))
+        ctx.video_validate(pics, mbs, len(coeffs))
+        ctx.video_decode_pictures(pics, mbs, coeffs)
+        for i, (fs, (m, c)) in enumerate(zip(oracles, per)):
+            p1, m1, c1 = wl.batch_pictures([(m, c)], [0], wl.PIC_B, [(0, 1, 2)])
+            assert fs.exec_pictures(p1, m1, c1) == 0
+            assert_frames_equal(ctx, fs, sids[i], 0, msg="mixed geometries")
+
+    run_batch()                                   # all streams TMA-capable: fast path, three slabs' worth of maps
+    g_odd = wl.Geometry(72, 40)                   # mb_w = 5: chroma pitch 40 bytes
+    fresh_stream(ctx, 33, g_odd.width, g_odd.height)
+    fs_odd = ol.FrameSet(1, g_odd.width, g_odd.height)
+    for b in range(3):
+        buf = wl.random_reference_frame(rng, g_odd)
+        fs_odd.whole(0, b)[:] = buf
+        ctx.video_write_frame(33, b, buf)
+    geos.append(g_odd)
+    sids.append(33)
+    oracles.append(fs_odd)
+    run_batch()                                   # generic kernel for everybody
+    ctx.video_close(33)
+    geos.pop(); sids.pop(); oracles.pop()
+    run_batch()                                   # back on the fast path
+    # closing and re-opening a stream re-uses its slab slot and starts from zeroed buffers (video.go:340)
+    ctx.video_close(31)
+    ctx.video_open(31, 96, 64)
+    assert not ctx.video_read_frame(31, 0).any()
+    for s in (30, 31, 32):
+        ctx.video_close(s)

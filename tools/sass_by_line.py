@@ -14,8 +14,9 @@ rep, cubin, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-# first kernel block only
-hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+# the block of the kernel whose name contains <kernel-substring> (first match)
+start = next((i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kname in ",".join(r)), 0)
+hdr_i = next(i for i, r in enumerate(rows) if i >= start and r and r[0] == "Address")
 hdr = rows[hdr_i]
 ie = hdr.index("Instructions Executed")
 ist = hdr.index("Warp Stall Sampling (All Samples)")
@@ -51,6 +52,10 @@ for (txt, cnt, st), ln in zip(insts[:n], lines[:n]):
 print(f"total warp instructions executed: {tot}, stall samples {tots}")
 for ln, (c, s, k) in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{str(ln):34s} exec {c:12d} ({100*c/tot:5.1f}%)  stalls {100*s/max(tots,1):5.1f}%  sass {k}")
+if '--by-stall' in sys.argv:
+    print('--- by stall samples')
+    for ln, (c, s, k) in sorted(per.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"{str(ln):34s} exec {c:12d} ({100*c/tot:5.1f}%)  stalls {100*s/max(tots,1):5.1f}%  sass {k}")
 
 if len(sys.argv) > 5:
     # ranges "name:lo-hi,name:lo-hi" over the main .cu file; helper headers are attributed by name
