@@ -48,18 +48,16 @@ __device__ __forceinline__ void lee_dct(float (&x)[N]) {
 }
 
 constexpr int kSlicePitch = 65;  // floats per V slice in shared memory (64 + 1: conflict-free column writes)
-constexpr int kSlots = 64;       // slices kept per channel (>= 15 history + 36 of the frame)
-constexpr int kSamplePitch = 33; // ints per time slot of staged samples
+constexpr int kSlots = 52;       // slices kept per channel (>= 15 history + 36 of the frame)
 constexpr int kAudioThreads = 128;
 
 struct AudioSmem {
-    float v[2][kSlots * kSlicePitch];       // 33,280 B
-    int samples[2 * 36 * kSamplePitch];     //  9,504 B
+    float v[2][kSlots * kSlicePitch];       // 27,040 B: 8 CTAs per SM, so 1024 streams are resident in one wave
 };
 
 // One CTA per stream; frames are processed in order, each in three barriers:
-//   (a) stage the frame's 2x36x32 requantised samples (coalesced 16-byte loads)
-//   (b) 72 threads: one 32-point DCT each (channel, time slot) -> V slice (audio.go:708-771 placement)
+//   (b) 72 threads: one 32-point DCT each (channel, time slot) on samples read straight from global memory
+//       -> V slice (audio.go:708-771 placement)
 //   (c) 4 warps: the 36 time slots' windows, lane = output sample, both channels -> coalesced store
 __global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* __restrict__ states, int max_streams,
                                                                     const int32_t* __restrict__ stream_ids,
@@ -89,20 +87,17 @@ __global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* 
     const size_t frame_vals = 2 * MPEGB200_SAMPLES_PER_FRAME;
     for (int f = 0; f < frames_per_stream; f++) {
         const size_t fidx = (size_t)sidx * frames_per_stream + f;
-        // (a) samples[fidx][ch][step][sb] -> shared, pitch 33
-        const int4* src = reinterpret_cast<const int4*>(samples + fidx * (2 * 36 * 32));
-        for (int i = tid; i < 2 * 36 * 8; i += kAudioThreads) {
-            const int4 w = src[i];
-            const int slot = i >> 3, sb = (i & 7) * 4;
-            int* d = &sm.samples[slot * kSamplePitch + sb];
-            d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
-        }
-        __syncthreads();
-
         // (b) matrixing
         if (tid < 72) {
             const int ch = tid / 36, step = tid - ch * 36;
-            const int* s = &sm.samples[tid * kSamplePitch];
+            // the time slot's 32 subband samples: 128 contiguous bytes, read straight from global memory
+            const int4* sp = reinterpret_cast<const int4*>(samples + fidx * (2 * 36 * 32) + tid * 32);
+            int s[32];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int4 w = __ldg(sp + i);
+                s[4 * i] = w.x; s[4 * i + 1] = w.y; s[4 * i + 2] = w.z; s[4 * i + 3] = w.w;
+            }
             float e[16], o[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
