@@ -154,6 +154,18 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
                                        size_t n_mb, const mpegb200_mb* d_mbs,
                                        size_t n_blocks, const int16_t* d_coeffs);
 
+/* 12-bit transfer form of the coefficients: every level of video.go:737-741 lies in [-2048, 2047] and so does
+ * a valid intra DC in its dc*8 form (dc <= 255), hence 64 x 12 bits = 96 bytes per block instead of 128 -- a quarter
+ * less host-to-device traffic, which is what bounds the end-to-end rate.  Value i of a block occupies bits
+ * [12i, 12i+12) of its 96-byte little-endian bit string (two's complement).  mpegb200_pack_coeffs12 converts the
+ * int16 form (returns MPEGB200_ERECORD if a value does not fit: use the 16-bit entry point then); the _packed entry
+ * point copies the packed blocks to the device, expands them there and continues like
+ * mpegb200_video_decode_pictures. */
+int mpegb200_pack_coeffs12(const int16_t* coeffs, size_t n_blocks, uint8_t* packed /* 96 * n_blocks */);
+int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics,
+                                          size_t n_mb, const mpegb200_mb* mbs, size_t n_blocks,
+                                          const uint8_t* coeffs12);
+
 /* Plane read-back for *Frame (Plane.Data, video.go:50-54): copies the macroblock-padded
  * planes of physical buffer `buf` to host memory.  Any of y/cb/cr may be NULL. */
 int mpegb200_video_read_planes(mpegb200_ctx* ctx, int stream, int buf,

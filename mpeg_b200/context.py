@@ -102,6 +102,21 @@ class Context:
         self._keep = (pics, mbs, coeffs)  # keep alive until the stream has consumed them
         self._ck(self.L.mpegb200_video_decode_pictures(self.h, len(pics), _ptr(pics), len(mbs), _ptr(mbs), len(coeffs), _ptr(coeffs)))
 
+    def pack_coeffs12(self, coeffs) -> np.ndarray:
+        """int16 blocks -> the 96-byte transfer form (raises if a value does not fit 12 bits)."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.int16).reshape(-1, 64)
+        out = np.empty((len(coeffs), 96), np.uint8)
+        self._ck(self.L.mpegb200_pack_coeffs12(_ptr(coeffs), len(coeffs), _ptr(out)))
+        return out
+
+    def video_decode_pictures_packed(self, pics, mbs, coeffs12):
+        """Like video_decode_pictures, with the coefficients in the 12-bit transfer form."""
+        pics = np.ascontiguousarray(pics, dtype=PICTURE_DTYPE)
+        mbs = np.ascontiguousarray(mbs, dtype=MB_DTYPE)
+        coeffs12 = np.ascontiguousarray(coeffs12, dtype=np.uint8).reshape(-1, 96)
+        self._keep = (pics, mbs, coeffs12)
+        self._ck(self.L.mpegb200_video_decode_pictures_packed(self.h, len(pics), _ptr(pics), len(mbs), _ptr(mbs), len(coeffs12), _ptr(coeffs12)))
+
     def video_decode_pictures_dev(self, n_pics: int, d_pics: int, n_mb: int, d_mbs: int, n_blocks: int, d_coeffs: int):
         """Device pointers (ints) of arrays already resident in HBM."""
         self._ck(self.L.mpegb200_video_decode_pictures_dev(self.h, n_pics, C.c_void_p(d_pics), n_mb, C.c_void_p(d_mbs), n_blocks, C.c_void_p(d_coeffs)))

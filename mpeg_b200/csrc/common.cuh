@@ -64,6 +64,8 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
                              uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream);
 size_t fused_plan_bytes(uint32_t n_mb);
+// 12-bit packed coefficient blocks (96 B) -> int16 blocks (128 B)
+cudaError_t launch_unpack12(const uint8_t* d_packed, int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

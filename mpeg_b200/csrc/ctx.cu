@@ -56,7 +56,7 @@ struct mpegb200_ctx {
     std::vector<uint8_t> audio_open;
     AudioState* d_audio = nullptr;
     float* d_window = nullptr;
-    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans;
+    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_packed[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans;
     // host-pointer pipeline: uploads and read-backs run on their own streams so that the H2D copy of the
     // next step overlaps the kernels and the D2H copy of the current one (double-buffered staging)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
@@ -216,7 +216,7 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     if (ctx->down_stream) cudaStreamSynchronize(ctx->down_stream);
     for (DevBuf* b : {&ctx->s_pics[0], &ctx->s_pics[1], &ctx->s_mbs[0], &ctx->s_mbs[1], &ctx->s_coeffs[0],
                       &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out,
-                      &ctx->s_plans})
+                      &ctx->s_plans, &ctx->s_packed[0], &ctx->s_packed[1]})
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
@@ -345,6 +345,7 @@ int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
         size_t cap = ((size_t)1 << 30) / per_stream;
         if (cap < 1) cap = 1;
         if (cap > (size_t)ctx->max_streams) cap = (size_t)ctx->max_streams;
+        if (cap > 21000) cap = 21000;  // 3 * slot + buffer travels as 16 bits in the group plans
         sl.capacity = (int)cap;
         sl.width = width;
         sl.height = height;
@@ -552,6 +553,53 @@ int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpeg
     CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
     if (int rc = join_readback(ctx)) return rc;
+    int rc = mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
+                                                (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks,
+                                                (const int16_t*)ctx->s_coeffs[slot].p);
+    CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
+    return rc;
+}
+
+int mpegb200_pack_coeffs12(const int16_t* coeffs, size_t n_blocks, uint8_t* packed) {
+    if ((!coeffs || !packed) && n_blocks) return MPEGB200_EINVAL;
+    for (size_t b = 0; b < n_blocks; b++) {
+        const int16_t* in = coeffs + b * 64;
+        uint8_t* out = packed + b * 96;
+        for (int i = 0; i < 64; i += 2) {  // two values -> three bytes
+            const int a = in[i], c = in[i + 1];
+            if (a < -2048 || a > 2047 || c < -2048 || c > 2047) return MPEGB200_ERECORD;
+            const uint32_t u = ((uint32_t)a & 0xfffu) | (((uint32_t)c & 0xfffu) << 12);
+            out[0] = (uint8_t)u;
+            out[1] = (uint8_t)(u >> 8);
+            out[2] = (uint8_t)(u >> 16);
+            out += 3;
+        }
+    }
+    return 0;
+}
+
+int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics, size_t n_mb,
+                                          const mpegb200_mb* mbs, size_t n_blocks, const uint8_t* coeffs12) {
+    if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && !coeffs12))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n_mb == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    const int slot = (int)(ctx->upload_seq++ & 1);
+    if (int rc = ensure(ctx, ctx->s_pics[slot], sizeof(mpegb200_picture) * (size_t)n_pictures)) return rc;
+    if (int rc = ensure(ctx, ctx->s_mbs[slot], sizeof(mpegb200_mb) * n_mb)) return rc;
+    if (int rc = ensure(ctx, ctx->s_packed[slot], 96 * (n_blocks ? n_blocks : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_coeffs[slot], 128 * (n_blocks ? n_blocks : 1))) return rc;
+    CU(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_free[slot], 0));
+    CU(cudaMemcpyAsync(ctx->s_pics[slot].p, pics, sizeof(mpegb200_picture) * (size_t)n_pictures, cudaMemcpyHostToDevice,
+                       ctx->up_stream));
+    CU(cudaMemcpyAsync(ctx->s_mbs[slot].p, mbs, sizeof(mpegb200_mb) * n_mb, cudaMemcpyHostToDevice, ctx->up_stream));
+    if (n_blocks)
+        CU(cudaMemcpyAsync(ctx->s_packed[slot].p, coeffs12, 96 * n_blocks, cudaMemcpyHostToDevice, ctx->up_stream));
+    CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
+    if (int rc = join_readback(ctx)) return rc;
+    CU(launch_unpack12((const uint8_t*)ctx->s_packed[slot].p, (int16_t*)ctx->s_coeffs[slot].p, n_blocks, ctx->stream));
+    ctx->launches++;
     int rc = mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
                                                 (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks,
                                                 (const int16_t*)ctx->s_coeffs[slot].p);

@@ -19,9 +19,6 @@
 // The arithmetic is the reference's, bit for bit.
 #include <cuda.h>
 
-#include <cstdlib>
-#include <cstring>
-
 #include "common.cuh"
 
 namespace mpegb200 {
@@ -516,88 +513,6 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Experimental variant (MPEGB200_FUSED=ring): persistent CTAs, warp 0 streams plans and TMA boxes through a
-// ring of kRingStages stages, warps 1..3 consume.  Same arithmetic (process_block).
-// ------------------------------------------------------------------------------------------------
-constexpr int kRingStages = 2;
-constexpr int kRingThreads = 32 + kNT;
-struct Ring {
-    static constexpr int stage_bytes = (Smem::plan + (int)sizeof(GroupPlan) + 1023) & ~1023;
-    static constexpr int bars = kRingStages * stage_bytes;
-    static constexpr int total = bars + 2 * kRingStages * 8;
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__global__ void __launch_bounds__(kRingThreads) fused_ring_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                                 const SlabMaps* __restrict__ slab_maps,
-                                                                 const GroupPlan* __restrict__ plans, uint32_t n_groups) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Ring::bars);
-    uint64_t* empty = full + kRingStages;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        if (smem_u32(smem) & 1023u) __trap();
-        for (int s = 0; s < kRingStages; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kNT / 32);
-        }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // plans are fetched one iteration ahead: lane l holds uint4 #l and (l < 16) #32+l of the next plan
-        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-        uint32_t g = blockIdx.x;
-        if (g < n_groups) {
-            const uint4* src = reinterpret_cast<const uint4*>(plans + g);
-            n0 = src[lane];
-            if (lane < 16) n1 = src[32 + lane];
-        }
-        for (uint32_t it = 0; g < n_groups; g += gridDim.x, it++) {
-            const uint4 c0 = n0, c1 = n1;
-            const uint32_t gn = g + gridDim.x;
-            if (gn < n_groups) {
-                const uint4* src = reinterpret_cast<const uint4*>(plans + gn);
-                n0 = src[lane];
-                if (lane < 16) n1 = src[32 + lane];
-            }
-            const uint32_t s = it % kRingStages, use = it / kRingStages;
-            if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-            uint8_t* st = smem + s * Ring::stage_bytes;
-            GroupPlan& P = *reinterpret_cast<GroupPlan*>(st + Smem::plan);
-            reinterpret_cast<uint4*>(&P)[lane] = c0;
-            if (lane < 16) reinterpret_cast<uint4*>(&P)[32 + lane] = c1;
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
-            if (lane < (int)P.n_box)
-                tma_load_2d(st + Smem::coef + lane * (kCoefBox * 128), &coef_map, &full[s], 0, (int)(P.block0 + lane * kCoefBox));
-            if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
-                const PlanMb& t = P.mb[lane];
-                const SlabMaps* maps = slab_maps + t.slab;
-                uint8_t* w = st + Smem::win + lane * kWinBytes;
-                tma_load_3d(w, maps->luma, &full[s], t.lx, t.ly, t.z);
-                tma_load_4d(w + kWinY, maps->chroma, &full[s], t.cx, t.cy, 0, t.z);
-            }
-        }
-    } else {
-        const int t = tid - 32;
-        uint32_t it = 0;
-        for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
-            const uint32_t s = it % kRingStages, use = it / kRingStages;
-            const uint8_t* st = smem + s * Ring::stage_bytes;
-            // the plan itself is written by the producer before its (releasing) arrival on full[s]
-            mbar_wait(&full[s], use & 1);
-            process_block(*reinterpret_cast<const GroupPlan*>(st + Smem::plan), st + Smem::coef, st + Smem::win, t, &full[s], use & 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-    }
-}
-
 }  // namespace
 
 size_t fused_plan_bytes(uint32_t n_mb) { return (size_t)((n_mb + kG - 1) / kG) * sizeof(GroupPlan); }
@@ -616,28 +531,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
-    static int ring = -1, resident = 0;
-    if (ring < 0) {
-        const char* sel = getenv("MPEGB200_FUSED");
-        ring = sel && strcmp(sel, "ring") == 0;
-        if (ring) {
-            cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring::total);
-            if (e != cudaSuccess) return e;
-            int dev = 0, sms = 0, per_sm = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_ring_kernel, kRingThreads, Ring::total);
-            if (e != cudaSuccess) return e;
-            resident = sms * (per_sm > 0 ? per_sm : 1);
-        }
-    }
-    if (ring) {
-        const uint32_t grid = n_groups < (uint32_t)resident ? n_groups : (uint32_t)resident;
-        fused_ring_kernel<<<grid, kRingThreads, Ring::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps,
-                                                                     plans, n_groups);
-    } else {
-        fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
-    }
+    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
     return cudaGetLastError();
 }
 

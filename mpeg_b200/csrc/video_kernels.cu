@@ -480,6 +480,29 @@ cudaError_t launch_rgba(const StreamInfo* d_streams, int max_streams, const int3
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Transfer form -> working form of the coefficients: 8 values per thread, 12 bytes in, 16 bytes out.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack12_kernel(const uint32_t* __restrict__ packed, uint4* __restrict__ out,
+                                                       size_t n_groups /* of 8 values */) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_groups) return;
+    const uint32_t w0 = packed[3 * i], w1 = packed[3 * i + 1], w2 = packed[3 * i + 2];
+    // 96 bits = v0..v7, 12 bits each, little-endian; sign-extend by shifting through the top of a 32-bit lane
+    auto sx = [](uint32_t v) { return (uint32_t)(((int32_t)(v << 20)) >> 20) & 0xffffu; };
+    const uint32_t v0 = sx(w0), v1 = sx(w0 >> 12), v2 = sx((w0 >> 24) | (w1 << 8)), v3 = sx(w1 >> 4), v4 = sx(w1 >> 16),
+                   v5 = sx((w1 >> 28) | (w2 << 4)), v6 = sx(w2 >> 8), v7 = sx(w2 >> 20);
+    out[i] = make_uint4(v0 | (v1 << 16), v2 | (v3 << 16), v4 | (v5 << 16), v6 | (v7 << 16));
+}
+
+cudaError_t launch_unpack12(const uint8_t* d_packed, int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    const size_t n_groups = n_blocks * 8;
+    unpack12_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_packed),
+                                                                           reinterpret_cast<uint4*>(d_coeffs), n_groups);
+    return cudaGetLastError();
+}
+
 cudaError_t configure_kernels() {
     return cudaFuncSetAttribute(fused_mc_idct_kernel<kG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 FusedSmem<kG>::total);

@@ -376,3 +376,33 @@ def test_mixed_geometries_slabs_and_kernel_selection(ctx):
     assert not ctx.video_read_frame(31, 0).any()
     for s in (30, 31, 32):
         ctx.video_close(s)
+
+
+def test_packed_12bit_transfer_form_is_equivalent(ctx):
+    """mpegb200_video_decode_pictures_packed: the 96-byte transfer form expands on the device to the same int16 blocks."""
+    import mpeg_b200
+    g = wl.CIF
+    rng = wl.stream_rng(2, 5)
+    fs = ol.FrameSet(1, g.width, g.height)
+    fresh_stream(ctx, 40, g.width, g.height)
+    for b in range(3):
+        buf = wl.random_reference_frame(rng, g)
+        fs.whole(0, b)[:] = buf
+        ctx.video_write_frame(40, b, buf)
+    for t, bufs in [(wl.PIC_P, (0, 1, 2)), (wl.PIC_B, (2, 0, 1)), (wl.PIC_I, (1, 2, 0))]:
+        mbs, coeffs = wl.make_picture(rng, g, t, "natural", adversarial=False)
+        coeffs = np.clip(coeffs, -2048, 2047)          # intra dc*8 <= 2040 already; keep the extremes in
+        coeffs[0, :4] = [2047, -2048, 1, -1]
+        pics, mbs, coeffs = wl.batch_pictures([(mbs, coeffs)], [40], t, [bufs])
+        packed = ctx.pack_coeffs12(coeffs)
+        assert packed.shape == (len(coeffs), 96)
+        ctx.video_decode_pictures_packed(pics, mbs, packed)
+        op = pics.copy()
+        op["stream"] = 0
+        assert fs.exec_pictures(op, mbs, coeffs) == 0
+        assert_frames_equal(ctx, fs, 40, 0, msg=f"packed path, picture type {t}")
+    too_big = np.zeros((1, 64), np.int16)
+    too_big[0, 0] = 2048
+    with pytest.raises(mpeg_b200.MpegB200Error):
+        ctx.pack_coeffs12(too_big)
+    ctx.video_close(40)

@@ -1,0 +1,125 @@
+#!/usr/bin/env python3
+"""Secondary BASELINE.md rows (not the headline bench): config 1 (testdata through the CPU oracle), config 2 (one
+CIF stream on the GPU, bit-exact check + frames/s), host parser throughput, and the end-to-end mirror API on the clip.
+Prints one JSON object.  Run on the GPU box: python tools/bench_configs.py"""
+import ctypes as C
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    import oracle_lib as ol
+    import mpeg_b200
+    from mpeg_b200 import _lib, workload as wl
+    from mpeg_b200.mpeg import VideoStep
+    out = {}
+    ps = (ROOT / "tests/golden/test.mpg").read_bytes()
+    es = (ROOT / "tests/golden/test.mpeg1video").read_bytes()
+    mp2 = (ROOT / "tests/golden/test.mp2").read_bytes()
+
+    # config 1: testdata/test.mpg, full decode through the CPU restatement of the reference (one thread)
+    t0 = time.perf_counter()
+    v_es, a_es, _, _ = ol.demux_split(ps)
+    v = ol.VideoOracle(v_es)
+    n = 0
+    while v.decode() is not None:
+        n += 1
+    a = ol.AudioOracle(a_es)
+    m = 0
+    while a.decode() is not None:
+        m += 1
+    dt = time.perf_counter() - t0
+    out["config1_cpu_oracle_test_mpg"] = {"video_frames": n, "audio_frames": m, "seconds": dt,
+                                          "video_frames_per_sec_1thread": n / dt, "size": "160x120"}
+
+    # host parser alone (product C++): pictures/s on the 160x120 clip
+    L = _lib.load()
+    h = L.mpegb200_video_parser_new(es, len(es))
+    st = VideoStep()
+    t0 = time.perf_counter()
+    k = mbs = 0
+    while L.mpegb200_video_parser_next(h, C.byref(st)) == 0 and st.has_frame:
+        k += 1
+        for i in range(st.n_launches):
+            mbs += st.launches[i].n_mb
+    dt = time.perf_counter() - t0
+    L.mpegb200_video_parser_free(h)
+    out["host_parser_160x120"] = {"frames": k, "macroblocks": mbs, "seconds": dt, "frames_per_sec_1thread": k / dt,
+                                  "macroblocks_per_sec_1thread": mbs / dt}
+
+    ctx = mpeg_b200.Context(0, 8)
+    # the mirror API end to end on the clip (parse + H2D + kernels + plane read-back per frame, one stream: latency bound)
+    video = mpeg_b200.Video(es, ctx, 0)
+    t0 = time.perf_counter()
+    k = 0
+    hsh = ol.FNV_OFFSET
+    while True:
+        f = video.decode()
+        if f is None:
+            break
+        hsh = ol.fnv(hsh, f.y); hsh = ol.fnv(hsh, f.cb); hsh = ol.fnv(hsh, f.cr)
+        k += 1
+    dt = time.perf_counter() - t0
+    out["api_video_decode_160x120_single_stream"] = {"frames": k, "seconds": dt, "frames_per_sec": k / dt,
+                                                     "golden_hash_ok": hsh == 0xEA6D7FCB1340BA3F}
+    video.close()
+    audio = mpeg_b200.Audio(mp2, ctx, 0)
+    t0 = time.perf_counter()
+    k = 0
+    hsh = ol.FNV_OFFSET
+    while True:
+        s = audio.decode()
+        if s is None:
+            break
+        hsh = ol.fnv(hsh, s.interleaved)
+        k += 1
+    dt = time.perf_counter() - t0
+    out["api_audio_decode_single_stream"] = {"frames": k, "seconds": dt, "frames_per_sec": k / dt,
+                                             "golden_hash_ok": hsh == 0xF1B76CDF8E6CDEA5}
+    audio.close()
+
+    # config 2: single CIF stream, synthetic I P B B ... sequence, bit-exact vs oracle, device-resident launches
+    g = wl.CIF
+    rng = wl.stream_rng(2, 0)
+    fs = ol.FrameSet(1, g.width, g.height)
+    ctx.video_open(1, g.width, g.height)
+    rot = wl.BufferRotation()
+    types = [wl.PIC_I] + [wl.PIC_P, wl.PIC_B, wl.PIC_B] * 10
+    batches = []
+    for t in types[:30]:
+        dst, fwd, bwd = rot.begin(t)
+        mb, co = wl.make_picture(rng, g, t, "natural")
+        batches.append(wl.batch_pictures([(mb, co)], [1], t, [(dst, fwd, bwd)]))
+        rot.end(t)
+    ok = True
+    for pics, mb, co in batches:
+        ctx.video_decode_pictures(pics, mb, co)
+        op = pics.copy(); op["stream"] = 0
+        fs.exec_pictures(op, mb, co)
+    for b in range(3):
+        ok &= bool(np.array_equal(ctx.video_read_frame(1, b), fs.whole(0, b)))
+    ctx.sync()
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        for pics, mb, co in batches:
+            ctx.video_decode_pictures(pics, mb, co)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    out["config2_single_cif_stream"] = {"bit_exact_all_buffers": ok, "pictures": reps * len(batches), "seconds": dt,
+                                        "pictures_per_sec": reps * len(batches) / dt,
+                                        "note": "one 396-macroblock picture per launch from host arrays: launch/latency bound by design; throughput comes from batching streams (bench.py)"}
+    ctx.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
