@@ -121,6 +121,9 @@ const char* mpegb200_last_error(mpegb200_ctx* ctx);
 int  mpegb200_set_stream(mpegb200_ctx* ctx, void* cuda_stream);
 void* mpegb200_get_stream(mpegb200_ctx* ctx);
 int  mpegb200_sync(mpegb200_ctx* ctx);
+/* Wait only for the host-to-device copies enqueued so far: after it the host arrays passed to the
+ * host-pointer entry points may be overwritten while the kernels are still running. */
+int  mpegb200_sync_uploads(mpegb200_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx);
 

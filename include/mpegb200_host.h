@@ -63,6 +63,39 @@ int    mpegb200_video_parser_has_ended(mpegb200_video_parser* v);
  * the next call on the same parser.  Returns 0, or MPEGB200_EINVAL. */
 int    mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* out);
 
+/* ---- many video streams in lock-step (the batched deployment of INTEGRATION.md section 6) ------- */
+
+typedef struct mpegb200_video_batch mpegb200_video_batch;
+
+/* One kernel launch for many streams: the w-th launch of every stream's current Decode() step.
+ * At most one picture per stream; pics[i].stream is the stream's index in the batch. */
+typedef struct mpegb200_wave {
+    int n_pictures;
+    const mpegb200_picture* pics;
+    size_t n_mb;
+    const mpegb200_mb* mbs;        /* pic = index into pics, coeff_block = index into coeffs */
+    size_t n_blocks;
+    const int16_t* coeffs;
+} mpegb200_wave;
+
+typedef struct mpegb200_batch_step {
+    int n_streams;
+    const int* has_frame;          /* per stream: 1 if this step returns a frame (0 = that stream has ended) */
+    const int* frame_buf;          /* per stream: physical buffer 0..2 of the frame */
+    const double* time;            /* per stream: Frame.Time */
+    int n_waves;
+    const mpegb200_wave* waves;    /* launch in order; each wave is duplicate-free (see mpegb200_launch) */
+} mpegb200_batch_step;
+
+/* n_streams parsers driven by `threads` host threads.  The wave arrays are allocated with alloc/free when
+ * given (pass mpegb200_host_alloc / mpegb200_host_free to get pinned staging), else with malloc. */
+mpegb200_video_batch* mpegb200_video_batch_new(int n_streams, int threads, void* (*alloc)(size_t), void (*free_fn)(void*));
+void mpegb200_video_batch_free(mpegb200_video_batch* b);
+int  mpegb200_video_batch_set_stream(mpegb200_video_batch* b, int index, const uint8_t* data, size_t len);
+int  mpegb200_video_batch_stream_size(mpegb200_video_batch* b, int index, int* width, int* height);
+/* One Video.Decode() step of every stream, parsed in parallel and merged into waves. */
+int  mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out);
+
 /* ---- MP2 elementary stream --------------------------------------------------------------------- */
 
 typedef struct mpegb200_audio_parser mpegb200_audio_parser;

@@ -55,6 +55,7 @@ def load():
         "mpegb200_set_stream": (C.c_int, [vp, vp]),
         "mpegb200_get_stream": (vp, [vp]),
         "mpegb200_sync": (C.c_int, [vp]),
+        "mpegb200_sync_uploads": (C.c_int, [vp]),
         "mpegb200_launch_count": (C.c_uint64, [vp]),
         "mpegb200_video_open": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "mpegb200_video_close": (C.c_int, [vp, C.c_int]),
@@ -92,6 +93,11 @@ def load():
         "mpegb200_video_parser_rewind": (None, [vp]),
         "mpegb200_video_parser_has_ended": (C.c_int, [vp]),
         "mpegb200_video_parser_next": (C.c_int, [vp, vp]),
+        "mpegb200_video_batch_new": (vp, [C.c_int, C.c_int, vp, vp]),
+        "mpegb200_video_batch_free": (None, [vp]),
+        "mpegb200_video_batch_set_stream": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_size_t]),
+        "mpegb200_video_batch_stream_size": (C.c_int, [vp, C.c_int, ip, ip]),
+        "mpegb200_video_batch_next": (C.c_int, [vp, vp]),
         "mpegb200_audio_parser_new": (vp, [C.c_char_p, C.c_size_t]),
         "mpegb200_audio_parser_free": (None, [vp]),
         "mpegb200_audio_parser_has_header": (C.c_int, [vp]),

@@ -257,6 +257,13 @@ int mpegb200_sync(mpegb200_ctx* ctx) {
     return 0;
 }
 
+int mpegb200_sync_uploads(mpegb200_ctx* ctx) {
+    if (!ctx) return MPEGB200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->up_stream));
+    return 0;
+}
+
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 /* ---------------------------------------------------------------------------------------- video */

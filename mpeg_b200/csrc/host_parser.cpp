@@ -966,3 +966,185 @@ int mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_
 void mpegb200_buffer_free(void* p) { free(p); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Many streams in lock-step: parse one Decode() step of every stream on a pool of host threads and
+// merge the per-stream launches into waves (one kernel launch each, at most one picture per stream).
+// ------------------------------------------------------------------------------------------------
+#include <atomic>
+#include <thread>
+
+struct mpegb200_video_batch {
+    int n = 0, threads = 1;
+    void* (*alloc)(size_t) = nullptr;
+    void (*free_fn)(void*) = nullptr;
+    std::vector<mpegb200_video_parser*> parsers;
+    std::vector<mpegb200_video_step> steps;
+    std::vector<int> has_frame, frame_buf;
+    std::vector<double> time;
+    struct WaveBuf {
+        mpegb200_picture* pics = nullptr;
+        mpegb200_mb* mbs = nullptr;
+        int16_t* coeffs = nullptr;
+        size_t cap_pics = 0, cap_mbs = 0, cap_blocks = 0;
+    };
+    std::vector<WaveBuf> bufs[2];   // double-buffered: the previous step's arrays stay intact while the next is parsed
+    int flip = 0;
+    std::vector<mpegb200_wave> waves;
+
+    void* get(size_t bytes) { return alloc ? alloc(bytes ? bytes : 1) : malloc(bytes ? bytes : 1); }
+    void put(void* p) {
+        if (!p) return;
+        if (free_fn) free_fn(p); else free(p);
+    }
+    template <typename T>
+    bool reserve(T*& p, size_t& cap, size_t need) {
+        if (need <= cap) return true;
+        put(p);
+        cap = need + need / 4 + 64;
+        p = (T*)get(cap * sizeof(T));
+        return p != nullptr;
+    }
+};
+
+namespace {
+
+template <typename F>
+void parallel_for(int n, int threads, F f) {
+    if (threads <= 1 || n <= 1) {
+        for (int i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    const int t = std::min(threads, n);
+    for (int k = 0; k < t; k++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+mpegb200_video_batch* mpegb200_video_batch_new(int n_streams, int threads, void* (*alloc)(size_t), void (*free_fn)(void*)) {
+    if (n_streams <= 0 || n_streams > 65536) return nullptr;  // 16-bit picture index per launch
+    auto* b = new (std::nothrow) mpegb200_video_batch();
+    if (!b) return nullptr;
+    b->n = n_streams;
+    b->threads = threads > 0 ? threads : 1;
+    b->alloc = alloc;
+    b->free_fn = free_fn;
+    b->parsers.assign((size_t)n_streams, nullptr);
+    b->steps.resize((size_t)n_streams);
+    b->has_frame.assign((size_t)n_streams, 0);
+    b->frame_buf.assign((size_t)n_streams, 0);
+    b->time.assign((size_t)n_streams, 0.0);
+    return b;
+}
+
+void mpegb200_video_batch_free(mpegb200_video_batch* b) {
+    if (!b) return;
+    for (auto* p : b->parsers) delete p;
+    for (auto& set : b->bufs)
+        for (auto& w : set) {
+            b->put(w.pics);
+            b->put(w.mbs);
+            b->put(w.coeffs);
+        }
+    delete b;
+}
+
+int mpegb200_video_batch_set_stream(mpegb200_video_batch* b, int index, const uint8_t* data, size_t len) {
+    if (!b || index < 0 || index >= b->n) return MPEGB200_EINVAL;
+    delete b->parsers[(size_t)index];
+    b->parsers[(size_t)index] = mpegb200_video_parser_new(data, len);
+    return b->parsers[(size_t)index] ? 0 : MPEGB200_ENOMEM;
+}
+
+int mpegb200_video_batch_stream_size(mpegb200_video_batch* b, int index, int* width, int* height) {
+    if (!b || index < 0 || index >= b->n || !b->parsers[(size_t)index]) return MPEGB200_EINVAL;
+    if (width) *width = mpegb200_video_parser_width(b->parsers[(size_t)index]);
+    if (height) *height = mpegb200_video_parser_height(b->parsers[(size_t)index]);
+    return 0;
+}
+
+int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out) {
+    if (!b || !out) return MPEGB200_EINVAL;
+    memset(out, 0, sizeof(*out));
+    const int n = b->n;
+    parallel_for(n, b->threads, [&](int i) {
+        mpegb200_video_step& st = b->steps[(size_t)i];
+        memset(&st, 0, sizeof(st));
+        if (b->parsers[(size_t)i]) mpegb200_video_parser_next(b->parsers[(size_t)i], &st);
+        b->has_frame[(size_t)i] = st.has_frame;
+        b->frame_buf[(size_t)i] = st.frame_buf;
+        b->time[(size_t)i] = st.time;
+    });
+    int n_waves = 0;
+    for (int i = 0; i < n; i++) n_waves = std::max(n_waves, b->steps[(size_t)i].has_frame ? b->steps[(size_t)i].n_launches : 0);
+    b->flip ^= 1;
+    auto& bufs = b->bufs[b->flip];
+    if ((int)bufs.size() < n_waves) bufs.resize((size_t)n_waves);
+    b->waves.assign((size_t)n_waves, mpegb200_wave{});
+    std::vector<uint32_t> pic_of((size_t)n), mb_off((size_t)n), blk_off((size_t)n);
+    for (int w = 0; w < n_waves; w++) {
+        // sizes and offsets of wave w (streams that have a w-th launch with work in it)
+        uint32_t np = 0, nm = 0, nb = 0;
+        for (int i = 0; i < n; i++) {
+            const mpegb200_video_step& st = b->steps[(size_t)i];
+            pic_of[(size_t)i] = 0xffffffffu;
+            if (!st.has_frame || w >= st.n_launches || st.launches[w].n_mb == 0) continue;
+            pic_of[(size_t)i] = np++;
+            mb_off[(size_t)i] = nm;
+            blk_off[(size_t)i] = nb;
+            nm += st.launches[w].n_mb;
+            nb += st.launches[w].n_blocks;
+        }
+        auto& buf = bufs[(size_t)w];
+        if (!b->reserve(buf.pics, buf.cap_pics, np) || !b->reserve(buf.mbs, buf.cap_mbs, nm) ||
+            !b->reserve(buf.coeffs, buf.cap_blocks, (size_t)nb * 64))
+            return MPEGB200_ENOMEM;
+        parallel_for(n, b->threads, [&](int i) {
+            const uint32_t p = pic_of[(size_t)i];
+            if (p == 0xffffffffu) return;
+            const mpegb200_video_step& st = b->steps[(size_t)i];
+            const mpegb200_launch& L = st.launches[w];
+            mpegb200_picture pic = L.picture;
+            pic.stream = i;
+            pic.first_mb = mb_off[(size_t)i];
+            pic.n_mb = L.n_mb;
+            buf.pics[p] = pic;
+            const mpegb200_mb* src = st.mbs + L.first_mb;
+            mpegb200_mb* dst = buf.mbs + mb_off[(size_t)i];
+            for (uint32_t k = 0; k < L.n_mb; k++) {
+                dst[k] = src[k];
+                dst[k].pic = (uint16_t)p;
+                dst[k].coeff_block += blk_off[(size_t)i];
+            }
+            memcpy(buf.coeffs + (size_t)blk_off[(size_t)i] * 64, st.coeffs + (size_t)L.first_block * 64, (size_t)L.n_blocks * 128);
+        });
+        mpegb200_wave& W = b->waves[(size_t)w];
+        W.n_pictures = (int)np;
+        W.pics = buf.pics;
+        W.n_mb = nm;
+        W.mbs = buf.mbs;
+        W.n_blocks = nb;
+        W.coeffs = buf.coeffs;
+    }
+    out->n_streams = n;
+    out->has_frame = b->has_frame.data();
+    out->frame_buf = b->frame_buf.data();
+    out->time = b->time.data();
+    out->n_waves = n_waves;
+    out->waves = b->waves.data();
+    return 0;
+}
+
+}  // extern "C"

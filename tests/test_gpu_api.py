@@ -106,3 +106,44 @@ def test_mpeg_program_stream(ctx, golden_dir):
         k += 1
     assert k > 30
     m.close()
+
+
+def test_video_batch_lockstep_golden(golden_dir):
+    # many streams decoded in lock-step (one launch per wave for all of them): every stream must reproduce
+    # TestVideoGolden's hash (mpeg_test.go:203-231) / the oracle's hash for its own bitstream
+    import mpeg_b200
+    from test_batch_parser import cut_at_picture
+    es = (golden_dir / "test.mpeg1video").read_bytes()
+    ps_video = ol.demux_split((golden_dir / "test.mpg").read_bytes())[0]
+    kinds = [es, ps_video, cut_at_picture(es, 7), cut_at_picture(ps_video, 33)]
+    want = []
+    for k, d in enumerate(kinds):
+        o, h = ol.VideoOracle(d), ol.FNV_OFFSET
+        while (f := o.decode()) is not None:
+            for which in ("y", "cb", "cr"):
+                h = ol.fnv(h, f.plane(which))
+        want.append(h)
+    n = 24
+    datas = [kinds[i % len(kinds)] for i in range(n)]
+    with mpeg_b200.Context(device=0, max_streams=32) as c:
+        batch = mpeg_b200.VideoBatch(c, datas, threads=4, first_stream=3)
+        geo = c.video_geometry(3)
+        pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
+        hashes, frames = [ol.FNV_OFFSET] * n, [0] * n
+        host = np.empty((n, pic_bytes), np.uint8)
+        while True:
+            has, buf, t = batch.step()
+            if not has.any():
+                break
+            live = np.nonzero(has)[0]
+            c.video_read_pictures(live + 3, buf[live], host.ctypes.data, pic_bytes)
+            c.sync()
+            for k, i in enumerate(live):
+                hashes[i] = ol.fnv(hashes[i], host[k])
+                frames[i] += 1
+        batch.close()
+    assert frames[0] > frames[2] > 0
+    for i in range(n):
+        assert hashes[i] == want[i % len(kinds)], f"stream {i}: {hashes[i]:#018x}"
+    # the oracle's hash of the elementary stream is the reference's golden value
+    assert want[0] == VIDEO_GOLDEN
