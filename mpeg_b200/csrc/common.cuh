@@ -34,6 +34,10 @@ static_assert(sizeof(StreamInfo) == 48, "StreamInfo layout");
 //           window crossing the right edge continues on the next row exactly like linear addressing does.
 //   chroma: 4-D {chroma_w + 32, rows to the end of the buffer, plane (Cb, Cr: chroma_bytes apart), 3 * capacity}:
 //           one box fetches the Cb and the Cr window of a macroblock together.
+// Box heights: 17 (9) rows of window plus 3 (1) rows of head-room for the per-macroblock row phase of the staging
+// (video_fused_tma.cu).
+constexpr int kLumaBoxRows = 20, kChromaBoxRows = 10;
+
 struct alignas(128) SlabMaps {
     unsigned char luma[128];
     unsigned char chroma[128];

@@ -285,7 +285,7 @@ static bool encode_slab_maps(mpegb200_ctx* ctx, const Slab& sl, const HostStream
     {
         const cuuint64_t dims[3] = {(cuuint64_t)g.luma_w + 32, sl.buf_stride / g.luma_w, (cuuint64_t)3 * sl.capacity};
         const cuuint64_t strides[2] = {(cuuint64_t)g.luma_w, sl.buf_stride};
-        const cuuint32_t box[3] = {32, 17, 1};
+        const cuuint32_t box[3] = {32, kLumaBoxRows, 1};
         if (enc((CUtensorMap*)out->luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, sl.dev, dims, strides, box, ones,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -296,7 +296,7 @@ static bool encode_slab_maps(mpegb200_ctx* ctx, const Slab& sl, const HostStream
         const cuuint64_t dims[4] = {(cuuint64_t)g.chroma_w + 32, (sl.buf_stride - g.luma_bytes - g.chroma_bytes) / g.chroma_w, 2,
                                     (cuuint64_t)3 * sl.capacity};
         const cuuint64_t strides[3] = {(cuuint64_t)g.chroma_w, g.chroma_bytes, sl.buf_stride};
-        const cuuint32_t box[4] = {32, 9, 2, 1}, ones4[4] = {1, 1, 1, 1};
+        const cuuint32_t box[4] = {32, kChromaBoxRows, 2, 1}, ones4[4] = {1, 1, 1, 1};
         if (enc((CUtensorMap*)out->chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, sl.dev + g.luma_bytes, dims, strides, box,
                 ones4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -19,6 +19,8 @@
 // The arithmetic is the reference's, bit for bit.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mpegb200 {
@@ -158,9 +160,13 @@ __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b, uint32_t c, uin
 constexpr int kG = 16;                 // macroblock records per CTA
 constexpr int kNT = 6 * kG;            // one thread per output block (8x8)
 constexpr int kCoefBox = 32;           // blocks per coefficient TMA box (32 x 128 B = 4 KiB)
-constexpr int kWinY = 640, kWinC = 288;            // luma box: 32x17 = 544 B in 640; chroma box: Cb 32x9 then Cr 32x9 = 576 B in 640
-constexpr int kWinBytes = kWinY + 640;             // 1280 per macroblock, both boxes 128-byte aligned
-constexpr int kWinTx = 32 * 17 + 2 * 32 * 9;       // bytes the two boxes deliver: 1120
+// Windows are staged with a per-macroblock row phase: macroblock j's luma box starts (j & 3) rows above its window
+// and its chroma box (j & 1) rows above, so that the same window row of different macroblocks lands in
+// different shared-memory banks (a 32-byte row is 8 banks; without the phase the 32 block threads of a warp
+// all pulled their row from the same 8 banks: profiles/r1_final_video_summary.md).
+constexpr int kWinY = 32 * kLumaBoxRows, kWinC = 32 * kChromaBoxRows;   // luma box 32x20 = 640 B; chroma box: Cb 32x10 then Cr 32x10 = 640 B
+constexpr int kWinBytes = kWinY + 2 * kWinC;       // 1280 per macroblock, both boxes 128-byte aligned
+constexpr int kWinTx = kWinBytes;                  // bytes the two boxes deliver
 
 // ------------------------------------------------------------------------------------------------
 // Group plan: everything a CTA needs to know about its kG records, computed once by a pre-pass
@@ -348,7 +354,7 @@ struct Smem {
 
 // One output block: interpolate, IDCT, add, saturate, store.  `t` = index into the plan's block list.
 __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t* s_coef, const uint8_t* s_win, int t,
-                                              uint64_t* bar, uint32_t parity) {
+                                              uint64_t* bar, uint32_t parity, uint32_t phases) {
     const uint32_t e = P.map[t];
     if (e == kNoBlock) return;
     const int j = e & 15, k = (e >> 4) & 7;
@@ -371,7 +377,8 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
     uint32_t p0[8], p1[8];
     if (pred) {
         // s_win is 128-byte aligned, so the byte offset decides the word alignment
-        const uint32_t a = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + (mcb & 15u);
+        const uint32_t ph = (uint32_t)j & (k < 4 ? phases & 0xffu : phases >> 8);
+        const uint32_t a = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + ph * 32 + (mcb & 15u);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_win + (a & ~3u));
         const uint32_t sh = (a & 3u) * 8;
         const uint32_t mode = (mcb >> 4) & 3u;
@@ -476,7 +483,7 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
                                                        const SlabMaps* __restrict__ slab_maps,
-                                                       const GroupPlan* __restrict__ plans) {
+                                                       const GroupPlan* __restrict__ plans, uint32_t phases) {
     extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
     uint8_t* s_coef = smem + Smem::coef;
     uint8_t* s_win = smem + Smem::win;
@@ -497,9 +504,9 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
         const SlabMaps* maps = slab_maps + t.slab;
         uint8_t* w = s_win + lane * kWinBytes;
         if (warp == 0)
-            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly, t.z);
+            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly - (int)(lane & (phases & 0xffu)), t.z);
         else if (warp == 1)  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
-            tma_load_4d(w + kWinY, maps->chroma, s_bar, t.cx, t.cy, 0, t.z);
+            tma_load_4d(w + kWinY, maps->chroma, s_bar, t.cx, t.cy - (int)(lane & (phases >> 8)), 0, t.z);
     }
     if (warp == 0) {
         // complete_tx of boxes issued before this arrival is fine: the phase cannot complete before the
@@ -509,7 +516,7 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
             tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(P.block0 + lane * kCoefBox));
     }
 
-    process_block(P, s_coef, s_win, tid, s_bar, 0);
+    process_block(P, s_coef, s_win, tid, s_bar, 0, phases);
 }
 
 
@@ -531,7 +538,12 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
-    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
+    static uint32_t phases = 0xffffffffu;
+    if (phases == 0xffffffffu) {
+        const char* e = getenv("MPEGB200_WIN_PHASES");   // experiment switch: "0" stages every window at row 0
+        phases = (e && e[0] == '0') ? 0u : ((kLumaBoxRows - 17) | ((kChromaBoxRows - 9) << 8));
+    }
+    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
     return cudaGetLastError();
 }
 
