@@ -10,7 +10,8 @@ import subprocess
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmpegb200.so"
+# MPEGB200_LIB selects another build of the same library (A/B runs of kernel variants, tools/build_variants.sh)
+LIB_PATH = Path(os.environ["MPEGB200_LIB"]).resolve() if os.environ.get("MPEGB200_LIB") else PKG / "libmpegb200.so"
 
 
 class MpegB200Error(RuntimeError):

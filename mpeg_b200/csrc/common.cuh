@@ -36,7 +36,13 @@ static_assert(sizeof(StreamInfo) == 48, "StreamInfo layout");
 //           one box fetches the Cb and the Cr window of a macroblock together.
 // Box heights: 17 (9) rows of window plus 3 (1) rows of head-room for the per-macroblock row phase of the staging
 // (video_fused_tma.cu).
-constexpr int kLumaBoxRows = 20, kChromaBoxRows = 10;
+#ifndef MPEGB200_LUMA_BOX_ROWS
+#define MPEGB200_LUMA_BOX_ROWS 20
+#endif
+#ifndef MPEGB200_CHROMA_BOX_ROWS
+#define MPEGB200_CHROMA_BOX_ROWS 10
+#endif
+constexpr int kLumaBoxRows = MPEGB200_LUMA_BOX_ROWS, kChromaBoxRows = MPEGB200_CHROMA_BOX_ROWS;
 
 struct alignas(128) SlabMaps {
     unsigned char luma[128];

@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -164,9 +165,10 @@ constexpr int kCoefBox = 32;           // blocks per coefficient TMA box (32 x 1
 // and its chroma box (j & 1) rows above, so that the same window row of different macroblocks lands in
 // different shared-memory banks (a 32-byte row is 8 banks; without the phase the 32 block threads of a warp
 // all pulled their row from the same 8 banks: profiles/r1_final_video_summary.md).
-constexpr int kWinY = 32 * kLumaBoxRows, kWinC = 32 * kChromaBoxRows;   // luma box 32x20 = 640 B; chroma box: Cb 32x10 then Cr 32x10 = 640 B
-constexpr int kWinBytes = kWinY + 2 * kWinC;       // 1280 per macroblock, both boxes 128-byte aligned
-constexpr int kWinTx = kWinBytes;                  // bytes the two boxes deliver
+constexpr int kWinY = (32 * kLumaBoxRows + 127) / 128 * 128;          // luma box 32x20 = 640 B
+constexpr int kWinC = 32 * kChromaBoxRows;                            // chroma box: Cb 32x10 then Cr 32x10 = 640 B
+constexpr int kWinBytes = kWinY + (2 * kWinC + 127) / 128 * 128;      // 1280 per macroblock, both boxes 128-byte aligned
+constexpr int kWinTx = 32 * kLumaBoxRows + 2 * kWinC;                 // bytes the two boxes deliver
 
 // ------------------------------------------------------------------------------------------------
 // Group plan: everything a CTA needs to know about its kG records, computed once by a pre-pass
@@ -352,36 +354,50 @@ struct Smem {
     static constexpr int total = bar + 16;
 };
 
-// One output block: interpolate, IDCT, add, saturate, store.  `t` = index into the plan's block list.
-__device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t* s_coef, const uint8_t* s_win, int t,
-                                              uint64_t* bar, uint32_t parity, uint32_t phases) {
-    const uint32_t e = P.map[t];
-    if (e == kNoBlock) return;
-    const int j = e & 15, k = (e >> 4) & 7;
-    const bool coded = e & 0x80u;
-    const PlanMb& cx = P.mb[j];
-    const uint32_t mcb = (uint32_t)(cx.mcw >> (k < 4 ? 0 : 8)) & 0xffu;
-    const bool pred = mcb & 0x80u;
+// One output block in three steps, so that a kernel can put a barrier between the part that reads shared memory
+// and the part that only works on registers:
+//   block_setup : the block-list entry -> destination, window address, mode (reads the plan)
+//   block_load  : interpolate the prediction from the staged window, fetch + premultiply the coefficients
+//   block_finish: IDCT, add, saturate, store
+struct BlockCtx {
     uint8_t* dst;
     uint32_t pitch;
-    if (k < 4) {
-        pitch = cx.luma_w;
-        dst = cx.dst_y + (size_t)((k >> 1) * 8) * pitch + (k & 1) * 8;
-    } else {
-        pitch = cx.luma_w >> 1;
-        dst = cx.dst_y + cx.dst_c_off + (k == 5 ? pitch * (uint32_t)cx.chroma_h : 0u);
-    }
-    mbar_wait(bar, parity);   // all tiles of the group have landed
+    uint32_t win;      // byte offset of the block's pixel (0,0) in the window area
+    uint32_t slot;     // coefficient slot in the tile
+    uint32_t mode;     // bit 0 horizontal, bit 1 vertical half-pel
+    bool live, pred, coded;
+};
 
+__device__ __forceinline__ void block_setup(const GroupPlan& P, int t, uint32_t phases, BlockCtx& B) {
+    const uint32_t e = P.map[t];
+    B.live = e != kNoBlock;
+    const int j = e & 15, k = (e >> 4) & 7;
+    B.coded = B.live && (e & 0x80u);
+    B.slot = e >> 8;
+    const PlanMb& cx = P.mb[j];
+    const uint32_t mcb = (uint32_t)(cx.mcw >> (k < 4 ? 0 : 8)) & 0xffu;
+    B.pred = B.live && (mcb & 0x80u);
+    B.mode = (mcb >> 4) & 3u;
+    if (k < 4) {
+        B.pitch = cx.luma_w;
+        B.dst = cx.dst_y + (size_t)((k >> 1) * 8) * B.pitch + (k & 1) * 8;
+    } else {
+        B.pitch = cx.luma_w >> 1;
+        B.dst = cx.dst_y + cx.dst_c_off + (k == 5 ? B.pitch * (uint32_t)cx.chroma_h : 0u);
+    }
+    const uint32_t ph = (uint32_t)j & (k < 4 ? phases & 0xffu : phases >> 8);
+    B.win = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + ph * 32 + (mcb & 15u);
+}
+
+__device__ __forceinline__ void block_load(const BlockCtx& B, const uint8_t* s_coef, const uint8_t* s_win,
+                                           uint32_t (&p0)[8], uint32_t (&p1)[8], int (&c)[64]) {
     // prediction: eight rows of eight bytes, straight from the staged window (video_noasm.go:44-80)
-    uint32_t p0[8], p1[8];
-    if (pred) {
+    if (B.pred) {
         // s_win is 128-byte aligned, so the byte offset decides the word alignment
-        const uint32_t ph = (uint32_t)j & (k < 4 ? phases & 0xffu : phases >> 8);
-        const uint32_t a = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + ph * 32 + (mcb & 15u);
+        const uint32_t a = B.win;
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_win + (a & ~3u));
         const uint32_t sh = (a & 3u) * 8;
-        const uint32_t mode = (mcb >> 4) & 3u;
+        const uint32_t mode = B.mode;
 #define LOAD_ROW(R, W0, W1, W2) \
     do {                        \
         W0 = wp[(R) * 8];       \
@@ -434,16 +450,8 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
         }
 #undef LOAD_ROW
     }
-
-    if (!coded) {  // predicted block without residual: the prediction is the result (skipped / cbp bit clear)
-#pragma unroll
-        for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) = make_uint2(p0[r], p1[r]);
-        return;
-    }
-
-    int c[64];
-    {
-        const int slot = e >> 8;
+    if (B.coded) {
+        const int slot = (int)B.slot;
         const uint8_t* src = s_coef + slot * 128;
         const int sw = (slot & 7) << 4;  // 128-byte swizzle: 16-byte chunk index ^= row index mod 8
 #pragma unroll
@@ -457,6 +465,17 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
             }
         }
     }
+}
+
+__device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (&p0)[8], const uint32_t (&p1)[8], int (&c)[64]) {
+    if (!B.live) return;
+    uint8_t* dst = B.dst;
+    const uint32_t pitch = B.pitch;
+    if (!B.coded) {  // predicted block without residual: the prediction is the result (skipped / cbp bit clear)
+#pragma unroll
+        for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) = make_uint2(p0[r], p1[r]);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++)  // columns, video.go:869-896
         idct_pass8(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
@@ -464,7 +483,7 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
     for (int r = 0; r < 8; r++) {  // rows, video.go:899-926, then copy/addBlockToDest (:943-971)
         int v[8];
         idct_row8(&c[r * 8], v);
-        if (pred) {
+        if (B.pred) {
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 v[x] = (int)__dp4a(p0[r], 1u << (8 * x), (uint32_t)v[x]);
@@ -474,6 +493,18 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
         *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) =
             make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
     }
+}
+
+__device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t* s_coef, const uint8_t* s_win, int t,
+                                              uint64_t* bar, uint32_t parity, uint32_t phases) {
+    BlockCtx B;
+    block_setup(P, t, phases, B);
+    if (!B.live) return;
+    mbar_wait(bar, parity);   // all tiles of the group have landed
+    uint32_t p0[8], p1[8];
+    int c[64];
+    block_load(B, s_coef, s_win, p0, p1, c);
+    block_finish(B, p0, p1, c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -520,6 +551,103 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant: the registers are the second pipeline stage.  A thread needs shared memory only until its
+// prediction (16 registers) and its premultiplied coefficients (64 registers) are loaded -- about a quarter of
+// its work; the IDCT, the add and the stores run on registers.  So each CTA walks over groups b, b + grid, ...
+// and, as soon as all its threads have left the load step of group i, the tiles of group i + 1 are fetched
+// into the SAME shared memory while the IDCT of group i runs.  The load latency (plan -> TMA issue -> DRAM)
+// that the one-shot kernel pays per CTA with idle warps is hidden behind arithmetic, at unchanged shared memory
+// and register footprint (6 CTAs per SM).  Plans are double-buffered and fetched two groups ahead with a bulk copy.
+// ------------------------------------------------------------------------------------------------
+struct SmemP {
+    static constexpr int coef = 0;
+    static constexpr int win = coef + kNT * 128;
+    static constexpr int plan = win + kG * kWinBytes;                 // 2 x 768
+    static constexpr int bar = plan + 2 * (int)sizeof(GroupPlan);     // full, plan[0], plan[1]
+    static constexpr int total = bar + 32;
+};
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the TMA boxes of one group: warp 0 the luma windows, warp 1 the chroma windows, warp 2 the coefficients
+__device__ __forceinline__ void issue_group(const GroupPlan& P, const CUtensorMap* coef_map, const SlabMaps* slab_maps,
+                                            uint8_t* s_coef, uint8_t* s_win, uint64_t* bar, int warp, int lane, uint32_t phases) {
+    if (warp < 2) {
+        if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
+            const PlanMb& t = P.mb[lane];
+            const SlabMaps* maps = slab_maps + t.slab;
+            uint8_t* w = s_win + lane * kWinBytes;
+            if (warp == 0)
+                tma_load_3d(w, maps->luma, bar, t.lx, t.ly - (int)(lane & (phases & 0xffu)), t.z);
+            else
+                tma_load_4d(w + kWinY, maps->chroma, bar, t.cx, t.cy - (int)(lane & (phases >> 8)), 0, t.z);
+        }
+    } else {
+        if (lane == 0) mbar_arrive_expect_tx(bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
+        if (lane < (int)P.n_box) tma_load_2d(s_coef + lane * (kCoefBox * 128), coef_map, bar, 0, (int)(P.block0 + lane * kCoefBox));
+    }
+}
+
+__global__ void __launch_bounds__(kNT, 6) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                          const SlabMaps* __restrict__ slab_maps,
+                                                          const GroupPlan* __restrict__ plans, uint32_t n_groups,
+                                                          uint32_t phases) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_coef = smem + SmemP::coef;
+    uint8_t* s_win = smem + SmemP::win;
+    GroupPlan* s_plan = reinterpret_cast<GroupPlan*>(smem + SmemP::plan);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SmemP::bar);
+    uint64_t* bar_plan = bar_full + 1;   // [2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t stride = gridDim.x;
+    uint32_t g = blockIdx.x;
+
+    if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        mbar_init(bar_full, 1);
+        mbar_init(bar_plan, 1);
+        mbar_init(bar_plan + 1, 1);
+        fence_barrier_init();
+        // the first two plans
+        mbar_arrive_expect_tx(bar_plan, (uint32_t)sizeof(GroupPlan));
+        bulk_load(&s_plan[0], plans + g, (uint32_t)sizeof(GroupPlan), bar_plan);
+        if (g + stride < n_groups) {
+            mbar_arrive_expect_tx(bar_plan + 1, (uint32_t)sizeof(GroupPlan));
+            bulk_load(&s_plan[1], plans + g + stride, (uint32_t)sizeof(GroupPlan), bar_plan + 1);
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar_plan, 0);
+    issue_group(s_plan[0], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane, phases);
+
+    for (uint32_t i = 0; g < n_groups; i++, g += stride) {
+        const uint32_t buf = i & 1;
+        const GroupPlan& P = s_plan[buf];
+        mbar_wait(bar_plan + buf, (i >> 1) & 1);
+        BlockCtx B;
+        block_setup(P, tid, phases, B);
+        uint32_t p0[8], p1[8];
+        int c[64];
+        mbar_wait(bar_full, i & 1);           // the group's tiles have landed
+        block_load(B, s_coef, s_win, p0, p1, c);
+        __syncthreads();                      // every thread has left shared memory: windows, coefficients, plan[buf]
+        if (g + stride < n_groups) {          // the next group's tiles, behind this group's arithmetic
+            mbar_wait(bar_plan + (buf ^ 1), ((i + 1) >> 1) & 1);
+            issue_group(s_plan[buf ^ 1], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane, phases);
+            if (tid == 64 && g + 2 * stride < n_groups) {   // and the plan after it
+                mbar_arrive_expect_tx(bar_plan + buf, (uint32_t)sizeof(GroupPlan));
+                bulk_load(&s_plan[buf], plans + g + 2 * stride, (uint32_t)sizeof(GroupPlan), bar_plan + buf);
+            }
+        }
+        block_finish(B, p0, p1, c);
+    }
+}
+
 }  // namespace
 
 size_t fused_plan_bytes(uint32_t n_mb) { return (size_t)((n_mb + kG - 1) / kG) * sizeof(GroupPlan); }
@@ -539,11 +667,28 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
     static uint32_t phases = 0xffffffffu;
+    static int variant = 0, stream_ctas = 0;
     if (phases == 0xffffffffu) {
         const char* e = getenv("MPEGB200_WIN_PHASES");   // experiment switch: "0" stages every window at row 0
         phases = (e && e[0] == '0') ? 0u : ((kLumaBoxRows - 17) | ((kChromaBoxRows - 9) << 8));
+        const char* v = getenv("MPEGB200_FUSED");        // "oneshot": one CTA per group (fused_tma_kernel)
+        variant = (v && strcmp(v, "oneshot") == 0) ? 0 : 1;
+        cudaError_t e2 = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemP::total);
+        if (e2 != cudaSuccess) return e2;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel, kNT, SmemP::total);
+        if (e2 != cudaSuccess) return e2;
+        stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
+        const char* c = getenv("MPEGB200_STREAM_CTAS");  // experiment switch: CTAs of the persistent kernel
+        if (c && atoi(c) > 0) stream_ctas = atoi(c);
     }
-    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
+    if (variant == 0)
+        fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
+    else
+        fused_stream_kernel<<<n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas, kNT, SmemP::total, stream>>>(
+            *reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, n_groups, phases);
     return cudaGetLastError();
 }
 
