@@ -6,7 +6,8 @@
 // re-aligning unaligned windows (profiles/r1_v1_fused_summary.md).  Here:
 //   * coefficients: one cp.async.bulk.tensor per 32 blocks, 128-byte swizzle, so that one thread per
 //     block reads its eight 16-byte rows bank-conflict free;
-//   * reference windows: two cp.async.bulk.tensor per predicted macroblock (32x17 luma; one rank-4 box
+//   * reference windows: two cp.async.bulk.tensor per predicted macroblock (32x20 luma: 17 rows of window + a row
+//     phase that spreads macroblocks over the shared-memory banks; one rank-4 box
 //     for 32x9 Cb + 32x9 Cr -- the TMA unit serves about one box per 46 cycles per SM however small, and that
 //     rate, not bytes or instructions, bounded the three-box version).  The TMA unit wants the innermost start coordinate on a 16-byte boundary (measured:
 //     tools/tma_probe.cu, an unaligned x raises "illegal instruction"), so the box starts at x & ~15
@@ -19,8 +20,6 @@
 // The arithmetic is the reference's, bit for bit.
 #include <cuda.h>
 
-#include <cstdlib>
-#include <cstring>
 
 #include "common.cuh"
 
@@ -162,11 +161,11 @@ constexpr int kG = 16;                 // macroblock records per CTA
 constexpr int kNT = 6 * kG;            // one thread per output block (8x8)
 constexpr int kCoefBox = 32;           // blocks per coefficient TMA box (32 x 128 B = 4 KiB)
 // Windows are staged with a per-macroblock row phase: macroblock j's luma box starts (j & 3) rows above its window
-// and its chroma box (j & 1) rows above, so that the same window row of different macroblocks lands in
+// (the phase masks follow from the box heights in common.cuh), so that the same window row of different macroblocks lands in
 // different shared-memory banks (a 32-byte row is 8 banks; without the phase the 32 block threads of a warp
 // all pulled their row from the same 8 banks: profiles/r1_final_video_summary.md).
 constexpr int kWinY = (32 * kLumaBoxRows + 127) / 128 * 128;          // luma box 32x20 = 640 B
-constexpr int kWinC = 32 * kChromaBoxRows;                            // chroma box: Cb 32x10 then Cr 32x10 = 640 B
+constexpr int kWinC = 32 * kChromaBoxRows;                            // chroma box: Cb 32x9 then Cr 32x9 = 576 B in 640
 constexpr int kWinBytes = kWinY + (2 * kWinC + 127) / 128 * 128;      // 1280 per macroblock, both boxes 128-byte aligned
 constexpr int kWinTx = 32 * kLumaBoxRows + 2 * kWinC;                 // bytes the two boxes deliver
 
@@ -551,102 +550,6 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Persistent variant: the registers are the second pipeline stage.  A thread needs shared memory only until its
-// prediction (16 registers) and its premultiplied coefficients (64 registers) are loaded -- about a quarter of
-// its work; the IDCT, the add and the stores run on registers.  So each CTA walks over groups b, b + grid, ...
-// and, as soon as all its threads have left the load step of group i, the tiles of group i + 1 are fetched
-// into the SAME shared memory while the IDCT of group i runs.  The load latency (plan -> TMA issue -> DRAM)
-// that the one-shot kernel pays per CTA with idle warps is hidden behind arithmetic, at unchanged shared memory
-// and register footprint (6 CTAs per SM).  Plans are double-buffered and fetched two groups ahead with a bulk copy.
-// ------------------------------------------------------------------------------------------------
-struct SmemP {
-    static constexpr int coef = 0;
-    static constexpr int win = coef + kNT * 128;
-    static constexpr int plan = win + kG * kWinBytes;                 // 2 x 768
-    static constexpr int bar = plan + 2 * (int)sizeof(GroupPlan);     // full, plan[0], plan[1]
-    static constexpr int total = bar + 32;
-};
-
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// the TMA boxes of one group: warp 0 the luma windows, warp 1 the chroma windows, warp 2 the coefficients
-__device__ __forceinline__ void issue_group(const GroupPlan& P, const CUtensorMap* coef_map, const SlabMaps* slab_maps,
-                                            uint8_t* s_coef, uint8_t* s_win, uint64_t* bar, int warp, int lane, uint32_t phases) {
-    if (warp < 2) {
-        if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
-            const PlanMb& t = P.mb[lane];
-            const SlabMaps* maps = slab_maps + t.slab;
-            uint8_t* w = s_win + lane * kWinBytes;
-            if (warp == 0)
-                tma_load_3d(w, maps->luma, bar, t.lx, t.ly - (int)(lane & (phases & 0xffu)), t.z);
-            else
-                tma_load_4d(w + kWinY, maps->chroma, bar, t.cx, t.cy - (int)(lane & (phases >> 8)), 0, t.z);
-        }
-    } else {
-        if (lane == 0) mbar_arrive_expect_tx(bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
-        if (lane < (int)P.n_box) tma_load_2d(s_coef + lane * (kCoefBox * 128), coef_map, bar, 0, (int)(P.block0 + lane * kCoefBox));
-    }
-}
-
-__global__ void __launch_bounds__(kNT, 6) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                          const SlabMaps* __restrict__ slab_maps,
-                                                          const GroupPlan* __restrict__ plans, uint32_t n_groups,
-                                                          uint32_t phases) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* s_coef = smem + SmemP::coef;
-    uint8_t* s_win = smem + SmemP::win;
-    GroupPlan* s_plan = reinterpret_cast<GroupPlan*>(smem + SmemP::plan);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SmemP::bar);
-    uint64_t* bar_plan = bar_full + 1;   // [2]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t stride = gridDim.x;
-    uint32_t g = blockIdx.x;
-
-    if (tid == 0) {
-        if (smem_u32(smem) & 1023u) __trap();
-        mbar_init(bar_full, 1);
-        mbar_init(bar_plan, 1);
-        mbar_init(bar_plan + 1, 1);
-        fence_barrier_init();
-        // the first two plans
-        mbar_arrive_expect_tx(bar_plan, (uint32_t)sizeof(GroupPlan));
-        bulk_load(&s_plan[0], plans + g, (uint32_t)sizeof(GroupPlan), bar_plan);
-        if (g + stride < n_groups) {
-            mbar_arrive_expect_tx(bar_plan + 1, (uint32_t)sizeof(GroupPlan));
-            bulk_load(&s_plan[1], plans + g + stride, (uint32_t)sizeof(GroupPlan), bar_plan + 1);
-        }
-    }
-    __syncthreads();
-    mbar_wait(bar_plan, 0);
-    issue_group(s_plan[0], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane, phases);
-
-    for (uint32_t i = 0; g < n_groups; i++, g += stride) {
-        const uint32_t buf = i & 1;
-        const GroupPlan& P = s_plan[buf];
-        mbar_wait(bar_plan + buf, (i >> 1) & 1);
-        BlockCtx B;
-        block_setup(P, tid, phases, B);
-        uint32_t p0[8], p1[8];
-        int c[64];
-        mbar_wait(bar_full, i & 1);           // the group's tiles have landed
-        block_load(B, s_coef, s_win, p0, p1, c);
-        __syncthreads();                      // every thread has left shared memory: windows, coefficients, plan[buf]
-        if (g + stride < n_groups) {          // the next group's tiles, behind this group's arithmetic
-            mbar_wait(bar_plan + (buf ^ 1), ((i + 1) >> 1) & 1);
-            issue_group(s_plan[buf ^ 1], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane, phases);
-            if (tid == 64 && g + 2 * stride < n_groups) {   // and the plan after it
-                mbar_arrive_expect_tx(bar_plan + buf, (uint32_t)sizeof(GroupPlan));
-                bulk_load(&s_plan[buf], plans + g + 2 * stride, (uint32_t)sizeof(GroupPlan), bar_plan + buf);
-            }
-        }
-        block_finish(B, p0, p1, c);
-    }
-}
 
 }  // namespace
 
@@ -666,29 +569,8 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
-    static uint32_t phases = 0xffffffffu;
-    static int variant = 0, stream_ctas = 0;
-    if (phases == 0xffffffffu) {
-        const char* e = getenv("MPEGB200_WIN_PHASES");   // experiment switch: "0" stages every window at row 0
-        phases = (e && e[0] == '0') ? 0u : ((kLumaBoxRows - 17) | ((kChromaBoxRows - 9) << 8));
-        const char* v = getenv("MPEGB200_FUSED");        // "oneshot": one CTA per group (fused_tma_kernel)
-        variant = (v && strcmp(v, "oneshot") == 0) ? 0 : 1;
-        cudaError_t e2 = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemP::total);
-        if (e2 != cudaSuccess) return e2;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel, kNT, SmemP::total);
-        if (e2 != cudaSuccess) return e2;
-        stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
-        const char* c = getenv("MPEGB200_STREAM_CTAS");  // experiment switch: CTAs of the persistent kernel
-        if (c && atoi(c) > 0) stream_ctas = atoi(c);
-    }
-    if (variant == 0)
-        fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
-    else
-        fused_stream_kernel<<<n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas, kNT, SmemP::total, stream>>>(
-            *reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, n_groups, phases);
+    constexpr uint32_t phases = (uint32_t)(kLumaBoxRows - 17) | ((uint32_t)(kChromaBoxRows - 9) << 8);
+    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
     return cudaGetLastError();
 }
 
