@@ -20,9 +20,6 @@
 // The arithmetic is the reference's, bit for bit.
 #include <cuda.h>
 
-#include <cstdlib>
-#include <cstring>
-
 
 #include "common.cuh"
 
@@ -553,194 +550,6 @@ __global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Two threads per output block.  The one-thread version holds 64 coefficients + 16 prediction words per
-// thread (95 registers -> 18 warps per SM) and runs at ~55 % of the issue slots: long dependent butterfly chains and
-// too few warps to cover them.  Here thread H of a pair owns columns 4H..4H+3 for the column pass and rows
-// 4H..4H+3 for the row pass; the 16 values each needs from the other travel through the block's own (dead)
-// coefficient slot in shared memory, with the tile's 128-byte swizzle so both directions are conflict free.
-// H is warp-uniform (warps 0-2: H = 0, warps 3-5: H = 1, partner warps w and w + 3 meet at a 64-thread named
-// barrier), so every H-dependent index below is a compile-time constant and nothing is selected at run time.
-// ------------------------------------------------------------------------------------------------
-constexpr int kNT2 = 2 * kNT;
-#ifndef MPEGB200_PAIR_CTAS
-#define MPEGB200_PAIR_CTAS 6
-#endif
-
-__device__ __forceinline__ void pair_barrier(int id) {  // literal ids, so that only four barriers are reserved per CTA
-    if (id == 1)
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-    else if (id == 2)
-        asm volatile("bar.sync 2, 64;" ::: "memory");
-    else
-        asm volatile("bar.sync 3, 64;" ::: "memory");
-}
-
-template <int H>
-__device__ __forceinline__ void pair_block(const BlockCtx& B, uint8_t* s_coef, const uint8_t* s_win, int bar_id) {
-    // prediction rows 4H..4H+3 (video_noasm.go:44-80)
-    uint32_t p0[4], p1[4];
-    if (B.pred) {
-        const uint32_t a = B.win + 4 * H * 32;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_win + (a & ~3u));
-        const uint32_t sh = (a & 3u) * 8;
-#define LOAD_ROW(R, W0, W1, W2) \
-    do {                        \
-        W0 = wp[(R) * 8];       \
-        W1 = wp[(R) * 8 + 1];   \
-        W2 = wp[(R) * 8 + 2];   \
-    } while (0)
-        if (B.mode == 0) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                uint32_t w0, w1, w2;
-                LOAD_ROW(r, w0, w1, w2);
-                p0[r] = __funnelshift_rc(w0, w1, sh);
-                p1[r] = __funnelshift_rc(w1, w2, sh);
-            }
-        } else if (B.mode == 1) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                uint32_t w0, w1, w2;
-                LOAD_ROW(r, w0, w1, w2);
-                p0[r] = avg2(__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w0, w1, sh + 8));
-                p1[r] = avg2(__funnelshift_rc(w1, w2, sh), __funnelshift_rc(w1, w2, sh + 8));
-            }
-        } else if (B.mode == 2) {
-            uint32_t w0, w1, w2;
-            LOAD_ROW(0, w0, w1, w2);
-            uint32_t u0 = __funnelshift_rc(w0, w1, sh), u1 = __funnelshift_rc(w1, w2, sh);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                LOAD_ROW(r + 1, w0, w1, w2);
-                const uint32_t n0 = __funnelshift_rc(w0, w1, sh), n1 = __funnelshift_rc(w1, w2, sh);
-                p0[r] = avg2(u0, n0);
-                p1[r] = avg2(u1, n1);
-                u0 = n0;
-                u1 = n1;
-            }
-        } else {
-            uint32_t w0, w1, w2;
-            LOAD_ROW(0, w0, w1, w2);
-            uint32_t u0 = __funnelshift_rc(w0, w1, sh), u1 = __funnelshift_rc(w1, w2, sh);
-            uint32_t s0 = __funnelshift_rc(w0, w1, sh + 8), s1 = __funnelshift_rc(w1, w2, sh + 8);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                LOAD_ROW(r + 1, w0, w1, w2);
-                const uint32_t n0 = __funnelshift_rc(w0, w1, sh), n1 = __funnelshift_rc(w1, w2, sh);
-                const uint32_t t0 = __funnelshift_rc(w0, w1, sh + 8), t1 = __funnelshift_rc(w1, w2, sh + 8);
-                p0[r] = avg4(u0, s0, n0, t0);
-                p1[r] = avg4(u1, s1, n1, t1);
-                u0 = n0; u1 = n1; s0 = t0; s1 = t1;
-            }
-        }
-#undef LOAD_ROW
-    }
-
-    uint8_t* dst = B.dst + (size_t)(4 * H) * B.pitch;
-    const uint32_t pitch = B.pitch;
-    int c[32];   // c[r * 4 + x]: row r, column 4H + x
-    uint8_t* slot = s_coef + (B.slot & 127u) * 128;
-    const int sw = (int)(B.slot & 7u) << 4;  // 128-byte swizzle: 16-byte chunk index ^= row index mod 8
-    if (B.coded) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) {  // level * premultiplier (video.go:744) straight from the int16 pairs
-            const uint2 w = *reinterpret_cast<const uint2*>(slot + ((r << 4) ^ sw) + 8 * H);
-            c[r * 4 + 0] = __dp2a_lo((int)w.x, premult(r * 8 + 4 * H + 0), 0);
-            c[r * 4 + 1] = __dp2a_lo((int)w.x, premult(r * 8 + 4 * H + 1) << 8, 0);
-            c[r * 4 + 2] = __dp2a_lo((int)w.y, premult(r * 8 + 4 * H + 2), 0);
-            c[r * 4 + 3] = __dp2a_lo((int)w.y, premult(r * 8 + 4 * H + 3) << 8, 0);
-        }
-#pragma unroll
-        for (int x = 0; x < 4; x++)  // columns, video.go:869-896
-            idct_pass8(c[x], c[4 + x], c[8 + x], c[12 + x], c[16 + x], c[20 + x], c[24 + x], c[28 + x]);
-    }
-    pair_barrier(bar_id);   // both halves have read the slot's coefficients
-    if (B.coded) {
-        // hand the partner the rows it transforms: H = 0 gives rows 4..7 (chunks 0..3), H = 1 rows 0..3 (chunks 4..7)
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int row = (H == 0 ? 4 : 0) + r;
-            *reinterpret_cast<int4*>(slot + (((4 * H + r) << 4) ^ sw)) =
-                make_int4(c[row * 4], c[row * 4 + 1], c[row * 4 + 2], c[row * 4 + 3]);
-        }
-    }
-    pair_barrier(bar_id);
-    if (!B.live) return;
-    if (!B.coded) {  // predicted block without residual: the prediction is the result (skipped / cbp bit clear)
-#pragma unroll
-        for (int r = 0; r < 4; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) = make_uint2(p0[r], p1[r]);
-        return;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {  // rows 4H + r, video.go:899-926, then copy/addBlockToDest (:943-971)
-        const int4 o = *reinterpret_cast<const int4*>(slot + (((4 * (1 - H) + r) << 4) ^ sw));
-        const int row = 4 * H + r;
-        int s[8], v[8];
-        if (H == 0) {
-            s[0] = c[row * 4]; s[1] = c[row * 4 + 1]; s[2] = c[row * 4 + 2]; s[3] = c[row * 4 + 3];
-            s[4] = o.x; s[5] = o.y; s[6] = o.z; s[7] = o.w;
-        } else {
-            s[0] = o.x; s[1] = o.y; s[2] = o.z; s[3] = o.w;
-            s[4] = c[row * 4]; s[5] = c[row * 4 + 1]; s[6] = c[row * 4 + 2]; s[7] = c[row * 4 + 3];
-        }
-        idct_row8(s, v);
-        if (B.pred) {
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                v[x] = (int)__dp4a(p0[r], 1u << (8 * x), (uint32_t)v[x]);
-                v[4 + x] = (int)__dp4a(p1[r], 1u << (8 * x), (uint32_t)v[4 + x]);
-            }
-        }
-        *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) =
-            make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
-    }
-}
-
-__global__ void __launch_bounds__(kNT2, MPEGB200_PAIR_CTAS) fused_pair_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                                             const SlabMaps* __restrict__ slab_maps,
-                                                                             const GroupPlan* __restrict__ plans, uint32_t phases) {
-    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
-    uint8_t* s_coef = smem + Smem::coef;
-    uint8_t* s_win = smem + Smem::win;
-    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid < 48) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
-    if (tid == 64) {
-        if (smem_u32(smem) & 1023u) __trap();
-        mbar_init(s_bar, 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-
-    if (warp < 2 && lane < kG && (P.mb[lane].mcw & 0x80u)) {
-        const PlanMb& t = P.mb[lane];
-        const SlabMaps* maps = slab_maps + t.slab;
-        uint8_t* w = s_win + lane * kWinBytes;
-        if (warp == 0)
-            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly - (int)(lane & (phases & 0xffu)), t.z);
-        else  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
-            tma_load_4d(w + kWinY, maps->chroma, s_bar, t.cx, t.cy - (int)(lane & (phases >> 8)), 0, t.z);
-    }
-    if (warp == 2) {
-        if (lane == 0) mbar_arrive_expect_tx(s_bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
-        if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
-            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(P.block0 + lane * kCoefBox));
-    }
-
-    const int h = warp >= 3;                 // warp-uniform half
-    BlockCtx B;
-    block_setup(P, tid - h * kNT, phases, B);
-    mbar_wait(s_bar, 0);                     // all tiles of the group have landed
-    const int bar_id = 1 + (warp - 3 * h);   // partner warps w and w + 3
-    if (h == 0)
-        pair_block<0>(B, s_coef, s_win, bar_id);
-    else
-        pair_block<1>(B, s_coef, s_win, bar_id);
-}
-
 }  // namespace
 
 size_t fused_plan_bytes(uint32_t n_mb) { return (size_t)((n_mb + kG - 1) / kG) * sizeof(GroupPlan); }
@@ -760,17 +569,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
     constexpr uint32_t phases = (uint32_t)(kLumaBoxRows - 17) | ((uint32_t)(kChromaBoxRows - 9) << 8);
-    static int variant = -1;
-    if (variant < 0) {
-        const char* v = getenv("MPEGB200_FUSED");   // experiment switch: "single" = one thread per block
-        variant = (v && strcmp(v, "single") == 0) ? 0 : 1;
-        cudaError_t e = cudaFuncSetAttribute(fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
-        if (e != cudaSuccess) return e;
-    }
-    if (variant == 0)
-        fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
-    else
-        fused_pair_kernel<<<n_groups, kNT2, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
+    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
     return cudaGetLastError();
 }
 
