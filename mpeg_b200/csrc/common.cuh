@@ -44,9 +44,17 @@ static_assert(sizeof(StreamInfo) == 48, "StreamInfo layout");
 #endif
 constexpr int kLumaBoxRows = MPEGB200_LUMA_BOX_ROWS, kChromaBoxRows = MPEGB200_CHROMA_BOX_ROWS;
 
+// Strip maps: the same two tensors seen as 8-byte elements (box dimensions are limited to 256 ELEMENTS, so the
+// wider element buys a 304-byte wide box): one box holds every window of a group of 16 neighbouring macroblocks
+// whose vectors stay within +-16 pixels (video_fused_tma.cu, strip mode).
+constexpr int kStripLW = 304, kStripLH = 48;   // luma strip: 16*16 + 32 (vector range) + 1 + 15 (alignment) x 16 + 32
+constexpr int kStripCW = 160, kStripCH = 24;   // chroma strip (per plane): 8*16 + 16 + 1 + 15 x 8 + 16
+
 struct alignas(128) SlabMaps {
     unsigned char luma[128];
     unsigned char chroma[128];
+    unsigned char luma_strip[128];
+    unsigned char chroma_strip[128];
 };
 
 // Per-stream MP2 synthesis state in the reference's own form (audio.go:63,78).

@@ -302,6 +302,26 @@ static bool encode_slab_maps(mpegb200_ctx* ctx, const Slab& sl, const HostStream
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return false;
     }
+    // the strip maps: same bytes, 8-byte elements (luma_w + 32 and chroma_w + 32 are multiples of 8)
+    {
+        const cuuint64_t dims[3] = {((cuuint64_t)g.luma_w + 32) / 8, sl.buf_stride / g.luma_w, (cuuint64_t)3 * sl.capacity};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.luma_w, sl.buf_stride};
+        const cuuint32_t box[3] = {kStripLW / 8, kStripLH, 1};
+        if (enc((CUtensorMap*)out->luma_strip, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, sl.dev, dims, strides, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    {
+        const cuuint64_t dims[4] = {((cuuint64_t)g.chroma_w + 32) / 8, (sl.buf_stride - g.luma_bytes - g.chroma_bytes) / g.chroma_w, 2,
+                                    (cuuint64_t)3 * sl.capacity};
+        const cuuint64_t strides[3] = {(cuuint64_t)g.chroma_w, g.chroma_bytes, sl.buf_stride};
+        const cuuint32_t box[4] = {kStripCW / 8, kStripCH, 2, 1}, ones4[4] = {1, 1, 1, 1};
+        if (enc((CUtensorMap*)out->chroma_strip, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, sl.dev + g.luma_bytes, dims, strides, box,
+                ones4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
     return true;
 }
 

@@ -20,6 +20,11 @@
 // The arithmetic is the reference's, bit for bit.
 #include <cuda.h>
 
+#include <climits>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+
 
 #include "common.cuh"
 
@@ -119,8 +124,9 @@ __device__ __forceinline__ void idct_pass8(int& s0, int& s1, int& s2, int& s3, i
     s7 = y4 - b7;
 }
 
-// row pass with the final (x + 128) >> 8 of video.go:918-925 folded into the last additions
-__device__ __forceinline__ void idct_row8(const int* s, int* o) {
+// row pass, video.go:899-926; the caller has put the +128 on the DC term and passes k[i] = prediction << 8, so
+// o[i] = 256 * (result before the final >> 8) + low bits; the shift happens in the saturating pack
+__device__ __forceinline__ void idct_row8(const int* s, const int* k, int* o) {
     const int b1 = s[4];
     const int b3 = s[2] + s[6];
     const int b4 = s[5] - s[3];
@@ -139,35 +145,43 @@ __device__ __forceinline__ void idct_row8(const int* s, int* o) {
     const int y5 = x1 - x2;
     const int y6 = x3 - b3;
     const int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
-    o[0] = (b7 + y4 + 128) >> 8;
-    o[1] = (x4 + y3 + 128) >> 8;
-    o[2] = (y5 - x0 + 128) >> 8;
-    o[3] = (y6 - y7 + 128) >> 8;
-    o[4] = (y6 + y7 + 128) >> 8;
-    o[5] = (x0 + y5 + 128) >> 8;
-    o[6] = (y3 - x4 + 128) >> 8;
-    o[7] = (y4 - b7 + 128) >> 8;
+    o[0] = b7 + y4 + k[0];
+    o[1] = x4 + y3 + k[1];
+    o[2] = y5 - x0 + k[2];
+    o[3] = y6 - y7 + k[3];
+    o[4] = y6 + y7 + k[4];
+    o[5] = x0 + y5 + k[5];
+    o[6] = y3 - x4 + k[6];
+    o[7] = y4 - b7 + k[7];
 }
 
 __device__ __forceinline__ uint32_t avg2(uint32_t a, uint32_t b) { return __vavgu4(a, b); }  // (a+b+1)>>1 per byte
-__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {  // (a+b+c+d+2)>>2 per byte
-    const uint32_t m = 0x00ff00ffu;
-    const uint32_t lo = (((a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u) >> 2) & m;
-    const uint32_t hi = ((((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u) >> 2) & m;
-    return lo | (hi << 8);
-}
 
 constexpr int kG = 16;                 // macroblock records per CTA
 constexpr int kNT = 6 * kG;            // one thread per output block (8x8)
 constexpr int kCoefBox = 32;           // blocks per coefficient TMA box (32 x 128 B = 4 KiB)
-// Windows are staged with a per-macroblock row phase: macroblock j's luma box starts (j & 3) rows above its window
-// (the phase masks follow from the box heights in common.cuh), so that the same window row of different macroblocks lands in
-// different shared-memory banks (a 32-byte row is 8 banks; without the phase the 32 block threads of a warp
-// all pulled their row from the same 8 banks: profiles/r1_final_video_summary.md).
+
+// Two ways to stage the reference windows of a group (the plan pre-pass picks one per group):
+//  * strip mode: when every predicted macroblock of the group reads the same reference buffer and all windows fit a
+//    304x48 luma / 160x24 chroma rectangle (16 neighbouring macroblocks with vectors within +-16 pixels do), the
+//    whole rectangle comes in with ONE luma box and ONE rank-4 chroma box.  The TMA unit serves about one box per
+//    46 cycles per SM however small (profiles/r1_final_video_summary.md); two boxes per macroblock made the box
+//    rate, not bytes or instructions, the limit of the predicted steps.  Overlapping parts of neighbouring strips
+//    are L2 hits, DRAM traffic stays the algorithmic one.
+//  * box mode (any vectors, any record order): two boxes per predicted macroblock (32x20 luma, 32x9 Cb + 32x9 Cr),
+//    staged with a per-macroblock row phase (macroblock j's luma box starts (j & 3) rows above its window) so that
+//    the same window row of different macroblocks lands in different shared-memory banks.
+// Either way a block thread sees: byte offset of its pixel (0,0) in the window area + a row pitch.
 constexpr int kWinY = (32 * kLumaBoxRows + 127) / 128 * 128;          // luma box 32x20 = 640 B
 constexpr int kWinC = 32 * kChromaBoxRows;                            // chroma box: Cb 32x9 then Cr 32x9 = 576 B in 640
 constexpr int kWinBytes = kWinY + (2 * kWinC + 127) / 128 * 128;      // 1280 per macroblock, both boxes 128-byte aligned
 constexpr int kWinTx = 32 * kLumaBoxRows + 2 * kWinC;                 // bytes the two boxes deliver
+constexpr uint32_t kPhaseY = (uint32_t)(kLumaBoxRows - 17), kPhaseC = (uint32_t)(kChromaBoxRows - 9);  // masks: 3 / 0
+constexpr int kStripLBytes = kStripLW * kStripLH;                     // 14592
+constexpr int kStripCBytes = kStripCW * kStripCH;                     // 3840 per plane
+constexpr int kStripTx = kStripLBytes + 2 * kStripCBytes;             // 22272
+constexpr int kWinArea = (kG * kWinBytes > kStripTx ? kG * kWinBytes : kStripTx + 127) / 128 * 128;
+constexpr int kStripMinPred = 3;       // fewer predicted macroblocks than this: their own boxes are cheaper
 
 // ------------------------------------------------------------------------------------------------
 // Group plan: everything a CTA needs to know about its kG records, computed once by a pre-pass
@@ -176,55 +190,77 @@ constexpr int kWinTx = 32 * kLumaBoxRows + 2 * kWinC;                 // bytes t
 // ------------------------------------------------------------------------------------------------
 struct PlanMb {               // 32 bytes
     uint8_t* dst_y;           // destination of the macroblock's luma (row 0, col 0 of the MB)
-    uint32_t dst_c_off;       // Cb destination = dst_y + dst_c_off; Cr at + (luma_w/2) * chroma_h
-    uint16_t luma_w, chroma_h;
-    uint16_t mcw;             // byte 0 luma, byte 1 chroma: (x & 15) | mode << 4 | 0x80 if predicted;
+    uint32_t dst_c_off;       // Cb destination = dst_y + dst_c_off
+    uint32_t dst_cr_off;      // Cr destination = Cb destination + dst_cr_off
+    uint16_t luma_w;
+    uint16_t mcw;             // byte 0 luma, byte 1 chroma: mode << 4 | 0x80 if predicted;
                               // mode bit 0 = horizontal half-pel, bit 1 = vertical half-pel
-    uint16_t slab;            // tensor-map pair of the stream's slab
-    int16_t lx, ly, cx, cy;   // box origins (x folded into [0, pitch) and aligned down to 16)
-    uint16_t z;               // 3 * slot + reference buffer
-    uint16_t pad;
+    uint16_t woff_y, woff_c;  // byte offset of luma / Cb pixel (0,0) of the staged window in the window area
+    uint32_t pad[2];
 };
 static_assert(sizeof(PlanMb) == 32, "PlanMb size");
 
-struct GroupPlan {            // 768 bytes = 48 x 16
-    uint32_t n_box, n_pred, block0, pad0;
+struct PlanBox {              // 16 bytes, box mode only: where the two boxes of a macroblock come from
+    int16_t lx, ly, cx, cy;   // box origins (x folded into [0, pitch) and aligned down to 16, y minus the row phase)
+    uint16_t z;               // 3 * slot + reference buffer
+    uint16_t slab;            // tensor-map set of the stream's slab
+    uint16_t pred;            // 1 if the macroblock has windows
+    uint16_t pad;
+};
+static_assert(sizeof(PlanBox) == 16, "PlanBox size");
+
+struct GroupPlan {            // 1024 bytes = 64 x 16
+    uint32_t n_box, n_pred, block0, tx_bytes;   // coefficient boxes, predicted macroblocks, first block, expect_tx
+    uint16_t strip, slab, z;                    // strip mode: one luma + one chroma box at (sx, sy) / (scx, scy)
+    uint16_t pitch_y, pitch_c, cr_win;          // window row pitches; Cb -> Cr window distance
+    int16_t sx, sy, scx, scy;                   // strip origins in bytes / rows (x multiples of 16)
+    uint32_t pad0[3];
     uint16_t map[kNT];        // output-block list, sorted by (coded?, interpolation mode)
     PlanMb mb[kG];
-    uint8_t pad1[768 - 16 - 2 * kNT - 32 * kG];
+    uint8_t pad1[16];
+    PlanBox box[kG];
 };
-static_assert(sizeof(GroupPlan) == 768, "GroupPlan size");
+static_assert(sizeof(GroupPlan) == 1024, "GroupPlan size");
+static_assert(offsetof(GroupPlan, box) == 768, "the boxes are the last quarter");
 
 // Output-block list entry: [3:0] macroblock in group, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
 constexpr uint32_t kNoBlock = 0xFFFFu;
 
 constexpr int kPlanGroupsPerCta = 8;   // 16 lanes per group
 
+// reductions of the plan pre-pass, one row per group
+enum { R_MINLX, R_MAXLX, R_MINLY, R_MAXLY, R_MINCX, R_MAXCX, R_MINCY, R_MAXCY, R_MINZ, R_MAXZ, R_LW, R_N };
+
 __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan* __restrict__ plans,
                                                                      const StreamInfo* __restrict__ streams,
                                                                      int max_streams,
                                                                      const mpegb200_picture* __restrict__ pics,
                                                                      int n_pics, const mpegb200_mb* __restrict__ mbs,
-                                                                     uint32_t n_mb, uint32_t n_blocks) {
+                                                                     uint32_t n_mb, uint32_t n_blocks, int allow_strip) {
     __shared__ __align__(16) GroupPlan s_plan[kPlanGroupsPerCta];
     __shared__ uint32_t s_cnt[kPlanGroupsPerCta][10];  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
+    __shared__ int s_red[kPlanGroupsPerCta][R_N];
     const int tid = threadIdx.x, gl = tid >> 4, lane = tid & 15;
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     const uint32_t group = blockIdx.x * kPlanGroupsPerCta + gl;
     GroupPlan& P = s_plan[gl];
-    for (int i = lane; i < kNT; i += 16) P.map[i] = (uint16_t)kNoBlock;
-    if (lane < 10) s_cnt[gl][lane] = 0;
     {
-        PlanMb z;
-        memset(&z, 0, sizeof(z));
-        P.mb[lane] = z;
+        uint4* z = reinterpret_cast<uint4*>(&P);
+        for (int i = lane; i < (int)(sizeof(GroupPlan) / 16); i += 16) z[i] = make_uint4(0, 0, 0, 0);
     }
+    if (lane < 10) s_cnt[gl][lane] = 0;
+    if (lane < R_N) s_red[gl][lane] = ((lane & 1) || lane == R_LW) ? INT_MIN : INT_MAX;   // even slots are minima, odd ones (and R_LW) maxima
     __syncthreads();
+    for (int i = lane; i < kNT; i += 16) P.map[i] = (uint16_t)kNoBlock;
 
     const uint32_t m0 = group * (uint32_t)kG;
     const bool have = group < n_groups && m0 + lane < n_mb;
     uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0;
     uint32_t block0 = 0;
+    bool predicted = false;
+    int lx = 0, ly = 0, cx = 0, cy = 0, lw = 0, zslab = 0;
+    PlanMb c;
+    memset(&c, 0, sizeof(c));
     if (group < n_groups) block0 = mbs[m0].coeff_block;
     if (have) {
         const uint4 raw = reinterpret_cast<const uint4*>(mbs)[m0 + lane];
@@ -245,49 +281,35 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                 const uint32_t rel = cblock - block0;
                 if (ncoded) ok = ok && rel <= (uint32_t)kNT && rel + ncoded <= (uint32_t)kNT && cblock + ncoded <= n_blocks;
                 if (ok) {
-                    const uint32_t lw = si.luma_w, cw = lw >> 1;
+                    lw = si.luma_w;
+                    const uint32_t cw = (uint32_t)lw >> 1;
                     uint8_t* dst = si.base + (size_t)dst_b * si.buf_stride;
-                    PlanMb c;
-                    memset(&c, 0, sizeof(c));
                     c.dst_y = dst + (size_t)(row << 4) * lw + (col << 4);
                     c.dst_c_off = (uint32_t)((size_t)lw * si.luma_h + (size_t)(row << 3) * cw + (col << 3) -
                                              ((size_t)(row << 4) * lw + (col << 4)));
+                    c.dst_cr_off = cw * (uint32_t)(si.luma_h >> 1);
                     c.luma_w = (uint16_t)lw;
-                    c.chroma_h = (uint16_t)(si.luma_h >> 1);
-                    c.slab = si.slab;
-                    const bool predicted = (flags & MPEGB200_MB_PREDICT) != 0 && !(flags & MPEGB200_MB_INTRA);
+                    predicted = (flags & MPEGB200_MB_PREDICT) != 0 && !(flags & MPEGB200_MB_INTRA);
                     uint32_t mode_y = 0, mode_c = 0;
-                    if (predicted) {  // window origins, video_noasm.go:29-42
-                        int lx = (int)(col << 4) + (mv_h >> 1);
-                        int ly = (int)(row << 4) + (mv_v >> 1);
+                    if (predicted) {  // window origins, video_noasm.go:29-42 (not yet folded into the row)
+                        lx = (int)(col << 4) + (mv_h >> 1);
+                        ly = (int)(row << 4) + (mv_v >> 1);
                         const int cmh = mv_h / 2, cmv = mv_v / 2;  // toward zero
-                        int cx = (int)(col << 3) + (cmh >> 1);
-                        int cy = (int)(row << 3) + (cmv >> 1);
-                        // The reference indexes linearly (si = y*stride + x, video_noasm.go:31,39), so a window
-                        // starting left of column 0 really starts near the end of the row above.  Fold x into
-                        // [0, pitch): same bytes, and inside the tensor's (overlapping) rows.
-                        {
-                            int q = lx / (int)lw, r = lx - q * (int)lw;
-                            if (r < 0) { r += (int)lw; q--; }
-                            lx = r;
-                            ly += q;
-                            q = cx / (int)cw;
-                            r = cx - q * (int)cw;
-                            if (r < 0) { r += (int)cw; q--; }
-                            cx = r;
-                            cy += q;
-                        }
+                        cx = (int)(col << 3) + (cmh >> 1);
+                        cy = (int)(row << 3) + (cmv >> 1);
                         mode_y = (uint32_t)((mv_h & 1) | ((mv_v & 1) << 1));
                         mode_c = (uint32_t)((cmh & 1) | ((cmv & 1) << 1));
-                        c.mcw = (uint16_t)(((lx & 15) | (mode_y << 4) | 0x80) | (((cx & 15) | (mode_c << 4) | 0x80) << 8));
-                        c.lx = (int16_t)(lx & ~15);  // the TMA unit needs x on a 16-byte boundary
-                        c.ly = (int16_t)ly;
-                        c.cx = (int16_t)(cx & ~15);
-                        c.cy = (int16_t)cy;
-                        c.z = (uint16_t)(si.slot * 3 + ((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b));
+                        c.mcw = (uint16_t)(((mode_y << 4) | 0x80) | (((mode_c << 4) | 0x80) << 8));
+                        zslab = (int)(((uint32_t)si.slab << 16) | (uint32_t)(si.slot * 3 + ((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b)));
                         atomicAdd(&s_cnt[gl][9], 1u);
+                        int* R = s_red[gl];
+                        atomicMin(&R[R_MINLX], lx); atomicMax(&R[R_MAXLX], lx);
+                        atomicMin(&R[R_MINLY], ly); atomicMax(&R[R_MAXLY], ly);
+                        atomicMin(&R[R_MINCX], cx); atomicMax(&R[R_MAXCX], cx);
+                        atomicMin(&R[R_MINCY], cy); atomicMax(&R[R_MAXCY], cy);
+                        atomicMin(&R[R_MINZ], zslab); atomicMax(&R[R_MAXZ], zslab);
+                        atomicMax(&R[R_LW], lw);
                     }
-                    P.mb[lane] = c;
                     if (ncoded) atomicMax(&s_cnt[gl][8], rel + ncoded);
                     // every 8x8 block whose pixels this record defines goes on the output list, binned by
                     // (coded?, interpolation mode) so that the threads of a warp take the same code path
@@ -308,6 +330,62 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         }
     }
     __syncthreads();
+    // strip or boxes?  Every lane of the group takes the same decision from the reductions.
+    const int* R = s_red[gl];
+    const uint32_t n_pred = s_cnt[gl][9];
+    bool strip = false;
+    int X0 = 0, Y0 = 0, CX0 = 0, CY0 = 0;
+    if (allow_strip && n_pred >= (uint32_t)kStripMinPred && R[R_MINZ] == R[R_MAXZ]) {
+        const int slw = R[R_LW], scw = slw >> 1;
+        X0 = R[R_MINLX] & ~15;   // two's complement: rounds toward minus infinity
+        Y0 = R[R_MINLY];
+        CX0 = R[R_MINCX] & ~15;
+        CY0 = R[R_MINCY];
+        // The rectangle must hold every window, start inside the row (x >= 0: a window left of column 0 belongs to the
+        // end of the row above in the reference's linear addressing -- box mode folds it, a strip cannot) and every
+        // needed byte must lie inside the tensor's rows (luma_w + 32 wide; what the box reads beyond is zero fill
+        // that no window uses).
+        strip = X0 >= 0 && R[R_MAXLX] + 17 - X0 <= kStripLW && R[R_MAXLX] + 17 <= slw + 32 &&
+                R[R_MAXLY] + 17 - Y0 <= kStripLH && Y0 > -32768 + 64 && R[R_MAXLY] < 32767 - 64 &&
+                CX0 >= 0 && R[R_MAXCX] + 9 - CX0 <= kStripCW && R[R_MAXCX] + 9 <= scw + 32 &&
+                R[R_MAXCY] + 9 - CY0 <= kStripCH;
+    }
+    if (have && c.dst_y) {
+        PlanBox b;
+        memset(&b, 0, sizeof(b));
+        if (predicted) {
+            if (strip) {
+                c.woff_y = (uint16_t)((ly - Y0) * kStripLW + (lx - X0));
+                c.woff_c = (uint16_t)(kStripLBytes + (cy - CY0) * kStripCW + (cx - CX0));
+            } else {
+                // The reference indexes linearly (si = y*stride + x, video_noasm.go:31,39), so a window
+                // starting left of column 0 really starts near the end of the row above.  Fold x into
+                // [0, pitch): same bytes, and inside the tensor's (overlapping) rows.
+                const int cw = lw >> 1;
+                int q = lx / lw, r = lx - q * lw;
+                if (r < 0) { r += lw; q--; }
+                lx = r;
+                ly += q;
+                q = cx / cw;
+                r = cx - q * cw;
+                if (r < 0) { r += cw; q--; }
+                cx = r;
+                cy += q;
+                const int phy = lane & (int)kPhaseY, phc = lane & (int)kPhaseC;
+                c.woff_y = (uint16_t)(lane * kWinBytes + phy * 32 + (lx & 15));
+                c.woff_c = (uint16_t)(lane * kWinBytes + kWinY + phc * 32 + (cx & 15));
+                b.lx = (int16_t)(lx & ~15);  // the TMA unit needs x on a 16-byte boundary
+                b.ly = (int16_t)(ly - phy);
+                b.cx = (int16_t)(cx & ~15);
+                b.cy = (int16_t)(cy - phc);
+                b.z = (uint16_t)(zslab & 0xffff);
+                b.slab = (uint16_t)((uint32_t)zslab >> 16);
+                b.pred = 1;
+            }
+        }
+        P.mb[lane] = c;
+        P.box[lane] = b;
+    }
     if (out_mask) {
         uint32_t run = 0, base_of[8];
 #pragma unroll
@@ -331,30 +409,40 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         }
     }
     if (lane == 0) {
-        P.n_box = (s_cnt[gl][8] + kCoefBox - 1) / kCoefBox;
-        P.n_pred = s_cnt[gl][9];
+        const uint32_t n_box = (s_cnt[gl][8] + kCoefBox - 1) / kCoefBox;
+        P.n_box = n_box;
+        P.n_pred = n_pred;
         P.block0 = block0;
-        P.pad0 = 0;
+        P.strip = strip ? 1 : 0;
+        if (strip) {
+            P.tx_bytes = n_box * (kCoefBox * 128) + kStripTx;
+            P.slab = (uint16_t)((uint32_t)R[R_MINZ] >> 16);
+            P.z = (uint16_t)(R[R_MINZ] & 0xffff);
+            P.pitch_y = kStripLW;
+            P.pitch_c = kStripCW;
+            P.cr_win = kStripCBytes;
+            P.sx = (int16_t)X0;
+            P.sy = (int16_t)Y0;
+            P.scx = (int16_t)CX0;
+            P.scy = (int16_t)CY0;
+        } else {
+            P.tx_bytes = n_box * (kCoefBox * 128) + n_pred * kWinTx;
+            P.pitch_y = 32;
+            P.pitch_c = 32;
+            P.cr_win = kWinC;
+        }
     }
     __syncthreads();
-    if (group < n_groups) {  // 768 bytes out, 16 bytes per lane per step
+    if (group < n_groups) {  // 1024 bytes out, 16 bytes per lane per step
         const uint4* src = reinterpret_cast<const uint4*>(&P);
         uint4* dstp = reinterpret_cast<uint4*>(plans + group);
 #pragma unroll
-        for (int i = 0; i < 3; i++) dstp[lane + 16 * i] = src[lane + 16 * i];
+        for (int i = 0; i < 4; i++) dstp[lane + 16 * i] = src[lane + 16 * i];
     }
 }
 
-struct Smem {
-    static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
-    static constexpr int win = coef + kNT * 128;                 // kG x 1408
-    static constexpr int plan = win + kG * kWinBytes;            // 768: the group's plan
-    static constexpr int bar = plan + (int)sizeof(GroupPlan);    // 8 bytes
-    static constexpr int total = bar + 16;
-};
-
-// One output block in three steps, so that a kernel can put a barrier between the part that reads shared memory
-// and the part that only works on registers:
+// One output block in three steps, so that a kernel can put the next group's fetch between the part that reads
+// shared memory and the part that only works on registers:
 //   block_setup : the block-list entry -> destination, window address, mode (reads the plan)
 //   block_load  : interpolate the prediction from the staged window, fetch + premultiply the coefficients
 //   block_finish: IDCT, add, saturate, store
@@ -362,12 +450,13 @@ struct BlockCtx {
     uint8_t* dst;
     uint32_t pitch;
     uint32_t win;      // byte offset of the block's pixel (0,0) in the window area
+    uint32_t wpitch;   // row pitch of the staged window
     uint32_t slot;     // coefficient slot in the tile
     uint32_t mode;     // bit 0 horizontal, bit 1 vertical half-pel
     bool live, pred, coded;
 };
 
-__device__ __forceinline__ void block_setup(const GroupPlan& P, int t, uint32_t phases, BlockCtx& B) {
+__device__ __forceinline__ void block_setup(const GroupPlan& P, int t, BlockCtx& B) {
     const uint32_t e = P.map[t];
     B.live = e != kNoBlock;
     const int j = e & 15, k = (e >> 4) & 7;
@@ -380,28 +469,53 @@ __device__ __forceinline__ void block_setup(const GroupPlan& P, int t, uint32_t 
     if (k < 4) {
         B.pitch = cx.luma_w;
         B.dst = cx.dst_y + (size_t)((k >> 1) * 8) * B.pitch + (k & 1) * 8;
+        B.wpitch = P.pitch_y;
+        B.win = cx.woff_y + (uint32_t)((k >> 1) * 8) * B.wpitch + (k & 1) * 8;
     } else {
         B.pitch = cx.luma_w >> 1;
-        B.dst = cx.dst_y + cx.dst_c_off + (k == 5 ? B.pitch * (uint32_t)cx.chroma_h : 0u);
+        B.dst = cx.dst_y + cx.dst_c_off + (k == 5 ? cx.dst_cr_off : 0u);
+        B.wpitch = P.pitch_c;
+        B.win = cx.woff_c + (k == 5 ? (uint32_t)P.cr_win : 0u);
     }
-    const uint32_t ph = (uint32_t)j & (k < 4 ? phases & 0xffu : phases >> 8);
-    B.win = j * kWinBytes + (k < 4 ? (k >> 1) * 256 + (k & 1) * 8 : kWinY + (k - 4) * kWinC) + ph * 32 + (mcb & 15u);
+}
+
+// (a + b + c + d + 2) >> 2 per byte without cascaded averages (video_noasm.go:72-77), on sums kept as two 16-bit lanes:
+// HSum holds, for one source row, a[x] + a[x+1] for x = 0,2 / 1,3 / 4,6 / 5,7.
+struct HSum { uint32_t p02, p13, p46, p57; };
+__device__ __forceinline__ HSum hsum_row(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t sh) {
+    const uint32_t u0 = __funnelshift_rc(w0, w1, sh), u1 = __funnelshift_rc(w1, w2, sh);   // bytes 0..3, 4..7
+    const uint32_t s1 = __funnelshift_rc(w1, w2, sh + 8);                                   // bytes 5..8
+    const uint32_t e0 = u0 & 0x00ff00ffu, o0 = __byte_perm(u0, 0, 0x4341);                  // [b0,b2] [b1,b3]
+    const uint32_t e1 = u1 & 0x00ff00ffu, o1 = __byte_perm(u1, 0, 0x4341);                  // [b4,b6] [b5,b7]
+    const uint32_t m0 = __funnelshift_r(e0, e1, 16);                                        // [b2,b4]
+    const uint32_t m1 = __byte_perm(s1, 0, 0x4341);                                         // [b6,b8]
+    HSum h;
+    h.p02 = e0 + o0;
+    h.p13 = o0 + m0;
+    h.p46 = e1 + o1;
+    h.p57 = o1 + m1;
+    return h;
+}
+__device__ __forceinline__ uint32_t vsum_pack(uint32_t a_even, uint32_t b_even, uint32_t a_odd, uint32_t b_odd) {
+    const uint32_t ve = (a_even + b_even + 0x00020002u) >> 2, vo = (a_odd + b_odd + 0x00020002u) >> 2;
+    return __byte_perm(ve, vo, 0x6240);   // bytes: even lane 0, odd lane 0, even lane 1, odd lane 1
 }
 
 __device__ __forceinline__ void block_load(const BlockCtx& B, const uint8_t* s_coef, const uint8_t* s_win,
                                            uint32_t (&p0)[8], uint32_t (&p1)[8], int (&c)[64]) {
     // prediction: eight rows of eight bytes, straight from the staged window (video_noasm.go:44-80)
     if (B.pred) {
-        // s_win is 128-byte aligned, so the byte offset decides the word alignment
+        // s_win is 128-byte aligned and every pitch a multiple of 4, so the byte offset decides the word alignment
         const uint32_t a = B.win;
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_win + (a & ~3u));
+        const uint32_t wq = B.wpitch >> 2;
         const uint32_t sh = (a & 3u) * 8;
         const uint32_t mode = B.mode;
-#define LOAD_ROW(R, W0, W1, W2) \
-    do {                        \
-        W0 = wp[(R) * 8];       \
-        W1 = wp[(R) * 8 + 1];   \
-        W2 = wp[(R) * 8 + 2];   \
+#define LOAD_ROW(R, W0, W1, W2)  \
+    do {                         \
+        W0 = wp[(R) * wq];       \
+        W1 = wp[(R) * wq + 1];   \
+        W2 = wp[(R) * wq + 2];   \
     } while (0)
         if (mode == 0) {
 #pragma unroll
@@ -435,19 +549,20 @@ __device__ __forceinline__ void block_load(const BlockCtx& B, const uint8_t* s_c
         } else {
             uint32_t w0, w1, w2;
             LOAD_ROW(0, w0, w1, w2);
-            uint32_t u0 = __funnelshift_rc(w0, w1, sh), u1 = __funnelshift_rc(w1, w2, sh);
-            uint32_t s0 = __funnelshift_rc(w0, w1, sh + 8), s1 = __funnelshift_rc(w1, w2, sh + 8);
+            HSum up = hsum_row(w0, w1, w2, sh);
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 LOAD_ROW(r + 1, w0, w1, w2);
-                const uint32_t n0 = __funnelshift_rc(w0, w1, sh), n1 = __funnelshift_rc(w1, w2, sh);
-                const uint32_t t0 = __funnelshift_rc(w0, w1, sh + 8), t1 = __funnelshift_rc(w1, w2, sh + 8);
-                p0[r] = avg4(u0, s0, n0, t0);
-                p1[r] = avg4(u1, s1, n1, t1);
-                u0 = n0; u1 = n1; s0 = t0; s1 = t1;
+                const HSum dn = hsum_row(w0, w1, w2, sh);
+                p0[r] = vsum_pack(up.p02, dn.p02, up.p13, dn.p13);
+                p1[r] = vsum_pack(up.p46, dn.p46, up.p57, dn.p57);
+                up = dn;
             }
         }
 #undef LOAD_ROW
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) p0[r] = p1[r] = 0;   // intra: the residual is added to nothing
     }
     if (B.coded) {
         const int slot = (int)B.slot;
@@ -463,7 +578,23 @@ __device__ __forceinline__ void block_load(const BlockCtx& B, const uint8_t* s_c
                 c[r * 8 + 2 * p + 1] = __dp2a_lo((int)ww[p], premult(r * 8 + 2 * p + 1) << 8, 0);
             }
         }
+        // The +128 of the final (x + 128) >> 8 (video.go:918-925) rides on the DC term: s0 enters every output of both
+        // passes exactly once with weight +1 and never passes through a rounding shift (x1 = m0 - b1, x3 = m0 + b1).
+        c[0] += 128;
     }
+}
+
+// d = (sat_u16(a) << 16) | sat_u16(b)
+__device__ __forceinline__ uint32_t pack_sat_u16(int a, int b) {
+    uint32_t d;
+    asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+// ((v >> 8) + pred) clamped to 0..255 for four pixels (addBlockToDest video.go:957-971; copyBlockToDest with pred = 0):
+// t = v + (pred << 8) is clamped to 0..65535 first, its high byte is floor(t / 256) clamped to 0..255.
+__device__ __forceinline__ uint32_t finish4(int t0, int t1, int t2, int t3) {
+    return __byte_perm(pack_sat_u16(t1, t0), pack_sat_u16(t3, t2), 0x7531);
 }
 
 __device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (&p0)[8], const uint32_t (&p1)[8], int (&c)[64]) {
@@ -480,26 +611,83 @@ __device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (
         idct_pass8(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
 #pragma unroll
     for (int r = 0; r < 8; r++) {  // rows, video.go:899-926, then copy/addBlockToDest (:943-971)
-        int v[8];
-        idct_row8(&c[r * 8], v);
-        if (B.pred) {
+        int k[8], v[8];
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                v[x] = (int)__dp4a(p0[r], 1u << (8 * x), (uint32_t)v[x]);
-                v[4 + x] = (int)__dp4a(p1[r], 1u << (8 * x), (uint32_t)v[4 + x]);
-            }
+        for (int x = 0; x < 4; x++) {   // prediction pixel x, shifted left by 8
+            k[x] = (int)__byte_perm(p0[r], 0, 0x4404 | (x << 4));
+            k[4 + x] = (int)__byte_perm(p1[r], 0, 0x4404 | (x << 4));
         }
+        idct_row8(&c[r * 8], k, v);
         *reinterpret_cast<uint2*>(dst + (size_t)r * pitch) =
-            make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
+            make_uint2(finish4(v[0], v[1], v[2], v[3]), finish4(v[4], v[5], v[6], v[7]));
     }
 }
 
-__device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t* s_coef, const uint8_t* s_win, int t,
-                                              uint64_t* bar, uint32_t parity, uint32_t phases) {
+struct Smem {
+    static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
+    static constexpr int win = coef + kNT * 128;                 // the window area: one strip or kG x 1280
+    static constexpr int plan = win + kWinArea;                  // 2 x 1024: the group's plan (the one-shot kernel uses one)
+    static constexpr int bar = plan + 2 * (int)sizeof(GroupPlan);
+    static constexpr int total = bar + 64;
+    static constexpr int total_oneshot = plan + (int)sizeof(GroupPlan) + 16;
+};
+
+// The TMA boxes of one group.  Strip mode: lane 0 of warp 0 the luma strip, lane 0 of warp 1 the chroma strip.  Box mode:
+// warp 0 the luma boxes, warp 1 the chroma boxes, lane = macroblock.  Warp 2 the coefficient boxes and the expect_tx;
+// complete_tx of boxes issued before that arrival is fine: the phase cannot complete before the (single) arrival, and
+// the transaction count is allowed to run negative meanwhile.
+__device__ __forceinline__ void issue_group(const GroupPlan& P, const CUtensorMap* coef_map, const SlabMaps* slab_maps,
+                                            uint8_t* s_coef, uint8_t* s_win, uint64_t* bar, int warp, int lane) {
+    if (warp == 2) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, P.tx_bytes);
+        if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
+            tma_load_2d(s_coef + lane * (kCoefBox * 128), coef_map, bar, 0, (int)(P.block0 + lane * kCoefBox));
+    } else if (P.strip) {
+        if (lane == 0) {
+            const SlabMaps* maps = slab_maps + P.slab;
+            if (warp == 0)
+                tma_load_3d(s_win, maps->luma_strip, bar, P.sx >> 3, P.sy, P.z);
+            else
+                tma_load_4d(s_win + kStripLBytes, maps->chroma_strip, bar, P.scx >> 3, P.scy, 0, P.z);
+        }
+    } else if (lane < kG && P.box[lane].pred) {
+        const PlanBox& t = P.box[lane];
+        const SlabMaps* maps = slab_maps + t.slab;
+        uint8_t* w = s_win + lane * kWinBytes;
+        if (warp == 0)
+            tma_load_3d(w, maps->luma, bar, t.lx, t.ly, t.z);
+        else  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
+            tma_load_4d(w + kWinY, maps->chroma, bar, t.cx, t.cy, 0, t.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-shot kernel: one CTA = one group plan = kG records.  Load the plan (64 x 16 bytes), issue the boxes, wait on
+// the one mbarrier, then one thread per output block: interpolate, IDCT, add, saturate, store.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                          const SlabMaps* __restrict__ slab_maps,
+                                                          const GroupPlan* __restrict__ plans) {
+    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
+    uint8_t* s_coef = smem + Smem::coef;
+    uint8_t* s_win = smem + Smem::win;
+    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::plan + sizeof(GroupPlan));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid < 64) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
+    if (tid == 64) {
+        if (smem_u32(smem) & 1023u) __trap();
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    issue_group(P, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane);
+
     BlockCtx B;
-    block_setup(P, t, phases, B);
+    block_setup(P, tid, B);
     if (!B.live) return;
-    mbar_wait(bar, parity);   // all tiles of the group have landed
+    mbar_wait(s_bar, 0);   // all tiles of the group have landed
     uint32_t p0[8], p1[8];
     int c[64];
     block_load(B, s_coef, s_win, p0, p1, c);
@@ -507,48 +695,94 @@ __device__ __forceinline__ void process_block(const GroupPlan& P, const uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// The arithmetic kernel: one CTA = one group plan = kG records.  Load the plan (48 x 16 bytes), issue
-// every TMA box (warp w: plane w of each predicted macroblock; warp 0 also the coefficient boxes), wait on
-// the one mbarrier, then one thread per output block: interpolate, IDCT, add, saturate, store.
+// Streaming kernel: the registers are the second pipeline stage.  A thread needs shared memory only until its
+// prediction (16 registers) and its premultiplied coefficients (64 registers) are loaded; the IDCT, the add and the
+// stores run on registers.  Each CTA walks over groups b, b + grid, ...; the warp that is LAST to leave the load step
+// of group i (a shared-memory counter tells it) fetches the tiles of group i + 1 into the same shared memory, so
+// that they land while the IDCT of group i runs, and nobody waits at a CTA-wide barrier.  Plans are double-buffered
+// and fetched two groups ahead with a bulk copy.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                       const SlabMaps* __restrict__ slab_maps,
-                                                       const GroupPlan* __restrict__ plans, uint32_t phases) {
-    extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __maxnreg__(112) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                             const SlabMaps* __restrict__ slab_maps,
+                                                             const GroupPlan* __restrict__ plans, uint32_t n_groups) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_coef = smem + Smem::coef;
     uint8_t* s_win = smem + Smem::win;
-    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+    GroupPlan* s_plan = reinterpret_cast<GroupPlan*>(smem + Smem::plan);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+    uint64_t* bar_plan = bar_full + 1;   // [2]
+    uint32_t* s_left = reinterpret_cast<uint32_t*>(bar_full + 3);   // warps that have left the load step
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t stride = gridDim.x;
+    uint32_t g = blockIdx.x;
 
-    if (tid < 48) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
-    if (tid == 64) {
+    if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
-        mbar_init(s_bar, 1);
+        mbar_init(bar_full, 1);
+        mbar_init(bar_plan, 1);
+        mbar_init(bar_plan + 1, 1);
+        *s_left = 0;
         fence_barrier_init();
+        // the first two plans
+        mbar_arrive_expect_tx(bar_plan, (uint32_t)sizeof(GroupPlan));
+        bulk_load(&s_plan[0], plans + g, (uint32_t)sizeof(GroupPlan), bar_plan);
+        if (g + stride < n_groups) {
+            mbar_arrive_expect_tx(bar_plan + 1, (uint32_t)sizeof(GroupPlan));
+            bulk_load(&s_plan[1], plans + g + stride, (uint32_t)sizeof(GroupPlan), bar_plan + 1);
+        }
     }
     __syncthreads();
+    mbar_wait(bar_plan, 0);
+    issue_group(s_plan[0], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane);
+    __syncthreads();   // all three warps have issued their part before anybody can count them out below
 
-    if (lane < kG && (P.mb[lane].mcw & 0x80u)) {
-        const PlanMb& t = P.mb[lane];
-        const SlabMaps* maps = slab_maps + t.slab;
-        uint8_t* w = s_win + lane * kWinBytes;
-        if (warp == 0)
-            tma_load_3d(w, maps->luma, s_bar, t.lx, t.ly - (int)(lane & (phases & 0xffu)), t.z);
-        else if (warp == 1)  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
-            tma_load_4d(w + kWinY, maps->chroma, s_bar, t.cx, t.cy - (int)(lane & (phases >> 8)), 0, t.z);
+    for (uint32_t i = 0; g < n_groups; i++, g += stride) {
+        const uint32_t buf = i & 1;
+        const GroupPlan& P = s_plan[buf];
+        mbar_wait(bar_plan + buf, (i >> 1) & 1);
+        BlockCtx B;
+        block_setup(P, tid, B);
+        uint32_t p0[8], p1[8];
+        int c[64];
+        mbar_wait(bar_full, i & 1);           // the group's tiles have landed
+        if (B.live) block_load(B, s_coef, s_win, p0, p1, c);
+        // This warp has left shared memory (windows, coefficients, plan[buf]).  The last warp to get here fetches the
+        // next group's tiles; the other two go straight on to their arithmetic.
+        __syncwarp();
+        uint32_t left = 0;
+        if (lane == 0) left = atomicAdd(s_left, 1u);
+        left = __shfl_sync(0xffffffffu, left, 0);
+        if (left == 2) {
+            const bool more = g + stride < n_groups;
+            if (lane == 0) {
+                *s_left = 0;
+                __threadfence_block();
+                fence_proxy_async();          // generic-proxy reads of the tiles before the async-proxy writes
+            }
+            __syncwarp();
+            if (more) {
+                mbar_wait(bar_plan + (buf ^ 1), ((i + 1) >> 1) & 1);
+                const GroupPlan& N = s_plan[buf ^ 1];
+                // one warp plays all three roles of issue_group
+                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 0, lane);
+                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 1, lane);
+                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 2, lane);
+                if (lane == 0 && g + 2 * stride < n_groups) {   // and the plan after it
+                    mbar_arrive_expect_tx(bar_plan + buf, (uint32_t)sizeof(GroupPlan));
+                    bulk_load(&s_plan[buf], plans + g + 2 * stride, (uint32_t)sizeof(GroupPlan), bar_plan + buf);
+                }
+            }
+        }
+        block_finish(B, p0, p1, c);
     }
-    if (warp == 0) {
-        // complete_tx of boxes issued before this arrival is fine: the phase cannot complete before the
-        // (single) arrival, and the transaction count is allowed to run negative meanwhile
-        if (lane == 0) mbar_arrive_expect_tx(s_bar, P.n_box * (kCoefBox * 128) + P.n_pred * kWinTx);
-        if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
-            tma_load_2d(s_coef + lane * (kCoefBox * 128), &coef_map, s_bar, 0, (int)(P.block0 + lane * kCoefBox));
-    }
-
-    process_block(P, s_coef, s_win, tid, s_bar, 0, phases);
 }
-
 
 }  // namespace
 
@@ -558,18 +792,36 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
                              uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream) {
     if (n_mb == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
+    // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0
+    // makes the plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
+    static int variant = -1, allow_strip = 1, stream_ctas = 0;
+    if (variant < 0) {
+        cudaError_t e = cudaFuncSetAttribute(fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total_oneshot);
         if (e != cudaSuccess) return e;
-        configured = true;
+        e = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel, kNT, Smem::total);
+        if (e != cudaSuccess) return e;
+        stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
+        const char* c = getenv("MPEGB200_STREAM_CTAS");
+        if (c && atoi(c) > 0) stream_ctas = atoi(c);
+        const char* s = getenv("MPEGB200_STRIP");
+        allow_strip = !(s && s[0] == '0');
+        const char* v = getenv("MPEGB200_FUSED");
+        variant = (v && strcmp(v, "oneshot") == 0) ? 0 : 1;
     }
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
-        plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks);
-    constexpr uint32_t phases = (uint32_t)(kLumaBoxRows - 17) | ((uint32_t)(kChromaBoxRows - 9) << 8);
-    fused_tma_kernel<<<n_groups, kNT, Smem::total, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, phases);
+        plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks, allow_strip);
+    if (variant == 0)
+        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
+    else
+        fused_stream_kernel<<<n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas, kNT, Smem::total, stream>>>(
+            *reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, n_groups);
     return cudaGetLastError();
 }
 

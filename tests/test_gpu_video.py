@@ -406,3 +406,84 @@ def test_packed_12bit_transfer_form_is_equivalent(ctx):
     with pytest.raises(mpeg_b200.MpegB200Error):
         ctx.pack_coeffs12(too_big)
     ctx.video_close(40)
+
+
+def _run_pictures_and_compare(ctx, fs, sid, g, pictures, msg):
+    """pictures: list of (type, (dst, fwd, bwd), mbs, coeffs); each decoded on the GPU and by the oracle, all three
+    buffers compared after every one."""
+    for i, (t, bufs, mbs, coeffs) in enumerate(pictures):
+        pics, m, c = wl.batch_pictures([(mbs, coeffs)], [sid], t, [bufs])
+        ctx.video_validate(pics, m, len(c))
+        ctx.video_decode_pictures(pics, m, c)
+        op = pics.copy()
+        op["stream"] = 0
+        assert fs.exec_pictures(op, m, c) == 0
+        assert_frames_equal(ctx, fs, sid, 0, msg=f"{msg} picture {i}")
+
+
+@pytest.mark.parametrize("width,height", [(256, 80), (512, 64), (1280, 48)])
+def test_strip_staging_of_neighbouring_macroblocks(ctx, width, height):
+    """Groups of 16 records whose windows fit one 304x48 / 160x24 rectangle in one reference buffer are staged as one
+    luma and one chroma box (video_fused_tma.cu, strip mode); every other group with boxes per macroblock.  Widths
+    that are multiples of 256 put whole groups on one macroblock row, so natural P pictures (vectors within +-16
+    pixels, ~10 % intra macroblocks) run in strip mode, B pictures (two reference buffers inside a group) mix the
+    two modes from group to group."""
+    g = wl.Geometry(width, height)
+    rng = wl.stream_rng(2, 31)
+    fs = ol.FrameSet(1, g.width, g.height)
+    fresh_stream(ctx, 9, g.width, g.height)
+    for b in range(3):
+        buf = wl.random_reference_frame(rng, g)
+        fs.whole(0, b)[:] = buf
+        ctx.video_write_frame(9, b, buf)
+    rot = wl.BufferRotation()
+    pictures = []
+    for t in [wl.PIC_I, wl.PIC_P, wl.PIC_P, wl.PIC_B, wl.PIC_B, wl.PIC_P, wl.PIC_B]:
+        bufs = rot.begin(t)
+        mbs, coeffs = wl.make_picture(rng, g, t, "natural")
+        pictures.append((t, bufs, mbs, coeffs))
+        rot.end(t)
+    _run_pictures_and_compare(ctx, fs, 9, g, pictures, f"natural {width}x{height}")
+    ctx.video_close(9)
+
+
+def test_strip_staging_edge_vectors(ctx):
+    """The corner cases of the strip decision on a 256-wide picture (one group = one macroblock row):
+    the same vector for a whole row pointing past the right edge (the strip uses the rows' 32-byte overlap), left of
+    column 0 (x < 0: back to folded boxes), a row whose vertical spread exceeds the strip (boxes), a row with two
+    predicted macroblocks only (below the strip threshold), dense residuals everywhere."""
+    g = wl.Geometry(256, 96)
+    rng = wl.stream_rng(2, 32)
+    fs = ol.FrameSet(1, g.width, g.height)
+    fresh_stream(ctx, 9, g.width, g.height)
+    for b in range(3):
+        buf = wl.random_reference_frame(rng, g)
+        fs.whole(0, b)[:] = buf
+        ctx.video_write_frame(9, b, buf)
+    mbs, coeffs = wl.make_picture(rng, g, wl.PIC_P, "dense")
+    mv_h = mbs["mv_h"].reshape(g.mb_h, g.mb_w)
+    mv_v = mbs["mv_v"].reshape(g.mb_h, g.mb_w)
+    flags = mbs["flags"].reshape(g.mb_h, g.mb_w)
+    mv_h[1, :] = 31            # rightmost window ends at 256 + 15 + 17: inside the overlap
+    mv_v[1, :] = 5
+    mv_h[2, :] = -31           # leftmost window starts at -16: linear addressing reads the row above
+    mv_v[2, :] = -3
+    mv_v[3, ::2] = -32         # 16 rows up and 15 down in one group: 17 + 31 + 1 > 48
+    mv_v[3, 1::2] = 31
+    flags[4, :] = wl.MB_INTRA  # two predicted macroblocks in the group
+    flags[4, 3] = flags[4, 12] = wl.MB_PREDICT
+    mv_h[4, :] = np.where(flags[4] == wl.MB_PREDICT, mv_h[4], 0)
+    mv_v[4, :] = np.where(flags[4] == wl.MB_PREDICT, mv_v[4], 0)
+    mv_h[5, :] = np.arange(16) * 4 - 32   # a steady drift, half-pel phases of every kind
+    mv_v[5, :] = 31 - np.arange(16) * 4
+    mbs["mv_h"], mbs["mv_v"], mbs["flags"] = mv_h.ravel(), mv_v.ravel(), flags.ravel()
+    intra_dc = np.repeat(mbs["flags"] == wl.MB_INTRA, 6)
+    coeffs[intra_dc, 0] = (rng.integers(0, 256, int(intra_dc.sum())) * 8).astype(np.int16)
+    _run_pictures_and_compare(ctx, fs, 9, g, [(wl.PIC_P, (0, 1, 2), mbs, coeffs)], "edge vectors")
+    # the same records in reverse order: groups now run right to left, the rectangle is the same
+    order = np.arange(len(mbs))[::-1]
+    mbs_r = mbs[order].copy()
+    coeffs_r = coeffs.reshape(len(mbs), 6, 64)[order].reshape(-1, 64).copy()
+    mbs_r["coeff_block"] = np.arange(len(mbs)) * 6
+    _run_pictures_and_compare(ctx, fs, 9, g, [(wl.PIC_P, (2, 1, 0), mbs_r, coeffs_r)], "reverse order")
+    ctx.video_close(9)
