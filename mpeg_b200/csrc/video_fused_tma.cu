@@ -22,11 +22,16 @@
 
 #include <climits>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 
 #include "common.cuh"
+
+#ifndef MPEGB200_PAIRED
+#define MPEGB200_PAIRED 1
+#endif
 
 namespace mpegb200 {
 
@@ -82,9 +87,6 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
-    return pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
-}
 
 // videoPremultiplierMatrix, video.go:1077-1086
 __device__ __forceinline__ constexpr int premult(int i) {
@@ -105,7 +107,8 @@ __device__ __forceinline__ void idct_pass8(int& s0, int& s1, int& s2, int& s3, i
     const int b7 = tmp1 + tmp2;
     const int m0 = s0;
     const int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
-    const int x0 = x4 - (((tmp1 - tmp2) * 362 + 128) >> 8);
+    // -(u >> 8) == (-u + 255) >> 8 for the arithmetic shift, so the subtraction of video.go:879 becomes shift-and-add (one LEA.HI.SX32)
+    const int x0 = x4 + (((tmp2 - tmp1) * 362 + 127) >> 8);
     const int x1 = m0 - b1;
     const int x2 = (((s2 - s6) * 362 + 128) >> 8) - b3;
     const int x3 = m0 + b1;
@@ -113,12 +116,41 @@ __device__ __forceinline__ void idct_pass8(int& s0, int& s1, int& s2, int& s3, i
     const int y4 = x3 + b3;
     const int y5 = x1 - x2;
     const int y6 = x3 - b3;
-    const int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
+    const int ny7 = x0 + ((b4 * 473 + b6 * 196 + 128) >> 8);   // -y7 of video.go:887
     s0 = b7 + y4;
     s1 = x4 + y3;
     s2 = y5 - x0;
-    s3 = y6 - y7;
-    s4 = y6 + y7;
+    s3 = y6 + ny7;
+    s4 = y6 - ny7;
+    s5 = x0 + y5;
+    s6 = y3 - x4;
+    s7 = y4 - b7;
+}
+
+// premultiplier pairs for dp2a, in constant memory so that they are instruction operands (c[bank][offset]) instead of
+// one uniform-register move each: [pair (0,4) (1,7) (3,5) (2,6)][column]; sum = pa | pb << 8, difference = pa | -pb << 8
+// (pair (3,5): -pa | pb << 8, video.go:872 b4 = s5 - s3)
+__constant__ int kPairSum[32] = {0x2020, 0x2c2c, 0x2a2a, 0x2626, 0x2020, 0x1919, 0x1111, 0x0909, 0x092c, 0x0c3e, 0x0c3a, 0x0a34, 0x092c, 0x0723, 0x0518, 0x020c, 0x1926, 0x2334, 0x2131, 0x1e2c, 0x1926, 0x141e, 0x0e14, 0x070a, 0x112a, 0x183a, 0x1737, 0x1431, 0x112a, 0x0e21, 0x0917, 0x050c};
+__constant__ int kPairDif[32] = {0xe020, 0xd42c, 0xd62a, 0xda26, 0xe020, 0xe719, 0xef11, 0xf709, 0xf72c, 0xf43e, 0xf43a, 0xf634, 0xf72c, 0xf923, 0xfb18, 0xfe0c, 0x19da, 0x23cc, 0x21cf, 0x1ed4, 0x19da, 0x14e2, 0x0eec, 0x07f6, 0xef2a, 0xe83a, 0xe937, 0xec31, 0xef2a, 0xf221, 0xf717, 0xfb0c};
+
+// column pass whose first additions were already made by the coefficient load (block_load, MPEGB200_PAIRED):
+// in: s0 = x3 (s0+s4), s1 = tmp1, s2 = b3, s3 = tmp2, s4 = x1 (s0-s4), s5 = b4, s6 = s2-s6, s7 = b6
+__device__ __forceinline__ void idct_pass8_pre(int& s0, int& s1, int& s2, int& s3, int& s4, int& s5, int& s6, int& s7) {
+    const int x3 = s0, tmp1 = s1, b3 = s2, tmp2 = s3, x1 = s4, b4 = s5, d26 = s6, b6 = s7;
+    const int b7 = tmp1 + tmp2;
+    const int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
+    const int x0 = x4 + (((tmp2 - tmp1) * 362 + 127) >> 8);
+    const int x2 = ((d26 * 362 + 128) >> 8) - b3;
+    const int y3 = x1 + x2;
+    const int y4 = x3 + b3;
+    const int y5 = x1 - x2;
+    const int y6 = x3 - b3;
+    const int ny7 = x0 + ((b4 * 473 + b6 * 196 + 128) >> 8);
+    s0 = b7 + y4;
+    s1 = x4 + y3;
+    s2 = y5 - x0;
+    s3 = y6 + ny7;
+    s4 = y6 - ny7;
     s5 = x0 + y5;
     s6 = y3 - x4;
     s7 = y4 - b7;
@@ -136,7 +168,7 @@ __device__ __forceinline__ void idct_row8(const int* s, const int* k, int* o) {
     const int b7 = tmp1 + tmp2;
     const int m0 = s[0];
     const int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
-    const int x0 = x4 - (((tmp1 - tmp2) * 362 + 128) >> 8);
+    const int x0 = x4 + (((tmp2 - tmp1) * 362 + 127) >> 8);
     const int x1 = m0 - b1;
     const int x2 = (((s[2] - s[6]) * 362 + 128) >> 8) - b3;
     const int x3 = m0 + b1;
@@ -144,12 +176,12 @@ __device__ __forceinline__ void idct_row8(const int* s, const int* k, int* o) {
     const int y4 = x3 + b3;
     const int y5 = x1 - x2;
     const int y6 = x3 - b3;
-    const int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
+    const int ny7 = x0 + ((b4 * 473 + b6 * 196 + 128) >> 8);
     o[0] = b7 + y4 + k[0];
     o[1] = x4 + y3 + k[1];
     o[2] = y5 - x0 + k[2];
-    o[3] = y6 - y7 + k[3];
-    o[4] = y6 + y7 + k[4];
+    o[3] = y6 + ny7 + k[3];
+    o[4] = y6 - ny7 + k[4];
     o[5] = x0 + y5 + k[5];
     o[6] = y3 - x4 + k[6];
     o[7] = y4 - b7 + k[7];
@@ -188,7 +220,7 @@ constexpr int kStripMinPred = 3;       // fewer predicted macroblocks than this:
 // (plan_kernel) so that the decode, the record -> picture -> stream pointer chase and the sorting of
 // the output blocks are neither repeated nor serialised inside the arithmetic kernel.
 // ------------------------------------------------------------------------------------------------
-struct PlanMb {               // 32 bytes
+struct PlanMb {               // 32 bytes; the pre-pass builds one per record, the plan stores it field by field
     uint8_t* dst_y;           // destination of the macroblock's luma (row 0, col 0 of the MB)
     uint32_t dst_c_off;       // Cb destination = dst_y + dst_c_off
     uint32_t dst_cr_off;      // Cr destination = Cb destination + dst_cr_off
@@ -216,8 +248,12 @@ struct GroupPlan {            // 1024 bytes = 64 x 16
     int16_t sx, sy, scx, scy;                   // strip origins in bytes / rows (x multiples of 16)
     uint32_t pad0[3];
     uint16_t map[kNT];        // output-block list, sorted by (coded?, interpolation mode)
-    PlanMb mb[kG];
-    uint8_t pad1[16];
+    // The per-macroblock fields as arrays (PlanMb, field by field): the 32 block threads of a warp read the fields of up to
+    // 16 different macroblocks, and an array of 16 entries of 8 bytes or less never puts two of them on one bank.
+    uint8_t* dst_y[kG];
+    uint32_t dst_c_off[kG], dst_cr_off[kG];
+    uint16_t luma_w[kG], mcw[kG], woff_y[kG], woff_c[kG];
+    uint8_t pad1[768 - 48 - 2 * kNT - 8 * kG - 8 * kG - 8 * kG];
     PlanBox box[kG];
 };
 static_assert(sizeof(GroupPlan) == 1024, "GroupPlan size");
@@ -240,6 +276,7 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
     __shared__ __align__(16) GroupPlan s_plan[kPlanGroupsPerCta];
     __shared__ uint32_t s_cnt[kPlanGroupsPerCta][10];  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
     __shared__ int s_red[kPlanGroupsPerCta][R_N];
+    __shared__ uint32_t s_cnt2[kPlanGroupsPerCta][8][8];   // [bin][coefficient slot & 7]
     const int tid = threadIdx.x, gl = tid >> 4, lane = tid & 15;
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     const uint32_t group = blockIdx.x * kPlanGroupsPerCta + gl;
@@ -249,13 +286,14 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         for (int i = lane; i < (int)(sizeof(GroupPlan) / 16); i += 16) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (lane < 10) s_cnt[gl][lane] = 0;
+    for (int i = lane; i < 64; i += 16) (&s_cnt2[gl][0][0])[i] = 0;
     if (lane < R_N) s_red[gl][lane] = ((lane & 1) || lane == R_LW) ? INT_MIN : INT_MAX;   // even slots are minima, odd ones (and R_LW) maxima
     __syncthreads();
     for (int i = lane; i < kNT; i += 16) P.map[i] = (uint16_t)kNoBlock;
 
     const uint32_t m0 = group * (uint32_t)kG;
     const bool have = group < n_groups && m0 + lane < n_mb;
-    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0;
+    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0, ress = 0;
     uint32_t block0 = 0;
     bool predicted = false;
     int lx = 0, ly = 0, cx = 0, cy = 0, lw = 0, zslab = 0;
@@ -316,13 +354,22 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                     out_mask = predicted ? 0x3fu : cbp;
                     cbp_r = cbp;
                     rel_r = rel;
+                    // Inside a bin the blocks are ordered round-robin over (coefficient slot & 7): the 128-byte swizzle of the
+                    // coefficient tile makes the eight LDS.128 of a quarter-warp conflict free exactly when its eight
+                    // slots differ mod 8 (profiles/r1_final_video_summary.md: 9.1 wavefronts per instruction, ideal 4).
+                    uint32_t slot_run = rel;
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
                         if (out_mask & (0x20u >> k)) {
-                            const uint32_t bin = ((cbp & (0x20u >> k)) ? 0u : 4u) + (predicted ? (k < 4 ? mode_y : mode_c) : 0u);
-                            const uint32_t pp = atomicAdd(&s_cnt[gl][bin], 1u);  // < 96
+                            const bool coded = (cbp & (0x20u >> k)) != 0;
+                            const uint32_t bin = (coded ? 0u : 4u) + (predicted ? (k < 4 ? mode_y : mode_c) : 0u);
+                            const uint32_t res = coded ? (slot_run & 7u) : ((uint32_t)(lane + k) & 7u);
+                            const uint32_t pp = atomicAdd(&s_cnt2[gl][bin][res], 1u);  // < 96
+                            atomicAdd(&s_cnt[gl][bin], 1u);
                             bins |= bin << (4 * k);
+                            ress |= res << (4 * k);
                             if (k < 4) pos |= pp << (8 * k); else pos_hi |= pp << (8 * (k - 4));
+                            if (coded) slot_run++;
                         }
                     }
                 }
@@ -383,7 +430,13 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                 b.pred = 1;
             }
         }
-        P.mb[lane] = c;
+        P.dst_y[lane] = c.dst_y;
+        P.dst_c_off[lane] = c.dst_c_off;
+        P.dst_cr_off[lane] = c.dst_cr_off;
+        P.luma_w[lane] = c.luma_w;
+        P.mcw[lane] = c.mcw;
+        P.woff_y[lane] = c.woff_y;
+        P.woff_c[lane] = c.woff_c;
         P.box[lane] = b;
     }
     if (out_mask) {
@@ -397,12 +450,15 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             if (out_mask & (0x20u >> k)) {
-                const uint32_t bin = (bins >> (4 * k)) & 15u;
-                const uint32_t pp = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
+                const uint32_t bin = (bins >> (4 * k)) & 15u, res = (ress >> (4 * k)) & 15u;
+                const uint32_t idx = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
                 const bool coded = cbp_r & (0x20u >> k);
-                uint32_t bsel = 0;
+                uint32_t bsel = 0, pp = 0;   // rank of (idx, res) among the bin's entries in (idx, res) order
 #pragma unroll
-                for (int b = 0; b < 8; b++) bsel = bin == (uint32_t)b ? base_of[b] : bsel;
+                for (int b = 0; b < 8; b++) {
+                    bsel = bin == (uint32_t)b ? base_of[b] : bsel;
+                    pp += min(s_cnt2[gl][bin][b], idx + ((uint32_t)b < res ? 1u : 0u));
+                }
                 P.map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
                 if (coded) slot++;
             }
@@ -462,20 +518,20 @@ __device__ __forceinline__ void block_setup(const GroupPlan& P, int t, BlockCtx&
     const int j = e & 15, k = (e >> 4) & 7;
     B.coded = B.live && (e & 0x80u);
     B.slot = e >> 8;
-    const PlanMb& cx = P.mb[j];
-    const uint32_t mcb = (uint32_t)(cx.mcw >> (k < 4 ? 0 : 8)) & 0xffu;
+    const uint32_t mcb = (uint32_t)(P.mcw[j] >> (k < 4 ? 0 : 8)) & 0xffu;
     B.pred = B.live && (mcb & 0x80u);
     B.mode = (mcb >> 4) & 3u;
+    const uint32_t lw = P.luma_w[j];
     if (k < 4) {
-        B.pitch = cx.luma_w;
-        B.dst = cx.dst_y + (size_t)((k >> 1) * 8) * B.pitch + (k & 1) * 8;
+        B.pitch = lw;
+        B.dst = P.dst_y[j] + (size_t)((k >> 1) * 8) * B.pitch + (k & 1) * 8;
         B.wpitch = P.pitch_y;
-        B.win = cx.woff_y + (uint32_t)((k >> 1) * 8) * B.wpitch + (k & 1) * 8;
+        B.win = P.woff_y[j] + (uint32_t)((k >> 1) * 8) * B.wpitch + (k & 1) * 8;
     } else {
-        B.pitch = cx.luma_w >> 1;
-        B.dst = cx.dst_y + cx.dst_c_off + (k == 5 ? cx.dst_cr_off : 0u);
+        B.pitch = lw >> 1;
+        B.dst = P.dst_y[j] + P.dst_c_off[j] + (k == 5 ? P.dst_cr_off[j] : 0u);
         B.wpitch = P.pitch_c;
-        B.win = cx.woff_c + (k == 5 ? (uint32_t)P.cr_win : 0u);
+        B.win = P.woff_c[j] + (k == 5 ? (uint32_t)P.cr_win : 0u);
     }
 }
 
@@ -568,6 +624,39 @@ __device__ __forceinline__ void block_load(const BlockCtx& B, const uint8_t* s_c
         const int slot = (int)B.slot;
         const uint8_t* src = s_coef + slot * 128;
         const int sw = (slot & 7) << 4;  // 128-byte swizzle: 16-byte chunk index ^= row index mod 8
+#if MPEGB200_PAIRED
+        // The first step of the column pass only ever needs s1 +- s7, s3 +- s5, s2 +- s6 and s0 +- s4 (video.go:870-878).
+        // With the two levels of such a pair side by side in one register, dp2a (int16 pair x int8 pair, summed)
+        // premultiplies (video.go:744) AND forms the sum or the difference: 1 byte permute + 2 dp2a per pair
+        // instead of 2 dp2a + 2 additions.  c[] then holds, per column i:
+        //   c[i] = s0 + s4, c[32+i] = s0 - s4, c[8+i] = s1 + s7, c[56+i] = s1 - s7,
+        //   c[24+i] = s3 + s5, c[40+i] = s5 - s3, c[16+i] = s2 + s6, c[48+i] = s2 - s6.
+        uint32_t w[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint4 q = *reinterpret_cast<const uint4*>(src + ((r << 4) ^ sw));
+            w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = 2 * p + h;
+                const uint32_t sel = h ? 0x7632u : 0x5410u;
+#define PAIR(K, RA, RB)                                                                              \
+    do {                                                                                            \
+        const int ab = (int)__byte_perm(w[RA][p], w[RB][p], sel);                                   \
+        c[RA * 8 + i] = __dp2a_lo(ab, kPairSum[K * 8 + i], K == 0 && i == 0 ? 128 : 0);             \
+        c[RB * 8 + i] = __dp2a_lo(ab, kPairDif[K * 8 + i], K == 0 && i == 0 ? 128 : 0);             \
+    } while (0)
+                PAIR(0, 0, 4);
+                PAIR(1, 1, 7);
+                PAIR(2, 3, 5);
+                PAIR(3, 2, 6);
+#undef PAIR
+            }
+        }
+#else
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const uint4 w = *reinterpret_cast<const uint4*>(src + ((r << 4) ^ sw));
@@ -581,6 +670,7 @@ __device__ __forceinline__ void block_load(const BlockCtx& B, const uint8_t* s_c
         // The +128 of the final (x + 128) >> 8 (video.go:918-925) rides on the DC term: s0 enters every output of both
         // passes exactly once with weight +1 and never passes through a rounding shift (x1 = m0 - b1, x3 = m0 + b1).
         c[0] += 128;
+#endif
     }
 }
 
@@ -608,7 +698,11 @@ __device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (
     }
 #pragma unroll
     for (int i = 0; i < 8; i++)  // columns, video.go:869-896
+#if MPEGB200_PAIRED
+        idct_pass8_pre(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
+#else
         idct_pass8(c[i], c[8 + i], c[16 + i], c[24 + i], c[32 + i], c[40 + i], c[48 + i], c[56 + i]);
+#endif
 #pragma unroll
     for (int r = 0; r < 8; r++) {  // rows, video.go:899-926, then copy/addBlockToDest (:943-971)
         int k[8], v[8];
@@ -626,9 +720,7 @@ __device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (
 struct Smem {
     static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
     static constexpr int win = coef + kNT * 128;                 // the window area: one strip or kG x 1280
-    static constexpr int plan = win + kWinArea;                  // 2 x 1024: the group's plan (the one-shot kernel uses one)
-    static constexpr int bar = plan + 2 * (int)sizeof(GroupPlan);
-    static constexpr int total = bar + 64;
+    static constexpr int plan = win + kWinArea;                  // 1024: the group's plan, then the mbarrier
     static constexpr int total_oneshot = plan + (int)sizeof(GroupPlan) + 16;
 };
 
@@ -709,19 +801,37 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __maxnreg__(112) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                             const SlabMaps* __restrict__ slab_maps,
-                                                             const GroupPlan* __restrict__ plans, uint32_t n_groups) {
+// kHalves independent 96-thread halves per CTA, each with its own shared-memory set: shared memory and registers are
+// both allocated per CTA, and a 192-thread CTA with 2 x 36 KB packs the SM's 228 KB better than 96-thread ones do
+// (measured: 5 CTAs of one half fit, but 3 CTAs of two).  The halves never synchronise with each other.
+template <int kHalves>
+struct SmemS {
+    static constexpr int coef = 0;                                   // kHalves x kNT x 128, 1024-aligned tiles
+    static constexpr int rest = kHalves * kNT * 128;
+    static constexpr int win = 0;                                    // per half, relative to rest + half * per_half
+    static constexpr int plan = kWinArea;                            // 2 x 1024
+    static constexpr int bar = plan + 2 * (int)sizeof(GroupPlan);    // full, plan[0], plan[1], counter
+    static constexpr int per_half = bar + 128;                        // keeps every TMA destination 128-byte aligned
+    static constexpr int total = rest + kHalves * per_half;
+};
+
+template <int kHalves>
+__global__ void __maxnreg__(104) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                    const SlabMaps* __restrict__ slab_maps,
+                                                    const GroupPlan* __restrict__ plans, uint32_t n_groups) {
+    using S = SmemS<kHalves>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* s_coef = smem + Smem::coef;
-    uint8_t* s_win = smem + Smem::win;
-    GroupPlan* s_plan = reinterpret_cast<GroupPlan*>(smem + Smem::plan);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+    const int half = kHalves > 1 ? (int)threadIdx.x / kNT : 0;
+    const int tid = (int)threadIdx.x - half * kNT, lane = tid & 31, warp = tid >> 5;
+    uint8_t* s_coef = smem + S::coef + half * (kNT * 128);
+    uint8_t* s_half = smem + S::rest + half * S::per_half;
+    uint8_t* s_win = s_half + S::win;
+    GroupPlan* s_plan = reinterpret_cast<GroupPlan*>(s_half + S::plan);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_half + S::bar);
     uint64_t* bar_plan = bar_full + 1;   // [2]
     uint32_t* s_left = reinterpret_cast<uint32_t*>(bar_full + 3);   // warps that have left the load step
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t stride = gridDim.x;
-    uint32_t g = blockIdx.x;
+    const uint32_t stride = gridDim.x * kHalves;
+    uint32_t g = blockIdx.x * kHalves + half;
 
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -731,17 +841,19 @@ __global__ void __maxnreg__(112) fused_stream_kernel(const __grid_constant__ CUt
         *s_left = 0;
         fence_barrier_init();
         // the first two plans
-        mbar_arrive_expect_tx(bar_plan, (uint32_t)sizeof(GroupPlan));
-        bulk_load(&s_plan[0], plans + g, (uint32_t)sizeof(GroupPlan), bar_plan);
+        if (g < n_groups) {
+            mbar_arrive_expect_tx(bar_plan, (uint32_t)sizeof(GroupPlan));
+            bulk_load(&s_plan[0], plans + g, (uint32_t)sizeof(GroupPlan), bar_plan);
+        }
         if (g + stride < n_groups) {
             mbar_arrive_expect_tx(bar_plan + 1, (uint32_t)sizeof(GroupPlan));
             bulk_load(&s_plan[1], plans + g + stride, (uint32_t)sizeof(GroupPlan), bar_plan + 1);
         }
     }
     __syncthreads();
+    if (g >= n_groups) return;   // whole half: nothing to do (no CTA-wide barrier below)
     mbar_wait(bar_plan, 0);
     issue_group(s_plan[0], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane);
-    __syncthreads();   // all three warps have issued their part before anybody can count them out below
 
     for (uint32_t i = 0; g < n_groups; i++, g += stride) {
         const uint32_t buf = i & 1;
@@ -753,27 +865,30 @@ __global__ void __maxnreg__(112) fused_stream_kernel(const __grid_constant__ CUt
         int c[64];
         mbar_wait(bar_full, i & 1);           // the group's tiles have landed
         if (B.live) block_load(B, s_coef, s_win, p0, p1, c);
-        // This warp has left shared memory (windows, coefficients, plan[buf]).  The last warp to get here fetches the
-        // next group's tiles; the other two go straight on to their arithmetic.
+        // This warp has left shared memory (windows, coefficients, plan[buf]).  The last warp of the half to get here
+        // fetches the next group's tiles; the other two go straight on to their arithmetic.  (In the first round the
+        // three warps issued their own share above; a warp cannot be counted out before it has done that.)
         __syncwarp();
         uint32_t left = 0;
-        if (lane == 0) left = atomicAdd(s_left, 1u);
+        if (lane == 0) {
+            __threadfence_block();
+            left = atomicAdd(s_left, 1u);
+        }
         left = __shfl_sync(0xffffffffu, left, 0);
         if (left == 2) {
-            const bool more = g + stride < n_groups;
             if (lane == 0) {
                 *s_left = 0;
                 __threadfence_block();
                 fence_proxy_async();          // generic-proxy reads of the tiles before the async-proxy writes
             }
             __syncwarp();
-            if (more) {
+            if (g + stride < n_groups) {
                 mbar_wait(bar_plan + (buf ^ 1), ((i + 1) >> 1) & 1);
                 const GroupPlan& N = s_plan[buf ^ 1];
                 // one warp plays all three roles of issue_group
+                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 2, lane);
                 issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 0, lane);
                 issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 1, lane);
-                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 2, lane);
                 if (lane == 0 && g + 2 * stride < n_groups) {   // and the plan after it
                     mbar_arrive_expect_tx(bar_plan + buf, (uint32_t)sizeof(GroupPlan));
                     bulk_load(&s_plan[buf], plans + g + 2 * stride, (uint32_t)sizeof(GroupPlan), bar_plan + buf);
@@ -792,36 +907,50 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
                              uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream) {
     if (n_mb == 0) return cudaSuccess;
-    // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0
-    // makes the plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
+    // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream|stream1 picks the arithmetic kernel (stream: two
+    // halves per CTA, stream1: one), MPEGB200_STRIP=0 makes the plan pre-pass stage every window with its own boxes,
+    // MPEGB200_STREAM_CTAS sets the streaming grid.
     static int variant = -1, allow_strip = 1, stream_ctas = 0;
     if (variant < 0) {
+        const char* v = getenv("MPEGB200_FUSED");
+        int want = (v && strcmp(v, "stream") == 0) ? 2 : (v && strcmp(v, "stream1") == 0) ? 1 : 0;   // default: the one-shot kernel
         cudaError_t e = cudaFuncSetAttribute(fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total_oneshot);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
+        e = cudaFuncSetAttribute(fused_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS<1>::total);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fused_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS<2>::total);
         if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel, kNT, Smem::total);
+        if (want == 2)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel<2>, 2 * kNT, SmemS<2>::total);
+        else
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel<1>, kNT, SmemS<1>::total);
         if (e != cudaSuccess) return e;
         stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
         const char* c = getenv("MPEGB200_STREAM_CTAS");
         if (c && atoi(c) > 0) stream_ctas = atoi(c);
         const char* s = getenv("MPEGB200_STRIP");
         allow_strip = !(s && s[0] == '0');
-        const char* v = getenv("MPEGB200_FUSED");
-        variant = (v && strcmp(v, "oneshot") == 0) ? 0 : 1;
+        if (getenv("MPEGB200_DEBUG")) fprintf(stderr, "[mpegb200] fused variant %d, %d CTAs per SM, grid %d\n", want, per_sm, stream_ctas);
+        variant = want;
     }
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks, allow_strip);
-    if (variant == 0)
-        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(*reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans);
-    else
-        fused_stream_kernel<<<n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas, kNT, Smem::total, stream>>>(
-            *reinterpret_cast<const CUtensorMap*>(coef_map), d_maps, plans, n_groups);
+    const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
+    if (variant == 0) {
+        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans);
+    } else if (variant == 1) {
+        const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
+        fused_stream_kernel<1><<<grid, kNT, SmemS<1>::total, stream>>>(cm, d_maps, plans, n_groups);
+    } else {
+        const uint32_t want_ctas = (n_groups + 1) / 2;
+        const uint32_t grid = want_ctas < (uint32_t)stream_ctas ? want_ctas : (uint32_t)stream_ctas;
+        fused_stream_kernel<2><<<grid, 2 * kNT, SmemS<2>::total, stream>>>(cm, d_maps, plans, n_groups);
+    }
     return cudaGetLastError();
 }
 

@@ -1,0 +1,20 @@
+#!/bin/bash
+# usage (under gpurun): bash tools/ab_run2.sh tag "name|ENV=..;ENV=.." ...   -- bench each variant, then ncu of the variants named in $NCU
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e"
+for spec in "$@"; do
+  name=${spec%%|*}; envs=${spec#*|}; envs=${envs//;/ }
+  if [ -n "$TESTS" ]; then echo "== tests $name"; env $envs timeout 600 python -m pytest tests/test_gpu_video.py -m gpu -x -q 2>&1 | tail -3 | tee $OUT/tests_$name.log; fi
+  echo "== bench $name"
+  env $envs timeout 600 $B 2> $OUT/bench_$name.err | tee $OUT/bench_$name.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['fused_ms'], d['roofline']['frac'], d['value'], d['clocks'])"
+done
+for spec in $NCU; do
+  name=${spec%%|*}; envs=${spec#*|}; envs=${envs//;/ }
+  echo "== ncu $name"
+  env $envs timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fused" -s 3 -c 1 -f -o $OUT/ncu_$name \
+      python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > $OUT/ncu_$name.log 2>&1
+  tail -2 $OUT/ncu_$name.log
+done
+ls -la $OUT
