@@ -213,6 +213,7 @@ constexpr int kStripLBytes = kStripLW * kStripLH;                     // 14592
 constexpr int kStripCBytes = kStripCW * kStripCH;                     // 3840 per plane
 constexpr int kStripTx = kStripLBytes + 2 * kStripCBytes;             // 22272
 constexpr int kWinArea = (kG * kWinBytes > kStripTx ? kG * kWinBytes : kStripTx + 127) / 128 * 128;
+constexpr int kDefaultVariant = 0;     // 0: one-shot kernel, 1: streaming kernel (MPEGB200_FUSED overrides)
 constexpr int kStripMinPred = 3;       // fewer predicted macroblocks than this: their own boxes are cheaper
 
 // ------------------------------------------------------------------------------------------------
@@ -241,23 +242,34 @@ struct PlanBox {              // 16 bytes, box mode only: where the two boxes of
 };
 static_assert(sizeof(PlanBox) == 16, "PlanBox size");
 
-struct GroupPlan {            // 1024 bytes = 64 x 16
-    uint32_t n_box, n_pred, block0, tx_bytes;   // coefficient boxes, predicted macroblocks, first block, expect_tx
+// A group plan in global memory: head (what the fetch needs), body (what the block threads need), boxes (box mode only).
+struct PlanHead {             // 48 bytes
+    uint32_t n_box, n_pred, block0, tx_bytes;   // coefficient boxes, predicted macroblocks, first block, bytes the boxes deliver
     uint16_t strip, slab, z;                    // strip mode: one luma + one chroma box at (sx, sy) / (scx, scy)
     uint16_t pitch_y, pitch_c, cr_win;          // window row pitches; Cb -> Cr window distance
     int16_t sx, sy, scx, scy;                   // strip origins in bytes / rows (x multiples of 16)
     uint32_t pad0[3];
+};
+static_assert(sizeof(PlanHead) == 48, "PlanHead size");
+
+struct PlanBody {             // 576 bytes
     uint16_t map[kNT];        // output-block list, sorted by (coded?, interpolation mode)
     // The per-macroblock fields as arrays (PlanMb, field by field): the 32 block threads of a warp read the fields of up to
     // 16 different macroblocks, and an array of 16 entries of 8 bytes or less never puts two of them on one bank.
     uint8_t* dst_y[kG];
     uint32_t dst_c_off[kG], dst_cr_off[kG];
     uint16_t luma_w[kG], mcw[kG], woff_y[kG], woff_c[kG];
-    uint8_t pad1[768 - 48 - 2 * kNT - 8 * kG - 8 * kG - 8 * kG];
+};
+static_assert(sizeof(PlanBody) == 576, "PlanBody size");
+
+struct GroupPlan {            // 1024 bytes = 64 x 16
+    PlanHead h;
+    PlanBody b;
+    uint8_t pad1[768 - 48 - 576];
     PlanBox box[kG];
 };
 static_assert(sizeof(GroupPlan) == 1024, "GroupPlan size");
-static_assert(offsetof(GroupPlan, box) == 768, "the boxes are the last quarter");
+static_assert(offsetof(GroupPlan, b) == 48 && offsetof(GroupPlan, box) == 768, "GroupPlan layout");
 
 // Output-block list entry: [3:0] macroblock in group, [6:4] block 0..5, [7] coded, [14:8] coefficient slot.
 constexpr uint32_t kNoBlock = 0xFFFFu;
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
     for (int i = lane; i < 64; i += 16) (&s_cnt2[gl][0][0])[i] = 0;
     if (lane < R_N) s_red[gl][lane] = ((lane & 1) || lane == R_LW) ? INT_MIN : INT_MAX;   // even slots are minima, odd ones (and R_LW) maxima
     __syncthreads();
-    for (int i = lane; i < kNT; i += 16) P.map[i] = (uint16_t)kNoBlock;
+    for (int i = lane; i < kNT; i += 16) P.b.map[i] = (uint16_t)kNoBlock;
 
     const uint32_t m0 = group * (uint32_t)kG;
     const bool have = group < n_groups && m0 + lane < n_mb;
@@ -362,7 +374,11 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                     for (int k = 0; k < 6; k++) {
                         if (out_mask & (0x20u >> k)) {
                             const bool coded = (cbp & (0x20u >> k)) != 0;
-                            const uint32_t bin = (coded ? 0u : 4u) + (predicted ? (k < 4 ? mode_y : mode_c) : 0u);
+                            // Bin order H, copy, V, HV: a warp that straddles two bins runs both interpolation paths, and
+                            // with 96 blocks in four bins the two middle bins are the ones that get split over warps --
+                            // so the two cheapest paths (copy, V) sit in the middle.  Intra blocks (no window) count as copy.
+                            const uint32_t mode_k = predicted ? (k < 4 ? mode_y : mode_c) : 0u;
+                            const uint32_t bin = (coded ? 0u : 4u) + ((0x3201u >> (4 * mode_k)) & 3u);
                             const uint32_t res = coded ? (slot_run & 7u) : ((uint32_t)(lane + k) & 7u);
                             const uint32_t pp = atomicAdd(&s_cnt2[gl][bin][res], 1u);  // < 96
                             atomicAdd(&s_cnt[gl][bin], 1u);
@@ -430,13 +446,13 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                 b.pred = 1;
             }
         }
-        P.dst_y[lane] = c.dst_y;
-        P.dst_c_off[lane] = c.dst_c_off;
-        P.dst_cr_off[lane] = c.dst_cr_off;
-        P.luma_w[lane] = c.luma_w;
-        P.mcw[lane] = c.mcw;
-        P.woff_y[lane] = c.woff_y;
-        P.woff_c[lane] = c.woff_c;
+        P.b.dst_y[lane] = c.dst_y;
+        P.b.dst_c_off[lane] = c.dst_c_off;
+        P.b.dst_cr_off[lane] = c.dst_cr_off;
+        P.b.luma_w[lane] = c.luma_w;
+        P.b.mcw[lane] = c.mcw;
+        P.b.woff_y[lane] = c.woff_y;
+        P.b.woff_c[lane] = c.woff_c;
         P.box[lane] = b;
     }
     if (out_mask) {
@@ -459,41 +475,43 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                     bsel = bin == (uint32_t)b ? base_of[b] : bsel;
                     pp += min(s_cnt2[gl][bin][b], idx + ((uint32_t)b < res ? 1u : 0u));
                 }
-                P.map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
+                P.b.map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
                 if (coded) slot++;
             }
         }
     }
     if (lane == 0) {
         const uint32_t n_box = (s_cnt[gl][8] + kCoefBox - 1) / kCoefBox;
-        P.n_box = n_box;
-        P.n_pred = n_pred;
-        P.block0 = block0;
-        P.strip = strip ? 1 : 0;
+        P.h.n_box = n_box;
+        P.h.n_pred = n_pred;
+        P.h.block0 = block0;
+        P.h.strip = strip ? 1 : 0;
         if (strip) {
-            P.tx_bytes = n_box * (kCoefBox * 128) + kStripTx;
-            P.slab = (uint16_t)((uint32_t)R[R_MINZ] >> 16);
-            P.z = (uint16_t)(R[R_MINZ] & 0xffff);
-            P.pitch_y = kStripLW;
-            P.pitch_c = kStripCW;
-            P.cr_win = kStripCBytes;
-            P.sx = (int16_t)X0;
-            P.sy = (int16_t)Y0;
-            P.scx = (int16_t)CX0;
-            P.scy = (int16_t)CY0;
+            P.h.tx_bytes = n_box * (kCoefBox * 128) + kStripTx;
+            P.h.slab = (uint16_t)((uint32_t)R[R_MINZ] >> 16);
+            P.h.z = (uint16_t)(R[R_MINZ] & 0xffff);
+            P.h.pitch_y = kStripLW;
+            P.h.pitch_c = kStripCW;
+            P.h.cr_win = kStripCBytes;
+            P.h.sx = (int16_t)X0;
+            P.h.sy = (int16_t)Y0;
+            P.h.scx = (int16_t)CX0;
+            P.h.scy = (int16_t)CY0;
         } else {
-            P.tx_bytes = n_box * (kCoefBox * 128) + n_pred * kWinTx;
-            P.pitch_y = 32;
-            P.pitch_c = 32;
-            P.cr_win = kWinC;
+            P.h.tx_bytes = n_box * (kCoefBox * 128) + n_pred * kWinTx;
+            P.h.pitch_y = 32;
+            P.h.pitch_c = 32;
+            P.h.cr_win = kWinC;
         }
     }
     __syncthreads();
-    if (group < n_groups) {  // 1024 bytes out, 16 bytes per lane per step
+    if (group < n_groups) {  // head + body (640 bytes with padding) out, 16 bytes per lane per step; the boxes only in box mode
         const uint4* src = reinterpret_cast<const uint4*>(&P);
         uint4* dstp = reinterpret_cast<uint4*>(plans + group);
-#pragma unroll
-        for (int i = 0; i < 4; i++) dstp[lane + 16 * i] = src[lane + 16 * i];
+        dstp[lane] = src[lane];
+        dstp[lane + 16] = src[lane + 16];
+        if (lane < 8) dstp[lane + 32] = src[lane + 32];
+        if (!strip) dstp[lane + 48] = src[lane + 48];
     }
 }
 
@@ -512,7 +530,7 @@ struct BlockCtx {
     bool live, pred, coded;
 };
 
-__device__ __forceinline__ void block_setup(const GroupPlan& P, int t, BlockCtx& B) {
+__device__ __forceinline__ void block_setup(const PlanHead& H, const PlanBody& P, int t, BlockCtx& B) {
     const uint32_t e = P.map[t];
     B.live = e != kNoBlock;
     const int j = e & 15, k = (e >> 4) & 7;
@@ -525,13 +543,13 @@ __device__ __forceinline__ void block_setup(const GroupPlan& P, int t, BlockCtx&
     if (k < 4) {
         B.pitch = lw;
         B.dst = P.dst_y[j] + (size_t)((k >> 1) * 8) * B.pitch + (k & 1) * 8;
-        B.wpitch = P.pitch_y;
+        B.wpitch = H.pitch_y;
         B.win = P.woff_y[j] + (uint32_t)((k >> 1) * 8) * B.wpitch + (k & 1) * 8;
     } else {
         B.pitch = lw >> 1;
         B.dst = P.dst_y[j] + P.dst_c_off[j] + (k == 5 ? P.dst_cr_off[j] : 0u);
-        B.wpitch = P.pitch_c;
-        B.win = P.woff_c[j] + (k == 5 ? (uint32_t)P.cr_win : 0u);
+        B.wpitch = H.pitch_c;
+        B.win = P.woff_c[j] + (k == 5 ? (uint32_t)H.cr_win : 0u);
     }
 }
 
@@ -728,10 +746,11 @@ struct Smem {
 // warp 0 the luma boxes, warp 1 the chroma boxes, lane = macroblock.  Warp 2 the coefficient boxes and the expect_tx;
 // complete_tx of boxes issued before that arrival is fine: the phase cannot complete before the (single) arrival, and
 // the transaction count is allowed to run negative meanwhile.
-__device__ __forceinline__ void issue_group(const GroupPlan& P, const CUtensorMap* coef_map, const SlabMaps* slab_maps,
-                                            uint8_t* s_coef, uint8_t* s_win, uint64_t* bar, int warp, int lane) {
+__device__ __forceinline__ void issue_group(const PlanHead& P, const PlanBox* boxes, const CUtensorMap* coef_map,
+                                            const SlabMaps* slab_maps, uint8_t* s_coef, uint8_t* s_win, uint64_t* bar,
+                                            int warp, int lane, uint32_t extra_tx) {
     if (warp == 2) {
-        if (lane == 0) mbar_arrive_expect_tx(bar, P.tx_bytes);
+        if (lane == 0) mbar_arrive_expect_tx(bar, P.tx_bytes + extra_tx);
         if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
             tma_load_2d(s_coef + lane * (kCoefBox * 128), coef_map, bar, 0, (int)(P.block0 + lane * kCoefBox));
     } else if (P.strip) {
@@ -742,14 +761,16 @@ __device__ __forceinline__ void issue_group(const GroupPlan& P, const CUtensorMa
             else
                 tma_load_4d(s_win + kStripLBytes, maps->chroma_strip, bar, P.scx >> 3, P.scy, 0, P.z);
         }
-    } else if (lane < kG && P.box[lane].pred) {
-        const PlanBox& t = P.box[lane];
-        const SlabMaps* maps = slab_maps + t.slab;
-        uint8_t* w = s_win + lane * kWinBytes;
-        if (warp == 0)
-            tma_load_3d(w, maps->luma, bar, t.lx, t.ly, t.z);
-        else  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
-            tma_load_4d(w + kWinY, maps->chroma, bar, t.cx, t.cy, 0, t.z);
+    } else if (lane < kG) {
+        const PlanBox t = boxes[lane];   // shared memory (one-shot kernel) or the plan in global memory (streaming kernel)
+        if (t.pred) {
+            const SlabMaps* maps = slab_maps + t.slab;
+            uint8_t* w = s_win + lane * kWinBytes;
+            if (warp == 0)
+                tma_load_3d(w, maps->luma, bar, t.lx, t.ly, t.z);
+            else  // one rank-4 box fetches the Cb and the Cr window (plane is the third dimension)
+                tma_load_4d(w + kWinY, maps->chroma, bar, t.cx, t.cy, 0, t.z);
+        }
     }
 }
 
@@ -774,10 +795,10 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
         fence_barrier_init();
     }
     __syncthreads();
-    issue_group(P, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane);
+    issue_group(P.h, P.box, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane, 0);
 
     BlockCtx B;
-    block_setup(P, tid, B);
+    block_setup(P.h, P.b, tid, B);
     if (!B.live) return;
     mbar_wait(s_bar, 0);   // all tiles of the group have landed
     uint32_t p0[8], p1[8];
@@ -801,73 +822,66 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// kHalves independent 96-thread halves per CTA, each with its own shared-memory set: shared memory and registers are
-// both allocated per CTA, and a 192-thread CTA with 2 x 36 KB packs the SM's 228 KB better than 96-thread ones do
-// (measured: 5 CTAs of one half fit, but 3 CTAs of two).  The halves never synchronise with each other.
-template <int kHalves>
 struct SmemS {
-    static constexpr int coef = 0;                                   // kHalves x kNT x 128, 1024-aligned tiles
-    static constexpr int rest = kHalves * kNT * 128;
-    static constexpr int win = 0;                                    // per half, relative to rest + half * per_half
-    static constexpr int plan = kWinArea;                            // 2 x 1024
-    static constexpr int bar = plan + 2 * (int)sizeof(GroupPlan);    // full, plan[0], plan[1], counter
-    static constexpr int per_half = bar + 128;                        // keeps every TMA destination 128-byte aligned
-    static constexpr int total = rest + kHalves * per_half;
+    static constexpr int coef = 0;                                   // kNT x 128, 1024-aligned, swizzled by TMA
+    static constexpr int win = coef + kNT * 128;
+    static constexpr int body = win + kWinArea;                      // the current group's PlanBody
+    static constexpr int head = body + (int)sizeof(PlanBody);        // 2 x PlanHead: current and next group
+    static constexpr int bar = head + 2 * (int)sizeof(PlanHead);     // full, head[0], head[1], counter
+    static constexpr int total = bar + 32;
 };
+// 6 CTAs per SM need at most 35,600 bytes each (measured: the one-shot kernel's 35,600 fit six times, 36,672 did not)
+// and at most 96 registers (16,384 per scheduler / (96 x 32) = 5 warps per scheduler = 20 per SM; 104 gives 16).
+static_assert(SmemS::total <= 35600, "streaming kernel: shared memory budget for 6 CTAs per SM");
 
-template <int kHalves>
-__global__ void __maxnreg__(104) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
-                                                    const SlabMaps* __restrict__ slab_maps,
-                                                    const GroupPlan* __restrict__ plans, uint32_t n_groups) {
-    using S = SmemS<kHalves>;
+__global__ void __maxnreg__(96) fused_stream_kernel(const __grid_constant__ CUtensorMap coef_map,
+                                                   const SlabMaps* __restrict__ slab_maps,
+                                                   const GroupPlan* __restrict__ plans, uint32_t n_groups) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int half = kHalves > 1 ? (int)threadIdx.x / kNT : 0;
-    const int tid = (int)threadIdx.x - half * kNT, lane = tid & 31, warp = tid >> 5;
-    uint8_t* s_coef = smem + S::coef + half * (kNT * 128);
-    uint8_t* s_half = smem + S::rest + half * S::per_half;
-    uint8_t* s_win = s_half + S::win;
-    GroupPlan* s_plan = reinterpret_cast<GroupPlan*>(s_half + S::plan);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_half + S::bar);
-    uint64_t* bar_plan = bar_full + 1;   // [2]
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* s_coef = smem + SmemS::coef;
+    uint8_t* s_win = smem + SmemS::win;
+    PlanBody& s_body = *reinterpret_cast<PlanBody*>(smem + SmemS::body);
+    PlanHead* s_head = reinterpret_cast<PlanHead*>(smem + SmemS::head);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SmemS::bar);
+    uint64_t* bar_head = bar_full + 1;   // [2]
     uint32_t* s_left = reinterpret_cast<uint32_t*>(bar_full + 3);   // warps that have left the load step
-    const uint32_t stride = gridDim.x * kHalves;
-    uint32_t g = blockIdx.x * kHalves + half;
+    const uint32_t stride = gridDim.x;
+    uint32_t g = blockIdx.x;
 
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         mbar_init(bar_full, 1);
-        mbar_init(bar_plan, 1);
-        mbar_init(bar_plan + 1, 1);
+        mbar_init(bar_head, 1);
+        mbar_init(bar_head + 1, 1);
         *s_left = 0;
         fence_barrier_init();
-        // the first two plans
-        if (g < n_groups) {
-            mbar_arrive_expect_tx(bar_plan, (uint32_t)sizeof(GroupPlan));
-            bulk_load(&s_plan[0], plans + g, (uint32_t)sizeof(GroupPlan), bar_plan);
-        }
+        // the heads of the first two groups
+        mbar_arrive_expect_tx(bar_head, (uint32_t)sizeof(PlanHead));
+        bulk_load(&s_head[0], &plans[g].h, (uint32_t)sizeof(PlanHead), bar_head);
         if (g + stride < n_groups) {
-            mbar_arrive_expect_tx(bar_plan + 1, (uint32_t)sizeof(GroupPlan));
-            bulk_load(&s_plan[1], plans + g + stride, (uint32_t)sizeof(GroupPlan), bar_plan + 1);
+            mbar_arrive_expect_tx(bar_head + 1, (uint32_t)sizeof(PlanHead));
+            bulk_load(&s_head[1], &plans[g + stride].h, (uint32_t)sizeof(PlanHead), bar_head + 1);
         }
     }
     __syncthreads();
-    if (g >= n_groups) return;   // whole half: nothing to do (no CTA-wide barrier below)
-    mbar_wait(bar_plan, 0);
-    issue_group(s_plan[0], &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane);
+    mbar_wait(bar_head, 0);
+    // first group: the three warps share the fetch (the body rides on the same mbarrier as the tiles)
+    issue_group(s_head[0], plans[g].box, &coef_map, slab_maps, s_coef, s_win, bar_full, warp, lane, (uint32_t)sizeof(PlanBody));
+    if (tid == 64) bulk_load(&s_body, &plans[g].b, (uint32_t)sizeof(PlanBody), bar_full);
 
     for (uint32_t i = 0; g < n_groups; i++, g += stride) {
         const uint32_t buf = i & 1;
-        const GroupPlan& P = s_plan[buf];
-        mbar_wait(bar_plan + buf, (i >> 1) & 1);
+        mbar_wait(bar_head + buf, (i >> 1) & 1);   // long since complete (the fetch below needed it); makes the head visible here
+        mbar_wait(bar_full, i & 1);           // the group's tiles and plan body have landed
         BlockCtx B;
-        block_setup(P, tid, B);
+        block_setup(s_head[buf], s_body, tid, B);
         uint32_t p0[8], p1[8];
         int c[64];
-        mbar_wait(bar_full, i & 1);           // the group's tiles have landed
         if (B.live) block_load(B, s_coef, s_win, p0, p1, c);
-        // This warp has left shared memory (windows, coefficients, plan[buf]).  The last warp of the half to get here
-        // fetches the next group's tiles; the other two go straight on to their arithmetic.  (In the first round the
-        // three warps issued their own share above; a warp cannot be counted out before it has done that.)
+        // This warp has left shared memory (windows, coefficients, plan).  The last warp to get here fetches the next
+        // group's tiles; the other two go straight on to their arithmetic.  (In the first round the three warps
+        // issued their own share above; nobody can pass the wait on bar_full before all of that has landed.)
         __syncwarp();
         uint32_t left = 0;
         if (lane == 0) {
@@ -882,16 +896,18 @@ __global__ void __maxnreg__(104) fused_stream_kernel(const __grid_constant__ CUt
                 fence_proxy_async();          // generic-proxy reads of the tiles before the async-proxy writes
             }
             __syncwarp();
-            if (g + stride < n_groups) {
-                mbar_wait(bar_plan + (buf ^ 1), ((i + 1) >> 1) & 1);
-                const GroupPlan& N = s_plan[buf ^ 1];
+            const uint32_t gn = g + stride;
+            if (gn < n_groups) {
+                mbar_wait(bar_head + (buf ^ 1), ((i + 1) >> 1) & 1);
+                const PlanHead& N = s_head[buf ^ 1];
                 // one warp plays all three roles of issue_group
-                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 2, lane);
-                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 0, lane);
-                issue_group(N, &coef_map, slab_maps, s_coef, s_win, bar_full, 1, lane);
-                if (lane == 0 && g + 2 * stride < n_groups) {   // and the plan after it
-                    mbar_arrive_expect_tx(bar_plan + buf, (uint32_t)sizeof(GroupPlan));
-                    bulk_load(&s_plan[buf], plans + g + 2 * stride, (uint32_t)sizeof(GroupPlan), bar_plan + buf);
+                issue_group(N, plans[gn].box, &coef_map, slab_maps, s_coef, s_win, bar_full, 2, lane, (uint32_t)sizeof(PlanBody));
+                if (lane == 0) bulk_load(&s_body, &plans[gn].b, (uint32_t)sizeof(PlanBody), bar_full);
+                issue_group(N, plans[gn].box, &coef_map, slab_maps, s_coef, s_win, bar_full, 0, lane, 0);
+                issue_group(N, plans[gn].box, &coef_map, slab_maps, s_coef, s_win, bar_full, 1, lane, 0);
+                if (lane == 0 && gn + stride < n_groups) {   // and the head after it, into the slot this group has left
+                    mbar_arrive_expect_tx(bar_head + buf, (uint32_t)sizeof(PlanHead));
+                    bulk_load(&s_head[buf], &plans[gn + stride].h, (uint32_t)sizeof(PlanHead), bar_head + buf);
                 }
             }
         }
@@ -907,33 +923,29 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
                              uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream) {
     if (n_mb == 0) return cudaSuccess;
-    // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream|stream1 picks the arithmetic kernel (stream: two
-    // halves per CTA, stream1: one), MPEGB200_STRIP=0 makes the plan pre-pass stage every window with its own boxes,
-    // MPEGB200_STREAM_CTAS sets the streaming grid.
+    // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the
+    // plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
     static int variant = -1, allow_strip = 1, stream_ctas = 0;
     if (variant < 0) {
         const char* v = getenv("MPEGB200_FUSED");
-        int want = (v && strcmp(v, "stream") == 0) ? 2 : (v && strcmp(v, "stream1") == 0) ? 1 : 0;   // default: the one-shot kernel
+        const int want = (v && strcmp(v, "stream") == 0) ? 1 : (v && strcmp(v, "oneshot") == 0) ? 0 : kDefaultVariant;
         cudaError_t e = cudaFuncSetAttribute(fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total_oneshot);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fused_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS<1>::total);
+        e = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS::total);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fused_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS<2>::total);
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
+        int dev = 0, sms = 0, per_sm = 0, per_sm1 = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (want == 2)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel<2>, 2 * kNT, SmemS<2>::total);
-        else
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel<1>, kNT, SmemS<1>::total);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel, kNT, SmemS::total);
         if (e != cudaSuccess) return e;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fused_tma_kernel, kNT, Smem::total_oneshot);
         stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
         const char* c = getenv("MPEGB200_STREAM_CTAS");
         if (c && atoi(c) > 0) stream_ctas = atoi(c);
         const char* s = getenv("MPEGB200_STRIP");
         allow_strip = !(s && s[0] == '0');
-        if (getenv("MPEGB200_DEBUG")) fprintf(stderr, "[mpegb200] fused variant %d, %d CTAs per SM, grid %d\n", want, per_sm, stream_ctas);
+        if (getenv("MPEGB200_DEBUG"))
+            fprintf(stderr, "[mpegb200] fused variant %d; CTAs per SM: streaming %d, one-shot %d; streaming grid %d\n", want, per_sm, per_sm1, stream_ctas);
         variant = want;
     }
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
@@ -943,13 +955,9 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
     if (variant == 0) {
         fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans);
-    } else if (variant == 1) {
-        const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
-        fused_stream_kernel<1><<<grid, kNT, SmemS<1>::total, stream>>>(cm, d_maps, plans, n_groups);
     } else {
-        const uint32_t want_ctas = (n_groups + 1) / 2;
-        const uint32_t grid = want_ctas < (uint32_t)stream_ctas ? want_ctas : (uint32_t)stream_ctas;
-        fused_stream_kernel<2><<<grid, 2 * kNT, SmemS<2>::total, stream>>>(cm, d_maps, plans, n_groups);
+        const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
+        fused_stream_kernel<<<grid, kNT, SmemS::total, stream>>>(cm, d_maps, plans, n_groups);
     }
     return cudaGetLastError();
 }
