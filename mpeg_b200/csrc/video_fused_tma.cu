@@ -81,6 +81,24 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* map, uint64_t
         : "memory");
 }
 
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// the same boxes, fetched into L2 only (for a group that a later CTA will decode)
+__device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const void* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)
 __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
     uint32_t d;
@@ -213,6 +231,7 @@ constexpr int kStripLBytes = kStripLW * kStripLH;                     // 14592
 constexpr int kStripCBytes = kStripCW * kStripCH;                     // 3840 per plane
 constexpr int kStripTx = kStripLBytes + 2 * kStripCBytes;             // 22272
 constexpr int kWinArea = (kG * kWinBytes > kStripTx ? kG * kWinBytes : kStripTx + 127) / 128 * 128;
+constexpr int kDefaultPrefetchDist = 0; // groups ahead to prefetch into L2 (MPEGB200_PREFETCH_DIST overrides)
 constexpr int kDefaultVariant = 0;     // 0: one-shot kernel, 1: streaming kernel (MPEGB200_FUSED overrides)
 constexpr int kStripMinPred = 3;       // fewer predicted macroblocks than this: their own boxes are cheaper
 
@@ -276,9 +295,8 @@ constexpr uint32_t kNoBlock = 0xFFFFu;
 
 constexpr int kPlanGroupsPerCta = 8;   // 16 lanes per group
 
-// reductions of the plan pre-pass, one row per group
-enum { R_MINLX, R_MAXLX, R_MINLY, R_MAXLY, R_MINCX, R_MAXCX, R_MINCY, R_MAXCY, R_MINZ, R_MAXZ, R_LW, R_N };
-
+// The plan pre-pass: 16 lanes = one group, two groups per warp, no CTA-wide barrier (a group never leaves its half-warp):
+// bounding boxes by warp reductions over the half-warp, the block order from 64 shared counters per group.
 __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan* __restrict__ plans,
                                                                      const StreamInfo* __restrict__ streams,
                                                                      int max_streams,
@@ -286,26 +304,20 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                                                                      int n_pics, const mpegb200_mb* __restrict__ mbs,
                                                                      uint32_t n_mb, uint32_t n_blocks, int allow_strip) {
     __shared__ __align__(16) GroupPlan s_plan[kPlanGroupsPerCta];
-    __shared__ uint32_t s_cnt[kPlanGroupsPerCta][10];  // [0..7] bins, [8] coded blocks to fetch, [9] predicted MBs
-    __shared__ int s_red[kPlanGroupsPerCta][R_N];
-    __shared__ uint32_t s_cnt2[kPlanGroupsPerCta][8][8];   // [bin][coefficient slot & 7]
+    __shared__ __align__(16) uint32_t s_cnt2[kPlanGroupsPerCta][8][8];   // [bin][coefficient slot & 7]
     const int tid = threadIdx.x, gl = tid >> 4, lane = tid & 15;
+    const unsigned seg = 0xffffu << (tid & 16);            // this group's lanes inside the warp
+    const int seg0 = tid & 16;                             // and their first lane
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     const uint32_t group = blockIdx.x * kPlanGroupsPerCta + gl;
     GroupPlan& P = s_plan[gl];
-    {
-        uint4* z = reinterpret_cast<uint4*>(&P);
-        for (int i = lane; i < (int)(sizeof(GroupPlan) / 16); i += 16) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    if (lane < 10) s_cnt[gl][lane] = 0;
     for (int i = lane; i < 64; i += 16) (&s_cnt2[gl][0][0])[i] = 0;
-    if (lane < R_N) s_red[gl][lane] = ((lane & 1) || lane == R_LW) ? INT_MIN : INT_MAX;   // even slots are minima, odd ones (and R_LW) maxima
-    __syncthreads();
     for (int i = lane; i < kNT; i += 16) P.b.map[i] = (uint16_t)kNoBlock;
+    __syncwarp();
 
     const uint32_t m0 = group * (uint32_t)kG;
     const bool have = group < n_groups && m0 + lane < n_mb;
-    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0, ress = 0;
+    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0, ress = 0, top = 0;
     uint32_t block0 = 0;
     bool predicted = false;
     int lx = 0, ly = 0, cx = 0, cy = 0, lw = 0, zslab = 0;
@@ -351,16 +363,8 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                         mode_c = (uint32_t)((cmh & 1) | ((cmv & 1) << 1));
                         c.mcw = (uint16_t)(((mode_y << 4) | 0x80) | (((mode_c << 4) | 0x80) << 8));
                         zslab = (int)(((uint32_t)si.slab << 16) | (uint32_t)(si.slot * 3 + ((flags & MPEGB200_MB_REF_BWD) ? bwd_b : fwd_b)));
-                        atomicAdd(&s_cnt[gl][9], 1u);
-                        int* R = s_red[gl];
-                        atomicMin(&R[R_MINLX], lx); atomicMax(&R[R_MAXLX], lx);
-                        atomicMin(&R[R_MINLY], ly); atomicMax(&R[R_MAXLY], ly);
-                        atomicMin(&R[R_MINCX], cx); atomicMax(&R[R_MAXCX], cx);
-                        atomicMin(&R[R_MINCY], cy); atomicMax(&R[R_MAXCY], cy);
-                        atomicMin(&R[R_MINZ], zslab); atomicMax(&R[R_MAXZ], zslab);
-                        atomicMax(&R[R_LW], lw);
                     }
-                    if (ncoded) atomicMax(&s_cnt[gl][8], rel + ncoded);
+                    if (ncoded) top = rel + ncoded;
                     // every 8x8 block whose pixels this record defines goes on the output list, binned by
                     // (coded?, interpolation mode) so that the threads of a warp take the same code path
                     out_mask = predicted ? 0x3fu : cbp;
@@ -381,7 +385,6 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                             const uint32_t bin = (coded ? 0u : 4u) + ((0x3201u >> (4 * mode_k)) & 3u);
                             const uint32_t res = coded ? (slot_run & 7u) : ((uint32_t)(lane + k) & 7u);
                             const uint32_t pp = atomicAdd(&s_cnt2[gl][bin][res], 1u);  // < 96
-                            atomicAdd(&s_cnt[gl][bin], 1u);
                             bins |= bin << (4 * k);
                             ress |= res << (4 * k);
                             if (k < 4) pos |= pp << (8 * k); else pos_hi |= pp << (8 * (k - 4));
@@ -392,28 +395,33 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
             }
         }
     }
-    __syncthreads();
-    // strip or boxes?  Every lane of the group takes the same decision from the reductions.
-    const int* R = s_red[gl];
-    const uint32_t n_pred = s_cnt[gl][9];
+    __syncwarp();   // the counters are complete
+    // strip or boxes?  Every lane of the group takes the same decision from reductions over the half-warp.
+    const uint32_t n_pred = (uint32_t)__popc(__ballot_sync(0xffffffffu, predicted) & seg);
+    const uint32_t n_top = __reduce_max_sync(seg, top);
+    const int min_lx = __reduce_min_sync(seg, predicted ? lx : INT_MAX), max_lx = __reduce_max_sync(seg, predicted ? lx : INT_MIN);
+    const int min_ly = __reduce_min_sync(seg, predicted ? ly : INT_MAX), max_ly = __reduce_max_sync(seg, predicted ? ly : INT_MIN);
+    const int min_cx = __reduce_min_sync(seg, predicted ? cx : INT_MAX), max_cx = __reduce_max_sync(seg, predicted ? cx : INT_MIN);
+    const int min_cy = __reduce_min_sync(seg, predicted ? cy : INT_MAX), max_cy = __reduce_max_sync(seg, predicted ? cy : INT_MIN);
+    const int min_z = __reduce_min_sync(seg, predicted ? zslab : INT_MAX), max_z = __reduce_max_sync(seg, predicted ? zslab : INT_MIN);
+    const int slw = __reduce_max_sync(seg, predicted ? lw : 0), scw = slw >> 1;
     bool strip = false;
     int X0 = 0, Y0 = 0, CX0 = 0, CY0 = 0;
-    if (allow_strip && n_pred >= (uint32_t)kStripMinPred && R[R_MINZ] == R[R_MAXZ]) {
-        const int slw = R[R_LW], scw = slw >> 1;
-        X0 = R[R_MINLX] & ~15;   // two's complement: rounds toward minus infinity
-        Y0 = R[R_MINLY];
-        CX0 = R[R_MINCX] & ~15;
-        CY0 = R[R_MINCY];
+    if (allow_strip && n_pred >= (uint32_t)kStripMinPred && min_z == max_z) {
+        X0 = min_lx & ~15;   // two's complement: rounds toward minus infinity
+        Y0 = min_ly;
+        CX0 = min_cx & ~15;
+        CY0 = min_cy;
         // The rectangle must hold every window, start inside the row (x >= 0: a window left of column 0 belongs to the
         // end of the row above in the reference's linear addressing -- box mode folds it, a strip cannot) and every
         // needed byte must lie inside the tensor's rows (luma_w + 32 wide; what the box reads beyond is zero fill
         // that no window uses).
-        strip = X0 >= 0 && R[R_MAXLX] + 17 - X0 <= kStripLW && R[R_MAXLX] + 17 <= slw + 32 &&
-                R[R_MAXLY] + 17 - Y0 <= kStripLH && Y0 > -32768 + 64 && R[R_MAXLY] < 32767 - 64 &&
-                CX0 >= 0 && R[R_MAXCX] + 9 - CX0 <= kStripCW && R[R_MAXCX] + 9 <= scw + 32 &&
-                R[R_MAXCY] + 9 - CY0 <= kStripCH;
+        strip = X0 >= 0 && max_lx + 17 - X0 <= kStripLW && max_lx + 17 <= slw + 32 &&
+                max_ly + 17 - Y0 <= kStripLH && Y0 > -32768 + 64 && max_ly < 32767 - 64 &&
+                CX0 >= 0 && max_cx + 9 - CX0 <= kStripCW && max_cx + 9 <= scw + 32 &&
+                max_cy + 9 - CY0 <= kStripCH;
     }
-    if (have && c.dst_y) {
+    {
         PlanBox b;
         memset(&b, 0, sizeof(b));
         if (predicted) {
@@ -455,12 +463,15 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         P.b.woff_c[lane] = c.woff_c;
         P.box[lane] = b;
     }
-    if (out_mask) {
+    {
+        // bin totals: lane b (and b + 8) sums bin b; everybody fetches the eight totals by shuffle
+        const uint4 ta = *reinterpret_cast<const uint4*>(&s_cnt2[gl][lane & 7][0]), tb = *reinterpret_cast<const uint4*>(&s_cnt2[gl][lane & 7][4]);
+        const uint32_t tot = ta.x + ta.y + ta.z + ta.w + tb.x + tb.y + tb.z + tb.w;
         uint32_t run = 0, base_of[8];
 #pragma unroll
         for (int b = 0; b < 8; b++) {
             base_of[b] = run;
-            run += s_cnt[gl][b];
+            run += __shfl_sync(0xffffffffu, tot, seg0 + b);
         }
         uint32_t slot = rel_r;
 #pragma unroll
@@ -470,10 +481,12 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                 const uint32_t idx = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
                 const bool coded = cbp_r & (0x20u >> k);
                 uint32_t bsel = 0, pp = 0;   // rank of (idx, res) among the bin's entries in (idx, res) order
+                const uint4 ca = *reinterpret_cast<const uint4*>(&s_cnt2[gl][bin][0]), cb = *reinterpret_cast<const uint4*>(&s_cnt2[gl][bin][4]);
+                const uint32_t cnt[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
                 for (int b = 0; b < 8; b++) {
                     bsel = bin == (uint32_t)b ? base_of[b] : bsel;
-                    pp += min(s_cnt2[gl][bin][b], idx + ((uint32_t)b < res ? 1u : 0u));
+                    pp += min(cnt[b], idx + ((uint32_t)b < res ? 1u : 0u));
                 }
                 P.b.map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
                 if (coded) slot++;
@@ -481,30 +494,34 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         }
     }
     if (lane == 0) {
-        const uint32_t n_box = (s_cnt[gl][8] + kCoefBox - 1) / kCoefBox;
-        P.h.n_box = n_box;
-        P.h.n_pred = n_pred;
-        P.h.block0 = block0;
-        P.h.strip = strip ? 1 : 0;
+        const uint32_t n_box = (n_top + kCoefBox - 1) / kCoefBox;
+        PlanHead h;
+        memset(&h, 0, sizeof(h));
+        h.n_box = n_box;
+        h.n_pred = n_pred;
+        h.block0 = block0;
+        h.strip = strip ? 1 : 0;
         if (strip) {
-            P.h.tx_bytes = n_box * (kCoefBox * 128) + kStripTx;
-            P.h.slab = (uint16_t)((uint32_t)R[R_MINZ] >> 16);
-            P.h.z = (uint16_t)(R[R_MINZ] & 0xffff);
-            P.h.pitch_y = kStripLW;
-            P.h.pitch_c = kStripCW;
-            P.h.cr_win = kStripCBytes;
-            P.h.sx = (int16_t)X0;
-            P.h.sy = (int16_t)Y0;
-            P.h.scx = (int16_t)CX0;
-            P.h.scy = (int16_t)CY0;
+            h.tx_bytes = n_box * (kCoefBox * 128) + kStripTx;
+            h.slab = (uint16_t)((uint32_t)min_z >> 16);
+            h.z = (uint16_t)(min_z & 0xffff);
+            h.pitch_y = kStripLW;
+            h.pitch_c = kStripCW;
+            h.cr_win = kStripCBytes;
+            h.sx = (int16_t)X0;
+            h.sy = (int16_t)Y0;
+            h.scx = (int16_t)CX0;
+            h.scy = (int16_t)CY0;
         } else {
-            P.h.tx_bytes = n_box * (kCoefBox * 128) + n_pred * kWinTx;
-            P.h.pitch_y = 32;
-            P.h.pitch_c = 32;
-            P.h.cr_win = kWinC;
+            h.tx_bytes = n_box * (kCoefBox * 128) + n_pred * kWinTx;
+            h.pitch_y = 32;
+            h.pitch_c = 32;
+            h.cr_win = kWinC;
         }
+        P.h = h;
+        *reinterpret_cast<uint4*>(P.pad1) = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
+    __syncwarp();
     if (group < n_groups) {  // head + body (640 bytes with padding) out, 16 bytes per lane per step; the boxes only in box mode
         const uint4* src = reinterpret_cast<const uint4*>(&P);
         uint4* dstp = reinterpret_cast<uint4*>(plans + group);
@@ -738,8 +755,8 @@ __device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (
 struct Smem {
     static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
     static constexpr int win = coef + kNT * 128;                 // the window area: one strip or kG x 1280
-    static constexpr int plan = win + kWinArea;                  // 1024: the group's plan, then the mbarrier
-    static constexpr int total_oneshot = plan + (int)sizeof(GroupPlan) + 16;
+    static constexpr int plan = win + kWinArea;                  // 640: the group's plan (head + body), then the mbarrier
+    static constexpr int total_oneshot = plan + 640 + 16;
 };
 
 // The TMA boxes of one group.  Strip mode: lane 0 of warp 0 the luma strip, lane 0 of warp 1 the chroma strip.  Box mode:
@@ -775,32 +792,67 @@ __device__ __forceinline__ void issue_group(const PlanHead& P, const PlanBox* bo
 }
 
 // ------------------------------------------------------------------------------------------------
-// One-shot kernel: one CTA = one group plan = kG records.  Load the plan (64 x 16 bytes), issue the boxes, wait on
-// the one mbarrier, then one thread per output block: interpolate, IDCT, add, saturate, store.
+// One-shot kernel: one CTA = one group plan = kG records.  The lanes that issue the boxes read the plan head straight
+// from global memory (an L2 hit: the pre-pass has just written it) while a bulk copy brings head + body into shared
+// memory on the same mbarrier as the tiles; then one thread per output block: interpolate, IDCT, add, saturate, store.
+// While it waits, the CTA also asks for the tiles of group blockIdx.x + prefetch_dist to be fetched into L2
+// (cp.async.bulk.prefetch.tensor): shared memory allows only six groups in flight per SM, which leaves the CTAs
+// waiting on DRAM for a quarter of their life (profiles/); the CTA that decodes that group later finds its tiles in L2.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ PlanHead load_head(const GroupPlan* gp) {
+    PlanHead h;
+    const uint4* src = reinterpret_cast<const uint4*>(&gp->h);
+    uint4* dst = reinterpret_cast<uint4*>(&h);
+    dst[0] = __ldg(src);
+    dst[1] = __ldg(src + 1);
+    dst[2] = __ldg(src + 2);
+    return h;
+}
+
+constexpr int kPlanSmemBytes = 640;   // head + body (624) rounded up to 16
+static_assert(sizeof(PlanHead) + sizeof(PlanBody) <= kPlanSmemBytes, "plan copy size");
+
 __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
                                                           const SlabMaps* __restrict__ slab_maps,
-                                                          const GroupPlan* __restrict__ plans) {
+                                                          const GroupPlan* __restrict__ plans, uint32_t n_groups,
+                                                          uint32_t prefetch_dist) {
     extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
     uint8_t* s_coef = smem + Smem::coef;
     uint8_t* s_win = smem + Smem::win;
-    GroupPlan& P = *reinterpret_cast<GroupPlan*>(smem + Smem::plan);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::plan + sizeof(GroupPlan));
+    const GroupPlan& P = *reinterpret_cast<const GroupPlan*>(smem + Smem::plan);   // head and body only
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + Smem::plan + kPlanSmemBytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GroupPlan* gp = plans + blockIdx.x;
 
-    if (tid < 64) reinterpret_cast<uint4*>(&P)[tid] = reinterpret_cast<const uint4*>(plans + blockIdx.x)[tid];
-    if (tid == 64) {
+    if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         mbar_init(s_bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
-    issue_group(P.h, P.box, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane, 0);
+    {
+        const PlanHead h = load_head(gp);
+        issue_group(h, gp->box, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane, kPlanSmemBytes);
+        if (tid == 64) bulk_load(smem + Smem::plan, gp, kPlanSmemBytes, s_bar);
+    }
+    if (prefetch_dist && blockIdx.x + prefetch_dist < n_groups) {
+        const GroupPlan* fp = gp + prefetch_dist;
+        const PlanHead f = load_head(fp);
+        if (warp == 2) {
+            if (lane < (int)f.n_box) tma_prefetch_2d(&coef_map, 0, (int)(f.block0 + lane * kCoefBox));
+        } else if (f.strip && lane == 0) {
+            const SlabMaps* maps = slab_maps + f.slab;
+            if (warp == 0)
+                tma_prefetch_3d(maps->luma_strip, f.sx >> 3, f.sy, f.z);
+            else
+                tma_prefetch_4d(maps->chroma_strip, f.scx >> 3, f.scy, 0, f.z);
+        }
+    }
 
+    mbar_wait(s_bar, 0);   // all tiles of the group and its plan have landed
     BlockCtx B;
     block_setup(P.h, P.b, tid, B);
     if (!B.live) return;
-    mbar_wait(s_bar, 0);   // all tiles of the group have landed
     uint32_t p0[8], p1[8];
     int c[64];
     block_load(B, s_coef, s_win, p0, p1, c);
@@ -815,12 +867,6 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
 // that they land while the IDCT of group i runs, and nobody waits at a CTA-wide barrier.  Plans are double-buffered
 // and fetched two groups ahead with a bulk copy.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct SmemS {
     static constexpr int coef = 0;                                   // kNT x 128, 1024-aligned, swizzled by TMA
@@ -925,7 +971,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     if (n_mb == 0) return cudaSuccess;
     // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the
     // plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
-    static int variant = -1, allow_strip = 1, stream_ctas = 0;
+    static int variant = -1, allow_strip = 1, stream_ctas = 0, prefetch_dist = kDefaultPrefetchDist;
     if (variant < 0) {
         const char* v = getenv("MPEGB200_FUSED");
         const int want = (v && strcmp(v, "stream") == 0) ? 1 : (v && strcmp(v, "oneshot") == 0) ? 0 : kDefaultVariant;
@@ -942,6 +988,8 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
         const char* c = getenv("MPEGB200_STREAM_CTAS");
         if (c && atoi(c) > 0) stream_ctas = atoi(c);
+        const char* pd = getenv("MPEGB200_PREFETCH_DIST");   // groups ahead whose tiles the one-shot kernel pulls into L2; 0: off
+        if (pd) prefetch_dist = atoi(pd) > 0 ? atoi(pd) : 0;
         const char* s = getenv("MPEGB200_STRIP");
         allow_strip = !(s && s[0] == '0');
         if (getenv("MPEGB200_DEBUG"))
@@ -954,7 +1002,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks, allow_strip);
     const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
     if (variant == 0) {
-        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans);
+        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans, n_groups, (uint32_t)prefetch_dist);
     } else {
         const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
         fused_stream_kernel<<<grid, kNT, SmemS::total, stream>>>(cm, d_maps, plans, n_groups);
