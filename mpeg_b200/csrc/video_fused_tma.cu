@@ -815,7 +815,7 @@ static_assert(sizeof(PlanHead) + sizeof(PlanBody) <= kPlanSmemBytes, "plan copy 
 __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
                                                           const SlabMaps* __restrict__ slab_maps,
                                                           const GroupPlan* __restrict__ plans, uint32_t n_groups,
-                                                          uint32_t prefetch_dist) {
+                                                          uint32_t prefetch_dist, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
     uint8_t* s_coef = smem + Smem::coef;
     uint8_t* s_win = smem + Smem::win;
@@ -830,7 +830,12 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
         fence_barrier_init();
     }
     __syncthreads();
-    {
+    if (dbg == 2) {   // measurement only: the arithmetic and the stores without the tile fetch (works on whatever shared memory holds)
+        if (tid == 64) {
+            mbar_arrive_expect_tx(s_bar, kPlanSmemBytes);
+            bulk_load(smem + Smem::plan, gp, kPlanSmemBytes, s_bar);
+        }
+    } else {
         const PlanHead h = load_head(gp);
         issue_group(h, gp->box, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane, kPlanSmemBytes);
         if (tid == 64) bulk_load(smem + Smem::plan, gp, kPlanSmemBytes, s_bar);
@@ -850,6 +855,7 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
     }
 
     mbar_wait(s_bar, 0);   // all tiles of the group and its plan have landed
+    if (dbg == 1) return;  // measurement only: the fetch without the arithmetic
     BlockCtx B;
     block_setup(P.h, P.b, tid, B);
     if (!B.live) return;
@@ -971,7 +977,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     if (n_mb == 0) return cudaSuccess;
     // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the
     // plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
-    static int variant = -1, allow_strip = 1, stream_ctas = 0, prefetch_dist = kDefaultPrefetchDist;
+    static int variant = -1, allow_strip = 1, stream_ctas = 0, prefetch_dist = kDefaultPrefetchDist, dbg = 0;
     if (variant < 0) {
         const char* v = getenv("MPEGB200_FUSED");
         const int want = (v && strcmp(v, "stream") == 0) ? 1 : (v && strcmp(v, "oneshot") == 0) ? 0 : kDefaultVariant;
@@ -990,6 +996,8 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         if (c && atoi(c) > 0) stream_ctas = atoi(c);
         const char* pd = getenv("MPEGB200_PREFETCH_DIST");   // groups ahead whose tiles the one-shot kernel pulls into L2; 0: off
         if (pd) prefetch_dist = atoi(pd) > 0 ? atoi(pd) : 0;
+        const char* dm = getenv("MPEGB200_MEASURE");   // "fetch": tile fetch only, "math": arithmetic + stores only (wrong pixels; timing experiments)
+        dbg = dm && strcmp(dm, "fetch") == 0 ? 1 : dm && strcmp(dm, "math") == 0 ? 2 : 0;
         const char* s = getenv("MPEGB200_STRIP");
         allow_strip = !(s && s[0] == '0');
         if (getenv("MPEGB200_DEBUG"))
@@ -1002,7 +1010,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks, allow_strip);
     const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
     if (variant == 0) {
-        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans, n_groups, (uint32_t)prefetch_dist);
+        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans, n_groups, (uint32_t)prefetch_dist, dbg);
     } else {
         const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
         fused_stream_kernel<<<grid, kNT, SmemS::total, stream>>>(cm, d_maps, plans, n_groups);
