@@ -231,7 +231,7 @@ constexpr int kStripLBytes = kStripLW * kStripLH;                     // 14592
 constexpr int kStripCBytes = kStripCW * kStripCH;                     // 3840 per plane
 constexpr int kStripTx = kStripLBytes + 2 * kStripCBytes;             // 22272
 constexpr int kWinArea = (kG * kWinBytes > kStripTx ? kG * kWinBytes : kStripTx + 127) / 128 * 128;
-constexpr int kDefaultPrefetchDist = 0; // groups ahead to prefetch into L2 (MPEGB200_PREFETCH_DIST overrides)
+constexpr int kDefaultPrefetchDist = 444; // groups ahead to prefetch into L2: three per SM (MPEGB200_PREFETCH_DIST overrides; measured 0: 0.333 ms, 444: 0.327, 888: 0.327, 1776: 0.332, 3552: 0.402)
 constexpr int kDefaultVariant = 0;     // 0: one-shot kernel, 1: streaming kernel (MPEGB200_FUSED overrides)
 constexpr int kStripMinPred = 3;       // fewer predicted macroblocks than this: their own boxes are cheaper
 
@@ -295,8 +295,23 @@ constexpr uint32_t kNoBlock = 0xFFFFu;
 
 constexpr int kPlanGroupsPerCta = 8;   // 16 lanes per group
 
+// max per 16-bit lane over the 16 lanes of a group (xor butterflies of 8, 4, 2, 1 never leave the half-warp, so the
+// whole warp runs them together: no divergence between the two groups of a warp)
+__device__ __forceinline__ uint32_t group_max_s16x2(uint32_t v) {
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) v = __vmaxs2(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+// (hi, lo) = (v, -v) as 16-bit lanes: one max reduction yields max(v) and -min(v).  Lanes that do not take part pass the identity.
+__device__ __forceinline__ uint32_t span_s16x2(int v, bool take) {
+    return take ? (((uint32_t)v << 16) | ((uint32_t)(-v) & 0xffffu)) : 0x80008000u;
+}
+__device__ __forceinline__ int span_max(uint32_t r) { return (int)r >> 16; }
+__device__ __forceinline__ int span_min(uint32_t r) { return -(int)(int16_t)(r & 0xffffu); }
+
 // The plan pre-pass: 16 lanes = one group, two groups per warp, no CTA-wide barrier (a group never leaves its half-warp):
-// bounding boxes by warp reductions over the half-warp, the block order from 64 shared counters per group.
+// bounding boxes by 16-bit-pair max butterflies over the half-warp, the block order from 64 shared 16-bit counters per group
+// (two per word, so that a rank is four packed min + add steps instead of eight scalar ones).
 __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan* __restrict__ plans,
                                                                      const StreamInfo* __restrict__ streams,
                                                                      int max_streams,
@@ -304,20 +319,26 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                                                                      int n_pics, const mpegb200_mb* __restrict__ mbs,
                                                                      uint32_t n_mb, uint32_t n_blocks, int allow_strip) {
     __shared__ __align__(16) GroupPlan s_plan[kPlanGroupsPerCta];
-    __shared__ __align__(16) uint32_t s_cnt2[kPlanGroupsPerCta][8][8];   // [bin][coefficient slot & 7]
+    __shared__ __align__(16) uint32_t s_cnt2[kPlanGroupsPerCta][8][4];   // [bin][(coefficient slot & 7) >> 1], counter of an odd slot in the high half
+    __shared__ __align__(16) uint4 s_lt[16 * kPlanGroupsPerCta / 32][8]; // per warp: [r] = 16-bit lanes b < r set to 1
     const int tid = threadIdx.x, gl = tid >> 4, lane = tid & 15;
-    const unsigned seg = 0xffffu << (tid & 16);            // this group's lanes inside the warp
-    const int seg0 = tid & 16;                             // and their first lane
+    const int seg0 = tid & 16;                             // first lane of this group inside the warp
+    const unsigned seg = 0xffffu << seg0;                  // and all its lanes
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     const uint32_t group = blockIdx.x * kPlanGroupsPerCta + gl;
     GroupPlan& P = s_plan[gl];
-    for (int i = lane; i < 64; i += 16) (&s_cnt2[gl][0][0])[i] = 0;
-    for (int i = lane; i < kNT; i += 16) P.b.map[i] = (uint16_t)kNoBlock;
+    if (lane < 8) reinterpret_cast<uint4*>(&s_cnt2[gl][0][0])[lane] = make_uint4(0, 0, 0, 0);
+    if (lane < 12) reinterpret_cast<uint4*>(P.b.map)[lane] = make_uint4(~0u, ~0u, ~0u, ~0u);   // kNoBlock everywhere
+    if ((tid & 31) < 8) {
+        const int r = tid & 31;
+        s_lt[tid >> 5][r] = make_uint4((r > 0 ? 1u : 0u) | (r > 1 ? 0x10000u : 0u), (r > 2 ? 1u : 0u) | (r > 3 ? 0x10000u : 0u),
+                                       (r > 4 ? 1u : 0u) | (r > 5 ? 0x10000u : 0u), (r > 6 ? 1u : 0u) | (r > 7 ? 0x10000u : 0u));
+    }
     __syncwarp();
 
     const uint32_t m0 = group * (uint32_t)kG;
     const bool have = group < n_groups && m0 + lane < n_mb;
-    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bins = 0, pos = 0, pos_hi = 0, ress = 0, top = 0;
+    uint32_t out_mask = 0, cbp_r = 0, rel_r = 0, bin_y = 0, bin_c = 0, pos = 0, pos_hi = 0, top = 0;
     uint32_t block0 = 0;
     bool predicted = false;
     int lx = 0, ly = 0, cx = 0, cy = 0, lw = 0, zslab = 0;
@@ -373,20 +394,20 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                     // Inside a bin the blocks are ordered round-robin over (coefficient slot & 7): the 128-byte swizzle of the
                     // coefficient tile makes the eight LDS.128 of a quarter-warp conflict free exactly when its eight
                     // slots differ mod 8 (profiles/r1_final_video_summary.md: 9.1 wavefronts per instruction, ideal 4).
+                    // Bin order H, copy, V, HV: a warp that straddles two bins runs both interpolation paths, and
+                    // with 96 blocks in four bins the two middle bins are the ones that get split over warps --
+                    // so the two cheapest paths (copy, V) sit in the middle.  Intra blocks (no window) count as copy.
+                    bin_y = (0x3201u >> (4 * mode_y)) & 3u;
+                    bin_c = (0x3201u >> (4 * mode_c)) & 3u;
                     uint32_t slot_run = rel;
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
                         if (out_mask & (0x20u >> k)) {
                             const bool coded = (cbp & (0x20u >> k)) != 0;
-                            // Bin order H, copy, V, HV: a warp that straddles two bins runs both interpolation paths, and
-                            // with 96 blocks in four bins the two middle bins are the ones that get split over warps --
-                            // so the two cheapest paths (copy, V) sit in the middle.  Intra blocks (no window) count as copy.
-                            const uint32_t mode_k = predicted ? (k < 4 ? mode_y : mode_c) : 0u;
-                            const uint32_t bin = (coded ? 0u : 4u) + ((0x3201u >> (4 * mode_k)) & 3u);
+                            const uint32_t bin = (k < 4 ? bin_y : bin_c) + (coded ? 0u : 4u);
                             const uint32_t res = coded ? (slot_run & 7u) : ((uint32_t)(lane + k) & 7u);
-                            const uint32_t pp = atomicAdd(&s_cnt2[gl][bin][res], 1u);  // < 96
-                            bins |= bin << (4 * k);
-                            ress |= res << (4 * k);
+                            const uint32_t sh = (res & 1u) << 4;
+                            const uint32_t pp = (atomicAdd(&s_cnt2[gl][bin][res >> 1], 1u << sh) >> sh) & 0xffffu;  // < 96
                             if (k < 4) pos |= pp << (8 * k); else pos_hi |= pp << (8 * (k - 4));
                             if (coded) slot_run++;
                         }
@@ -396,18 +417,22 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         }
     }
     __syncwarp();   // the counters are complete
-    // strip or boxes?  Every lane of the group takes the same decision from reductions over the half-warp.
-    const uint32_t n_pred = (uint32_t)__popc(__ballot_sync(0xffffffffu, predicted) & seg);
-    const uint32_t n_top = __reduce_max_sync(seg, top);
-    const int min_lx = __reduce_min_sync(seg, predicted ? lx : INT_MAX), max_lx = __reduce_max_sync(seg, predicted ? lx : INT_MIN);
-    const int min_ly = __reduce_min_sync(seg, predicted ? ly : INT_MAX), max_ly = __reduce_max_sync(seg, predicted ? ly : INT_MIN);
-    const int min_cx = __reduce_min_sync(seg, predicted ? cx : INT_MAX), max_cx = __reduce_max_sync(seg, predicted ? cx : INT_MIN);
-    const int min_cy = __reduce_min_sync(seg, predicted ? cy : INT_MAX), max_cy = __reduce_max_sync(seg, predicted ? cy : INT_MIN);
-    const int min_z = __reduce_min_sync(seg, predicted ? zslab : INT_MAX), max_z = __reduce_max_sync(seg, predicted ? zslab : INT_MIN);
-    const int slw = __reduce_max_sync(seg, predicted ? lw : 0), scw = slw >> 1;
+    // strip or boxes?  Every lane of the group takes the same decision from reductions over the half-warp.  All window
+    // origins fit 16 bits (pictures are at most 4095 wide and high, vectors are int16 half-pels).
+    const unsigned pmask = __ballot_sync(0xffffffffu, predicted) & seg;
+    const uint32_t n_pred = (uint32_t)__popc(pmask);
+    const int first = pmask ? __ffs((int)pmask) - 1 : seg0;       // the group's first predicted lane
+    const int z0 = __shfl_sync(0xffffffffu, zslab, first);
+    const int slw = __shfl_sync(0xffffffffu, lw, first), scw = slw >> 1;   // one reference buffer => one stream => one pitch
+    const bool one_ref = (__ballot_sync(0xffffffffu, predicted && zslab != z0) & seg) == 0;
+    const uint32_t r_lx = group_max_s16x2(span_s16x2(lx, predicted)), r_ly = group_max_s16x2(span_s16x2(ly, predicted));
+    const uint32_t r_cx = group_max_s16x2(span_s16x2(cx, predicted)), r_cy = group_max_s16x2(span_s16x2(cy, predicted));
+    const uint32_t n_top = group_max_s16x2(top) & 0xffffu;        // top <= 96
+    const int min_lx = span_min(r_lx), max_lx = span_max(r_lx), min_ly = span_min(r_ly), max_ly = span_max(r_ly);
+    const int min_cx = span_min(r_cx), max_cx = span_max(r_cx), min_cy = span_min(r_cy), max_cy = span_max(r_cy);
     bool strip = false;
     int X0 = 0, Y0 = 0, CX0 = 0, CY0 = 0;
-    if (allow_strip && n_pred >= (uint32_t)kStripMinPred && min_z == max_z) {
+    if (allow_strip && n_pred >= (uint32_t)kStripMinPred && one_ref) {
         X0 = min_lx & ~15;   // two's complement: rounds toward minus infinity
         Y0 = min_ly;
         CX0 = min_cx & ~15;
@@ -417,7 +442,7 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         // needed byte must lie inside the tensor's rows (luma_w + 32 wide; what the box reads beyond is zero fill
         // that no window uses).
         strip = X0 >= 0 && max_lx + 17 - X0 <= kStripLW && max_lx + 17 <= slw + 32 &&
-                max_ly + 17 - Y0 <= kStripLH && Y0 > -32768 + 64 && max_ly < 32767 - 64 &&
+                max_ly + 17 - Y0 <= kStripLH &&
                 CX0 >= 0 && max_cx + 9 - CX0 <= kStripCW && max_cx + 9 <= scw + 32 &&
                 max_cy + 9 - CY0 <= kStripCH;
     }
@@ -464,31 +489,34 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         P.box[lane] = b;
     }
     {
-        // bin totals: lane b (and b + 8) sums bin b; everybody fetches the eight totals by shuffle
-        const uint4 ta = *reinterpret_cast<const uint4*>(&s_cnt2[gl][lane & 7][0]), tb = *reinterpret_cast<const uint4*>(&s_cnt2[gl][lane & 7][4]);
-        const uint32_t tot = ta.x + ta.y + ta.z + ta.w + tb.x + tb.y + tb.z + tb.w;
-        uint32_t run = 0, base_of[8];
+        // bin totals: lane b (and b + 8) sums bin b, an exclusive scan over each 8 lanes turns them into the bins' first
+        // positions; a block fetches its bin's by shuffle
+        const uint4 ta = *reinterpret_cast<const uint4*>(&s_cnt2[gl][lane & 7][0]);
+        const uint32_t t2 = ta.x + ta.y + ta.z + ta.w;            // two 16-bit sums, each <= 96
+        const uint32_t tot = (t2 & 0xffffu) + (t2 >> 16);
+        uint32_t incl = tot;
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            base_of[b] = run;
-            run += __shfl_sync(0xffffffffu, tot, seg0 + b);
+        for (int d = 1; d < 8; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d, 8);
+            if ((lane & 7) >= d) incl += up;
         }
+        const uint32_t base = incl - tot;
         uint32_t slot = rel_r;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
+            const bool coded = cbp_r & (0x20u >> k);
+            const uint32_t bin = (k < 4 ? bin_y : bin_c) + (coded ? 0u : 4u);   // as in the counting loop above
+            const uint32_t res = coded ? (slot & 7u) : ((uint32_t)(lane + k) & 7u);
+            const uint32_t bsel = __shfl_sync(0xffffffffu, base, seg0 + (int)bin);   // every lane, whether it has block k or not
             if (out_mask & (0x20u >> k)) {
-                const uint32_t bin = (bins >> (4 * k)) & 15u, res = (ress >> (4 * k)) & 15u;
                 const uint32_t idx = (k < 4 ? pos >> (8 * k) : pos_hi >> (8 * (k - 4))) & 0xffu;
-                const bool coded = cbp_r & (0x20u >> k);
-                uint32_t bsel = 0, pp = 0;   // rank of (idx, res) among the bin's entries in (idx, res) order
-                const uint4 ca = *reinterpret_cast<const uint4*>(&s_cnt2[gl][bin][0]), cb = *reinterpret_cast<const uint4*>(&s_cnt2[gl][bin][4]);
-                const uint32_t cnt[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-#pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    bsel = bin == (uint32_t)b ? base_of[b] : bsel;
-                    pp += min(cnt[b], idx + ((uint32_t)b < res ? 1u : 0u));
-                }
-                P.b.map[bsel + pp] = (uint16_t)((uint32_t)lane | ((uint32_t)k << 4) | (coded ? 0x80u : 0u) | (slot << 8));
+                // rank of (idx, res) among the bin's entries in (idx, res) order: sum over r of min(count[r], idx + (r < res))
+                const uint4 cn = *reinterpret_cast<const uint4*>(&s_cnt2[gl][bin][0]);
+                const uint4 lt = s_lt[tid >> 5][res];
+                const uint32_t iv = idx * 0x00010001u;
+                const uint32_t s2 = __vminu2(cn.x, iv + lt.x) + __vminu2(cn.y, iv + lt.y) + __vminu2(cn.z, iv + lt.z) + __vminu2(cn.w, iv + lt.w);
+                const uint32_t pp = (s2 & 0xffffu) + (s2 >> 16);
+                P.b.map[bsel + pp] = (uint16_t)((uint32_t)(lane + 16 * k) | (coded ? 0x80u : 0u) | (slot << 8));
                 if (coded) slot++;
             }
         }
@@ -503,8 +531,8 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
         h.strip = strip ? 1 : 0;
         if (strip) {
             h.tx_bytes = n_box * (kCoefBox * 128) + kStripTx;
-            h.slab = (uint16_t)((uint32_t)min_z >> 16);
-            h.z = (uint16_t)(min_z & 0xffff);
+            h.slab = (uint16_t)((uint32_t)z0 >> 16);
+            h.z = (uint16_t)(z0 & 0xffff);
             h.pitch_y = kStripLW;
             h.pitch_c = kStripCW;
             h.cr_win = kStripCBytes;
