@@ -126,6 +126,12 @@ int  mpegb200_sync(mpegb200_ctx* ctx);
 int  mpegb200_sync_uploads(mpegb200_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx);
+/* Measurement aid (bench.py's roofline): while on, every mpegb200_video_decode_pictures* call brackets its plan
+ * pre-pass and its arithmetic kernel with CUDA events on the context's stream.  mpegb200_kernel_times synchronises
+ * the stream, writes the per-call durations in milliseconds (oldest first, at most `cap` calls; either array may be
+ * NULL), forgets them and returns the number of calls written, or a negative error code. */
+int  mpegb200_set_kernel_timing(mpegb200_ctx* ctx, int on);
+int  mpegb200_kernel_times(mpegb200_ctx* ctx, float* plan_ms, float* fused_ms, int cap);
 
 /* ---- video ------------------------------------------------------------------------ */
 

@@ -71,6 +71,18 @@ class Context:
     def launch_count(self) -> int:
         return int(self.L.mpegb200_launch_count(self.h))
 
+    def set_kernel_timing(self, on: bool):
+        """Measurement aid: bracket the kernels of every decode call with CUDA events (mpegb200_set_kernel_timing)."""
+        self._ck(self.L.mpegb200_set_kernel_timing(self.h, int(on)))
+
+    def kernel_times(self, cap: int = 4096):
+        """(plan_ms, fused_ms) arrays of the decode calls since the last read; synchronises the stream."""
+        a, b = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = self.L.mpegb200_kernel_times(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), cap)
+        if n < 0:
+            self._ck(n)
+        return a[:n].copy(), b[:n].copy()
+
     # ---- video
     def video_open(self, stream: int, width: int, height: int):
         self._ck(self.L.mpegb200_video_open(self.h, stream, width, height))

@@ -77,10 +77,11 @@ cudaError_t launch_audio_synth(AudioState* d_states, int max_streams, const int3
                                const float* d_window, cudaStream_t stream);
 // TMA kernel (video_fused_tma.cu).  coef_map: 128-byte CUtensorMap over the coefficient array (host copy,
 // passed by value as a __grid_constant__ parameter); d_maps: per-slab window tensor maps in global memory.
-// d_plans: scratch of fused_plan_bytes(n_mb) bytes, 16-byte aligned (one 768-byte plan per 16 records).
+// d_plans: scratch of fused_plan_bytes(n_mb) bytes, 16-byte aligned (one 1024-byte plan per 16 records).
+// timing: optional three events recorded before the pre-pass, between the two kernels and after the arithmetic kernel.
 cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void* d_plans, const StreamInfo* d_streams,
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
-                             uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream);
+                             uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream, const cudaEvent_t* timing = nullptr);
 size_t fused_plan_bytes(uint32_t n_mb);
 // 12-bit packed coefficient blocks (96 B) -> int16 blocks (128 B)
 cudaError_t launch_unpack12(const uint8_t* d_packed, int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream);

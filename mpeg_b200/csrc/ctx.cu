@@ -69,6 +69,8 @@ struct mpegb200_ctx {
     bool force_generic = false;   // MPEGB200_FUSED=generic (A/B measurements)
     void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
     uint64_t launches = 0;
+    bool kernel_timing = false;              // mpegb200_set_kernel_timing
+    std::vector<cudaEvent_t> timing_events;  // three per timed decode call
     int max_w = 0, max_h = 0;
     char err[512] = {0};
 };
@@ -118,6 +120,11 @@ static int join_readback(mpegb200_ctx* ctx) {
         ctx->down_pending = false;
     }
     return 0;
+}
+
+static void drop_timing_events(mpegb200_ctx* ctx) {
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    ctx->timing_events.clear();
 }
 
 static int flush_info(mpegb200_ctx* ctx) {
@@ -222,6 +229,7 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
         if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
     }
+    drop_timing_events(ctx);
     if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
     if (ctx->ev_down) cudaEventDestroy(ctx->ev_down);
     if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
@@ -265,6 +273,33 @@ int mpegb200_sync_uploads(mpegb200_ctx* ctx) {
 }
 
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mpegb200_set_kernel_timing(mpegb200_ctx* ctx, int on) {
+    if (!ctx) return MPEGB200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (!on) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        drop_timing_events(ctx);
+    }
+    ctx->kernel_timing = on != 0;
+    return 0;
+}
+
+int mpegb200_kernel_times(mpegb200_ctx* ctx, float* plan_ms, float* fused_ms, int cap) {
+    if (!ctx || cap < 0) return fail(ctx, MPEGB200_EINVAL, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int calls = (int)(ctx->timing_events.size() / 3), n = calls < cap ? calls : cap;
+    for (int i = 0; i < n; i++) {
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, ctx->timing_events[3 * i], ctx->timing_events[3 * i + 1]));
+        CU(cudaEventElapsedTime(&b, ctx->timing_events[3 * i + 1], ctx->timing_events[3 * i + 2]));
+        if (plan_ms) plan_ms[i] = a;
+        if (fused_ms) fused_ms[i] = b;
+    }
+    drop_timing_events(ctx);
+    return n;
+}
 
 /* ---------------------------------------------------------------------------------------- video */
 
@@ -549,8 +584,15 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
     }
     if (use_tma) {
         if (int rc = ensure(ctx, ctx->s_plans, fused_plan_bytes((uint32_t)n_mb))) return rc;
+        const cudaEvent_t* timing = nullptr;
+        if (ctx->kernel_timing) {
+            cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+            for (int i = 0; i < 3; i++) CU(cudaEventCreate(&ev[i]));
+            ctx->timing_events.insert(ctx->timing_events.end(), ev, ev + 3);
+            timing = ctx->timing_events.data() + ctx->timing_events.size() - 3;
+        }
         CU(launch_fused_tma(&coef_map, ctx->d_maps, ctx->s_plans.p, ctx->d_info, ctx->max_streams, d_pics, n_pictures,
-                            d_mbs, (uint32_t)n_mb, (uint32_t)n_blocks, ctx->stream));
+                            d_mbs, (uint32_t)n_mb, (uint32_t)n_blocks, ctx->stream, timing));
         ctx->launches++;  // the plan pre-pass
     } else {
         CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,

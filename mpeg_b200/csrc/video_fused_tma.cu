@@ -1001,7 +1001,7 @@ size_t fused_plan_bytes(uint32_t n_mb) { return (size_t)((n_mb + kG - 1) / kG) *
 
 cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void* d_plans, const StreamInfo* d_streams,
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
-                             uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream) {
+                             uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream, const cudaEvent_t* timing) {
     if (n_mb == 0) return cudaSuccess;
     // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the
     // plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
@@ -1034,8 +1034,10 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     }
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
+    if (timing) cudaEventRecord(timing[0], stream);
     plan_kernel<<<(n_groups + kPlanGroupsPerCta - 1) / kPlanGroupsPerCta, 16 * kPlanGroupsPerCta, 0, stream>>>(
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks, allow_strip);
+    if (timing) cudaEventRecord(timing[1], stream);
     const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
     if (variant == 0) {
         fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans, n_groups, (uint32_t)prefetch_dist, dbg);
@@ -1043,6 +1045,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
         fused_stream_kernel<<<grid, kNT, SmemS::total, stream>>>(cm, d_maps, plans, n_groups);
     }
+    if (timing) cudaEventRecord(timing[2], stream);
     return cudaGetLastError();
 }
 
