@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--mode", default="dense", choices=["dense", "natural"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-form", default="vlen", choices=["vlen", "packed12", "int16"], help="coefficient transfer form of the end-to-end leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU work for cpu_baseline")
     return ap.parse_args()
 
@@ -320,10 +321,17 @@ def main():
         return t
 
     h_mbs, h_coeffs = pinned(mbs), pinned(coeffs)
-    try:  # 12-bit transfer form for the end-to-end path (a quarter less PCIe traffic); dense-P levels always fit
-        h_packed = pinned(ctx.pack_coeffs12(coeffs))
-    except mpeg_b200.MpegB200Error:
-        h_packed = None
+    # transfer form of the coefficients on the end-to-end path (PCIe bound): variable-width groups (about 53 B per dense
+    # block), the fixed 12-bit form (96 B) or the plain int16 blocks (128 B)
+    h_packed = h_vlen = None
+    if not args.no_e2e:
+        try:
+            if args.e2e_form == "vlen":
+                h_vlen = tuple(pinned(a) for a in ctx.pack_coeffs_vlen(coeffs))
+            elif args.e2e_form == "packed12":
+                h_packed = pinned(ctx.pack_coeffs12(coeffs))
+        except mpeg_b200.MpegB200Error:
+            h_packed = h_vlen = None
     h_pics = [pinned(p) for p, _ in variants]
     d_mbs, d_coeffs = h_mbs.cuda(), h_coeffs.cuda()
     d_pics = [p.cuda() for p in h_pics]
@@ -346,7 +354,10 @@ def main():
     def step_e2e(k):
         p, dst = variants[k % 3]
         L = ctx.L
-        if h_packed is not None:
+        if h_vlen is not None:
+            rc = L.mpegb200_video_decode_pictures_vlen(ctx.h, len(p), h_pics[k % 3].data_ptr(), len(mbs), h_mbs.data_ptr(), len(coeffs),
+                                                       h_vlen[0].data_ptr(), h_vlen[1].data_ptr(), h_vlen[2].data_ptr(), h_vlen[2].numel())
+        elif h_packed is not None:
             rc = L.mpegb200_video_decode_pictures_packed(ctx.h, len(p), h_pics[k % 3].data_ptr(), len(mbs), h_mbs.data_ptr(), len(coeffs), h_packed.data_ptr())
         else:
             rc = L.mpegb200_video_decode_pictures(ctx.h, len(p), h_pics[k % 3].data_ptr(), len(mbs), h_mbs.data_ptr(), len(coeffs), h_coeffs.data_ptr())
@@ -412,9 +423,11 @@ def main():
         e_steps = max(3, min(args.steps, 10))
         ems, _ = timed(step_e2e, e_steps)
         e2e = {"value": S * world * e_steps / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_mbs.numel() + (h_packed if h_packed is not None else h_coeffs).numel() + h_pics[0].numel()),
+               "h2d_bytes_per_step": int(h_mbs.numel() + h_pics[0].numel() + (sum(t.numel() for t in h_vlen) if h_vlen is not None else
+                                                                              (h_packed if h_packed is not None else h_coeffs).numel())),
                "d2h_bytes_per_step": int(h_planes.numel()), "steps": e_steps, "ms_per_step": ems / e_steps,
-               "path": ("mpegb200_video_decode_pictures_packed (pinned host records, 12-bit coefficient transfer form)" if h_packed is not None
+               "path": ("mpegb200_video_decode_pictures_vlen (pinned host records, variable-width coefficient transfer form)" if h_vlen is not None
+                        else "mpegb200_video_decode_pictures_packed (pinned host records, 12-bit coefficient transfer form)" if h_packed is not None
                         else "mpegb200_video_decode_pictures (pinned host records)") + " + rgba_batch_dev + read_pictures_host (pinned)"}
 
     # ---- NCCL gather of the decoded frames (the only collective of the path), timed on its own

@@ -175,6 +175,30 @@ int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, con
                                           size_t n_mb, const mpegb200_mb* mbs, size_t n_blocks,
                                           const uint8_t* coeffs12);
 
+/* Variable-width transfer form ("vlen") of the coefficients.  Every level the bitstream carried is odd after the
+ * oddification of video.go:732-736, every level it did not carry is 0, only an intra DC (dc*8, video.go:672) is even;
+ * neighbours in zig-zag order (video.go:1044-1053) have similar magnitude.  A block travels as
+ *   header  : uint32, eight 4-bit codes, code g for zig-zag positions 8g..8g+7:
+ *             0      all eight values are zero, no payload
+ *             1..12  eight w-bit two's-complement fields (w = code, value i in bits [i*w, i*w+w) of the group's w-byte
+ *                    little-endian string) holding c = (x + sign(x)) / 2, i.e. x = 2c - sign(c)
+ *             13     eight raw 12-bit two's-complement values (a group with an even non-zero value)
+ *   payload : the groups' bytes back to back, blocks back to back; 32 blocks form a chunk,
+ *             chunk_offsets[k] = byte offset of block 32k in the payload.
+ * The dense blocks of BASELINE config 3 take about 53 bytes instead of 128 (96 in the 12-bit form), sparse blocks of a
+ * real stream 4 bytes plus a few.  mpegb200_pack_coeffs_vlen converts the int16 form (multi-threaded; returns
+ * MPEGB200_ERECORD if a value lies outside [-2048, 2047], MPEGB200_EINVAL if payload_cap is too small;
+ * mpegb200_vlen_payload_bound(n_blocks) always suffices; *payload_bytes includes 16 bytes of padding that must be
+ * transferred with it).  The _vlen entry point copies headers, chunk offsets and payload to the device, expands them
+ * there (expand_vlen_kernel) and continues like mpegb200_video_decode_pictures. */
+size_t mpegb200_vlen_payload_bound(size_t n_blocks);
+int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* headers /* n_blocks */,
+                              uint64_t* chunk_offsets /* (n_blocks + 31) / 32 */, uint8_t* payload, size_t payload_cap,
+                              size_t* payload_bytes);
+int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics,
+                                        size_t n_mb, const mpegb200_mb* mbs, size_t n_blocks, const uint32_t* headers,
+                                        const uint64_t* chunk_offsets, const uint8_t* payload, size_t payload_bytes);
+
 /* Plane read-back for *Frame (Plane.Data, video.go:50-54): copies the macroblock-padded
  * planes of physical buffer `buf` to host memory.  Any of y/cb/cr may be NULL. */
 int mpegb200_video_read_planes(mpegb200_ctx* ctx, int stream, int buf,

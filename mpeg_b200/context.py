@@ -129,6 +129,29 @@ class Context:
         self._keep = (pics, mbs, coeffs12)
         self._ck(self.L.mpegb200_video_decode_pictures_packed(self.h, len(pics), _ptr(pics), len(mbs), _ptr(mbs), len(coeffs12), _ptr(coeffs12)))
 
+    def pack_coeffs_vlen(self, coeffs):
+        """int16 blocks -> the variable-width transfer form: (headers u32[n], chunk_offsets u64[ceil(n/32)], payload u8[...])."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.int16).reshape(-1, 64)
+        n = len(coeffs)
+        headers = np.empty(n, np.uint32)
+        chunks = np.empty((n + 31) // 32, np.uint64)
+        cap = int(self.L.mpegb200_vlen_payload_bound(n))
+        payload = np.empty(cap, np.uint8)
+        used = C.c_size_t(0)
+        self._ck(self.L.mpegb200_pack_coeffs_vlen(_ptr(coeffs), n, _ptr(headers), _ptr(chunks), _ptr(payload), cap, C.byref(used)))
+        return headers, chunks, payload[:used.value].copy()
+
+    def video_decode_pictures_vlen(self, pics, mbs, headers, chunks, payload):
+        """Like video_decode_pictures, with the coefficients in the variable-width transfer form."""
+        pics = np.ascontiguousarray(pics, dtype=PICTURE_DTYPE)
+        mbs = np.ascontiguousarray(mbs, dtype=MB_DTYPE)
+        headers = np.ascontiguousarray(headers, dtype=np.uint32)
+        chunks = np.ascontiguousarray(chunks, dtype=np.uint64)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        self._keep = (pics, mbs, headers, chunks, payload)
+        self._ck(self.L.mpegb200_video_decode_pictures_vlen(self.h, len(pics), _ptr(pics), len(mbs), _ptr(mbs), len(headers),
+                                                            _ptr(headers), _ptr(chunks), _ptr(payload), len(payload)))
+
     def video_decode_pictures_dev(self, n_pics: int, d_pics: int, n_mb: int, d_mbs: int, n_blocks: int, d_coeffs: int):
         """Device pointers (ints) of arrays already resident in HBM."""
         self._ck(self.L.mpegb200_video_decode_pictures_dev(self.h, n_pics, C.c_void_p(d_pics), n_mb, C.c_void_p(d_mbs), n_blocks, C.c_void_p(d_coeffs)))

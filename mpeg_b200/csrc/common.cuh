@@ -85,6 +85,9 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
 size_t fused_plan_bytes(uint32_t n_mb);
 // 12-bit packed coefficient blocks (96 B) -> int16 blocks (128 B)
 cudaError_t launch_unpack12(const uint8_t* d_packed, int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream);
+// variable-width transfer form (coeff_vlen.cu) -> int16 blocks
+cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chunk_offsets, const uint8_t* d_payload,
+                               int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

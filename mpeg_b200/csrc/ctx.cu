@@ -56,13 +56,15 @@ struct mpegb200_ctx {
     std::vector<uint8_t> audio_open;
     AudioState* d_audio = nullptr;
     float* d_window = nullptr;
-    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_packed[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans;
+    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_packed[2], s_headers[2], s_chunks[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans;
     // host-pointer pipeline: uploads and read-backs run on their own streams so that the H2D copy of the
     // next step overlaps the kernels and the D2H copy of the current one (double-buffered staging)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_kernel = nullptr, ev_down = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_kernel = nullptr;
+    // one read-back event per physical buffer index: a decode only waits for the read-backs of the buffers it writes
+    cudaEvent_t ev_down[3] = {nullptr, nullptr, nullptr};
     uint64_t upload_seq = 0;
-    bool down_pending = false;
+    bool down_pending[3] = {false, false, false};
     std::vector<Slab> slabs;
     SlabMaps* d_maps = nullptr;   // kMaxSlabs entries
     int n_generic_streams = 0;    // open streams that cannot use the TMA kernel (odd mb_w or encode failure)
@@ -114,12 +116,23 @@ static int ensure(mpegb200_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 // the compute stream must not overwrite a frame buffer that an asynchronous read-back is still copying
-static int join_readback(mpegb200_ctx* ctx) {
-    if (ctx->down_pending) {
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_down, 0));
-        ctx->down_pending = false;
-    }
+// (buf_mask: bit b = the work about to be enqueued writes physical buffer b of some stream; with the reference's
+// rotation (video.go:406-433) the buffer a picture is decoded into is never the one just handed out for reading, so
+// the read-back of step k overlaps the decode of step k+1)
+static int join_readback(mpegb200_ctx* ctx, unsigned buf_mask = 7u) {
+    for (int b = 0; b < 3; b++)
+        if ((buf_mask >> b & 1u) && ctx->down_pending[b]) {
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_down[b], 0));
+            ctx->down_pending[b] = false;
+        }
     return 0;
+}
+
+// which physical buffers a batch of pictures (host copy) writes
+static unsigned dst_buffers(const mpegb200_picture* pics, int n_pictures) {
+    unsigned m = 0;
+    for (int i = 0; i < n_pictures; i++) m |= pics[i].dst_buf < 3 ? 1u << pics[i].dst_buf : 7u;
+    return m;
 }
 
 static void drop_timing_events(mpegb200_ctx* ctx) {
@@ -181,7 +194,7 @@ mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) {
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_kernel, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_down, cudaEventDisableTiming) == cudaSuccess;
+    for (int b = 0; b < 3; b++) ok = ok && cudaEventCreateWithFlags(&ctx->ev_down[b], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_info, sizeof(StreamInfo) * max_streams) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_info, 0, sizeof(StreamInfo) * max_streams) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_window, sizeof(float) * 1024) == cudaSuccess;
@@ -223,7 +236,8 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     if (ctx->down_stream) cudaStreamSynchronize(ctx->down_stream);
     for (DevBuf* b : {&ctx->s_pics[0], &ctx->s_pics[1], &ctx->s_mbs[0], &ctx->s_mbs[1], &ctx->s_coeffs[0],
                       &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out,
-                      &ctx->s_plans, &ctx->s_packed[0], &ctx->s_packed[1]})
+                      &ctx->s_plans, &ctx->s_packed[0], &ctx->s_packed[1], &ctx->s_headers[0], &ctx->s_headers[1],
+                      &ctx->s_chunks[0], &ctx->s_chunks[1]})
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
@@ -231,7 +245,8 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     }
     drop_timing_events(ctx);
     if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
-    if (ctx->ev_down) cudaEventDestroy(ctx->ev_down);
+    for (int b = 0; b < 3; b++)
+        if (ctx->ev_down[b]) cudaEventDestroy(ctx->ev_down[b]);
     if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
     if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     if (ctx->d_info) cudaFree(ctx->d_info);
@@ -261,7 +276,7 @@ int mpegb200_sync(mpegb200_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->up_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->down_stream));
-    ctx->down_pending = false;
+    for (int b = 0; b < 3; b++) ctx->down_pending[b] = false;
     return 0;
 }
 
@@ -556,8 +571,8 @@ int mpegb200_video_validate(mpegb200_ctx* ctx, int n_pictures, const mpegb200_pi
     return 0;
 }
 
-int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* d_pics, size_t n_mb,
-                                       const mpegb200_mb* d_mbs, size_t n_blocks, const int16_t* d_coeffs) {
+static int decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* d_pics, size_t n_mb,
+                               const mpegb200_mb* d_mbs, size_t n_blocks, const int16_t* d_coeffs, unsigned dst_mask) {
     if (!ctx || n_pictures < 0 || (n_mb && (!d_pics || !d_mbs)) || (n_blocks && !d_coeffs))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
     if (n_mb > 0xffffffffull || n_blocks > 0xffffffffull || n_pictures > 65536)
@@ -568,7 +583,7 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     if (int rc = flush_info(ctx)) return rc;
-    if (int rc = join_readback(ctx)) return rc;
+    if (int rc = join_readback(ctx, dst_mask)) return rc;
     bool use_tma = !ctx->force_generic && ctx->n_generic_streams == 0 && ctx->encode_fn;
     CUtensorMap coef_map;
     if (use_tma) {
@@ -602,6 +617,12 @@ int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const 
     return 0;
 }
 
+// device-resident records: which buffers the pictures write is not known on the host, so every pending read-back is joined
+int mpegb200_video_decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* d_pics, size_t n_mb,
+                                       const mpegb200_mb* d_mbs, size_t n_blocks, const int16_t* d_coeffs) {
+    return decode_pictures_dev(ctx, n_pictures, d_pics, n_mb, d_mbs, n_blocks, d_coeffs, 7u);
+}
+
 int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics, size_t n_mb,
                                    const mpegb200_mb* mbs, size_t n_blocks, const int16_t* coeffs) {
     if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && !coeffs))
@@ -621,10 +642,9 @@ int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpeg
         CU(cudaMemcpyAsync(ctx->s_coeffs[slot].p, coeffs, 128 * n_blocks, cudaMemcpyHostToDevice, ctx->up_stream));
     CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
-    if (int rc = join_readback(ctx)) return rc;
-    int rc = mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
-                                                (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks,
-                                                (const int16_t*)ctx->s_coeffs[slot].p);
+    int rc = decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
+                                 (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks, (const int16_t*)ctx->s_coeffs[slot].p,
+                                 dst_buffers(pics, n_pictures));
     CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
     return rc;
 }
@@ -666,12 +686,48 @@ int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, con
         CU(cudaMemcpyAsync(ctx->s_packed[slot].p, coeffs12, 96 * n_blocks, cudaMemcpyHostToDevice, ctx->up_stream));
     CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
-    if (int rc = join_readback(ctx)) return rc;
     CU(launch_unpack12((const uint8_t*)ctx->s_packed[slot].p, (int16_t*)ctx->s_coeffs[slot].p, n_blocks, ctx->stream));
     ctx->launches++;
-    int rc = mpegb200_video_decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
-                                                (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks,
-                                                (const int16_t*)ctx->s_coeffs[slot].p);
+    int rc = decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
+                                 (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks, (const int16_t*)ctx->s_coeffs[slot].p,
+                                 dst_buffers(pics, n_pictures));
+    CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
+    return rc;
+}
+
+int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics, size_t n_mb,
+                                        const mpegb200_mb* mbs, size_t n_blocks, const uint32_t* headers,
+                                        const uint64_t* chunk_offsets, const uint8_t* payload, size_t payload_bytes) {
+    if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && (!headers || !chunk_offsets || !payload)))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n_blocks && payload_bytes < 16) return fail(ctx, MPEGB200_EINVAL, "payload without its 16 bytes of padding");
+    if (n_mb == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    const size_t chunks = (n_blocks + 31) / 32;
+    const int slot = (int)(ctx->upload_seq++ & 1);
+    if (int rc = ensure(ctx, ctx->s_pics[slot], sizeof(mpegb200_picture) * (size_t)n_pictures)) return rc;
+    if (int rc = ensure(ctx, ctx->s_mbs[slot], sizeof(mpegb200_mb) * n_mb)) return rc;
+    if (int rc = ensure(ctx, ctx->s_headers[slot], 4 * (n_blocks ? n_blocks : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_chunks[slot], 8 * (chunks ? chunks : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_packed[slot], payload_bytes ? payload_bytes : 16)) return rc;
+    if (int rc = ensure(ctx, ctx->s_coeffs[slot], 128 * (n_blocks ? n_blocks : 1))) return rc;
+    CU(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_free[slot], 0));
+    CU(cudaMemcpyAsync(ctx->s_pics[slot].p, pics, sizeof(mpegb200_picture) * (size_t)n_pictures, cudaMemcpyHostToDevice,
+                       ctx->up_stream));
+    CU(cudaMemcpyAsync(ctx->s_mbs[slot].p, mbs, sizeof(mpegb200_mb) * n_mb, cudaMemcpyHostToDevice, ctx->up_stream));
+    if (n_blocks) {
+        CU(cudaMemcpyAsync(ctx->s_headers[slot].p, headers, 4 * n_blocks, cudaMemcpyHostToDevice, ctx->up_stream));
+        CU(cudaMemcpyAsync(ctx->s_chunks[slot].p, chunk_offsets, 8 * chunks, cudaMemcpyHostToDevice, ctx->up_stream));
+        CU(cudaMemcpyAsync(ctx->s_packed[slot].p, payload, payload_bytes, cudaMemcpyHostToDevice, ctx->up_stream));
+    }
+    CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
+    CU(launch_expand_vlen((const uint32_t*)ctx->s_headers[slot].p, (const uint64_t*)ctx->s_chunks[slot].p,
+                          (const uint8_t*)ctx->s_packed[slot].p, (int16_t*)ctx->s_coeffs[slot].p, n_blocks, ctx->stream));
+    if (n_blocks) ctx->launches++;
+    int rc = decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
+                                 (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks, (const int16_t*)ctx->s_coeffs[slot].p,
+                                 dst_buffers(pics, n_pictures));
     CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
     return rc;
 }
@@ -704,7 +760,7 @@ int mpegb200_video_write_planes(mpegb200_ctx* ctx, int stream, int buf, const ui
     HostStream* s = nullptr;
     if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
     CU(cudaSetDevice(ctx->device));
-    if (int rc = join_readback(ctx)) return rc;
+    if (int rc = join_readback(ctx, 1u << buf)) return rc;
     uint8_t* base = s->dev + (size_t)buf * s->buf_stride;
     if (y) CU(cudaMemcpyAsync(base, y, s->luma_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (cb) CU(cudaMemcpyAsync(base + s->luma_bytes, cb, s->chroma_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -730,7 +786,7 @@ int mpegb200_video_write_frame(mpegb200_ctx* ctx, int stream, int buf, const uin
     if (int rc = check_buf(ctx, stream, buf, &s)) return rc;
     if (!src || src_bytes != s->buf_bytes) return fail(ctx, MPEGB200_EINVAL, "source must be %zu bytes", s->buf_bytes);
     CU(cudaSetDevice(ctx->device));
-    if (int rc = join_readback(ctx)) return rc;
+    if (int rc = join_readback(ctx, 1u << buf)) return rc;
     CU(cudaMemcpyAsync(s->dev + (size_t)buf * s->buf_stride, src, s->buf_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -755,8 +811,13 @@ static int read_pictures(mpegb200_ctx* ctx, int n, const int32_t* streams, const
         CU(cudaMemcpyAsync(dst + (size_t)i * dst_stride, s->dev + (size_t)bufs[i] * s->buf_stride, bytes, kind, q));
     }
     if (kind == cudaMemcpyDeviceToHost) {
-        CU(cudaEventRecord(ctx->ev_down, ctx->down_stream));
-        ctx->down_pending = true;
+        unsigned m = 0;
+        for (int i = 0; i < n; i++) m |= 1u << bufs[i];
+        for (int b = 0; b < 3; b++)
+            if (m >> b & 1u) {
+                CU(cudaEventRecord(ctx->ev_down[b], ctx->down_stream));
+                ctx->down_pending[b] = true;
+            }
     }
     return 0;
 }

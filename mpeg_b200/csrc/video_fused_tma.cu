@@ -318,6 +318,10 @@ __global__ void __launch_bounds__(16 * kPlanGroupsPerCta) plan_kernel(GroupPlan*
                                                                      const mpegb200_picture* __restrict__ pics,
                                                                      int n_pics, const mpegb200_mb* __restrict__ mbs,
                                                                      uint32_t n_mb, uint32_t n_blocks, int allow_strip) {
+    // Programmatic dependent launch: once every CTA of this grid has started, the CTAs of the arithmetic kernel may take
+    // the SM slots that free up and run their prologue; they wait for this grid's completion (griddepcontrol.wait)
+    // before they touch a plan.
+    asm volatile("griddepcontrol.launch_dependents;");
     __shared__ __align__(16) GroupPlan s_plan[kPlanGroupsPerCta];
     __shared__ __align__(16) uint32_t s_cnt2[kPlanGroupsPerCta][8][4];   // [bin][(coefficient slot & 7) >> 1], counter of an odd slot in the high half
     __shared__ __align__(16) uint4 s_lt[16 * kPlanGroupsPerCta / 32][8]; // per warp: [r] = 16-bit lanes b < r set to 1
@@ -858,6 +862,7 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
         fence_barrier_init();
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the plan pre-pass has completed and its plans are visible
     if (dbg == 2) {   // measurement only: the arithmetic and the stores without the tile fetch (works on whatever shared memory holds)
         if (tid == 64) {
             mbar_arrive_expect_tx(s_bar, kPlanSmemBytes);
@@ -1005,7 +1010,7 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     if (n_mb == 0) return cudaSuccess;
     // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the
     // plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
-    static int variant = -1, allow_strip = 1, stream_ctas = 0, prefetch_dist = kDefaultPrefetchDist, dbg = 0;
+    static int variant = -1, allow_strip = 1, stream_ctas = 0, prefetch_dist = kDefaultPrefetchDist, dbg = 0, pdl = 1;
     if (variant < 0) {
         const char* v = getenv("MPEGB200_FUSED");
         const int want = (v && strcmp(v, "stream") == 0) ? 1 : (v && strcmp(v, "oneshot") == 0) ? 0 : kDefaultVariant;
@@ -1026,6 +1031,8 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         if (pd) prefetch_dist = atoi(pd) > 0 ? atoi(pd) : 0;
         const char* dm = getenv("MPEGB200_MEASURE");   // "fetch": tile fetch only, "math": arithmetic + stores only (wrong pixels; timing experiments)
         dbg = dm && strcmp(dm, "fetch") == 0 ? 1 : dm && strcmp(dm, "math") == 0 ? 2 : 0;
+        const char* pl = getenv("MPEGB200_PDL");   // "0": plain stream order between the pre-pass and the arithmetic kernel
+        pdl = !(pl && pl[0] == '0');
         const char* s = getenv("MPEGB200_STRIP");
         allow_strip = !(s && s[0] == '0');
         if (getenv("MPEGB200_DEBUG"))
@@ -1040,7 +1047,21 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
     if (timing) cudaEventRecord(timing[1], stream);
     const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
     if (variant == 0) {
-        fused_tma_kernel<<<n_groups, kNT, Smem::total_oneshot, stream>>>(cm, d_maps, plans, n_groups, (uint32_t)prefetch_dist, dbg);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_groups);
+        cfg.blockDim = dim3(kNT);
+        cfg.dynamicSmemBytes = Smem::total_oneshot;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (pdl && !timing) ? 1 : 0;   // with timing events between the two kernels there is nothing to overlap
+        const SlabMaps* maps_arg = d_maps;
+        const GroupPlan* plans_arg = plans;
+        const uint32_t pf = (uint32_t)prefetch_dist;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, fused_tma_kernel, cm, maps_arg, plans_arg, n_groups, pf, dbg);
+        if (e != cudaSuccess) return e;
     } else {
         const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
         fused_stream_kernel<<<grid, kNT, SmemS::total, stream>>>(cm, d_maps, plans, n_groups);

@@ -408,6 +408,37 @@ def test_packed_12bit_transfer_form_is_equivalent(ctx):
     ctx.video_close(40)
 
 
+def test_vlen_transfer_form_is_equivalent(ctx):
+    """mpegb200_video_decode_pictures_vlen: the variable-width transfer form (eight groups per block in zig-zag order, each
+    with its own bit width; coeff_vlen.cu) expands on the device to the same int16 blocks: natural P/B/I pictures (sparse
+    blocks, even intra DCs -> raw groups), a dense-P picture, the extremes, and a block count that is no multiple of 32."""
+    g = wl.CIF
+    rng = wl.stream_rng(2, 6)
+    fs = ol.FrameSet(1, g.width, g.height)
+    fresh_stream(ctx, 41, g.width, g.height)
+    for b in range(3):
+        buf = wl.random_reference_frame(rng, g)
+        fs.whole(0, b)[:] = buf
+        ctx.video_write_frame(41, b, buf)
+    steps = [(wl.PIC_P, (0, 1, 2), "natural"), (wl.PIC_B, (2, 0, 1), "natural"), (wl.PIC_I, (1, 2, 0), "natural"),
+             (wl.PIC_P, (0, 1, 2), "dense")]
+    for t, bufs, mode in steps:
+        mbs, coeffs = wl.make_picture(rng, g, t, mode, adversarial=False)
+        coeffs = np.clip(coeffs, -2048, 2047)
+        coeffs[0, :4] = [2047, -2048, 1, -1]
+        coeffs[1, :] = 0
+        coeffs[2, :] = -2047
+        pics, mbs, coeffs = wl.batch_pictures([(mbs, coeffs)], [41], t, [bufs])
+        headers, chunks, payload = ctx.pack_coeffs_vlen(coeffs)
+        assert len(headers) == len(coeffs) and len(chunks) == (len(coeffs) + 31) // 32
+        ctx.video_decode_pictures_vlen(pics, mbs, headers, chunks, payload)
+        op = pics.copy()
+        op["stream"] = 0
+        assert fs.exec_pictures(op, mbs, coeffs) == 0
+        assert_frames_equal(ctx, fs, 41, 0, msg=f"vlen path, picture type {t}, {mode}")
+    ctx.video_close(41)
+
+
 def _run_pictures_and_compare(ctx, fs, sid, g, pictures, msg):
     """pictures: list of (type, (dst, fwd, bwd), mbs, coeffs); each decoded on the GPU and by the oracle, all three
     buffers compared after every one."""

@@ -1,0 +1,112 @@
+"""CPU-only: the variable-width ("vlen") transfer form of the coefficient blocks (include/mpegb200.h).
+The host packer (mpegb200_pack_coeffs_vlen, pure host code) is checked against an independent numpy reading of the
+format as the header documents it; the device expansion is checked in tests/test_gpu_video.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mpeg_b200 import _lib
+from mpeg_b200 import workload as wl
+
+
+def pack(coeffs):
+    L = _lib.load()
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.int16).reshape(-1, 64)
+    n = len(coeffs)
+    headers = np.zeros(n, np.uint32)
+    chunks = np.zeros((n + 31) // 32, np.uint64)
+    cap = int(L.mpegb200_vlen_payload_bound(n))
+    payload = np.zeros(cap, np.uint8)
+    used = C.c_size_t(0)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    rc = L.mpegb200_pack_coeffs_vlen(vp(coeffs), n, vp(headers), vp(chunks), vp(payload), cap, C.byref(used))
+    return rc, headers, chunks, payload[:used.value]
+
+
+def unpack_reference(headers, chunks, payload):
+    """Slow reading of the format, straight from the header's description."""
+    n = len(headers)
+    out = np.zeros((n, 64), np.int16)
+    for b in range(n):
+        if b % 32 == 0:
+            off = int(chunks[b // 32])
+        h = int(headers[b])
+        for g in range(8):
+            code = (h >> (4 * g)) & 15
+            assert code <= 13
+            if code == 0:
+                continue
+            w = 12 if code == 13 else code
+            bits = int.from_bytes(payload[off:off + w].tobytes(), "little")
+            off += w
+            for i in range(8):
+                c = (bits >> (i * w)) & ((1 << w) - 1)
+                if c >= 1 << (w - 1):
+                    c -= 1 << w
+                x = c if code == 13 else 2 * c - (c > 0) + (c < 0)
+                out[b, wl.ZIGZAG[8 * g + i]] = x
+    return out
+
+
+def dense_blocks(n, seed):
+    rng = np.random.default_rng(seed)
+    return wl._draw_blocks(rng, n, np.zeros(n, bool), dense=True)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000])
+def test_round_trip_dense(n):
+    coeffs = dense_blocks(n, n)
+    rc, h, c, p = pack(coeffs)
+    assert rc == 0
+    assert np.array_equal(unpack_reference(h, c, p), coeffs)
+    assert len(p) >= 16 and not p[-16:].any()          # the padding the kernel's word reads rely on
+
+
+def test_round_trip_natural_intra_and_extremes():
+    rng = np.random.default_rng(7)
+    n = 600
+    intra = rng.random(n) < 0.3
+    coeffs = wl._draw_blocks(rng, n, intra, dense=False)       # sparse blocks, even intra DC values
+    coeffs[0] = 0                                              # an all-zero block: header 0, no payload
+    coeffs[1, :] = 2047
+    coeffs[2, :] = -2048                                       # even: raw groups
+    coeffs[3, :] = -2047
+    coeffs[4, ::2] = 1
+    coeffs[4, 1::2] = -1
+    coeffs[5, 63] = 2                                          # a lone even value in the last group
+    rc, h, c, p = pack(coeffs)
+    assert rc == 0
+    assert h[0] == 0
+    assert h[2] == 0xDDDDDDDD
+    assert np.array_equal(unpack_reference(h, c, p), coeffs)
+
+
+def test_sizes():
+    """Dense blocks of BASELINE config 3: about 53 bytes instead of 128; sparse blocks: a few bytes."""
+    coeffs = dense_blocks(4096, 3)
+    rc, h, c, p = pack(coeffs)
+    assert rc == 0
+    per_block = 4 + (len(p) - 16) / len(coeffs) + 8 / 32
+    assert per_block < 56, per_block
+    rng = np.random.default_rng(9)
+    sparse = wl._draw_blocks(rng, 4096, np.zeros(4096, bool), dense=False)
+    rc, h, c, p = pack(sparse)
+    assert rc == 0
+    assert 4 + (len(p) - 16) / 4096 < 24
+
+
+def test_out_of_range_and_capacity():
+    L = _lib.load()
+    bad = np.zeros((1, 64), np.int16)
+    bad[0, 10] = 2048
+    rc, *_ = pack(bad)
+    assert rc != 0
+    coeffs = dense_blocks(64, 1)
+    headers = np.zeros(64, np.uint32)
+    chunks = np.zeros(2, np.uint64)
+    payload = np.zeros(64, np.uint8)                           # far too small
+    used = C.c_size_t(0)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    assert L.mpegb200_pack_coeffs_vlen(vp(coeffs), 64, vp(headers), vp(chunks), vp(payload), 64, C.byref(used)) != 0
+    assert used.value > 64                                     # tells the caller what it needs
