@@ -439,6 +439,45 @@ def test_vlen_transfer_form_is_equivalent(ctx):
     ctx.video_close(41)
 
 
+def test_async_readback_is_ordered_against_later_decodes():
+    """Host read-backs run on their own stream; a decode waits only for the read-backs of the buffers it writes
+    (one event per physical buffer index).  Picture A goes into buffer 0 and is read back asynchronously; a decode
+    into buffer 1 and then picture B into buffer 0 are enqueued right behind it.  The host copy must hold A, not B."""
+    import mpeg_b200
+    import torch
+    g = wl.CIF
+    n = 48
+    c = mpeg_b200.Context(device=0, max_streams=n)
+    try:
+        rng = wl.stream_rng(2, 77)
+        fs = ol.FrameSet(n, g.width, g.height)
+        for s in range(n):
+            c.video_open(s, g.width, g.height)
+        ids = list(range(n))
+        def intra_batch(dst):
+            per = [wl.make_picture(rng, g, wl.PIC_I, "natural", adversarial=False) for _ in range(n)]
+            return wl.batch_pictures(per, ids, wl.PIC_I, [(dst, (dst + 1) % 3, (dst + 2) % 3)] * n)
+        a, mid, b = intra_batch(0), intra_batch(1), intra_batch(0)
+        host = torch.empty(n * g.picture_bytes, dtype=torch.uint8, pin_memory=True)
+        for rep in range(3):
+            c.video_decode_pictures(*a)
+            c.video_read_pictures(np.arange(n), np.zeros(n, np.uint8), host.data_ptr(), g.picture_bytes)
+            c.video_decode_pictures(*mid)        # writes buffer 1: need not wait for the read-back
+            c.video_decode_pictures(*b)          # overwrites buffer 0: must wait for it
+            c.sync()
+            assert fs.exec_pictures(a[0], a[1], a[2]) == 0
+            got = host.numpy().reshape(n, g.picture_bytes)
+            for s in range(n):
+                assert np.array_equal(got[s], fs.whole(s, 0)[:g.picture_bytes]), f"rep {rep} stream {s}: read-back raced a later decode"
+            assert fs.exec_pictures(mid[0], mid[1], mid[2]) == 0
+            assert fs.exec_pictures(b[0], b[1], b[2]) == 0
+            for s in (0, n - 1):
+                assert np.array_equal(c.video_read_frame(s, 0), fs.whole(s, 0))
+                assert np.array_equal(c.video_read_frame(s, 1), fs.whole(s, 1))
+    finally:
+        c.close()
+
+
 def _run_pictures_and_compare(ctx, fs, sid, g, pictures, msg):
     """pictures: list of (type, (dst, fwd, bwd), mbs, coeffs); each decoded on the GPU and by the oracle, all three
     buffers compared after every one."""
