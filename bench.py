@@ -321,7 +321,7 @@ def main():
         return t
 
     h_mbs, h_coeffs = pinned(mbs), pinned(coeffs)
-    # transfer form of the coefficients on the end-to-end path (PCIe bound): variable-width groups (about 53 B per dense
+    # transfer form of the coefficients on the end-to-end path (PCIe bound): variable-width groups (about 49 B per dense
     # block), the fixed 12-bit form (96 B) or the plain int16 blocks (128 B)
     h_packed = h_vlen = None
     if not args.no_e2e:

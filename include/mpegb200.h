@@ -185,7 +185,7 @@ int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, con
  *             13     eight raw 12-bit two's-complement values (a group with an even non-zero value)
  *   payload : the groups' bytes back to back, blocks back to back; 32 blocks form a chunk,
  *             chunk_offsets[k] = byte offset of block 32k in the payload.
- * The dense blocks of BASELINE config 3 take about 53 bytes instead of 128 (96 in the 12-bit form), sparse blocks of a
+ * The dense blocks of BASELINE config 3 take about 49 bytes instead of 128 (96 in the 12-bit form), sparse blocks of a
  * real stream 4 bytes plus a few.  mpegb200_pack_coeffs_vlen converts the int16 form (multi-threaded; returns
  * MPEGB200_ERECORD if a value lies outside [-2048, 2047], MPEGB200_EINVAL if payload_cap is too small;
  * mpegb200_vlen_payload_bound(n_blocks) always suffices; *payload_bytes includes 16 bytes of padding that must be

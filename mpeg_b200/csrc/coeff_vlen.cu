@@ -11,7 +11,7 @@
 // eight values of w bits are exactly w bytes, so groups never straddle bytes.  A group holding an even non-zero value
 // (intra DC) travels raw, 12 bits per value.  A block is a 32-bit header (eight 4-bit group codes: 0..12 = w, 13 = raw)
 // plus sum(w) payload bytes; 32 blocks form a chunk with one 64-bit payload offset, offsets inside a chunk come from a
-// warp scan over the headers.  The dense blocks of the benchmark shrink from 128 (96 in the 12-bit form) to about 53
+// warp scan over the headers.  The dense blocks of the benchmark shrink from 128 (96 in the 12-bit form) to about 49
 // bytes, typical sparse blocks of a real stream to 4 + a few bytes.
 #include <cstdint>
 #include <atomic>

@@ -83,12 +83,12 @@ def test_round_trip_natural_intra_and_extremes():
 
 
 def test_sizes():
-    """Dense blocks of BASELINE config 3: about 53 bytes instead of 128; sparse blocks: a few bytes."""
+    """Dense blocks of BASELINE config 3: about 49 bytes instead of 128; sparse blocks: a few bytes."""
     coeffs = dense_blocks(4096, 3)
     rc, h, c, p = pack(coeffs)
     assert rc == 0
     per_block = 4 + (len(p) - 16) / len(coeffs) + 8 / 32
-    assert per_block < 56, per_block
+    assert per_block < 52, per_block
     rng = np.random.default_rng(9)
     sparse = wl._draw_blocks(rng, 4096, np.zeros(4096, bool), dense=False)
     rc, h, c, p = pack(sparse)
