@@ -17,6 +17,7 @@ import mpeg_b200  # noqa: E402
 from mpeg_b200 import workload as wl  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+ONLY = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None   # e.g. "dense-P,natural-B"
 STEPS, WARM = 20, 3
 peak = 6569.0
 try:
@@ -36,6 +37,8 @@ for s in range(S):
 out = []
 for name, ptype, mode in [("dense-P", wl.PIC_P, "dense"), ("natural-P", wl.PIC_P, "natural"), ("I-only", wl.PIC_I, "natural"),
                           ("dense-I", wl.PIC_I, "dense"), ("natural-B", wl.PIC_B, "natural")]:
+    if ONLY is not None and name not in ONLY:
+        continue
     t0 = time.time()
     per = [wl.make_picture(wl.stream_rng(3, 5000 + s), g, ptype, mode) for s in range(S)]
     pics, mbs, coeffs = wl.batch_pictures(per, list(range(S)), ptype, [(0, 1, 2)] * S)
