@@ -99,13 +99,7 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* map, int c0, int c1,
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-// d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)
-__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
-    uint32_t d;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
+#if !MPEGB200_PAIRED
 // videoPremultiplierMatrix, video.go:1077-1086
 __device__ __forceinline__ constexpr int premult(int i) {
     constexpr int t[64] = {32, 44, 42, 38, 32, 25, 17, 9,  44, 62, 58, 52, 44, 35, 24, 12, 42, 58, 55, 49, 42, 33,
@@ -144,6 +138,8 @@ __device__ __forceinline__ void idct_pass8(int& s0, int& s1, int& s2, int& s3, i
     s6 = y3 - x4;
     s7 = y4 - b7;
 }
+
+#endif  // !MPEGB200_PAIRED
 
 // premultiplier pairs for dp2a, in constant memory so that they are instruction operands (c[bank][offset]) instead of
 // one uniform-register move each: [pair (0,4) (1,7) (3,5) (2,6)][column]; sum = pa | pb << 8, difference = pa | -pb << 8
