@@ -169,18 +169,23 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
     const uint8_t* base = payload + chunk_offsets[chunk];
     int16_t* tile = s_tile[warp];
 
+#pragma unroll 1
     for (int round = 0; round < 8; round++) {
         const int src = 4 * round + q;
         const uint32_t h = __shfl_sync(0xffffffffu, my_header, src);
         uint32_t off = __shfl_sync(0xffffffffu, my_off, src);
         if (b0 + 4 * round >= n_blocks) break;   // warp-uniform
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const uint32_t code = (h >> (4 * j)) & 15u;
-            if (j < g) off += code == 13u ? 12u : code;
-        }
         const uint32_t code = (h >> (4 * g)) & 15u;
-        const uint32_t w = code == 13u ? 12u : code;
+        const uint32_t w = code - (code == 13u ? 1u : 0u);
+        {   // the group's offset inside its block: exclusive scan of the widths over the block's eight lanes
+            uint32_t incl_w = w;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const uint32_t up_w = __shfl_up_sync(0xffffffffu, incl_w, d, 8);
+                if (g >= d) incl_w += up_w;
+            }
+            off += incl_w - w;
+        }
         int v[8];
         if (w == 0) {
 #pragma unroll
@@ -190,20 +195,26 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
             const uint32_t* p4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
             const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
             // the payload buffer is padded, so the fourth word is always readable
-            uint32_t r0 = __ldg(p4), r1 = __ldg(p4 + 1), r2 = __ldg(p4 + 2), r3 = __ldg(p4 + 3);
-            r0 = __funnelshift_r(r0, r1, sh);
+            uint32_t r0 = __ldg(p4), r1 = __ldg(p4 + 1), r2 = __ldg(p4 + 2);
+            const uint32_t r3 = __ldg(p4 + 3);
+            r0 = __funnelshift_r(r0, r1, sh);   // the group's (at most 96) bits, aligned
             r1 = __funnelshift_r(r1, r2, sh);
             r2 = __funnelshift_r(r2, r3, sh);
-            r3 >>= sh;
             const uint32_t up = 32u - w;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int c = (int)(r0 << up) >> up;   // sign-extended w-bit field
-                v[i] = code == 13u ? c : 2 * c - (c > 0) + (c < 0);
+                v[i] = (int)(r0 << up) >> up;   // sign-extended w-bit field
                 r0 = __funnelshift_r(r0, r1, w);
                 r1 = __funnelshift_r(r1, r2, w);
-                r2 = __funnelshift_r(r2, r3, w);
-                r3 >>= w;
+                r2 >>= w;
+            }
+            if (code != 13u) {   // undo c = (x + sign(x)) / 2: x = 2c - sign(c)
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int c = v[i];
+                    const int x = 2 * c - ((c >> 31) | 1);   // right for c != 0
+                    v[i] = c == 0 ? 0 : x;
+                }
             }
         }
 #pragma unroll

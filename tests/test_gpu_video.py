@@ -478,6 +478,36 @@ def test_async_readback_is_ordered_against_later_decodes():
         c.close()
 
 
+def test_kernel_timing_aid():
+    """mpegb200_set_kernel_timing / mpegb200_kernel_times (bench.py's roofline of the arithmetic kernel alone): one
+    (pre-pass, arithmetic kernel) pair of positive durations per decode call, oldest first, forgotten once read; the
+    decoded pixels are unaffected.  (Own context: only the TMA path is timed, and the shared one may hold a stream
+    of odd macroblock width that sends every batch to the generic kernel.)"""
+    import mpeg_b200
+    g = wl.CIF
+    rng = wl.stream_rng(2, 8)
+    fs = ol.FrameSet(1, g.width, g.height)
+    c = mpeg_b200.Context(device=0, max_streams=4)
+    try:
+        c.video_open(2, g.width, g.height)
+        c.set_kernel_timing(True)
+        for t, bufs in [(wl.PIC_I, (0, 1, 2)), (wl.PIC_P, (1, 0, 2)), (wl.PIC_P, (2, 1, 0))]:
+            mbs, coeffs = wl.make_picture(rng, g, t, "natural", adversarial=False)
+            pics, mbs, coeffs = wl.batch_pictures([(mbs, coeffs)], [2], t, [bufs])
+            c.video_decode_pictures(pics, mbs, coeffs)
+            op = pics.copy()
+            op["stream"] = 0
+            assert fs.exec_pictures(op, mbs, coeffs) == 0
+        plan_ms, fused_ms = c.kernel_times()
+        assert len(plan_ms) == len(fused_ms) == 3
+        assert (plan_ms > 0).all() and (fused_ms > 0).all() and (fused_ms < 50).all()
+        assert len(c.kernel_times()[0]) == 0          # read once
+        c.set_kernel_timing(False)
+        assert_frames_equal(c, fs, 2, 0, msg="decode with kernel timing on")
+    finally:
+        c.close()
+
+
 def _run_pictures_and_compare(ctx, fs, sid, g, pictures, msg):
     """pictures: list of (type, (dst, fwd, bwd), mbs, coeffs); each decoded on the GPU and by the oracle, all three
     buffers compared after every one."""
