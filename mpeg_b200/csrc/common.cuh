@@ -68,7 +68,7 @@ struct AudioState {
 // launch wrappers (video_kernels.cu / audio_kernels.cu); all return cudaGetLastError()
 cudaError_t launch_fused_mc_idct(const StreamInfo* d_streams, int max_streams, const mpegb200_picture* d_pics,
                                  int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb, const int16_t* d_coeffs,
-                                 uint32_t n_blocks, cudaStream_t stream);
+                                 uint32_t n_blocks, cudaStream_t stream, bool skip_tma_streams = false);
 cudaError_t launch_rgba(const StreamInfo* d_streams, int max_streams, const int32_t* d_stream_ids,
                         const uint8_t* d_bufs, int n, int max_w, int max_h, uint8_t* d_rgba,
                         size_t rgba_stride_bytes, cudaStream_t stream);

@@ -68,6 +68,7 @@ struct mpegb200_ctx {
     std::vector<Slab> slabs;
     SlabMaps* d_maps = nullptr;   // kMaxSlabs entries
     int n_generic_streams = 0;    // open streams that cannot use the TMA kernel (odd mb_w or encode failure)
+    int n_tma_streams = 0;        // open streams that can
     bool force_generic = false;   // MPEGB200_FUSED=generic (A/B measurements)
     void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
     uint64_t launches = 0;
@@ -466,7 +467,7 @@ int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
     info.open = 1;
     info.tma_ok = sl.tma_ok ? 1 : 0;
     s->open = true;
-    if (!sl.tma_ok) ctx->n_generic_streams++;
+    if (!sl.tma_ok) ctx->n_generic_streams++; else ctx->n_tma_streams++;
     ctx->info_dirty = true;
     if (width > ctx->max_w) ctx->max_w = width;
     if (height > ctx->max_h) ctx->max_h = height;
@@ -482,7 +483,7 @@ int mpegb200_video_close(mpegb200_ctx* ctx, int stream) {
     Slab& sl = ctx->slabs[s->slab];
     sl.slot_used[s->slot] = 0;
     sl.used--;
-    if (!sl.tma_ok) ctx->n_generic_streams--;
+    if (!sl.tma_ok) ctx->n_generic_streams--; else ctx->n_tma_streams--;
     if (sl.used == 0) {
         cudaFree(sl.dev);
         sl = Slab{};
@@ -584,7 +585,9 @@ static int decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200
     CU(cudaSetDevice(ctx->device));
     if (int rc = flush_info(ctx)) return rc;
     if (int rc = join_readback(ctx, dst_mask)) return rc;
-    bool use_tma = !ctx->force_generic && ctx->n_generic_streams == 0 && ctx->encode_fn;
+    // The TMA kernel serves every stream whose chroma pitch is a multiple of 16 bytes; streams of odd macroblock width
+    // go to the generic kernel.  A batch may mix both: each kernel skips the other's records.
+    bool use_tma = !ctx->force_generic && ctx->encode_fn && ctx->n_tma_streams > 0;
     CUtensorMap coef_map;
     if (use_tma) {
         // 2-D view of the coefficient array: n_blocks rows of 64 int16, boxes of 32 rows, 128-byte swizzle
@@ -608,12 +611,13 @@ static int decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200
         }
         CU(launch_fused_tma(&coef_map, ctx->d_maps, ctx->s_plans.p, ctx->d_info, ctx->max_streams, d_pics, n_pictures,
                             d_mbs, (uint32_t)n_mb, (uint32_t)n_blocks, ctx->stream, timing));
-        ctx->launches++;  // the plan pre-pass
-    } else {
-        CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,
-                                (uint32_t)n_blocks, ctx->stream));
+        ctx->launches += 2;  // the plan pre-pass and the arithmetic kernel
     }
-    ctx->launches++;
+    if (!use_tma || ctx->n_generic_streams > 0) {
+        CU(launch_fused_mc_idct(ctx->d_info, ctx->max_streams, d_pics, n_pictures, d_mbs, (uint32_t)n_mb, d_coeffs,
+                                (uint32_t)n_blocks, ctx->stream, use_tma));
+        ctx->launches++;
+    }
     return 0;
 }
 

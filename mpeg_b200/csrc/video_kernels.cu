@@ -128,7 +128,8 @@ template <int G>
 __global__ void __launch_bounds__(6 * G) fused_mc_idct_kernel(const StreamInfo* __restrict__ streams, int max_streams,
                                                             const mpegb200_picture* __restrict__ pics, int n_pics,
                                                             const mpegb200_mb* __restrict__ mbs, uint32_t n_mb,
-                                                            const int16_t* __restrict__ coeffs, uint32_t n_blocks) {
+                                                            const int16_t* __restrict__ coeffs, uint32_t n_blocks,
+                                                            int skip_tma_streams) {
     using L = FusedSmem<G>;
     constexpr int NT = L::NT;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(6 * G) fused_mc_idct_kernel(const StreamInfo* 
                 ok = stream >= 0 && stream < max_streams && dst_b < 3 && fwd_b < 3 && bwd_b < 3;
                 if (ok) {
                     const StreamInfo si = streams[stream];
-                    ok = si.open && row < si.mb_h && col < si.mb_w;
+                    // mixed batch: the records of streams the TMA kernel can serve are its business (ctx.cu)
+                    ok = si.open && !(skip_tma_streams && si.tma_ok) && row < si.mb_h && col < si.mb_w;
                     const uint32_t rel = cblock - block0;
                     if (ncoded) ok = ok && rel <= (uint32_t)NT && rel + ncoded <= (uint32_t)NT && cblock + ncoded <= n_blocks;
                     if (ok) {
@@ -382,11 +384,12 @@ constexpr int kG = 16;  // macroblock records per CTA (96 threads)
 
 cudaError_t launch_fused_mc_idct(const StreamInfo* d_streams, int max_streams, const mpegb200_picture* d_pics,
                                  int n_pics, const mpegb200_mb* d_mbs, uint32_t n_mb, const int16_t* d_coeffs,
-                                 uint32_t n_blocks, cudaStream_t stream) {
+                                 uint32_t n_blocks, cudaStream_t stream, bool skip_tma_streams) {
     if (n_mb == 0) return cudaSuccess;
     const uint32_t grid = (n_mb + kG - 1) / kG;
     fused_mc_idct_kernel<kG><<<grid, 6 * kG, FusedSmem<kG>::total, stream>>>(d_streams, max_streams, d_pics, n_pics,
-                                                                            d_mbs, n_mb, d_coeffs, n_blocks);
+                                                                            d_mbs, n_mb, d_coeffs, n_blocks,
+                                                                            skip_tma_streams ? 1 : 0);
     return cudaGetLastError();
 }
 

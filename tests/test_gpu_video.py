@@ -330,8 +330,8 @@ def test_windows_wrap_across_row_ends_like_linear_indexing(ctx):
 
 def test_mixed_geometries_slabs_and_kernel_selection(ctx):
     """Streams of different sizes live in different slabs (own tensor maps); a stream whose chroma pitch is not
-    a multiple of 16 bytes (odd macroblock width) forces the generic kernel for the launch.  Either way the
-    output is the oracle's."""
+    a multiple of 16 bytes (odd macroblock width) is served by the generic kernel, in the same batch as the streams
+    the TMA kernel serves (each kernel skips the other's records).  Either way the output is the oracle's."""
     geos = [wl.Geometry(64, 48), wl.Geometry(96, 64), wl.Geometry(64, 48)]
     sids = [30, 31, 32]
     rng = wl.stream_rng(2, 77)
@@ -366,7 +366,7 @@ def test_mixed_geometries_slabs_and_kernel_selection(ctx):
     geos.append(g_odd)
     sids.append(33)
     oracles.append(fs_odd)
-    run_batch()                                   # generic kernel for everybody
+    run_batch()                                   # mixed batch: TMA kernel for three streams, generic kernel for the fourth
     ctx.video_close(33)
     geos.pop(); sids.pop(); oracles.pop()
     run_batch()                                   # back on the fast path
@@ -481,8 +481,7 @@ def test_async_readback_is_ordered_against_later_decodes():
 def test_kernel_timing_aid():
     """mpegb200_set_kernel_timing / mpegb200_kernel_times (bench.py's roofline of the arithmetic kernel alone): one
     (pre-pass, arithmetic kernel) pair of positive durations per decode call, oldest first, forgotten once read; the
-    decoded pixels are unaffected.  (Own context: only the TMA path is timed, and the shared one may hold a stream
-    of odd macroblock width that sends every batch to the generic kernel.)"""
+    decoded pixels are unaffected."""
     import mpeg_b200
     g = wl.CIF
     rng = wl.stream_rng(2, 8)
