@@ -807,12 +807,33 @@ static int read_pictures(mpegb200_ctx* ctx, int n, const int32_t* streams, const
         CU(cudaStreamWaitEvent(ctx->down_stream, ctx->ev_kernel, 0));
         q = ctx->down_stream;
     }
-    for (int i = 0; i < n; i++) {
+    // Streams that sit at equal distances in one slab (consecutive slots: the normal case of a batch) and hand out the
+    // same buffer index go as ONE strided copy: a copy-engine operation costs a few microseconds however small, and a
+    // batch of 256 pictures should not pay that 256 times.
+    for (int i = 0; i < n;) {
         HostStream* s = nullptr;
         if (int rc = check_buf(ctx, streams[i], bufs[i], &s)) return rc;
         const size_t bytes = s->luma_bytes + 2 * s->chroma_bytes;
         if (bytes > dst_stride) return fail(ctx, MPEGB200_EINVAL, "stride %zu smaller than a picture (%zu)", dst_stride, bytes);
-        CU(cudaMemcpyAsync(dst + (size_t)i * dst_stride, s->dev + (size_t)bufs[i] * s->buf_stride, bytes, kind, q));
+        const uint8_t* src = s->dev + (size_t)bufs[i] * s->buf_stride;
+        int j = i + 1;
+        ptrdiff_t pitch = 0;
+        const HostStream* prev = s;
+        for (; j < n; j++) {
+            HostStream* t = nullptr;
+            if (int rc = check_buf(ctx, streams[j], bufs[j], &t)) return rc;
+            const ptrdiff_t d = t->dev - prev->dev;
+            if (bufs[j] != bufs[i] || t->luma_bytes != s->luma_bytes || t->chroma_bytes != s->chroma_bytes ||
+                t->buf_stride != s->buf_stride || d < (ptrdiff_t)bytes || d > (ptrdiff_t)0x7fffffff || (pitch && d != pitch))
+                break;
+            pitch = d;
+            prev = t;
+        }
+        if (j - i >= 2)
+            CU(cudaMemcpy2DAsync(dst + (size_t)i * dst_stride, dst_stride, src, (size_t)pitch, bytes, (size_t)(j - i), kind, q));
+        else
+            CU(cudaMemcpyAsync(dst + (size_t)i * dst_stride, src, bytes, kind, q));
+        i = j;
     }
     if (kind == cudaMemcpyDeviceToHost) {
         unsigned m = 0;
