@@ -478,6 +478,39 @@ def test_async_readback_is_ordered_against_later_decodes():
         c.close()
 
 
+def test_batched_readback_runs_and_singles():
+    """mpegb200_video_read_pictures_host copies a run of equally spaced streams (consecutive slots of one slab, same
+    buffer index) as ONE strided copy and everything else picture by picture.  Mixed order, two geometries, different
+    buffer indices, a descending run: every picture must equal the stream's own read-back."""
+    import mpeg_b200
+    import torch
+    ga, gb = wl.Geometry(96, 64), wl.Geometry(64, 48)
+    c = mpeg_b200.Context(device=0, max_streams=8)
+    try:
+        rng = wl.stream_rng(2, 91)
+        geo = {0: ga, 1: ga, 2: ga, 3: gb, 4: gb, 5: ga}
+        for s, g in geo.items():
+            c.video_open(s, g.width, g.height)
+            for b in range(3):
+                c.video_write_frame(s, b, wl.random_reference_frame(rng, g))
+        stride = ga.picture_bytes + 64
+        for streams, bufs in [([0, 1, 2, 5], [1, 1, 1, 1]),          # one run of three + (slot gap or not) the fourth
+                              ([0, 1, 3, 2, 4], [0, 0, 2, 0, 2]),      # run of two, then singles of two slabs
+                              ([2, 1, 0], [2, 2, 2]),                  # descending: no run
+                              ([0, 1, 2], [0, 1, 0]),                  # same spacing, different buffers: no run
+                              ([3, 4], [1, 1])]:
+            host = torch.zeros(len(streams) * stride, dtype=torch.uint8, pin_memory=True)
+            c.video_read_pictures(np.array(streams), np.array(bufs, np.uint8), host.data_ptr(), stride)
+            c.sync()
+            got = host.numpy().reshape(len(streams), stride)
+            for i, (s, b) in enumerate(zip(streams, bufs)):
+                n = geo[s].picture_bytes
+                assert np.array_equal(got[i, :n], c.video_read_frame(s, b)[:n]), (streams, bufs, i)
+                assert not got[i, n:].any()
+    finally:
+        c.close()
+
+
 def test_kernel_timing_aid():
     """mpegb200_set_kernel_timing / mpegb200_kernel_times (bench.py's roofline of the arithmetic kernel alone): one
     (pre-pass, arithmetic kernel) pair of positive durations per decode call, oldest first, forgotten once read; the

@@ -110,3 +110,24 @@ def test_out_of_range_and_capacity():
     vp = lambda a: C.c_void_p(a.ctypes.data)
     assert L.mpegb200_pack_coeffs_vlen(vp(coeffs), 64, vp(headers), vp(chunks), vp(payload), 64, C.byref(used)) != 0
     assert used.value > 64                                     # tells the caller what it needs
+
+
+def test_round_trip_property():
+    """Any int16 block content in [-2048, 2047] survives, whatever mixture of zeros, odd and even values the groups hold."""
+    from hypothesis import given, settings, strategies as st
+    import hypothesis.extra.numpy as hnp
+
+    value = st.one_of(st.just(0), st.integers(-2048, 2047), st.sampled_from([-2047, -1, 1, 2047, -2048, 2046]),
+                      st.integers(-40, 40).map(lambda t: 2 * t + 1))
+
+    @settings(max_examples=25, deadline=None)
+    @given(hnp.arrays(np.int16, st.tuples(st.integers(1, 40), st.just(64)), elements=value))
+    def check(coeffs):
+        rc, h, c, p = pack(coeffs)
+        assert rc == 0
+        assert np.array_equal(unpack_reference(h, c, p), coeffs)
+        # the size the header promises: 4-bit codes -> bytes
+        want = sum(12 if (int(x) >> (4 * g)) & 15 == 13 else (int(x) >> (4 * g)) & 15 for x in h for g in range(8))
+        assert len(p) == want + 16
+
+    check()
