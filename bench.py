@@ -155,6 +155,36 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> {0, 1, 2, 3, 8, 10, 11} (the format of /sys/.../local_cpulist)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_cpus(device_index, log):
+    """Multi-rank runs: keep this rank on the CPUs that are local to its GPU (sysfs local_cpulist of the PCI device), so
+    that the pinned staging buffers it allocates afterwards land on that NUMA node (first touch) and eight ranks do not all
+    pull their PCIe traffic through one socket's memory.  Best effort: any failure leaves the affinity as it was."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(path) as f:
+            local = parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        want = local & allowed
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+            log(f"rank bound to {len(want)} of {len(allowed)} CPUs local to GPU {device_index}")
+    except Exception as e:  # no sysfs entry, no NUMA information, a cpuset that forbids it ...
+        log(f"CPU binding skipped: {e!r}")
+
+
 def build_batch(streams, first_stream_id, mode, log=None):
     """Packed records of one picture step for `streams` 720p streams (one P picture each)."""
     from mpeg_b200 import workload as wl
@@ -297,6 +327,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1:
+        bind_to_gpu_cpus(local_rank, log)
     S = args.streams
     t0 = time.time()
     from mpeg_b200.sharding import stream_range
