@@ -178,7 +178,7 @@ def bind_to_gpu_cpus(device_index, log):
             local = parse_cpulist(f.read())
         allowed = os.sched_getaffinity(0)
         want = local & allowed
-        if want and want != allowed:
+        if len(want) >= 4 and want != allowed:   # never squeeze the launching thread and the clock sampler onto a core or two
             os.sched_setaffinity(0, want)
             log(f"rank bound to {len(want)} of {len(allowed)} CPUs local to GPU {device_index}")
     except Exception as e:  # no sysfs entry, no NUMA information, a cpuset that forbids it ...
