@@ -166,14 +166,14 @@ def parse_cpulist(text):
     return cpus
 
 
-def bind_to_gpu_cpus(device_index, log):
+def bind_to_gpu_cpus(device_index, log, sysfs_root="/sys/bus/pci/devices"):
     """Multi-rank runs: keep this rank on the CPUs that are local to its GPU (sysfs local_cpulist of the PCI device), so
     that the pinned staging buffers it allocates afterwards land on that NUMA node (first touch) and eight ranks do not all
     pull their PCIe traffic through one socket's memory.  Best effort: any failure leaves the affinity as it was."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(device_index)
-        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        path = "%s/%04x:%02x:%02x.0/local_cpulist" % (sysfs_root, pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         with open(path) as f:
             local = parse_cpulist(f.read())
         allowed = os.sched_getaffinity(0)

@@ -3,6 +3,7 @@ workload generator and buffer-rotation mirror behave, the int32 bound of the IDC
 import ctypes as C
 
 import numpy as np
+from pathlib import Path
 import pytest
 
 import oracle_lib as ol
@@ -135,3 +136,42 @@ def test_idct_intermediates_fit_int32():
         worst = max(worst, *[o + 128 + 255 * 256 for o in outs])  # + prediction << 8 (block_finish)
     assert worst < 2**31, worst
     assert worst > 1.5e9  # the bound is tight-ish: int32 has ~12 % headroom (1.897e9)
+
+
+def test_bench_rank_binding_to_gpu_local_cpus(tmp_path, monkeypatch):
+    """bench.py, multi-rank runs: a rank moves onto the CPUs sysfs lists as local to its GPU (so that its pinned buffers
+    land on that NUMA node), and leaves its affinity alone when the list is missing, tiny, or covers everything."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    spec = importlib.util.spec_from_file_location("bench_under_test", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert bench.parse_cpulist("") == set()
+
+    import torch
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    before = os.sched_getaffinity(0)
+    msgs = []
+    dev = tmp_path / "0000:1b:00.0"
+    dev.mkdir()
+    try:
+        bench.bind_to_gpu_cpus(0, msgs.append, sysfs_root=str(tmp_path))          # no local_cpulist: skipped
+        assert os.sched_getaffinity(0) == before and "skipped" in msgs[-1]
+        (dev / "local_cpulist").write_text(",".join(map(str, sorted(before))) + "\n")
+        bench.bind_to_gpu_cpus(0, msgs.append, sysfs_root=str(tmp_path))          # everything is local: nothing to do
+        assert os.sched_getaffinity(0) == before
+        if len(before) >= 5:
+            some = set(sorted(before)[:4])
+            (dev / "local_cpulist").write_text(",".join(map(str, sorted(some))) + ",100000\n")
+            bench.bind_to_gpu_cpus(0, msgs.append, sysfs_root=str(tmp_path))
+            assert os.sched_getaffinity(0) == some and "bound to 4" in msgs[-1]
+            os.sched_setaffinity(0, before)
+            (dev / "local_cpulist").write_text(str(sorted(before)[0]) + "\n")     # a single CPU: left alone
+            bench.bind_to_gpu_cpus(0, msgs.append, sysfs_root=str(tmp_path))
+            assert os.sched_getaffinity(0) == before
+    finally:
+        os.sched_setaffinity(0, before)
