@@ -190,8 +190,12 @@ int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, con
  * MPEGB200_ERECORD if a value lies outside [-2048, 2047], MPEGB200_EINVAL if payload_cap is too small;
  * mpegb200_vlen_payload_bound(n_blocks) always suffices; *payload_bytes includes 16 bytes of padding that must be
  * transferred with it).  The _vlen entry point copies headers, chunk offsets and payload to the device, expands them
- * there (expand_vlen_kernel) and continues like mpegb200_video_decode_pictures. */
+ * there (expand_vlen_kernel) and continues like mpegb200_video_decode_pictures.
+ * mpegb200_vlen_validate (pure host, one pass over the headers) checks what a foreign packer produced: codes 0..13, chunk offsets
+ * back to back and in order, payload_bytes = sum of the group sizes + 16; the device expansion clamps its reads to the payload
+ * either way, so a malformed stream yields wrong coefficients, never a fault. */
 size_t mpegb200_vlen_payload_bound(size_t n_blocks);
+int mpegb200_vlen_validate(const uint32_t* headers, const uint64_t* chunk_offsets, size_t n_blocks, size_t payload_bytes);
 int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* headers /* n_blocks */,
                               uint64_t* chunk_offsets /* (n_blocks + 31) / 32 */, uint8_t* payload, size_t payload_cap,
                               size_t* payload_bytes);

@@ -69,6 +69,7 @@ def load():
         "mpegb200_pack_coeffs12": (C.c_int, [vp, C.c_size_t, vp]),
         "mpegb200_video_decode_pictures_packed": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp]),
         "mpegb200_vlen_payload_bound": (C.c_size_t, [C.c_size_t]),
+        "mpegb200_vlen_validate": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
         "mpegb200_pack_coeffs_vlen": (C.c_int, [vp, C.c_size_t, vp, vp, vp, C.c_size_t, szp]),
         "mpegb200_video_decode_pictures_vlen": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp, vp, C.c_size_t]),
         "mpegb200_video_read_planes": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

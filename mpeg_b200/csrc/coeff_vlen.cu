@@ -141,7 +141,8 @@ constexpr int kWarpsPerCta = 8;
 __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const uint32_t* __restrict__ headers,
                                                                         const uint64_t* __restrict__ chunk_offsets,
                                                                         const uint8_t* __restrict__ payload,
-                                                                        uint4* __restrict__ out, size_t n_blocks) {
+                                                                        uint4* __restrict__ out, size_t n_blocks,
+                                                                        size_t payload_bytes) {
     __shared__ __align__(16) int16_t s_tile[kWarpsPerCta][4 * 64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t chunk = (size_t)blockIdx.x * kWarpsPerCta + warp;
@@ -166,7 +167,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
         if (lane >= d) incl += up;
     }
     const uint32_t my_off = incl - my_bytes;
-    const uint8_t* base = payload + chunk_offsets[chunk];
+    // memory safety only: offsets that mpegb200_pack_coeffs_vlen produced never need the clamps (mpegb200_vlen_validate)
+    const size_t chunk_off = min((size_t)chunk_offsets[chunk], payload_bytes - 16);
+    const uint8_t* base = payload + chunk_off;
+    const uint32_t off_max = (uint32_t)min(payload_bytes - 16 - chunk_off, (size_t)0xffffffffu);
     int16_t* tile = s_tile[warp];
 
 #pragma unroll 1
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = 0;
         } else {
-            const uint8_t* p = base + off;
+            const uint8_t* p = base + min(off, off_max);
             const uint32_t* p4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
             const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
             // the payload buffer is padded, so the fourth word is always readable
@@ -229,11 +233,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
 }  // namespace
 
 cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chunk_offsets, const uint8_t* d_payload,
-                               int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream) {
+                               int16_t* d_coeffs, size_t n_blocks, size_t payload_bytes, cudaStream_t stream) {
     if (n_blocks == 0) return cudaSuccess;
+    if (payload_bytes < 16) return cudaErrorInvalidValue;
     const size_t chunks = (n_blocks + 31) / 32;
     expand_vlen_kernel<<<(unsigned)((chunks + kWarpsPerCta - 1) / kWarpsPerCta), 32 * kWarpsPerCta, 0, stream>>>(
-        d_headers, d_chunk_offsets, d_payload, reinterpret_cast<uint4*>(d_coeffs), n_blocks);
+        d_headers, d_chunk_offsets, d_payload, reinterpret_cast<uint4*>(d_coeffs), n_blocks, payload_bytes);
     return cudaGetLastError();
 }
 
@@ -242,6 +247,24 @@ cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chun
 extern "C" {
 
 size_t mpegb200_vlen_payload_bound(size_t n_blocks) { return n_blocks * 96 + 16; }
+
+int mpegb200_vlen_validate(const uint32_t* headers, const uint64_t* chunk_offsets, size_t n_blocks, size_t payload_bytes) {
+    if (n_blocks == 0) return 0;
+    if (!headers || !chunk_offsets) return MPEGB200_EINVAL;
+    if (payload_bytes < 16) return MPEGB200_ERECORD;
+    uint64_t run = 0;
+    for (size_t b = 0; b < n_blocks; b++) {
+        if (b % 32 == 0) {
+            if (chunk_offsets[b / 32] != run) return MPEGB200_ERECORD;   // chunks back to back, in order
+        }
+        for (int g = 0; g < 8; g++) {
+            const uint32_t code = (headers[b] >> (4 * g)) & 15u;
+            if (code > 13u) return MPEGB200_ERECORD;
+            run += code == 13u ? 12u : code;
+        }
+    }
+    return run + 16 == payload_bytes ? 0 : MPEGB200_ERECORD;
+}
 
 int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* headers, uint64_t* chunk_offsets,
                               uint8_t* payload, size_t payload_cap, size_t* payload_bytes) {

@@ -87,7 +87,7 @@ size_t fused_plan_bytes(uint32_t n_mb);
 cudaError_t launch_unpack12(const uint8_t* d_packed, int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream);
 // variable-width transfer form (coeff_vlen.cu) -> int16 blocks
 cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chunk_offsets, const uint8_t* d_payload,
-                               int16_t* d_coeffs, size_t n_blocks, cudaStream_t stream);
+                               int16_t* d_coeffs, size_t n_blocks, size_t payload_bytes, cudaStream_t stream);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

@@ -727,7 +727,8 @@ int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const
     CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
     CU(launch_expand_vlen((const uint32_t*)ctx->s_headers[slot].p, (const uint64_t*)ctx->s_chunks[slot].p,
-                          (const uint8_t*)ctx->s_packed[slot].p, (int16_t*)ctx->s_coeffs[slot].p, n_blocks, ctx->stream));
+                          (const uint8_t*)ctx->s_packed[slot].p, (int16_t*)ctx->s_coeffs[slot].p, n_blocks, payload_bytes,
+                          ctx->stream));
     if (n_blocks) ctx->launches++;
     int rc = decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_pics[slot].p, n_mb,
                                  (const mpegb200_mb*)ctx->s_mbs[slot].p, n_blocks, (const int16_t*)ctx->s_coeffs[slot].p,

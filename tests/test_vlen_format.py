@@ -131,3 +131,24 @@ def test_round_trip_property():
         assert len(p) == want + 16
 
     check()
+
+
+def test_validate_foreign_streams():
+    """mpegb200_vlen_validate: accepts what the packer produces, rejects codes above 13, chunk offsets that are not back to
+    back, and a payload size that does not match the headers."""
+    L = _lib.load()
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    coeffs = dense_blocks(100, 5)
+    rc, h, c, p = pack(coeffs)
+    assert rc == 0
+    ok = lambda hh, cc, nbytes: L.mpegb200_vlen_validate(vp(hh), vp(cc), len(hh), nbytes)
+    assert ok(h, c, len(p)) == 0
+    assert ok(h, c, len(p) - 1) != 0
+    bad = h.copy(); bad[7] |= 0xF            # code 15
+    assert ok(bad, c, len(p)) != 0
+    bad = c.copy(); bad[1] += 1
+    assert ok(h, bad, len(p)) != 0
+    bad = h.copy(); bad[3] = 0               # a block that claims no payload: sizes no longer add up
+    if h[3] != 0:
+        assert ok(bad, c, len(p)) != 0
+    assert L.mpegb200_vlen_validate(None, None, 0, 0) == 0
