@@ -1,5 +1,5 @@
-// coeff_vlen.cu -- variable-width transfer form of the coefficient blocks (include/mpegb200.h, "vlen"): the host
-// packer and the kernel that expands it on the device to the int16[64] working form the decode kernel reads.
+// coeff_vlen.cu -- variable-width transfer form of the coefficient blocks (include/mpegb200.h, "vlen"): the kernel
+// that expands it on the device to the int16[64] working form the decode kernel reads.
 //
 // Why: the end-to-end rate of the host-pointer entry points is bound by PCIe, and the coefficients are nine tenths of
 // the upload.  What the reference leaves in blockData before the premultiply (video.go:729-741) is, for every
@@ -14,10 +14,6 @@
 // warp scan over the headers.  The dense blocks of the benchmark shrink from 128 (96 in the 12-bit form) to about 49
 // bytes, typical sparse blocks of a real stream to 4 + a few bytes.
 #include <cstdint>
-#include <atomic>
-#include <cstring>
-#include <thread>
-#include <vector>
 
 #include "common.cuh"
 
@@ -57,78 +53,6 @@ constexpr bool zigzag_list_matches() {
     return true;
 }
 static_assert(zigzag_list_matches(), "the device table is the generated zig-zag scan");
-
-inline int width_of(int c) {  // bits of c in two's complement
-    const unsigned a = (unsigned)(c < 0 ? ~c : c);
-    int b = 1;
-    while ((a >> (b - 1)) != 0) b++;
-    return b;
-}
-
-// header and payload size of one block; returns false if a value does not fit 12 bits
-inline bool plan_block(const int16_t* blk, uint32_t* header, uint32_t* bytes) {
-    uint32_t h = 0, total = 0;
-    for (int g = 0; g < 8; g++) {
-        int w = 0;
-        bool raw = false, any = false;
-        for (int i = 0; i < 8; i++) {
-            const int x = blk[kZigZag.nat[8 * g + i]];
-            if (x < -2048 || x > 2047) return false;
-            if (x == 0) continue;
-            any = true;
-            if ((x & 1) == 0) { raw = true; continue; }
-            const int c = (x + (x > 0 ? 1 : -1)) / 2;
-            const int b = width_of(c);
-            if (b > w) w = b;
-        }
-        const uint32_t code = raw ? 13u : (any ? (uint32_t)w : 0u);
-        h |= code << (4 * g);
-        total += raw ? 12u : (any ? (uint32_t)w : 0u);
-    }
-    *header = h;
-    *bytes = total;
-    return true;
-}
-
-inline void write_block(const int16_t* blk, uint32_t header, uint8_t* out) {
-    for (int g = 0; g < 8; g++) {
-        const uint32_t code = (header >> (4 * g)) & 15u;
-        if (code == 0) continue;
-        const int w = code == 13 ? 12 : (int)code;
-        uint64_t lo = 0, hi = 0;  // up to 96 bits
-        for (int i = 0; i < 8; i++) {
-            const int x = blk[kZigZag.nat[8 * g + i]];
-            const int v = code == 13 ? x : (x == 0 ? 0 : (x + (x > 0 ? 1 : -1)) / 2);
-            const uint64_t u = (uint64_t)((uint32_t)v & ((1u << w) - 1u));
-            const int bit = i * w;
-            if (bit < 64) {
-                lo |= u << bit;
-                if (bit + w > 64) hi |= u >> (64 - bit);
-            } else {
-                hi |= u << (bit - 64);
-            }
-        }
-        for (int k = 0; k < w; k++) out[k] = (uint8_t)(k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8)));
-        out += w;
-    }
-}
-
-template <class F>
-void parallel_for(size_t n, F f) {
-    unsigned t = std::thread::hardware_concurrency();
-    if (t == 0) t = 1;
-    if (t > 32) t = 32;
-    if (n < 4096) t = 1;
-    if (t == 1) { f(0, n); return; }
-    std::vector<std::thread> th;
-    const size_t per = ((n + t - 1) / t + 31) / 32 * 32;  // whole chunks
-    for (unsigned i = 0; i < t; i++) {
-        const size_t lo = (size_t)i * per, hi = lo + per < n ? lo + per : n;
-        if (lo >= hi) break;
-        th.emplace_back([=] { f(lo, hi); });
-    }
-    for (auto& x : th) x.join();
-}
 
 // ------------------------------------------------------------------------------------------------
 // Expansion kernel.  One warp = one chunk of 32 blocks: lane l reads the header of block l, a warp scan gives the
@@ -243,70 +167,3 @@ cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chun
 }
 
 }  // namespace mpegb200
-
-extern "C" {
-
-size_t mpegb200_vlen_payload_bound(size_t n_blocks) { return n_blocks * 96 + 16; }
-
-int mpegb200_vlen_validate(const uint32_t* headers, const uint64_t* chunk_offsets, size_t n_blocks, size_t payload_bytes) {
-    if (n_blocks == 0) return 0;
-    if (!headers || !chunk_offsets) return MPEGB200_EINVAL;
-    if (payload_bytes < 16) return MPEGB200_ERECORD;
-    uint64_t run = 0;
-    for (size_t b = 0; b < n_blocks; b++) {
-        if (b % 32 == 0) {
-            if (chunk_offsets[b / 32] != run) return MPEGB200_ERECORD;   // chunks back to back, in order
-        }
-        for (int g = 0; g < 8; g++) {
-            const uint32_t code = (headers[b] >> (4 * g)) & 15u;
-            if (code > 13u) return MPEGB200_ERECORD;
-            run += code == 13u ? 12u : code;
-        }
-    }
-    return run + 16 == payload_bytes ? 0 : MPEGB200_ERECORD;
-}
-
-int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* headers, uint64_t* chunk_offsets,
-                              uint8_t* payload, size_t payload_cap, size_t* payload_bytes) {
-    using namespace mpegb200;
-    if (!payload_bytes || (n_blocks && (!coeffs || !headers || !chunk_offsets || !payload))) return MPEGB200_EINVAL;
-    const size_t chunks = (n_blocks + 31) / 32;
-    std::vector<uint32_t> chunk_bytes(chunks, 0);
-    std::atomic<bool> ok{true};
-    parallel_for(n_blocks, [&](size_t lo, size_t hi) {  // ranges are whole chunks
-        for (size_t b = lo; b < hi; b++) {
-            uint32_t bytes = 0;
-            if (!plan_block(coeffs + b * 64, &headers[b], &bytes)) {
-                ok = false;
-                return;
-            }
-            chunk_bytes[b / 32] += bytes;
-        }
-    });
-    if (!ok) return MPEGB200_ERECORD;
-    uint64_t run = 0;
-    for (size_t c = 0; c < chunks; c++) {
-        chunk_offsets[c] = run;
-        run += chunk_bytes[c];
-    }
-    *payload_bytes = (size_t)run + 16;   // 16 bytes of padding: the kernel reads whole words around a group
-    if (*payload_bytes > payload_cap) return MPEGB200_EINVAL;
-    parallel_for(n_blocks, [&](size_t lo, size_t hi) {
-        for (size_t c = lo / 32; c * 32 < hi; c++) {
-            uint8_t* out = payload + chunk_offsets[c];
-            for (size_t b = c * 32; b < hi && b < c * 32 + 32; b++) {
-                write_block(coeffs + b * 64, headers[b], out);
-                uint32_t bytes = 0;
-                for (int g = 0; g < 8; g++) {
-                    const uint32_t code = (headers[b] >> (4 * g)) & 15u;
-                    bytes += code == 13u ? 12u : code;
-                }
-                out += bytes;
-            }
-        }
-    });
-    memset(payload + run, 0, 16);
-    return 0;
-}
-
-}  // extern "C"
