@@ -9,6 +9,7 @@
 // over the chunk sizes gives the offsets, and the ranges' bytes are copied to their places.
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -121,9 +122,13 @@ __attribute__((target("avx2"))) inline void encode_avx2(const int16_t* blk, Pack
 #endif
 
 using EncodeFn = void (*)(const int16_t*, Packed&);
+bool portable_only() {   // MPEGB200_PACK_PORTABLE=1: the plain C++ forms (tests run both)
+    const char* e = getenv("MPEGB200_PACK_PORTABLE");
+    return e && e[0] == '1';
+}
 EncodeFn pick_encoder() {
 #if defined(__x86_64__)
-    if (__builtin_cpu_supports("avx2")) return encode_avx2;
+    if (!portable_only() && __builtin_cpu_supports("avx2")) return encode_avx2;
 #endif
     return encode_scalar;
 }
@@ -176,7 +181,7 @@ __attribute__((target("bmi2"))) inline uint8_t* emit_bmi2(const Packed& p, uint8
 using EmitFn = uint8_t* (*)(const Packed&, uint8_t*, size_t);
 EmitFn pick_emitter() {
 #if defined(__x86_64__)
-    if (__builtin_cpu_supports("bmi2")) return emit_bmi2;
+    if (!portable_only() && __builtin_cpu_supports("bmi2")) return emit_bmi2;
 #endif
     return emit;
 }

@@ -152,3 +152,36 @@ def test_validate_foreign_streams():
     if h[3] != 0:
         assert ok(bad, c, len(p)) != 0
     assert L.mpegb200_vlen_validate(None, None, 0, 0) == 0
+
+
+def test_portable_packer_agrees_with_the_simd_one():
+    """The packer picks AVX2 / BMI2 forms at run time; MPEGB200_PACK_PORTABLE=1 forces the plain C++ forms.  Both must
+    produce the same bytes (checked in a subprocess, the choice is made once per process)."""
+    import os
+    import subprocess
+    import sys
+    import hashlib
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_vlen_format as t\n"
+        "from mpeg_b200 import workload as wl\n"
+        "rng = np.random.default_rng(11)\n"
+        "a = t.dense_blocks(700, 2)\n"
+        "b = wl._draw_blocks(rng, 700, rng.random(700) < 0.3, dense=False)\n"
+        "b[5, :] = -2048; b[6, :] = 2047; b[7, :] = 0\n"
+        "h = hashlib.sha256()\n"
+        "for c in (a, b):\n"
+        "    rc, hd, ch, p = t.pack(c)\n"
+        "    assert rc == 0\n"
+        "    assert np.array_equal(t.unpack_reference(hd[:64], ch[:2], p), c[:64])\n"
+        "    for x in (hd, ch, p): h.update(x.tobytes())\n"
+        "print(h.hexdigest())\n"
+    ) % (str(_lib.PKG.parent), str(_lib.PKG.parent / "tests"))
+    outs = []
+    for portable in ("0", "1"):
+        env = dict(os.environ, MPEGB200_PACK_PORTABLE=portable)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and len(outs[0]) == 64
