@@ -9,7 +9,11 @@ holds its own 256 streams (configs[4] layout: stream-parallel, no data-path coll
 
   value     whole-job frames/s with the packed records already resident in HBM (device-timed)
   e2e       the same step through the host-pointer C-ABI: pinned host records -> H2D -> kernels ->
-            D2H of the decoded Y/Cb/Cr planes into pinned host memory, all inside the timed region
+            D2H of the decoded Y/Cb/Cr planes into pinned host memory, all inside the timed region.  The records
+            are "pre-parsed block batches" in the transfer form the entry point takes (--e2e-form: variable-width
+            groups by default); producing that form from int16 blocks is host work done once before the loop, its
+            duration is reported as e2e.host_pack_ms_once
+            roofline.dominant_kernel = the arithmetic kernel alone (library events between pre-pass and kernel)
   roofline  fused MC+IDCT+add kernel: algorithmic bytes (1552 B per dense-P macroblock)
             / mean launch duration measured with CUDA events on the launching stream, against the
             measured HBM peak of MEASURED_PEAKS.json
@@ -356,10 +360,14 @@ def main():
     # transfer form of the coefficients on the end-to-end path (PCIe bound): variable-width groups (about 49 B per dense
     # block), the fixed 12-bit form (96 B) or the plain int16 blocks (128 B)
     h_packed = h_vlen = None
+    pack_ms = None
     if not args.no_e2e:
         try:
             if args.e2e_form == "vlen":
-                h_vlen = tuple(pinned(a) for a in ctx.pack_coeffs_vlen(coeffs))
+                t_pack = time.perf_counter()
+                packed_arrays = ctx.pack_coeffs_vlen(coeffs)
+                pack_ms = 1e3 * (time.perf_counter() - t_pack)   # host work outside the timed region, reported next to e2e
+                h_vlen = tuple(pinned(a) for a in packed_arrays)
             elif args.e2e_form == "packed12":
                 h_packed = pinned(ctx.pack_coeffs12(coeffs))
         except mpeg_b200.MpegB200Error:
@@ -458,6 +466,7 @@ def main():
                "h2d_bytes_per_step": int(h_mbs.numel() + h_pics[0].numel() + (sum(t.numel() for t in h_vlen) if h_vlen is not None else
                                                                               (h_packed if h_packed is not None else h_coeffs).numel())),
                "d2h_bytes_per_step": int(h_planes.numel()), "steps": e_steps, "ms_per_step": ems / e_steps,
+               "host_pack_ms_once": pack_ms, "host_pack_threads": min(64, os.cpu_count() or 1) if pack_ms is not None else None,
                "path": ("mpegb200_video_decode_pictures_vlen (pinned host records, variable-width coefficient transfer form)" if h_vlen is not None
                         else "mpegb200_video_decode_pictures_packed (pinned host records, 12-bit coefficient transfer form)" if h_packed is not None
                         else "mpegb200_video_decode_pictures (pinned host records)") + " + rgba_batch_dev + read_pictures_host (pinned)"}
