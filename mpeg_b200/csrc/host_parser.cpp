@@ -34,10 +34,19 @@ struct BitReader {
     uint32_t peek(int n) const {  // n <= 32
         const size_t b = (size_t)(pos >> 3);
         if (b >= len) return 0;
-        uint64_t w = 0;
-        for (int i = 0; i < 8; i++) w = (w << 8) | p[b + i];
+        uint64_t w;
+        memcpy(&w, p + b, 8);           // >= 8 readable bytes follow every position below len
+        w = __builtin_bswap64(w);       // most significant bit first
         w <<= (pos & 7);
         return n ? (uint32_t)(w >> (64 - n)) : 0;
+    }
+    // the next (at least) 57 bits, left-aligned: one load serves a whole code + sign / escape sequence
+    uint64_t window() const {
+        const size_t b = (size_t)(pos >> 3);
+        if (b >= len) return 0;
+        uint64_t w;
+        memcpy(&w, p + b, 8);
+        return __builtin_bswap64(w) << (pos & 7);
     }
     void skip_bits(int n) { pos += (uint64_t)n; }
     uint32_t read(int n) {
@@ -130,6 +139,19 @@ struct VlcTable {
                 for (uint32_t f = 0; f < (1u << (sub_bits - rest)); f++) sub[lo + f] = Entry{value, (uint8_t)len};
             }
         }
+    }
+    // the code at the top of a left-aligned window (>= max_bits valid bits): value, and its length through *len
+    // (max_bits for a prefix the tables of the standard do not assign, like read() below)
+    int lookup(uint64_t w, int* len) const {
+        const uint32_t bits = (uint32_t)(w >> (64 - max_bits));
+        Entry e = first[bits >> (max_bits - first_bits)];
+        if (e.len == 0) e = second[(size_t)e.value][bits & ((1u << (max_bits - first_bits)) - 1)];
+        if (e.len == 0xff) {
+            *len = max_bits;
+            return 0;
+        }
+        *len = e.len;
+        return e.value;
     }
     int read(BitReader& br) const {
         const uint32_t bits = br.peek(max_bits);
@@ -346,23 +368,40 @@ void decode_block(VP* v, int block) {  // video.go:639-799, up to the hand-over 
         q = v->non_intra_q;
     }
     for (;;) {
-        const int c = t.coeff.read(br);
-        if (c == 0x0001 && n > 0 && br.read1() == 0) break;  // end_of_block
+        // one window per coefficient: the code (at most 17 bits), then its sign bit or the 6 + 8 (+ 8) bits of an escape
+        uint64_t w = br.window();
+        int used;
+        const int c = t.coeff.lookup(w, &used);
+        w <<= used;
+        if (c == 0x0001 && n > 0) {   // "1" after the first coefficient: a 0 bit behind it ends the block (video.go:686) ...
+            if ((w >> 63) == 0) {
+                br.skip_bits(used + 1);
+                break;
+            }
+            w <<= 1;                  // ... a 1 bit is consumed, and the sign follows like after any other code
+            used += 1;
+        }
         int run, lv;
         if (c == 0xffff) {  // escape
-            run = (int)br.read(6);
-            lv = (int)br.read(8);
-            if (lv == 0)
-                lv = (int)br.read(8);
-            else if (lv == 128)
-                lv = (int)br.read(8) - 256;
-            else if (lv > 128)
+            run = (int)(w >> 58);
+            lv = (int)((w >> 50) & 0xff);
+            used += 14;
+            if (lv == 0) {
+                lv = (int)((w >> 42) & 0xff);
+                used += 8;
+            } else if (lv == 128) {
+                lv = (int)((w >> 42) & 0xff) - 256;
+                used += 8;
+            } else if (lv > 128) {
                 lv -= 256;
+            }
         } else {
             run = c >> 8;
             lv = c & 0xff;
-            if (br.read1()) lv = -lv;
+            if (w >> 63) lv = -lv;
+            used += 1;
         }
+        br.skip_bits(used);
         n += run;
         if (n < 0 || n >= 64) return;  // invalid run: the block is dropped, its coefficients stay (video.go:712-714)
         const int dz = t.zigzag[n++];
