@@ -166,10 +166,46 @@ struct VlcTable {
     }
 };
 
+// Direct table for the DCT coefficient codes AFTER the first coefficient of a block (video.go:686-708), indexed by the next
+// kCoefBits bits: code and sign bit resolved together, "10" = end of block.  len = bits consumed, 0 = not in this table
+// (escape, codes longer than kCoefBits - 1, unassigned prefixes: the general two-level table takes those).
+constexpr int kCoefBits = 12;
+struct CoefEntry {
+    int16_t level;   // signed
+    uint8_t run;     // kCoefEob: end of block
+    uint8_t len;
+};
+constexpr uint8_t kCoefEob = 0xff;
+
 struct Tables {
     VlcTable addr_inc, type_i, type_p, type_b, cbp, motion, dc_luma, dc_chroma, coeff;
     uint8_t zigzag[64];
+    CoefEntry coef_fast[1 << kCoefBits];
+    void build_coef_fast() {
+        for (auto& e : coef_fast) e = CoefEntry{0, 0, 0};
+        auto fill = [&](uint32_t code, int len, CoefEntry e) {   // every kCoefBits-bit word that starts with the code
+            e.len = (uint8_t)len;
+            const uint32_t lo = code << (kCoefBits - len);
+            for (uint32_t f = 0; f < (1u << (kCoefBits - len)); f++) coef_fast[lo + f] = e;
+        };
+        for (const vlc_code& r : VLC_DCT_COEFF) {
+            if (r.value == VLC_INVALID || r.value == 0xffff) continue;
+            const int len = (int)strlen(r.bits);
+            uint32_t code = 0;
+            for (int b = 0; b < len; b++) code = (code << 1) | (uint32_t)(r.bits[b] == '1');
+            const int run = r.value >> 8, level = r.value & 0xff;
+            if (len == 1) {                         // "1": "10" ends the block, "11s" is (0, +-1)
+                fill(0b10, 2, CoefEntry{0, kCoefEob, 0});
+                fill(0b110, 3, CoefEntry{(int16_t)level, (uint8_t)run, 0});
+                fill(0b111, 3, CoefEntry{(int16_t)-level, (uint8_t)run, 0});
+            } else if (len + 1 <= kCoefBits) {
+                fill(code << 1, len + 1, CoefEntry{(int16_t)level, (uint8_t)run, 0});
+                fill((code << 1) | 1, len + 1, CoefEntry{(int16_t)-level, (uint8_t)run, 0});
+            }
+        }
+    }
     Tables() {
+        build_coef_fast();
 #define BUILD(t, rows, fb) t.build(rows, sizeof(rows) / sizeof(rows[0]), fb)
         BUILD(addr_inc, VLC_MB_ADDR_INC, 11);
         BUILD(type_i, VLC_MB_TYPE_I, 8);
@@ -370,36 +406,46 @@ void decode_block(VP* v, int block) {  // video.go:639-799, up to the hand-over 
     for (;;) {
         // one window per coefficient: the code (at most 17 bits), then its sign bit or the 6 + 8 (+ 8) bits of an escape
         uint64_t w = br.window();
-        int used;
-        const int c = t.coeff.lookup(w, &used);
-        w <<= used;
-        if (c == 0x0001 && n > 0) {   // "1" after the first coefficient: a 0 bit behind it ends the block (video.go:686) ...
-            if ((w >> 63) == 0) {
-                br.skip_bits(used + 1);
+        int used, run, lv;
+        const CoefEntry fe = t.coef_fast[w >> (64 - kCoefBits)];
+        if (fe.len != 0 && n > 0) {   // the common case: a short code behind the first coefficient
+            if (fe.run == kCoefEob) {
+                br.skip_bits(fe.len);
                 break;
             }
-            w <<= 1;                  // ... a 1 bit is consumed, and the sign follows like after any other code
-            used += 1;
-        }
-        int run, lv;
-        if (c == 0xffff) {  // escape
-            run = (int)(w >> 58);
-            lv = (int)((w >> 50) & 0xff);
-            used += 14;
-            if (lv == 0) {
-                lv = (int)((w >> 42) & 0xff);
-                used += 8;
-            } else if (lv == 128) {
-                lv = (int)((w >> 42) & 0xff) - 256;
-                used += 8;
-            } else if (lv > 128) {
-                lv -= 256;
-            }
+            run = fe.run;
+            lv = fe.level;
+            used = fe.len;
         } else {
-            run = c >> 8;
-            lv = c & 0xff;
-            if (w >> 63) lv = -lv;
-            used += 1;
+            const int c = t.coeff.lookup(w, &used);
+            w <<= used;
+            if (c == 0x0001 && n > 0) {   // "1" after the first coefficient: a 0 bit behind it ends the block (video.go:686) ...
+                if ((w >> 63) == 0) {
+                    br.skip_bits(used + 1);
+                    break;
+                }
+                w <<= 1;                  // ... a 1 bit is consumed, and the sign follows like after any other code
+                used += 1;
+            }
+            if (c == 0xffff) {  // escape
+                run = (int)(w >> 58);
+                lv = (int)((w >> 50) & 0xff);
+                used += 14;
+                if (lv == 0) {
+                    lv = (int)((w >> 42) & 0xff);
+                    used += 8;
+                } else if (lv == 128) {
+                    lv = (int)((w >> 42) & 0xff) - 256;
+                    used += 8;
+                } else if (lv > 128) {
+                    lv -= 256;
+                }
+            } else {
+                run = c >> 8;
+                lv = c & 0xff;
+                if (w >> 63) lv = -lv;
+                used += 1;
+            }
         }
         br.skip_bits(used);
         n += run;
