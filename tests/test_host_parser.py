@@ -187,3 +187,24 @@ def test_demux_matches_the_oracle(golden_dir):
     from mpeg_b200.mpeg import ErrInvalidMPEG
     with pytest.raises(ErrInvalidMPEG):
         demux_split(b"\x00" * 100)
+
+
+def test_corrupted_streams_parse_like_the_oracle(golden_dir):
+    """Flipped bits and truncation exercise the early-outs (dropped blocks whose levels survive, invalid runs, slices that
+    stop half-way): the table-driven product parser and the bit-serial oracle must still emit the same records."""
+    base = (golden_dir / "test.mpeg1video").read_bytes()
+    rng = np.random.default_rng(5)
+    pictures = 0
+    for trial in range(10):
+        d = bytearray(base[:40000])
+        for pos in rng.integers(150, len(d), int(rng.integers(1, 40))):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        d = bytes(d[: len(d) - int(rng.integers(0, 3000))])
+        got, want = list(parser_steps(d)), list(oracle_steps(d))
+        assert len(got) == len(want), f"trial {trial}: {len(got)} steps, oracle {len(want)}"
+        for k, ((fb, t, la), (fb2, t2, lb)) in enumerate(zip(got, want)):
+            assert fb == fb2 and len(la) == len(lb), f"trial {trial} step {k}"
+            for (h1, m1, c1), (h2, m2, c2) in zip(la, lb):
+                assert h1 == h2 and np.array_equal(m1, m2) and np.array_equal(c1, c2), f"trial {trial} step {k}"
+        pictures += len(got)
+    assert pictures > 200
