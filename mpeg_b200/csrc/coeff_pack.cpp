@@ -181,7 +181,9 @@ __attribute__((target("bmi2"))) inline uint8_t* emit_bmi2(const Packed& p, uint8
 using EmitFn = uint8_t* (*)(const Packed&, uint8_t*, size_t);
 EmitFn pick_emitter() {
 #if defined(__x86_64__)
-    if (!portable_only() && __builtin_cpu_supports("bmi2")) return emit_bmi2;
+    // pext is microcoded (hundreds of cycles) on AMD Zen 1 / Zen 2: the shift-and-or form is faster there
+    if (!portable_only() && __builtin_cpu_supports("bmi2") && !__builtin_cpu_is("znver1") && !__builtin_cpu_is("znver2"))
+        return emit_bmi2;
 #endif
     return emit;
 }
