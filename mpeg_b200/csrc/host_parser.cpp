@@ -1057,9 +1057,91 @@ void mpegb200_buffer_free(void* p) { free(p); }
 // merge the per-stream launches into waves (one kernel launch each, at most one picture per stream).
 // ------------------------------------------------------------------------------------------------
 #include <atomic>
+#include <memory>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
+namespace {
+
+// Worker threads that live as long as the batch: a step hands them its two loops (parse every stream, merge every
+// stream's records into the waves) instead of creating and joining a set of threads twice per step -- with 64 threads
+// that was a couple of milliseconds per step, as much as the parsing of 4096 small pictures itself.
+class WorkerPool {
+public:
+    explicit WorkerPool(int threads) {
+        for (int k = 1; k < threads; k++) workers_.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_job_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // f(i) for i in [0, n), the calling thread takes part; returns when all are done
+    void run(int n, const std::function<void(int)>& f) {
+        if (workers_.empty() || n <= 1) {
+            for (int i = 0; i < n; i++) f(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &f;
+            n_ = n;
+            next_.store(0);
+            active_ = (int)workers_.size();
+            gen_++;
+        }
+        cv_job_.notify_all();
+        work(f, n);
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return active_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void work(const std::function<void(int)>& f, int n) {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= n) break;
+            f(i);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* f;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_job_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                f = job_;
+                n = n_;
+            }
+            work(*f, n);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--active_ == 0) cv_done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_job_, cv_done_;
+    const std::function<void(int)>* job_ = nullptr;
+    int n_ = 0, active_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace
+
 struct mpegb200_video_batch {
+    std::unique_ptr<WorkerPool> pool;
     int n = 0, threads = 1;
     void* (*alloc)(size_t) = nullptr;
     void (*free_fn)(void*) = nullptr;
@@ -1092,30 +1174,6 @@ struct mpegb200_video_batch {
     }
 };
 
-namespace {
-
-template <typename F>
-void parallel_for(int n, int threads, F f) {
-    if (threads <= 1 || n <= 1) {
-        for (int i = 0; i < n; i++) f(i);
-        return;
-    }
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    const int t = std::min(threads, n);
-    for (int k = 0; k < t; k++)
-        pool.emplace_back([&]() {
-            for (;;) {
-                const int i = next.fetch_add(1);
-                if (i >= n) break;
-                f(i);
-            }
-        });
-    for (auto& th : pool) th.join();
-}
-
-}  // namespace
-
 extern "C" {
 
 mpegb200_video_batch* mpegb200_video_batch_new(int n_streams, int threads, void* (*alloc)(size_t), void (*free_fn)(void*)) {
@@ -1124,6 +1182,11 @@ mpegb200_video_batch* mpegb200_video_batch_new(int n_streams, int threads, void*
     if (!b) return nullptr;
     b->n = n_streams;
     b->threads = threads > 0 ? threads : 1;
+    b->pool.reset(new (std::nothrow) WorkerPool(b->threads));
+    if (!b->pool) {
+        delete b;
+        return nullptr;
+    }
     b->alloc = alloc;
     b->free_fn = free_fn;
     b->parsers.assign((size_t)n_streams, nullptr);
@@ -1164,7 +1227,7 @@ int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out)
     if (!b || !out) return MPEGB200_EINVAL;
     memset(out, 0, sizeof(*out));
     const int n = b->n;
-    parallel_for(n, b->threads, [&](int i) {
+    b->pool->run(n, [&](int i) {
         mpegb200_video_step& st = b->steps[(size_t)i];
         memset(&st, 0, sizeof(st));
         if (b->parsers[(size_t)i]) mpegb200_video_parser_next(b->parsers[(size_t)i], &st);
@@ -1196,7 +1259,7 @@ int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out)
         if (!b->reserve(buf.pics, buf.cap_pics, np) || !b->reserve(buf.mbs, buf.cap_mbs, nm) ||
             !b->reserve(buf.coeffs, buf.cap_blocks, (size_t)nb * 64))
             return MPEGB200_ENOMEM;
-        parallel_for(n, b->threads, [&](int i) {
+        b->pool->run(n, [&](int i) {
             const uint32_t p = pic_of[(size_t)i];
             if (p == 0xffffffffu) return;
             const mpegb200_video_step& st = b->steps[(size_t)i];
