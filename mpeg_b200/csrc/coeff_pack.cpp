@@ -240,7 +240,7 @@ int mpegb200_vlen_validate(const uint32_t* headers, const uint64_t* chunk_offset
 }
 
 int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* headers, uint64_t* chunk_offsets,
-                              uint8_t* payload, size_t payload_cap, size_t* payload_bytes) {
+                              uint8_t* payload, size_t payload_cap, size_t* payload_bytes) try {
     if (!payload_bytes || (n_blocks && (!coeffs || !headers || !chunk_offsets || !payload))) return MPEGB200_EINVAL;
     static const EncodeFn encode = pick_encoder();
     static const EmitFn emit_block = pick_emitter();
@@ -261,7 +261,7 @@ int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* 
             good &= p.ok;
             headers[b] = p.header;
             chunk_bytes[b / 32] += p.bytes;
-            out = emit_block(p, out, 16);     // the scratch has room for a 16-byte store everywhere
+            out = emit_block(p, out, (size_t)(mine.data() + mine.size() - out));   // >= 16 everywhere: every group takes the single 16-byte store
         }
         if (!good) ok = false;
     });
@@ -281,6 +281,8 @@ int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* 
     });
     memset(payload + run, 0, 16);
     return 0;
+} catch (...) {  // bad_alloc / system_error (scratch vectors, threads) must not cross the C boundary
+    return MPEGB200_ENOMEM;
 }
 
 }  // extern "C"

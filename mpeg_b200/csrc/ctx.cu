@@ -155,7 +155,7 @@ extern "C" {
 
 int mpegb200_abi_version(void) { return MPEGB200_ABI_VERSION; }
 
-mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) {
+mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) try {
     auto set = [&](int e) {
         if (err) *err = e;
     };
@@ -224,6 +224,9 @@ mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) {
     }
     set(MPEGB200_OK);
     return ctx;
+} catch (...) {  // bad_alloc from the host-side bookkeeping must not cross the C boundary
+    if (err) *err = MPEGB200_ENOMEM;
+    return nullptr;
 }
 
 void mpegb200_destroy(mpegb200_ctx* ctx) {
@@ -376,7 +379,7 @@ static bool encode_slab_maps(mpegb200_ctx* ctx, const Slab& sl, const HostStream
     return true;
 }
 
-int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
+int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) try {
     HostStream* s = vstream(ctx, stream);
     if (!s) return fail(ctx, MPEGB200_EINVAL, "stream id %d out of range", stream);
     if (s->open) return fail(ctx, MPEGB200_ESTATE, "video stream %d already open", stream);
@@ -472,6 +475,8 @@ int mpegb200_video_open(mpegb200_ctx* ctx, int stream, int width, int height) {
     if (width > ctx->max_w) ctx->max_w = width;
     if (height > ctx->max_h) ctx->max_h = height;
     return 0;
+} catch (...) {  // bad_alloc from the host-side bookkeeping must not cross the C boundary
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
 }
 
 int mpegb200_video_close(mpegb200_ctx* ctx, int stream) {
@@ -513,7 +518,7 @@ static bool window_inside(long off, int stride, int size, int odd_h, int odd_v, 
 }
 
 int mpegb200_video_validate(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* pics, size_t n_mb,
-                            const mpegb200_mb* mbs, size_t n_blocks) {
+                            const mpegb200_mb* mbs, size_t n_blocks) try {
     if (!ctx || n_pictures < 0 || (n_pictures && !pics) || (n_mb && !mbs))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
     if (n_pictures > 65536) return fail(ctx, MPEGB200_ERECORD, "at most 65536 pictures per call (16-bit pic index)");
@@ -570,10 +575,12 @@ int mpegb200_video_validate(mpegb200_ctx* ctx, int n_pictures, const mpegb200_pi
         }
     }
     return 0;
+} catch (...) {  // bad_alloc from the host-side bookkeeping must not cross the C boundary
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
 }
 
 static int decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200_picture* d_pics, size_t n_mb,
-                               const mpegb200_mb* d_mbs, size_t n_blocks, const int16_t* d_coeffs, unsigned dst_mask) {
+                               const mpegb200_mb* d_mbs, size_t n_blocks, const int16_t* d_coeffs, unsigned dst_mask) try {
     if (!ctx || n_pictures < 0 || (n_mb && (!d_pics || !d_mbs)) || (n_blocks && !d_coeffs))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
     if (n_mb > 0xffffffffull || n_blocks > 0xffffffffull || n_pictures > 65536)
@@ -619,6 +626,8 @@ static int decode_pictures_dev(mpegb200_ctx* ctx, int n_pictures, const mpegb200
         ctx->launches++;
     }
     return 0;
+} catch (...) {  // bad_alloc from the host-side bookkeeping must not cross the C boundary
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
 }
 
 // device-resident records: which buffers the pictures write is not known on the host, so every pending read-back is joined
@@ -944,7 +953,7 @@ int mpegb200_audio_close(mpegb200_ctx* ctx, int stream) {
 static size_t audio_out_bytes(int format) { return (format == MPEGB200_AUDIO_S16 ? 2 : 4) * (size_t)2 * MPEGB200_SAMPLES_PER_FRAME; }
 
 int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,
-                             const int32_t* d_samples, int format, void* d_out) {
+                             const int32_t* d_samples, int format, void* d_out) try {
     if (!ctx || n_streams < 0 || frames_per_stream < 0 || (n_streams && (!stream_ids || !d_samples || !d_out)))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
     if (format < 0 || format > 3) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
@@ -968,6 +977,8 @@ int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* st
                           d_samples, format, d_out, ctx->d_window, ctx->stream));
     ctx->launches++;
     return 0;
+} catch (...) {  // bad_alloc from the host-side bookkeeping must not cross the C boundary
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
 }
 
 int mpegb200_audio_synth(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,

@@ -362,8 +362,8 @@ mpegb200_mb& new_record(VP* v) {
 void pack_prediction(VP* v, mpegb200_mb& m) {
     int h = v->fwd.h, w = v->fwd.v;
     if (v->fwd.full_px) {
-        h <<= 1;
-        w <<= 1;
+        h *= 2;
+        w *= 2;
     }
     bool use_bwd = false;
     if (v->picture_type == kPicB) {
@@ -373,8 +373,8 @@ void pack_prediction(VP* v, mpegb200_mb& m) {
             h = v->bwd.h;
             w = v->bwd.v;
             if (v->bwd.full_px) {
-                h <<= 1;
-                w <<= 1;
+                h *= 2;
+                w *= 2;
             }
         }
     }
@@ -512,7 +512,9 @@ void decode_macroblock(VP* v) {  // video.go:462-562
     }
     v->mb_row = v->mb_addr / v->mb_w;
     v->mb_col = v->mb_addr % v->mb_w;
-    if (v->mb_col >= v->mb_w || v->mb_row >= v->mb_h) return;
+    // mb_addr < 0: slice 1 whose first address increment is an unassigned code (value 0) leaves the address at -1;
+    // the reference indexes out of range there and panics, here the macroblock is dropped
+    if (v->mb_addr < 0 || v->mb_col >= v->mb_w || v->mb_row >= v->mb_h) return;
 
     const VlcTable& tt = v->picture_type == kPicI ? t.type_i : (v->picture_type == kPicP ? t.type_p : t.type_b);
     const int type = tt.read(br);
@@ -667,8 +669,13 @@ mpegb200_video_parser* mpegb200_video_parser_new(const uint8_t* data, size_t len
     if (!data && len) return nullptr;
     auto* v = new (std::nothrow) mpegb200_video_parser();
     if (!v) return nullptr;
-    v->data.assign(data, data + len);
-    v->data.resize(len + 16, 0);
+    try {
+        v->data.assign(data, data + len);
+        v->data.resize(len + 16, 0);
+    } catch (...) {  // bad_alloc must not cross the C boundary
+        delete v;
+        return nullptr;
+    }
     v->br.p = v->data.data();
     v->br.len = len;
     v->reset_levels();
@@ -697,8 +704,7 @@ void mpegb200_video_parser_rewind(mpegb200_video_parser* v) {  // video.go:195-2
     v->start_code = -1;
 }
 
-int mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* out) {  // Video.Decode, video.go:209-268
-    if (!v || !out) return MPEGB200_EINVAL;
+static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step* out) {  // Video.Decode, video.go:209-268
     memset(out, 0, sizeof(*out));
     v->launches.clear();
     v->mbs.clear();
@@ -739,6 +745,18 @@ int mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* ou
     out->mbs = v->mbs.data();
     out->coeffs = v->coeffs.data();
     return 0;
+}
+
+// The record vectors grow while parsing; an allocation failure must not unwind through the C boundary (cgo, ctypes)
+// nor reach std::terminate on a pool thread: it is reported as MPEGB200_ENOMEM and the step is empty.
+int mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* out) {
+    if (!v || !out) return MPEGB200_EINVAL;
+    try {
+        return video_parser_next_impl(v, out);
+    } catch (...) {
+        memset(out, 0, sizeof(*out));
+        return MPEGB200_ENOMEM;
+    }
 }
 
 }  // extern "C"
@@ -941,8 +959,13 @@ mpegb200_audio_parser* mpegb200_audio_parser_new(const uint8_t* data, size_t len
     if (!data && len) return nullptr;
     auto* a = new (std::nothrow) mpegb200_audio_parser();
     if (!a) return nullptr;
-    a->data.assign(data, data + len);
-    a->data.resize(len + 16, 0);
+    try {
+        a->data.assign(data, data + len);
+        a->data.resize(len + 16, 0);
+    } catch (...) {
+        delete a;
+        return nullptr;
+    }
     a->br.p = a->data.data();
     a->br.len = len;
     a->next_frame_data_size = decode_header(a);
@@ -982,9 +1005,8 @@ int mpegb200_audio_parser_next(mpegb200_audio_parser* a, int32_t* samples, doubl
 // ------------------------------------------------------------------------------------------------
 // program stream (demux.go): pack + system header, then PES packets of the wanted ids
 // ------------------------------------------------------------------------------------------------
-int mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_t* video_len, uint8_t** audio,
-                         size_t* audio_len, int* n_video_packets, int* n_audio_packets) {
-    if (!data || !video || !video_len || !audio || !audio_len) return MPEGB200_EINVAL;
+static int demux_split_impl(const uint8_t* data, size_t len, uint8_t** video, size_t* video_len, uint8_t** audio,
+                            size_t* audio_len, int* n_video_packets, int* n_audio_packets) {
     std::vector<uint8_t> padded(data, data + len);
     padded.resize(len + 16, 0);
     BitReader br;
@@ -1038,7 +1060,12 @@ int mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_
     }
     *video = (uint8_t*)malloc(v.size() ? v.size() : 1);
     *audio = (uint8_t*)malloc(a.size() ? a.size() : 1);
-    if (!*video || !*audio) return MPEGB200_ENOMEM;
+    if (!*video || !*audio) {
+        free(*video);
+        free(*audio);
+        *video = *audio = nullptr;
+        return MPEGB200_ENOMEM;
+    }
     memcpy(*video, v.data(), v.size());
     memcpy(*audio, a.data(), a.size());
     *video_len = v.size();
@@ -1046,6 +1073,17 @@ int mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_
     if (n_video_packets) *n_video_packets = nv;
     if (n_audio_packets) *n_audio_packets = na;
     return 0;
+}
+
+int mpegb200_demux_split(const uint8_t* data, size_t len, uint8_t** video, size_t* video_len, uint8_t** audio,
+                         size_t* audio_len, int* n_video_packets, int* n_audio_packets) {
+    if (!data || !video || !video_len || !audio || !audio_len) return MPEGB200_EINVAL;
+    *video = *audio = nullptr;
+    try {
+        return demux_split_impl(data, len, video, video_len, audio, audio_len, n_video_packets, n_audio_packets);
+    } catch (...) {
+        return MPEGB200_ENOMEM;
+    }
 }
 
 void mpegb200_buffer_free(void* p) { free(p); }
@@ -1081,10 +1119,12 @@ public:
         cv_job_.notify_all();
         for (auto& t : workers_) t.join();
     }
+    bool failed() { return failed_.exchange(false); }
     // f(i) for i in [0, n), the calling thread takes part; returns when all are done
     void run(int n, const std::function<void(int)>& f) {
         if (workers_.empty() || n <= 1) {
-            for (int i = 0; i < n; i++) f(i);
+            next_.store(0);
+            work(f, n);
             return;
         }
         {
@@ -1107,7 +1147,11 @@ private:
         for (;;) {
             const int i = next_.fetch_add(1);
             if (i >= n) break;
-            f(i);
+            try {
+                f(i);
+            } catch (...) {  // an exception on a pool thread would be std::terminate; the caller asks failed()
+                failed_.store(true);
+            }
         }
     }
     void loop() {
@@ -1134,6 +1178,7 @@ private:
     const std::function<void(int)>* job_ = nullptr;
     int n_ = 0, active_ = 0;
     std::atomic<int> next_{0};
+    std::atomic<bool> failed_{false};
     uint64_t gen_ = 0;
     bool stop_ = false;
 };
@@ -1180,20 +1225,21 @@ mpegb200_video_batch* mpegb200_video_batch_new(int n_streams, int threads, void*
     if (n_streams <= 0 || n_streams > 65536) return nullptr;  // 16-bit picture index per launch
     auto* b = new (std::nothrow) mpegb200_video_batch();
     if (!b) return nullptr;
-    b->n = n_streams;
-    b->threads = threads > 0 ? threads : 1;
-    b->pool.reset(new (std::nothrow) WorkerPool(b->threads));
-    if (!b->pool) {
+    try {
+        b->n = n_streams;
+        b->threads = threads > 0 ? threads : 1;
+        b->pool.reset(new WorkerPool(b->threads));   // std::thread may throw system_error
+        b->alloc = alloc;
+        b->free_fn = free_fn;
+        b->parsers.assign((size_t)n_streams, nullptr);
+        b->steps.resize((size_t)n_streams);
+        b->has_frame.assign((size_t)n_streams, 0);
+        b->frame_buf.assign((size_t)n_streams, 0);
+        b->time.assign((size_t)n_streams, 0.0);
+    } catch (...) {
         delete b;
         return nullptr;
     }
-    b->alloc = alloc;
-    b->free_fn = free_fn;
-    b->parsers.assign((size_t)n_streams, nullptr);
-    b->steps.resize((size_t)n_streams);
-    b->has_frame.assign((size_t)n_streams, 0);
-    b->frame_buf.assign((size_t)n_streams, 0);
-    b->time.assign((size_t)n_streams, 0.0);
     return b;
 }
 
@@ -1223,18 +1269,18 @@ int mpegb200_video_batch_stream_size(mpegb200_video_batch* b, int index, int* wi
     return 0;
 }
 
-int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out) {
-    if (!b || !out) return MPEGB200_EINVAL;
+static int video_batch_next_impl(mpegb200_video_batch* b, mpegb200_batch_step* out) {
     memset(out, 0, sizeof(*out));
     const int n = b->n;
     b->pool->run(n, [&](int i) {
         mpegb200_video_step& st = b->steps[(size_t)i];
         memset(&st, 0, sizeof(st));
-        if (b->parsers[(size_t)i]) mpegb200_video_parser_next(b->parsers[(size_t)i], &st);
+        if (b->parsers[(size_t)i] && mpegb200_video_parser_next(b->parsers[(size_t)i], &st) != 0) throw std::bad_alloc();
         b->has_frame[(size_t)i] = st.has_frame;
         b->frame_buf[(size_t)i] = st.frame_buf;
         b->time[(size_t)i] = st.time;
     });
+    if (b->pool->failed()) return MPEGB200_ENOMEM;
     int n_waves = 0;
     for (int i = 0; i < n; i++) n_waves = std::max(n_waves, b->steps[(size_t)i].has_frame ? b->steps[(size_t)i].n_launches : 0);
     b->flip ^= 1;
@@ -1293,6 +1339,16 @@ int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out)
     out->n_waves = n_waves;
     out->waves = b->waves.data();
     return 0;
+}
+
+int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out) {
+    if (!b || !out) return MPEGB200_EINVAL;
+    try {
+        return video_batch_next_impl(b, out);
+    } catch (...) {
+        memset(out, 0, sizeof(*out));
+        return MPEGB200_ENOMEM;
+    }
 }
 
 }  // extern "C"

@@ -302,15 +302,15 @@ static void decode_motion_vectors(orc_video* v) {
 static void predict_macroblock(orc_video* v, mpegb200_mb* rec) {
     int fw_h = v->motion_forward.h, fw_v = v->motion_forward.v;
     if (v->motion_forward.full_px) {
-        fw_h <<= 1;
-        fw_v <<= 1;
+        fw_h *= 2;
+        fw_v *= 2;
     }
     int use_bwd = 0, mv_h = fw_h, mv_v = fw_v;
     if (v->picture_type == PIC_B) {
         int bw_h = v->motion_backward.h, bw_v = v->motion_backward.v;
         if (v->motion_backward.full_px) {
-            bw_h <<= 1;
-            bw_v <<= 1;
+            bw_h *= 2;
+            bw_v *= 2;
         }
         if (v->motion_forward.is_set) {
             if (orc_copy_macroblock(fw_h, fw_v, v->mb_row, v->mb_col, &v->frame_forward, &v->frame_current) != 0)
@@ -489,7 +489,7 @@ static void decode_macroblock(orc_video* v) {
 
     v->mb_row = v->macroblock_address / v->mb_width;
     v->mb_col = v->macroblock_address % v->mb_width;
-    if (v->mb_col >= v->mb_width || v->mb_row >= v->mb_height) return; /* corrupt stream */
+    if (v->macroblock_address < 0 || v->mb_col >= v->mb_width || v->mb_row >= v->mb_height) return; /* corrupt stream (address -1: slice 1 + increment code of value 0; the Go code panics on the index) */
 
     const vlc_tree* type_tree = v->picture_type == PIC_I ? &T_TYPE_I : (v->picture_type == PIC_P ? &T_TYPE_P : &T_TYPE_B);
     v->macroblock_type = vlc_read(&v->buf, type_tree);

@@ -208,3 +208,68 @@ def test_corrupted_streams_parse_like_the_oracle(golden_dir):
                 assert h1 == h2 and np.array_equal(m1, m2) and np.array_equal(c1, c2), f"trial {trial} step {k}"
         pictures += len(got)
     assert pictures > 200
+
+
+class _Bits:
+    def __init__(self):
+        self.s = ""
+
+    def put(self, value, n):
+        self.s += format(value & ((1 << n) - 1), "0%db" % n) if n else ""
+        return self
+
+    def align(self):
+        self.s += "0" * (-len(self.s) % 8)
+        return self
+
+    def bytes(self):
+        self.align()
+        return int(self.s, 2).to_bytes(len(self.s) // 8, "big") if self.s else b""
+
+
+def crafted_negative_address_stream():
+    """Sequence header 160x120, one I picture, slice 1 whose first macroblock-address increment is the unassigned
+    prefix 00000000000 (value 0): the macroblock address stays at (1-1)*mb_w - 1 = -1 (video.go:436-443, 462-470)."""
+    seq = _Bits().put(160, 12).put(120, 12).put(1, 4).put(5, 4).put(0x3ffff, 18).put(1, 1).put(20, 10).put(0, 1).put(0, 1).put(0, 1)
+    pic = _Bits().put(0, 10).put(1, 3).put(0xffff, 16)
+    sl = _Bits().put(8, 5).put(0, 1).put(0, 11).put(0x15555, 17)   # quantiser, no extra info, increment code 0, then noise
+    return (b"\x00\x00\x01\xb3" + seq.bytes() + b"\x00" * 140 + b"\x00\x00\x01\x00" + pic.bytes() + b"\x00\x00\x01\x01" + sl.bytes()
+            + b"\x55" * 40 + b"\x00\x00\x01\x00" + pic.bytes() + b"\x00" * 16)
+
+
+def test_negative_macroblock_address_is_dropped():
+    """slice 1 + address increment of value 0 left mb_addr at -1 -> mb_col = -1 passed the range check,
+    last_writer[-1] was read and written and a record with mb_col 65535 went out.  Parser and oracle both drop it now."""
+    d = crafted_negative_address_stream()
+    got, want = list(parser_steps(d)), list(oracle_steps(d))
+    assert len(got) == len(want)
+    for (fb, t, la), (fb2, t2, lb) in zip(got, want):
+        assert fb == fb2 and len(la) == len(lb)
+        for (h1, m1, c1), (h2, m2, c2) in zip(la, lb):
+            assert h1 == h2 and np.array_equal(m1, m2) and np.array_equal(c1, c2)
+            assert (m1["mb_row"] < 8).all() and (m1["mb_col"] < 10).all()
+
+
+def test_heavy_mutation_keeps_records_in_range(golden_dir):
+    """1500 randomised streams (the rate at which ADVICE r1 hit the negative address): every record stays inside the
+    picture and the coefficient packing rule holds; tools/asan_parser.sh runs the same loop under AddressSanitizer."""
+    base = (golden_dir / "test.mpeg1video").read_bytes()[:12000]
+    rng = np.random.default_rng(11)
+    L = _lib.load()
+    for trial in range(1500):
+        d = bytearray(base)
+        for pos in rng.integers(12, len(d), int(rng.integers(1, 60))):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        d = bytes(d)
+        h = L.mpegb200_video_parser_new(d, len(d))
+        st = VideoStep()
+        steps = 0
+        while L.mpegb200_video_parser_next(h, C.byref(st)) == 0 and st.has_frame and steps < 200:
+            if st.n_launches:
+                last = st.launches[st.n_launches - 1]
+                n = last.first_mb + last.n_mb
+                mbs = np.frombuffer(C.string_at(st.mbs, 16 * n), dtype=ol.MB_DTYPE)
+                w, hgt = L.mpegb200_video_parser_width(h), L.mpegb200_video_parser_height(h)
+                assert (mbs["mb_row"] < (hgt + 15) // 16).all() and (mbs["mb_col"] < (w + 15) // 16).all(), f"trial {trial}"
+            steps += 1
+        L.mpegb200_video_parser_free(h)
