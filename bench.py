@@ -34,6 +34,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))   # workload generator and oracle bindings (test / bench infrastructure)
 
 METRIC = "mpeg1_720p_frames_per_sec_batched"
 UNIT = "frames/s"
@@ -191,7 +192,7 @@ def bind_to_gpu_cpus(device_index, log, sysfs_root="/sys/bus/pci/devices"):
 
 def build_batch(streams, first_stream_id, mode, log=None):
     """Packed records of one picture step for `streams` 720p streams (one P picture each)."""
-    from mpeg_b200 import workload as wl
+    import workload as wl
     g = wl.HD720
     per, refs = [], []
     for s in range(streams):
@@ -206,7 +207,7 @@ def build_batch(streams, first_stream_id, mode, log=None):
 
 def rotation_variants(pics):
     """The three (dst, fwd, bwd) assignments a chain of P pictures cycles through (video.go:406-433)."""
-    from mpeg_b200 import workload as wl
+    import workload as wl
     rot, out = wl.BufferRotation(), []
     for _ in range(3):
         dst, fwd, bwd = rot.begin(wl.PIC_P)
@@ -323,7 +324,7 @@ def main():
 
     import torch
     import mpeg_b200  # fails loudly if libmpegb200.so is missing
-    from mpeg_b200 import workload as wl
+    import workload as wl
 
     torch.cuda.set_device(local_rank)
     dist = None

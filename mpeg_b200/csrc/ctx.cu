@@ -212,8 +212,10 @@ mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) try {
             q != cudaDriverEntryPointSuccess)
             ctx->encode_fn = nullptr;
         cudaGetLastError();
-        const char* sel = getenv("MPEGB200_FUSED");
+#ifdef MPEGB200_EXPERIMENTS
+        const char* sel = getenv("MPEGB200_FUSED");   // experiment builds: "generic" sends every stream to the cp.async kernel
         ctx->force_generic = sel && strcmp(sel, "generic") == 0;
+#endif
     }
     ok = ok && configure_kernels() == cudaSuccess && configure_audio_kernel() == cudaSuccess;
     if (!ok) {

@@ -86,7 +86,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+#ifdef MPEGB200_EXPERIMENTS
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // the same boxes, fetched into L2 only (for a group that a later CTA will decode)
 __device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
@@ -228,7 +230,6 @@ constexpr int kStripCBytes = kStripCW * kStripCH;                     // 3840 pe
 constexpr int kStripTx = kStripLBytes + 2 * kStripCBytes;             // 22272
 constexpr int kWinArea = (kG * kWinBytes > kStripTx ? kG * kWinBytes : kStripTx + 127) / 128 * 128;
 constexpr int kDefaultPrefetchDist = 444; // groups ahead to prefetch into L2: three per SM (MPEGB200_PREFETCH_DIST overrides; measured 0: 0.333 ms, 444: 0.327, 888: 0.327, 1776: 0.332, 3552: 0.402)
-constexpr int kDefaultVariant = 0;     // 0: one-shot kernel, 1: streaming kernel (MPEGB200_FUSED overrides)
 constexpr int kStripMinPred = 3;       // fewer predicted macroblocks than this: their own boxes are cheaper
 
 // ------------------------------------------------------------------------------------------------
@@ -780,9 +781,19 @@ __device__ __forceinline__ void block_finish(const BlockCtx& B, const uint32_t (
     }
 }
 
+#if defined(MPEGB200_EXPERIMENTS) && defined(MPEGB200_EXP_COEF_ALIAS)
+// Occupancy probe (WRONG PIXELS): the third coefficient box lands on the first one, 8 KiB instead of 12 -> seven CTAs per SM
+// with the same bytes fetched and the same instructions executed.
+constexpr int kCoefSmem = 2 * kCoefBox * 128, kMinCtas = 7;
+#define COEF_BOX_OFFSET(lane) (((lane) & 1) * (kCoefBox * 128))
+#else
+constexpr int kCoefSmem = kNT * 128, kMinCtas = 6;
+#define COEF_BOX_OFFSET(lane) ((lane) * (kCoefBox * 128))
+#endif
+
 struct Smem {
     static constexpr int coef = 0;                               // kNT x 128, 1024-aligned, swizzled by TMA
-    static constexpr int win = coef + kNT * 128;                 // the window area: one strip or kG x 1280
+    static constexpr int win = coef + kCoefSmem;                 // the window area: one strip or kG x 1280
     static constexpr int plan = win + kWinArea;                  // 640: the group's plan (head + body), then the mbarrier
     static constexpr int total_oneshot = plan + 640 + 16;
 };
@@ -797,7 +808,7 @@ __device__ __forceinline__ void issue_group(const PlanHead& P, const PlanBox* bo
     if (warp == 2) {
         if (lane == 0) mbar_arrive_expect_tx(bar, P.tx_bytes + extra_tx);
         if (lane < (int)P.n_box)  // rows past n_blocks are zero-filled by the TMA unit
-            tma_load_2d(s_coef + lane * (kCoefBox * 128), coef_map, bar, 0, (int)(P.block0 + lane * kCoefBox));
+            tma_load_2d(s_coef + COEF_BOX_OFFSET(lane), coef_map, bar, 0, (int)(P.block0 + lane * kCoefBox));
     } else if (P.strip) {
         if (lane == 0) {
             const SlabMaps* maps = slab_maps + P.slab;
@@ -840,10 +851,13 @@ __device__ __forceinline__ PlanHead load_head(const GroupPlan* gp) {
 constexpr int kPlanSmemBytes = 640;   // head + body (624) rounded up to 16
 static_assert(sizeof(PlanHead) + sizeof(PlanBody) <= kPlanSmemBytes, "plan copy size");
 
-__global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
+__global__ void __launch_bounds__(kNT, kMinCtas) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
                                                           const SlabMaps* __restrict__ slab_maps,
                                                           const GroupPlan* __restrict__ plans, uint32_t n_groups,
                                                           uint32_t prefetch_dist, int dbg) {
+#ifndef MPEGB200_EXPERIMENTS
+    (void)dbg;   // the fetch-only / arithmetic-only timing modes exist in experiment builds only
+#endif
     extern __shared__ __align__(1024) uint8_t smem[];  // the swizzled TMA tile needs 1024-byte alignment
     uint8_t* s_coef = smem + Smem::coef;
     uint8_t* s_win = smem + Smem::win;
@@ -859,12 +873,15 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the plan pre-pass has completed and its plans are visible
+#ifdef MPEGB200_EXPERIMENTS
     if (dbg == 2) {   // measurement only: the arithmetic and the stores without the tile fetch (works on whatever shared memory holds)
         if (tid == 64) {
             mbar_arrive_expect_tx(s_bar, kPlanSmemBytes);
             bulk_load(smem + Smem::plan, gp, kPlanSmemBytes, s_bar);
         }
-    } else {
+    } else
+#endif
+    {
         const PlanHead h = load_head(gp);
         issue_group(h, gp->box, &coef_map, slab_maps, s_coef, s_win, s_bar, warp, lane, kPlanSmemBytes);
         if (tid == 64) bulk_load(smem + Smem::plan, gp, kPlanSmemBytes, s_bar);
@@ -884,7 +901,9 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
     }
 
     mbar_wait(s_bar, 0);   // all tiles of the group and its plan have landed
+#ifdef MPEGB200_EXPERIMENTS
     if (dbg == 1) return;  // measurement only: the fetch without the arithmetic
+#endif
     BlockCtx B;
     block_setup(P.h, P.b, tid, B);
     if (!B.live) return;
@@ -894,7 +913,9 @@ __global__ void __launch_bounds__(kNT, 6) fused_tma_kernel(const __grid_constant
     block_finish(B, p0, p1, c);
 }
 
+#ifdef MPEGB200_EXPERIMENTS
 // ------------------------------------------------------------------------------------------------
+// (experiment builds only: measured slower than the one-shot kernel, profiles/r1_s3_video_summary.md)
 // Streaming kernel: the registers are the second pipeline stage.  A thread needs shared memory only until its
 // prediction (16 registers) and its premultiplied coefficients (64 registers) are loaded; the IDCT, the add and the
 // stores run on registers.  Each CTA walks over groups b, b + grid, ...; the warp that is LAST to leave the load step
@@ -995,6 +1016,7 @@ __global__ void __maxnreg__(96) fused_stream_kernel(const __grid_constant__ CUte
         block_finish(B, p0, p1, c);
     }
 }
+#endif  // MPEGB200_EXPERIMENTS
 
 }  // namespace
 
@@ -1004,15 +1026,23 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
                              int max_streams, const mpegb200_picture* d_pics, int n_pics, const mpegb200_mb* d_mbs,
                              uint32_t n_mb, uint32_t n_blocks, cudaStream_t stream, const cudaEvent_t* timing) {
     if (n_mb == 0) return cudaSuccess;
-    // Experiment switches, read once: MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the
-    // plan pre-pass stage every window with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid.
-    static int variant = -1, allow_strip = 1, stream_ctas = 0, prefetch_dist = kDefaultPrefetchDist, dbg = 0, pdl = 1;
-    if (variant < 0) {
-        const char* v = getenv("MPEGB200_FUSED");
-        const int want = (v && strcmp(v, "stream") == 0) ? 1 : (v && strcmp(v, "oneshot") == 0) ? 0 : kDefaultVariant;
+    static bool configured = false;
+    int allow_strip = 1, prefetch_dist = kDefaultPrefetchDist, dbg = 0, pdl = 1;
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total_oneshot);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS::total);
+        configured = true;
+    }
+#ifdef MPEGB200_EXPERIMENTS
+    // Experiment builds (make EXTRA=-DMPEGB200_EXPERIMENTS): A/B switches read once from the environment.
+    // MPEGB200_FUSED=oneshot|stream picks the arithmetic kernel, MPEGB200_STRIP=0 makes the plan pre-pass stage every window
+    // with its own boxes, MPEGB200_STREAM_CTAS sets the streaming grid, MPEGB200_PREFETCH_DIST the L2 prefetch distance,
+    // MPEGB200_MEASURE=fetch|math times the tile fetch / the arithmetic alone (WRONG PIXELS), MPEGB200_PDL=0 plain stream order.
+    static int x_variant = -1, x_strip = 1, x_ctas = 0, x_pd = kDefaultPrefetchDist, x_dbg = 0, x_pdl = 1;
+    if (x_variant < 0) {
+        const char* v = getenv("MPEGB200_FUSED");
+        const int want = (v && strcmp(v, "stream") == 0) ? 1 : 0;
+        cudaError_t e = cudaFuncSetAttribute(fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemS::total);
         if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, per_sm = 0, per_sm1 = 0;
         cudaGetDevice(&dev);
@@ -1020,21 +1050,23 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_stream_kernel, kNT, SmemS::total);
         if (e != cudaSuccess) return e;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fused_tma_kernel, kNT, Smem::total_oneshot);
-        stream_ctas = sms * (per_sm > 0 ? per_sm : 1);
+        x_ctas = sms * (per_sm > 0 ? per_sm : 1);
         const char* c = getenv("MPEGB200_STREAM_CTAS");
-        if (c && atoi(c) > 0) stream_ctas = atoi(c);
-        const char* pd = getenv("MPEGB200_PREFETCH_DIST");   // groups ahead whose tiles the one-shot kernel pulls into L2; 0: off
-        if (pd) prefetch_dist = atoi(pd) > 0 ? atoi(pd) : 0;
-        const char* dm = getenv("MPEGB200_MEASURE");   // "fetch": tile fetch only, "math": arithmetic + stores only (wrong pixels; timing experiments)
-        dbg = dm && strcmp(dm, "fetch") == 0 ? 1 : dm && strcmp(dm, "math") == 0 ? 2 : 0;
-        const char* pl = getenv("MPEGB200_PDL");   // "0": plain stream order between the pre-pass and the arithmetic kernel
-        pdl = !(pl && pl[0] == '0');
-        const char* s = getenv("MPEGB200_STRIP");
-        allow_strip = !(s && s[0] == '0');
-        if (getenv("MPEGB200_DEBUG"))
-            fprintf(stderr, "[mpegb200] fused variant %d; CTAs per SM: streaming %d, one-shot %d; streaming grid %d\n", want, per_sm, per_sm1, stream_ctas);
-        variant = want;
+        if (c && atoi(c) > 0) x_ctas = atoi(c);
+        const char* pd = getenv("MPEGB200_PREFETCH_DIST");
+        if (pd) x_pd = atoi(pd) > 0 ? atoi(pd) : 0;
+        const char* dm = getenv("MPEGB200_MEASURE");
+        x_dbg = dm && strcmp(dm, "fetch") == 0 ? 1 : dm && strcmp(dm, "math") == 0 ? 2 : 0;
+        const char* pl = getenv("MPEGB200_PDL");
+        x_pdl = !(pl && pl[0] == '0');
+        const char* st = getenv("MPEGB200_STRIP");
+        x_strip = !(st && st[0] == '0');
+        fprintf(stderr, "[mpegb200 EXPERIMENT BUILD] fused variant %d; CTAs per SM: streaming %d, one-shot %d; smem %d\n", want, per_sm,
+                per_sm1, Smem::total_oneshot);
+        x_variant = want;
     }
+    allow_strip = x_strip, prefetch_dist = x_pd, dbg = x_dbg, pdl = x_pdl;
+#endif
     const uint32_t n_groups = (n_mb + kG - 1) / kG;
     GroupPlan* plans = reinterpret_cast<GroupPlan*>(d_plans);
     if (timing) cudaEventRecord(timing[0], stream);
@@ -1042,26 +1074,29 @@ cudaError_t launch_fused_tma(const void* coef_map, const SlabMaps* d_maps, void*
         plans, d_streams, max_streams, d_pics, n_pics, d_mbs, n_mb, n_blocks, allow_strip);
     if (timing) cudaEventRecord(timing[1], stream);
     const CUtensorMap& cm = *reinterpret_cast<const CUtensorMap*>(coef_map);
-    if (variant == 0) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(n_groups);
-        cfg.blockDim = dim3(kNT);
-        cfg.dynamicSmemBytes = Smem::total_oneshot;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = (pdl && !timing) ? 1 : 0;   // with timing events between the two kernels there is nothing to overlap
-        const SlabMaps* maps_arg = d_maps;
-        const GroupPlan* plans_arg = plans;
-        const uint32_t pf = (uint32_t)prefetch_dist;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, fused_tma_kernel, cm, maps_arg, plans_arg, n_groups, pf, dbg);
-        if (e != cudaSuccess) return e;
-    } else {
-        const uint32_t grid = n_groups < (uint32_t)stream_ctas ? n_groups : (uint32_t)stream_ctas;
+#ifdef MPEGB200_EXPERIMENTS
+    if (x_variant == 1) {
+        const uint32_t grid = n_groups < (uint32_t)x_ctas ? n_groups : (uint32_t)x_ctas;
         fused_stream_kernel<<<grid, kNT, SmemS::total, stream>>>(cm, d_maps, plans, n_groups);
+        if (timing) cudaEventRecord(timing[2], stream);
+        return cudaGetLastError();
     }
+#endif
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_groups);
+    cfg.blockDim = dim3(kNT);
+    cfg.dynamicSmemBytes = Smem::total_oneshot;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && !timing) ? 1 : 0;   // with timing events between the two kernels there is nothing to overlap
+    const SlabMaps* maps_arg = d_maps;
+    const GroupPlan* plans_arg = plans;
+    const uint32_t pf = (uint32_t)prefetch_dist;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fused_tma_kernel, cm, maps_arg, plans_arg, n_groups, pf, dbg);
+    if (e != cudaSuccess) return e;
     if (timing) cudaEventRecord(timing[2], stream);
     return cudaGetLastError();
 }

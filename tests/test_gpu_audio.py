@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from mpeg_b200 import workload as wl
+import workload as wl
 
 pytestmark = pytest.mark.gpu
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from mpeg_b200 import workload as wl
+import workload as wl
 from mpeg_b200.packing import resolve_rewrites
 
 pytestmark = pytest.mark.gpu

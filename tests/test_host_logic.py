@@ -47,7 +47,7 @@ def test_record_struct_layouts_match_the_header():
 
 
 def test_zigzag_and_geometry():
-    from mpeg_b200 import workload as wl
+    import workload as wl
     assert wl.ZIGZAG[:10].tolist() == [0, 1, 8, 16, 9, 2, 3, 10, 17, 24]  # video.go:1044-1046
     assert sorted(wl.ZIGZAG.tolist()) == list(range(64))
     g = wl.HD720
@@ -57,7 +57,7 @@ def test_zigzag_and_geometry():
 
 
 def test_workload_generator_obeys_the_packing_rules():
-    from mpeg_b200 import workload as wl
+    import workload as wl
     g = wl.CIF
     rng = wl.stream_rng(2, 0)
     for t, mode in [(wl.PIC_I, "natural"), (wl.PIC_P, "natural"), (wl.PIC_B, "natural"), (wl.PIC_P, "dense")]:
@@ -83,7 +83,7 @@ def test_workload_generator_obeys_the_packing_rules():
 def test_buffer_rotation_mirrors_the_decoder(golden_dir):
     """The host-side rotation mirror (video.go:406-409, 430-433) reproduces the buffer roles the
     oracle's decoder reports for the reference clip."""
-    from mpeg_b200 import workload as wl
+    import workload as wl
     v = ol.VideoOracle((golden_dir / "test.mpeg1video").read_bytes(), tap=True)
     rot = wl.BufferRotation()
     seen = 0

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from mpeg_b200 import _lib
-from mpeg_b200 import workload as wl
+import workload as wl
 
 
 def pack(coeffs):
@@ -165,7 +165,7 @@ def test_portable_packer_agrees_with_the_simd_one():
         "import sys, hashlib, numpy as np\n"
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "import test_vlen_format as t\n"
-        "from mpeg_b200 import workload as wl\n"
+        "import workload as wl\n"
         "rng = np.random.default_rng(11)\n"
         "a = t.dense_blocks(700, 2)\n"
         "b = wl._draw_blocks(rng, 700, rng.random(700) < 0.3, dense=False)\n"

@@ -1,4 +1,6 @@
-"""Synthetic pre-parsed block batches (BASELINE.json configs 2-5).
+"""TEST / BENCH INFRASTRUCTURE (not part of the product package).
+
+Synthetic pre-parsed block batches (BASELINE.json configs 2-5).
 
 Pure host-side numpy: produces the packed records of include/mpegb200.h that a bitstream
 parser would produce, with the distributions SURVEY 8d fixes.  Used by bench.py and by the
@@ -9,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .context import MB_DTYPE, MB_INTRA, MB_PREDICT, MB_REF_BWD, PIC_B, PIC_I, PIC_P, PICTURE_DTYPE
+from mpeg_b200.context import MB_DTYPE, MB_INTRA, MB_PREDICT, MB_REF_BWD, PIC_B, PIC_I, PIC_P, PICTURE_DTYPE
 
 BASE_SEED = 20260925
 

@@ -16,7 +16,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 def main():
     import torch
     import mpeg_b200
-    from mpeg_b200 import workload as wl
+    import workload as wl
     S, F, steps, warmup = 1024, 8, 20, 3
     if len(sys.argv) > 1:
         steps = int(sys.argv[1])

@@ -18,7 +18,8 @@ sys.path.insert(0, str(ROOT / "tests"))
 def main():
     import oracle_lib as ol
     import mpeg_b200
-    from mpeg_b200 import _lib, workload as wl
+    from mpeg_b200 import _lib
+    import workload as wl
     from mpeg_b200.mpeg import VideoStep
     out = {}
     ps = (ROOT / "tests/golden/test.mpg").read_bytes()

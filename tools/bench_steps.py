@@ -11,10 +11,11 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
 import torch  # noqa: E402
 
 import mpeg_b200  # noqa: E402
-from mpeg_b200 import workload as wl  # noqa: E402
+import workload as wl  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 ONLY = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None   # e.g. "dense-P,natural-B"
