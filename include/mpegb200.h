@@ -126,6 +126,14 @@ int  mpegb200_sync(mpegb200_ctx* ctx);
 int  mpegb200_sync_uploads(mpegb200_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx);
+/* Self-validation.  The decode entry points trust their records (a trusted packer pays nothing); the kernels are
+ * memory safe on malformed records but silently drop or clamp them.  With validation on, every host-pointer decode
+ * entry point (mpegb200_video_decode_pictures, _packed, _vlen) first runs mpegb200_video_validate (and
+ * mpegb200_vlen_validate) on its arrays and returns MPEGB200_ERECORD without enqueuing anything -- the loud failure
+ * the reference has as a Go panic (index out of range in copyMacroblock, video_noasm.go:49-50).  Use it for records
+ * parsed from untrusted bitstreams; the Python mirror (mpeg_b200.Video / VideoBatch) turns it on.  Setting the
+ * environment variable MPEGB200_VALIDATE=1 turns it on for every context (debug aid). */
+int  mpegb200_set_validate(mpegb200_ctx* ctx, int on);
 /* Measurement aid (bench.py's roofline): while on, every mpegb200_video_decode_pictures* call brackets its plan
  * pre-pass and its arithmetic kernel with CUDA events on the context's stream.  mpegb200_kernel_times synchronises
  * the stream, writes the per-call durations in milliseconds (oldest first, at most `cap` calls; either array may be

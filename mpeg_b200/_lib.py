@@ -58,6 +58,7 @@ def load():
         "mpegb200_sync": (C.c_int, [vp]),
         "mpegb200_sync_uploads": (C.c_int, [vp]),
         "mpegb200_launch_count": (C.c_uint64, [vp]),
+        "mpegb200_set_validate": (C.c_int, [vp, C.c_int]),
         "mpegb200_set_kernel_timing": (C.c_int, [vp, C.c_int]),
         "mpegb200_kernel_times": (C.c_int, [vp, vp, vp, C.c_int]),
         "mpegb200_video_open": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),

@@ -24,8 +24,9 @@ class BatchStep(C.Structure):
 
 
 class VideoBatch:
-    def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True):
+    def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True):
         self.L = _lib.load()
+        ctx.set_validate(validate)   # bitstream-derived records: a malformed wave raises instead of decoding (pass False for trusted input)
         self.ctx, self.n, self.first = ctx, len(streams), first_stream
         alloc = C.cast(self.L.mpegb200_host_alloc, C.c_void_p) if pinned else None
         free = C.cast(self.L.mpegb200_host_free, C.c_void_p) if pinned else None

@@ -71,6 +71,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.L.mpegb200_launch_count(self.h))
 
+    def set_validate(self, on: bool):
+        """Host-pointer decode calls validate their records first and raise instead of decoding malformed ones."""
+        self._ck(self.L.mpegb200_set_validate(self.h, int(on)))
+
     def set_kernel_timing(self, on: bool):
         """Measurement aid: bracket the kernels of every decode call with CUDA events (mpegb200_set_kernel_timing)."""
         self._ck(self.L.mpegb200_set_kernel_timing(self.h, int(on)))

@@ -72,6 +72,7 @@ struct mpegb200_ctx {
     bool force_generic = false;   // MPEGB200_FUSED=generic (A/B measurements)
     void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
     uint64_t launches = 0;
+    bool validate = false;                   // mpegb200_set_validate / MPEGB200_VALIDATE=1
     bool kernel_timing = false;              // mpegb200_set_kernel_timing
     std::vector<cudaEvent_t> timing_events;  // three per timed decode call
     int max_w = 0, max_h = 0;
@@ -217,6 +218,10 @@ mpegb200_ctx* mpegb200_create(int device, int max_streams, int* err) try {
         ctx->force_generic = sel && strcmp(sel, "generic") == 0;
 #endif
     }
+    {
+        const char* val = getenv("MPEGB200_VALIDATE");   // debug aid: same as mpegb200_set_validate(ctx, 1)
+        ctx->validate = val && val[0] == '1';
+    }
     ok = ok && configure_kernels() == cudaSuccess && configure_audio_kernel() == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
@@ -294,6 +299,12 @@ int mpegb200_sync_uploads(mpegb200_ctx* ctx) {
 }
 
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mpegb200_set_validate(mpegb200_ctx* ctx, int on) {
+    if (!ctx) return MPEGB200_EINVAL;
+    ctx->validate = on != 0;
+    return 0;
+}
 
 int mpegb200_set_kernel_timing(mpegb200_ctx* ctx, int on) {
     if (!ctx) return MPEGB200_EINVAL;
@@ -642,6 +653,9 @@ int mpegb200_video_decode_pictures(mpegb200_ctx* ctx, int n_pictures, const mpeg
                                    const mpegb200_mb* mbs, size_t n_blocks, const int16_t* coeffs) {
     if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && !coeffs))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (ctx->validate) {  // records from an untrusted bitstream: fail loudly like the reference panics, before anything is enqueued
+        if (int rc = mpegb200_video_validate(ctx, n_pictures, pics, n_mb, mbs, n_blocks)) return rc;
+    }
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     const int slot = (int)(ctx->upload_seq++ & 1);
@@ -686,6 +700,9 @@ int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, con
                                           const mpegb200_mb* mbs, size_t n_blocks, const uint8_t* coeffs12) {
     if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && !coeffs12))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (ctx->validate) {  // records from an untrusted bitstream: fail loudly like the reference panics, before anything is enqueued
+        if (int rc = mpegb200_video_validate(ctx, n_pictures, pics, n_mb, mbs, n_blocks)) return rc;
+    }
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     const int slot = (int)(ctx->upload_seq++ & 1);
@@ -716,6 +733,10 @@ int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const
     if (!ctx || n_pictures < 0 || (n_mb && (!pics || !mbs)) || (n_blocks && (!headers || !chunk_offsets || !payload)))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
     if (n_blocks && payload_bytes < 16) return fail(ctx, MPEGB200_EINVAL, "payload without its 16 bytes of padding");
+    if (ctx->validate) {  // records from an untrusted bitstream: fail loudly like the reference panics, before anything is enqueued
+        if (int rc = mpegb200_video_validate(ctx, n_pictures, pics, n_mb, mbs, n_blocks)) return rc;
+        if (int rc = mpegb200_vlen_validate(headers, chunk_offsets, n_blocks, payload_bytes)) return fail(ctx, rc, "malformed variable-width coefficient stream");
+    }
     if (n_mb == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     const size_t chunks = (n_blocks + 31) / 32;

@@ -108,6 +108,7 @@ class Video:
             return None
         if not self._opened:
             self.ctx.video_open(self.stream, self.width, self.height)
+            self.ctx.set_validate(True)   # records parsed from a bitstream are untrusted: malformed ones raise (the reference panics)
             self._opened = True
         step = VideoStep()
         rc = self.L.mpegb200_video_parser_next(self.h, C.byref(step))
