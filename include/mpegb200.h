@@ -103,6 +103,13 @@ typedef struct mpegb200_picture {
 #define MPEGB200_AUDIO_F32NLR  1   /* planar: 1152 left then 1152 right (Samples.Left/Right) */
 #define MPEGB200_AUDIO_F32     2   /* interleaved float32 scaled to int32 range (Samples.F32) */
 #define MPEGB200_AUDIO_S16     3   /* interleaved int16 (Samples.S16) */
+#define MPEGB200_AUDIO_FORMAT_MASK 0xff
+/* Window arithmetic, OR-ed into `format`.  The reference has two back-ends for synthWindow that differ in the last
+ * bits and holds a golden hash for each (mpeg_test.go:192-196): the pure-Go / SSE one rounds the product and the sum
+ * of every tap separately (audio_noasm.go:8-38, audio_amd64.s:33-105; hash 0xf1b76cdf8e6cdea5) -- the default here --
+ * and the AVX2 / NEON one uses one fused multiply-add per tap (audio_amd64.s:107-156, audio_arm64.s:36-85; hash
+ * 0x50f3ab75f5fb0fb5).  With this flag the kernel reproduces the fused back-end bit for bit (and runs faster). */
+#define MPEGB200_AUDIO_WINDOW_FMA  0x100
 
 #define MPEGB200_SAMPLES_PER_FRAME 1152   /* audio.go:9 */
 

@@ -5,7 +5,7 @@ compensation with residual add, YCbCr->RGBA and the MP2 synthesis filterbank run
 CUDA behind the C-ABI of include/mpegb200.h; the serial demux / VLC parse stays on the host.
 """
 from ._lib import MpegB200Error, build, load  # noqa: F401
-from .context import (AUDIO_F32, AUDIO_F32N, AUDIO_F32NLR, AUDIO_S16, MB_DTYPE, MB_INTRA, MB_PREDICT,  # noqa: F401
+from .context import (AUDIO_F32, AUDIO_F32N, AUDIO_F32NLR, AUDIO_S16, AUDIO_WINDOW_FMA, MB_DTYPE, MB_INTRA, MB_PREDICT,  # noqa: F401
                       MB_REF_BWD, PIC_B, PIC_I, PIC_P, PICTURE_DTYPE, SAMPLES_PER_FRAME, Context)
 
 from .batch import VideoBatch  # noqa: F401

@@ -18,6 +18,7 @@ PICTURE_DTYPE = np.dtype([
 MB_INTRA, MB_PREDICT, MB_REF_BWD = 0x01, 0x02, 0x04
 PIC_I, PIC_P, PIC_B = 1, 2, 3
 AUDIO_F32N, AUDIO_F32NLR, AUDIO_F32, AUDIO_S16 = 0, 1, 2, 3
+AUDIO_WINDOW_FMA = 0x100   # OR into the format: fused multiply-add window (the reference's AVX2 / NEON back-end)
 SAMPLES_PER_FRAME = 1152
 
 
@@ -218,7 +219,7 @@ class Context:
         ids = np.ascontiguousarray(stream_ids, np.int32)
         samples = np.ascontiguousarray(samples, np.int32)
         assert samples.size == len(ids) * frames_per_stream * 2 * 36 * 32
-        out = np.empty((len(ids), frames_per_stream, 2 * SAMPLES_PER_FRAME), np.int16 if fmt == AUDIO_S16 else np.float32)
+        out = np.empty((len(ids), frames_per_stream, 2 * SAMPLES_PER_FRAME), np.int16 if (fmt & 0xff) == AUDIO_S16 else np.float32)
         self._ck(self.L.mpegb200_audio_synth(self.h, len(ids), _ptr(ids), frames_per_stream, _ptr(samples), fmt, _ptr(out)))
         return out
 

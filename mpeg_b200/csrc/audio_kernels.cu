@@ -2,9 +2,18 @@
 //   idct36 ("matrixing", audio.go:492-772) + synthWindow (audio_noasm.go:8-38) + the synthesis
 //   loop with its output scaling (audio.go:377-422), for a rectangular batch of streams x frames.
 //
-// Numerics: every float32 operation is an explicitly rounded __fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn
-// (never contracted into FMA), in the reference's operand and accumulation order, so the result
-// is bit-identical to the reference's amd64 non-FMA path (golden hash 0xf1b76cdf8e6cdea5).
+// Numerics.  Two window modes, both bit-exact to a back-end of the reference:
+//   * default: every multiply and every add of the window rounds on its own (mul.rn.f32 / add.rn), in the reference's
+//     operand and accumulation order -- the amd64 SSE / pure-Go path, golden hash 0xf1b76cdf8e6cdea5 (mpeg_test.go:194);
+//   * MPEGB200_AUDIO_WINDOW_FMA: each tap is one fused multiply-add, u = fma(d, v, u), like the reference's AVX2 / NEON
+//     back-ends (audio_amd64.s:107-156 VFMADD231PS, audio_arm64.s:36-85 FMLA), golden hash 0x50f3ab75f5fb0fb5
+//     (mpeg_test.go:195).
+// The matrixing and the output scaling are the same in both (explicit .rn operations, never contracted).
+//
+// Layout.  The two channels of a stream sit side by side: a V slice is 64 float2 (channel 0, channel 1), so a window tap
+// is one LDS.64 and -- with the packed FP32 pipe of sm_100 -- one FFMA2 (fused mode: the window coefficient is a scalar
+// broadcast operand) or two FMUL + one FADD2 (default mode; ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+// whatever --fmad says, so the products stay scalar mul.rn.f32, whose no-contraction guarantee PTX documents).
 #include "common.cuh"
 
 namespace mpegb200 {
@@ -47,22 +56,37 @@ __device__ __forceinline__ void lee_dct(float (&x)[N]) {
     }
 }
 
-constexpr int kSlicePitch = 65;  // floats per V slice in shared memory (64 + 1: conflict-free column writes)
+constexpr int kSlicePitch = 65;  // float2 per V slice in shared memory (64 + 1): 130 words = 2 mod 32, so the 32 (slot, channel)
+                                 // threads of a warp write one element of their slices to 32 different banks
 constexpr int kHist = 15;        // slices of history a window reaches back over (taps of age 1..15)
 constexpr int kLin = kHist + 36; // a frame's slices lie linearly behind their history: tap address = slice - age * pitch
 constexpr int kAudioThreads = 128;
 
 struct AudioSmem {
-    float v[2][kLin * kSlicePitch];       // 26,520 B: 8 CTAs per SM, so 1024 streams are resident in one wave
+    float2 v[kLin * kSlicePitch];         // 26,520 B: 8 CTAs per SM, so 1024 streams are resident in one wave
 };
 
+__device__ __forceinline__ float2 fma2_bcast(float d, float2 v, float2 acc) {   // (d * v.x + acc.x, d * v.y + acc.y), fused
+    uint64_t r;
+    asm("{\n\t.reg .b64 dd;\n\tmov.b64 dd, {%1, %1};\n\tfma.rn.f32x2 %0, dd, %2, %3;\n\t}"
+        : "=l"(r)
+        : "r"(__float_as_uint(d)), "l"(*reinterpret_cast<const uint64_t*>(&v)), "l"(*reinterpret_cast<const uint64_t*>(&acc)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
 // synthWindow (audio_noasm.go:8-38) for one time slot whose vPos/64 is the compile-time P.  `s` points at
-// lane's element of the slot's own slice (channel 0; channel 1 lies kLin slices further); D[t] = window[32 t + lane].
-// With P fixed every tap's age (= which slice), half (= which 32 floats of it) and window index are constants:
-// the 16 taps are two loads, two multiplies and two adds each, accumulated in the reference's order
+// lane's element of the slot's own slice (both channels); D[t] = window[32 t + lane].
+// With P fixed every tap's age (= which slice), half (= which 32 elements of it) and window index are constants:
+// a tap is one LDS.64 with an immediate offset plus its arithmetic, accumulated in the reference's order
 // (first loop: V positions 128 m + base, second loop: 64 + 128 m + (32 - base)).
-template <int P>
-__device__ __forceinline__ void window_taps(const float* __restrict__ s, const float (&D)[32], float& u0, float& u1) {
+template <int P, bool FMA>
+__device__ __forceinline__ float2 window_taps(const float2* __restrict__ s, const float (&D)[32]) {
+    float2 u = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
@@ -71,26 +95,46 @@ __device__ __forceinline__ void window_taps(const float* __restrict__ s, const f
             const int age = (q - P) & 15;
             const int half = pass == 0 ? (P & 1) : 1 - (P & 1);
             const int t = ((pass == 0 ? 512 : 544) - 32 * P + 64 * m) / 32;  // window index / 32 (audio_noasm.go:9,24)
-            const int off = half * 32 - age * kSlicePitch;
-            u0 = __fadd_rn(u0, __fmul_rn(D[t], s[off]));
-            u1 = __fadd_rn(u1, __fmul_rn(D[t], s[off + kLin * kSlicePitch]));
+            const float2 vv = s[half * 32 - age * kSlicePitch];
+            if constexpr (FMA) {
+                u = fma2_bcast(D[t], vv, u);                             // audio_amd64.s:123-131
+            } else {
+                const float2 p = make_float2(__fmul_rn(D[t], vv.x), __fmul_rn(D[t], vv.y));
+                u = add2_rn(u, p);
+            }
         }
     }
+    return u;
+}
+
+// u / -1090519040.0 (audio.go:390), correctly rounded.  Fast path: q = u * y, r = fma(-q, c, u) (exact), q' = fma(r, y, q)
+// with y = RN(1 / c) equals the IEEE quotient for every float32 u with 2^-102 <= |u| < inf and for +-0 (checked over all
+// 2^32 bit patterns on the host, tools/check_fast_div.c); anything else takes the generic division.
+__device__ __forceinline__ float scale_out(float u) {
+    constexpr float c = -1090519040.0f;
+    constexpr float y = -0x1.f81f82p-31f;   // RN(1 / c)
+    const uint32_t mag = __float_as_uint(u) & 0x7fffffffu;
+    if (((mag - 1u) < 0x0d7fffffu) | (mag >= 0x7f800000u)) return __fdiv_rn(u, c);   // 0 < |u| < 2^-100, inf, nan
+    const float q = __fmul_rn(u, y);
+    const float r = __fmaf_rn(-q, c, u);
+    return __fmaf_rn(r, y, q);
 }
 
 // One CTA per stream; frames are processed in order, each in three barriers:
-//   (a) 72 threads: one 32-point DCT each (channel, time slot) on samples read straight from global memory
+//   (a) 72 threads: one 32-point DCT each (time slot, channel) on samples read straight from global memory
 //       -> V slice (audio.go:708-771 placement)
-//   (b) 4 warps: the 36 time slots' windows, lane = output sample, both channels -> coalesced store
+//   (b) 4 warps: the 36 time slots' windows, lane = output sample, both channels at once -> coalesced store
 //   (c) the last 15 slices move to the front as the next frame's history
-__global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* __restrict__ states, int max_streams,
-                                                                    const int32_t* __restrict__ stream_ids,
-                                                                    int frames_per_stream,
-                                                                    const int32_t* __restrict__ samples, int format,
-                                                                    void* __restrict__ out,
-                                                                    const float* __restrict__ window) {
+template <bool FMA>
+__global__ void __launch_bounds__(kAudioThreads, 7) audio_synth_kernel(AudioState* __restrict__ states, int max_streams,
+                                                                       const int32_t* __restrict__ stream_ids,
+                                                                       int frames_per_stream,
+                                                                       const int32_t* __restrict__ samples, int format,
+                                                                       void* __restrict__ out,
+                                                                       const float* __restrict__ window) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     AudioSmem& sm = *reinterpret_cast<AudioSmem*>(smem_raw);
+    float* vf = reinterpret_cast<float*>(sm.v);      // word view: element e of channel ch of slice i at (i * pitch + e) * 2 + ch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sidx = blockIdx.x;
     const int stream = stream_ids[sidx];
@@ -105,18 +149,22 @@ __global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* 
     for (int i = tid; i < 2 * 16 * 64; i += kAudioThreads) {
         const int ch = i >> 10, q = (i >> 6) & 15, e = i & 63;
         const int age = (q - p_init) & 15;
-        if (age < kHist) sm.v[ch][(kHist - 1 - age) * kSlicePitch + e] = st.v[ch][q * 64 + e];
+        if (age < kHist) vf[((kHist - 1 - age) * kSlicePitch + e) * 2 + ch] = st.v[ch][q * 64 + e];
     }
     // (the slice of age 15 is overwritten by the first new slot in the reference's ring and never read)
+
+    float D[32];  // the whole window table across the warp: D[t] = window[32 t + lane]
+#pragma unroll
+    for (int t = 0; t < 32; t++) D[t] = __ldg(&window[32 * t + lane]);
 
     const size_t frame_vals = 2 * MPEGB200_SAMPLES_PER_FRAME;
     for (int f = 0; f < frames_per_stream; f++) {
         const size_t fidx = (size_t)sidx * frames_per_stream + f;
         // (a) matrixing
         if (tid < 72) {
-            const int ch = tid / 36, step = tid - ch * 36;
+            const int step = tid >> 1, ch = tid & 1;
             // the time slot's 32 subband samples: 128 contiguous bytes, read straight from global memory
-            const int4* sp = reinterpret_cast<const int4*>(samples + fidx * (2 * 36 * 32) + tid * 32);
+            const int4* sp = reinterpret_cast<const int4*>(samples + fidx * (2 * 36 * 32) + (ch * 36 + step) * 32);
             int s[32];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -137,56 +185,53 @@ __global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* 
 #pragma unroll
             for (int k = 0; k < 15; k++) o[k] = __fadd_rn(o[k], o[k + 1]);  // audio.go:692-706
             // X[2k] = e[k], X[2k+1] = o[k]; placement audio.go:708-771
-            float* d = &sm.v[ch][(kHist + step) * kSlicePitch];
+            float* d = vf + (kHist + step) * kSlicePitch * 2 + ch;       // element i at d[2 i]
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const float xe = e[k], xo = o[k];  // X[2k], X[2k+1]
                 // X[m], m < 16:  d[48+m] = d[48-m] = -X[m];   m >= 16: d[m-16] = X[m], d[48-m] = -X[m]
                 if (2 * k < 16) {
-                    d[48 + 2 * k] = -xe;
-                    d[48 - 2 * k] = -xe;
-                    d[48 + 2 * k + 1] = -xo;
-                    d[48 - 2 * k - 1] = -xo;
+                    d[2 * (48 + 2 * k)] = -xe;
+                    d[2 * (48 - 2 * k)] = -xe;
+                    d[2 * (48 + 2 * k + 1)] = -xo;
+                    d[2 * (48 - 2 * k - 1)] = -xo;
                 } else {
-                    d[2 * k - 16] = xe;
-                    d[48 - 2 * k] = -xe;
-                    d[2 * k + 1 - 16] = xo;
-                    d[48 - 2 * k - 1] = -xo;
+                    d[2 * (2 * k - 16)] = xe;
+                    d[2 * (48 - 2 * k)] = -xe;
+                    d[2 * (2 * k + 1 - 16)] = xo;
+                    d[2 * (48 - 2 * k - 1)] = -xo;
                 }
             }
-            d[16] = 0.0f;
+            d[2 * 16] = 0.0f;
         }
         __syncthreads();
 
         // (b) windows: warp w takes time slots w, w+4, ...
         {
-            float D[32];  // the whole window table across the warp: D[t] = window[32 t + lane]
-#pragma unroll
-            for (int t = 0; t < 32; t++) D[t] = __ldg(&window[32 * t + lane]);
             const int p_frame = p_init - f * 36;
             for (int step = warp; step < 36; step += 4) {
                 const int p = (p_frame - step - 1) & 15;            // vPos / 64 for this slot (audio.go:380)
-                const float* s = &sm.v[0][(kHist + step) * kSlicePitch + lane];
-                float u0 = 0.0f, u1 = 0.0f;
+                const float2* s = &sm.v[(kHist + step) * kSlicePitch + lane];
+                float2 u;
                 switch (p) {
-                    case 0: window_taps<0>(s, D, u0, u1); break;
-                    case 1: window_taps<1>(s, D, u0, u1); break;
-                    case 2: window_taps<2>(s, D, u0, u1); break;
-                    case 3: window_taps<3>(s, D, u0, u1); break;
-                    case 4: window_taps<4>(s, D, u0, u1); break;
-                    case 5: window_taps<5>(s, D, u0, u1); break;
-                    case 6: window_taps<6>(s, D, u0, u1); break;
-                    case 7: window_taps<7>(s, D, u0, u1); break;
-                    case 8: window_taps<8>(s, D, u0, u1); break;
-                    case 9: window_taps<9>(s, D, u0, u1); break;
-                    case 10: window_taps<10>(s, D, u0, u1); break;
-                    case 11: window_taps<11>(s, D, u0, u1); break;
-                    case 12: window_taps<12>(s, D, u0, u1); break;
-                    case 13: window_taps<13>(s, D, u0, u1); break;
-                    case 14: window_taps<14>(s, D, u0, u1); break;
-                    default: window_taps<15>(s, D, u0, u1); break;
+                    case 0: u = window_taps<0, FMA>(s, D); break;
+                    case 1: u = window_taps<1, FMA>(s, D); break;
+                    case 2: u = window_taps<2, FMA>(s, D); break;
+                    case 3: u = window_taps<3, FMA>(s, D); break;
+                    case 4: u = window_taps<4, FMA>(s, D); break;
+                    case 5: u = window_taps<5, FMA>(s, D); break;
+                    case 6: u = window_taps<6, FMA>(s, D); break;
+                    case 7: u = window_taps<7, FMA>(s, D); break;
+                    case 8: u = window_taps<8, FMA>(s, D); break;
+                    case 9: u = window_taps<9, FMA>(s, D); break;
+                    case 10: u = window_taps<10, FMA>(s, D); break;
+                    case 11: u = window_taps<11, FMA>(s, D); break;
+                    case 12: u = window_taps<12, FMA>(s, D); break;
+                    case 13: u = window_taps<13, FMA>(s, D); break;
+                    case 14: u = window_taps<14, FMA>(s, D); break;
+                    default: u = window_taps<15, FMA>(s, D); break;
                 }
-                const float s0 = __fdiv_rn(u0, -1090519040.0f), s1 = __fdiv_rn(u1, -1090519040.0f);  // audio.go:390
+                const float s0 = scale_out(u.x), s1 = scale_out(u.y);  // audio.go:390
                 const int pos = step * 32 + lane;
                 if (format == MPEGB200_AUDIO_F32N) {
                     reinterpret_cast<float2*>(out)[fidx * MPEGB200_SAMPLES_PER_FRAME + pos] = make_float2(s0, s1);
@@ -209,13 +254,20 @@ __global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* 
 
         // (c) the frame's last 15 slices (36..50) become the next frame's history (0..14)
         if (f + 1 < frames_per_stream) {
-            float keep[kHist];
-            const int ch = tid >> 6, e = tid & 63;
+            constexpr int kMove = kHist * 64;             // float2 elements to move (the padding element stays)
+            constexpr int kPer = (kMove + kAudioThreads - 1) / kAudioThreads;
+            float2 keep[kPer];
 #pragma unroll
-            for (int i = 0; i < kHist; i++) keep[i] = sm.v[ch][(36 + i) * kSlicePitch + e];
-            __syncthreads();   // every read of 36..50 is done before the next frame's DCTs overwrite 15..50
+            for (int i = 0; i < kPer; i++) {
+                const int x = tid + i * kAudioThreads;
+                if (x < kMove) keep[i] = sm.v[(36 + (x >> 6)) * kSlicePitch + (x & 63)];
+            }
+            __syncthreads();   // every read of 36..50 is done before the stores below and the next frame's DCTs overwrite 15..50
 #pragma unroll
-            for (int i = 0; i < kHist; i++) sm.v[ch][i * kSlicePitch + e] = keep[i];
+            for (int i = 0; i < kPer; i++) {
+                const int x = tid + i * kAudioThreads;
+                if (x < kMove) sm.v[(x >> 6) * kSlicePitch + (x & 63)] = keep[i];
+            }
             // the barrier after (a) orders these stores before the windows read them
         }
     }
@@ -226,7 +278,7 @@ __global__ void __launch_bounds__(kAudioThreads) audio_synth_kernel(AudioState* 
     for (int i = tid; i < 2 * 16 * 64; i += kAudioThreads) {
         const int ch = i >> 10, q = (i >> 6) & 15, e = i & 63;
         const int age = (q - p_final) & 15;
-        st.v[ch][q * 64 + e] = sm.v[ch][(kLin - 1 - age) * kSlicePitch + e];
+        st.v[ch][q * 64 + e] = vf[((kLin - 1 - age) * kSlicePitch + e) * 2 + ch];
     }
     if (tid == 0) st.v_pos = p_final * 64;
 }
@@ -235,13 +287,20 @@ cudaError_t launch_audio_synth(AudioState* d_states, int max_streams, const int3
                                int frames_per_stream, const int32_t* d_samples, int format, void* d_out,
                                const float* d_window, cudaStream_t stream) {
     if (n_streams <= 0 || frames_per_stream <= 0) return cudaSuccess;
-    audio_synth_kernel<<<n_streams, kAudioThreads, sizeof(AudioSmem), stream>>>(
-        d_states, max_streams, d_stream_ids, frames_per_stream, d_samples, format, d_out, d_window);
+    const int fmt = format & MPEGB200_AUDIO_FORMAT_MASK;
+    if (format & MPEGB200_AUDIO_WINDOW_FMA)
+        audio_synth_kernel<true><<<n_streams, kAudioThreads, sizeof(AudioSmem), stream>>>(
+            d_states, max_streams, d_stream_ids, frames_per_stream, d_samples, fmt, d_out, d_window);
+    else
+        audio_synth_kernel<false><<<n_streams, kAudioThreads, sizeof(AudioSmem), stream>>>(
+            d_states, max_streams, d_stream_ids, frames_per_stream, d_samples, fmt, d_out, d_window);
     return cudaGetLastError();
 }
 
 cudaError_t configure_audio_kernel() {
-    return cudaFuncSetAttribute(audio_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AudioSmem));
+    cudaError_t e = cudaFuncSetAttribute(audio_synth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AudioSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(audio_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AudioSmem));
 }
 
 }  // namespace mpegb200

@@ -973,13 +973,18 @@ int mpegb200_audio_close(mpegb200_ctx* ctx, int stream) {
     return 0;
 }
 
-static size_t audio_out_bytes(int format) { return (format == MPEGB200_AUDIO_S16 ? 2 : 4) * (size_t)2 * MPEGB200_SAMPLES_PER_FRAME; }
+static bool audio_format_ok(int format) {
+    return format >= 0 && (format & ~(MPEGB200_AUDIO_FORMAT_MASK | MPEGB200_AUDIO_WINDOW_FMA)) == 0 && (format & MPEGB200_AUDIO_FORMAT_MASK) <= 3;
+}
+static size_t audio_out_bytes(int format) {
+    return ((format & MPEGB200_AUDIO_FORMAT_MASK) == MPEGB200_AUDIO_S16 ? 2 : 4) * (size_t)2 * MPEGB200_SAMPLES_PER_FRAME;
+}
 
 int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,
                              const int32_t* d_samples, int format, void* d_out) try {
     if (!ctx || n_streams < 0 || frames_per_stream < 0 || (n_streams && (!stream_ids || !d_samples || !d_out)))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
-    if (format < 0 || format > 3) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
+    if (!audio_format_ok(format)) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
     if (n_streams == 0 || frames_per_stream == 0) return 0;
     if ((reinterpret_cast<uintptr_t>(d_samples) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return fail(ctx, MPEGB200_EINVAL, "device arrays must be 16-byte aligned");
@@ -1008,7 +1013,7 @@ int mpegb200_audio_synth(mpegb200_ctx* ctx, int n_streams, const int32_t* stream
                          const int32_t* samples, int format, void* out) {
     if (!ctx || n_streams < 0 || frames_per_stream < 0 || (n_streams && (!stream_ids || !samples || !out)))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
-    if (format < 0 || format > 3) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
+    if (!audio_format_ok(format)) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
     if (n_streams == 0 || frames_per_stream == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     const size_t n_frames = (size_t)n_streams * frames_per_stream;

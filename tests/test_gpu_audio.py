@@ -125,3 +125,101 @@ def test_audio_argument_errors(ctx):
     want = ol.synth_batch(ol.synth_states(1), 1, 1, s)
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
     ctx.audio_close(3)
+
+
+AUDIO_GOLDEN_FMA = 0x50F3AB75F5FB0FB5    # mpeg_test.go:195 (AVX2 / NEON back-end of synthWindow)
+FMA = 0x100                              # MPEGB200_AUDIO_WINDOW_FMA
+
+
+def test_golden_clip_fused_window(ctx, golden_dir):
+    """The reference's second accepted hash (mpeg_test.go:195): synthWindow with one fused multiply-add per tap
+    (audio_amd64.s:107-156).  The kernel's opt-in fused mode reproduces it bit for bit through the GPU."""
+    a = ol.AudioOracle((golden_dir / "test.mp2").read_bytes(), fma=True)
+    ctx.audio_open(5)
+    h, frames, batch = ol.FNV_OFFSET, 0, []
+    while True:
+        want = a.decode()
+        if want is not None:
+            batch.append((a.last_samples(), want))
+        if batch and (want is None or len(batch) == 7):
+            got = ctx.audio_synth([5], len(batch), np.stack([b[0] for b in batch]), FMA)
+            for k, (_, w) in enumerate(batch):
+                assert np.array_equal(got[0, k].view(np.uint32), w.view(np.uint32)), f"frame {frames + k}"
+                h = ol.fnv(h, got[0, k])
+            frames += len(batch)
+            batch = []
+        if want is None:
+            break
+    assert h == AUDIO_GOLDEN_FMA, f"{h:#018x} frames={frames}"
+    ctx.audio_close(5)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+def test_batch_fused_window_matches_oracle(ctx, fmt):
+    n_streams, frames = 20, 4
+    ids = np.arange(40, 40 + n_streams)
+    for s in ids:
+        ctx.audio_open(int(s))
+    states = ol.synth_states(n_streams)
+    rng = wl.stream_rng(4, 100 + fmt)
+    for launch in range(2):
+        samples = wl.audio_samples(rng, n_streams * frames)
+        got = ctx.audio_synth(ids, frames, samples, fmt | FMA)
+        want = ol.synth_batch(states, n_streams, frames, samples, fmt, fma=True)
+        assert np.array_equal(got.view(np.uint16 if fmt == 3 else np.uint32), want.view(np.uint16 if fmt == 3 else np.uint32))
+        if fmt != 3:   # and the fused result stays within the reference's own 1e-5 rule of the unfused one (audio_test.go:59)
+            unfused = ol.synth_batch(ol.synth_states(n_streams), n_streams, frames, samples, fmt) if launch == 0 else None
+            if unfused is not None:
+                assert within_reference_tolerance(got, unfused)
+    for s in ids:
+        ctx.audio_close(int(s))
+
+
+def test_output_scaling_of_tiny_sums(ctx):
+    """The kernel replaces u / -1090519040 by a multiply and two fused multiply-adds where that is exact (|u| >= 2^-100)
+    and divides otherwise.  Single +-1 samples in one subband give tiny and ordinary u side by side; hand-made V states
+    with denormal and near-2^-100 entries exercise the guard itself."""
+    ctx.audio_open(6)
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        v = np.zeros((2, 1024), np.float32)
+        mags = [2.0 ** -149, 2.0 ** -130, 2.0 ** -110, 2.0 ** -101, 2.0 ** -99, 1e-30, 3e-39]
+        idx = rng.integers(0, 1024, 64)
+        v[0, idx] = (np.array(mags, np.float64)[rng.integers(0, len(mags), 64)] * rng.choice([-1, 1], 64)).astype(np.float32)
+        v[1, idx] = v[0, idx[::-1]]
+        pos = int(rng.integers(0, 16)) * 64
+        ctx.audio_write_state(6, v, pos)
+        st = ol.synth_states(1)
+        np.ctypeslib.as_array(st[0].v)[:] = v.reshape(-1)
+        st[0].v_pos = pos
+        s = np.zeros((2, 2, 36, 32), np.int32)
+        s[0, 0, 3, 1] = 1
+        s[1, 1, 20, 0] = -1
+        for fma in (False, True):
+            ctx.audio_write_state(6, v, pos)
+            st2 = ol.synth_states(1)
+            np.ctypeslib.as_array(st2[0].v)[:] = v.reshape(-1)
+            st2[0].v_pos = pos
+            got = ctx.audio_synth([6], 2, s, FMA if fma else 0)
+            want = ol.synth_batch(st2, 1, 2, s, 0, fma=fma)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"trial {trial} fma={fma}"
+    ctx.audio_close(6)
+
+
+def test_full_size_config4_parity(ctx):
+    """BASELINE configs[3] at full size: 1024 streams x 8 frames in one launch, every sample against the oracle."""
+    import mpeg_b200
+    n_streams, frames = 1024, 8
+    with mpeg_b200.Context(device=0, max_streams=n_streams) as c:
+        for s in range(n_streams):
+            c.audio_open(s)
+        rng = wl.stream_rng(4, 777)
+        samples = wl.audio_samples(rng, n_streams * frames)
+        threads = ol.lib().orc_max_threads()
+        for fma in (False, True):
+            got = c.audio_synth(np.arange(n_streams), frames, samples, FMA if fma else 0)
+            want = ol.synth_batch(ol.synth_states(n_streams), n_streams, frames, samples, 0, fma=fma, threads=threads)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"fma={fma}"
+            for s in range(n_streams):   # fresh state for the second mode
+                c.audio_close(s)
+                c.audio_open(s)
