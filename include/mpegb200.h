@@ -131,6 +131,9 @@ int  mpegb200_sync(mpegb200_ctx* ctx);
 /* Wait only for the host-to-device copies enqueued so far: after it the host arrays passed to the
  * host-pointer entry points may be overwritten while the kernels are still running. */
 int  mpegb200_sync_uploads(mpegb200_ctx* ctx);
+/* Make the context's compute stream wait for every asynchronous read-back enqueued so far (mpegb200_video_read_pictures_host
+ * runs on a private copy stream): afterwards an event recorded on the compute stream also covers those copies. */
+int  mpegb200_join_readbacks(mpegb200_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx);
 /* Self-validation.  The decode entry points trust their records (a trusted packer pays nothing); the kernels are

@@ -57,6 +57,7 @@ def load():
         "mpegb200_get_stream": (vp, [vp]),
         "mpegb200_sync": (C.c_int, [vp]),
         "mpegb200_sync_uploads": (C.c_int, [vp]),
+        "mpegb200_join_readbacks": (C.c_int, [vp]),
         "mpegb200_launch_count": (C.c_uint64, [vp]),
         "mpegb200_set_validate": (C.c_int, [vp, C.c_int]),
         "mpegb200_set_kernel_timing": (C.c_int, [vp, C.c_int]),

@@ -68,6 +68,10 @@ class Context:
     def sync(self):
         self._ck(self.L.mpegb200_sync(self.h))
 
+    def join_readbacks(self):
+        """The compute stream waits for the asynchronous read-backs enqueued so far (events on it then cover them)."""
+        self._ck(self.L.mpegb200_join_readbacks(self.h))
+
     @property
     def launch_count(self) -> int:
         return int(self.L.mpegb200_launch_count(self.h))

@@ -298,6 +298,12 @@ int mpegb200_sync_uploads(mpegb200_ctx* ctx) {
     return 0;
 }
 
+int mpegb200_join_readbacks(mpegb200_ctx* ctx) {
+    if (!ctx) return MPEGB200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    return join_readback(ctx, 7u);
+}
+
 uint64_t mpegb200_launch_count(mpegb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int mpegb200_set_validate(mpegb200_ctx* ctx, int on) {

@@ -71,6 +71,8 @@ int orc_copy_macroblock_swar(int motion_h, int motion_v, int mb_row, int mb_col,
 /* Frame.RGBA(): Go 1.23 image/draw -> image/internal/imageutil.DrawYCbCr, 4:2:0 case
  * (restated from the published standard-library source; parity unpinned). */
 void orc_rgba(const orc_frame* f, uint8_t* rgba /* width*height*4, stride 4*width */);
+void orc_rgba_batch(const orc_frame* frames, int n, const int32_t* streams, const uint8_t* bufs, uint8_t* out, size_t stride, int threads);
+void orc_use_swar_mc(int on);
 
 /* ---------- record-level executor (what the CUDA kernel is compared with) ---------- */
 /* Apply one packed macroblock record exactly as decodeMacroblock/decodeBlock would

@@ -301,6 +301,17 @@ void orc_rgba(const orc_frame* f, uint8_t* rgba) {
     }
 }
 
+/* Frame.RGBA() of many frames: frame i = frames[3 * streams[i] + bufs[i]] -> out + i * stride (one frame per task) */
+void orc_rgba_batch(const orc_frame* frames, int n, const int32_t* streams, const uint8_t* bufs, uint8_t* out, size_t stride,
+                    int threads) {
+#ifdef _OPENMP
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+#endif
+    for (int i = 0; i < n; i++) orc_rgba(&frames[(size_t)streams[i] * 3 + bufs[i]], out + (size_t)i * stride);
+    (void)threads;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Record-level executor: what decodeMacroblock + decodeBlock do once the bitstream has been
  * parsed (video.go:544-561, 747-798), driven by the packed records of include/mpegb200.h.
@@ -314,12 +325,18 @@ static const uint8_t k_premultiplier[64] = {
 };
 const uint8_t* orc_premultiplier(void) { return k_premultiplier; }
 
+/* Which restatement of copyMacroblock the record executor uses: 0 = per pixel (default), 1 = 8 bytes per step like the
+ * reference's portable Go path (video_noasm.go:44-80).  Same bytes (tests/test_oracle_golden.py sweeps both); bench.py's
+ * CPU arm takes the faster one. */
+static int g_swar_mc = 0;
+void orc_use_swar_mc(int on) { g_swar_mc = on != 0; }
+
 int orc_exec_macroblock(const mpegb200_mb* mb, const int16_t* coeffs, orc_frame* dst, const orc_frame* fwd,
                         const orc_frame* bwd) {
     int rc = 0;
     if (mb->flags & MPEGB200_MB_PREDICT) { /* video.go:544 -> predictMacroblock -> copyMacroblock */
         const orc_frame* ref = (mb->flags & MPEGB200_MB_REF_BWD) ? bwd : fwd;
-        if (orc_copy_macroblock(mb->mv_h, mb->mv_v, mb->mb_row, mb->mb_col, ref, dst) != 0) rc = -1;
+        if ((g_swar_mc ? orc_copy_macroblock_swar : orc_copy_macroblock)(mb->mv_h, mb->mv_v, mb->mb_row, mb->mb_col, ref, dst) != 0) rc = -1;
     }
     const int16_t* blk = coeffs + (size_t)mb->coeff_block * 64;
     const int intra = (mb->flags & MPEGB200_MB_INTRA) != 0;

@@ -85,6 +85,8 @@ def lib():
     L.orc_copy_macroblock.argtypes = [C.c_int] * 4 + [C.POINTER(Frame), C.POINTER(Frame)]
     L.orc_copy_macroblock_swar.argtypes = [C.c_int] * 4 + [C.POINTER(Frame), C.POINTER(Frame)]
     L.orc_rgba.argtypes = [C.POINTER(Frame), vp]
+    L.orc_rgba_batch.argtypes = [C.POINTER(Frame), C.c_int, vp, vp, vp, C.c_size_t, C.c_int]
+    L.orc_use_swar_mc.argtypes = [C.c_int]
     L.orc_exec_pictures.argtypes = [C.POINTER(Frame), C.c_int, vp, C.c_size_t, vp, vp, C.c_int]
     L.orc_max_threads.restype = C.c_int
     L.orc_video_open.restype = vp
@@ -172,6 +174,14 @@ class FrameSet:
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         lib().orc_rgba(C.byref(self.frame(stream, buf)), out.ctypes.data)
         return out
+
+    def rgba_batch(self, streams, bufs, out: np.ndarray, threads: int = 1):
+        """Frame.RGBA() of frames (streams[i], bufs[i]) into out[i] (uint8 [n, height, width, 4], preallocated)."""
+        streams = np.ascontiguousarray(streams, np.int32)
+        bufs = np.ascontiguousarray(bufs, np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape[0] >= len(streams)
+        lib().orc_rgba_batch(self.arr, len(streams), streams.ctypes.data, bufs.ctypes.data, out.ctypes.data,
+                             self.width * self.height * 4, threads)
 
     def close(self):
         for i in range(3 * self.n_streams):

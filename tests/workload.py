@@ -98,17 +98,17 @@ def stream_rng(config: int, stream_id: int) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64(BASE_SEED + 1000 * config + stream_id))
 
 
-def _draw_motion_vectors(rng, g: Geometry, rows, cols):
-    """mvH, mvV ~ U{-32..31} half-pel, re-drawn until the 17x17 luma and 9x9 chroma windows lie
-    inside their planes."""
+def _draw_motion_vectors(rng, g: Geometry, rows, cols, mv_range: int = 32):
+    """mvH, mvV ~ U{-mv_range..mv_range-1} half-pel (default 32: +-16 pixels), re-drawn until the 17x17 luma and 9x9
+    chroma windows lie inside their planes."""
     n = len(rows)
     mvh = np.zeros(n, np.int64)
     mvv = np.zeros(n, np.int64)
     todo = np.ones(n, bool)
     while todo.any():
         k = int(todo.sum())
-        h = rng.integers(-32, 32, k)
-        v = rng.integers(-32, 32, k)
+        h = rng.integers(-mv_range, mv_range, k)
+        v = rng.integers(-mv_range, mv_range, k)
         r, c = rows[todo], cols[todo]
         x0 = c * 16 + (h >> 1)
         y0 = r * 16 + (v >> 1)
@@ -154,7 +154,7 @@ def _draw_blocks(rng, n_blocks: int, intra_block, dense: bool):
     return out
 
 
-def make_picture(rng, g: Geometry, pic_type: int, mode: str = "natural", adversarial: bool = True):
+def make_picture(rng, g: Geometry, pic_type: int, mode: str = "natural", adversarial: bool = True, mv_range: int = 32):
     """Records of one picture of one stream: (mbs, coeffs) with pic = 0, coeff_block from 0.
 
     mode 'natural': intra w.p. 0.1 in P/B, cbp ~ U{0..63}, n ~ 1+Geom(0.15);
@@ -173,7 +173,7 @@ def make_picture(rng, g: Geometry, pic_type: int, mode: str = "natural", adversa
         # {fwd, bwd, both} w.p. 1/3 each; 'both' resolves to the backward reference (video.go:626-630)
         kind = rng.integers(0, 3, n_mb)
         flags = np.where(~intra & (kind != 0), flags | MB_REF_BWD, flags).astype(np.uint8)
-    mvh, mvv = _draw_motion_vectors(rng, g, rows, cols)
+    mvh, mvv = _draw_motion_vectors(rng, g, rows, cols, mv_range)
     mvh = np.where(intra, 0, mvh)
     mvv = np.where(intra, 0, mvv)
     if mode == "dense":
