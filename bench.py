@@ -19,7 +19,8 @@ holds its own 256 streams (configs[4] layout: stream-parallel, no data-path coll
   roofline  decode call (plan pre-pass + fused MC+IDCT+add kernel): algorithmic bytes (1552 B per dense-P
             macroblock) / mean launch duration measured with CUDA events on the launching stream, against the measured
             HBM peak of MEASURED_PEAKS.json
-  steps     the other picture steps of the configuration (natural P, natural B, I-only, dense P with +-64 pixel vectors),
+  picture_steps
+            the other picture steps of the configuration (natural P, natural B, I-only, dense P with +-64 pixel vectors),
             each parity-checked against the oracle and timed like the headline step, fraction of the roofline on ITS bytes
   audio     BASELINE configs[3]: 1024 MP2 streams x 8 frames per launch, both window modes, parity-checked
   sustained the headline step looped for --sustain-seconds with clocks sampled (burst vs sustained)
@@ -308,7 +309,7 @@ def cpu_baseline(args, log):
     arm = CpuArm(n, args.mode)
     threads = arm.best_thread_count(n)
     t1 = arm.step(threads)  # warm-up / calibration
-    rounds = int(max(2, min(200, args.cpu_seconds / max(t1, 1e-3))))
+    rounds = int(max(2, min(2000, args.cpu_seconds / max(t1, 1e-3))))
     t = sum(arm.step(threads) for _ in range(rounds))
     fps = arm.n * rounds / t
     log(f"cpu baseline: {fps:.1f} frames/s on {threads} threads ({rounds} rounds, {t:.1f} s)")
@@ -567,7 +568,7 @@ def main():
         extras["transfers"] = transfer_probe(torch)
     if not args.no_extras and world == 1:
         extras["sustained"] = sustained_leg(args, torch, stream, step_dev, local_rank, S, alg_total, peak)
-        extras["steps"] = picture_steps(torch, ctx, stream, g, S, peak, log)
+        extras["picture_steps"] = picture_steps(torch, ctx, stream, g, S, peak, log)
         extras["audio"] = audio_leg(torch, local_rank, peak, log)
 
     # ---- frames gathered to rank 0 over NVLink (the only collective of the path)

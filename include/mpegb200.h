@@ -201,15 +201,17 @@ int mpegb200_video_decode_pictures_packed(mpegb200_ctx* ctx, int n_pictures, con
  *             1..12  eight w-bit two's-complement fields (w = code, value i in bits [i*w, i*w+w) of the group's w-byte
  *                    little-endian string) holding c = (x + sign(x)) / 2, i.e. x = 2c - sign(c)
  *             13     eight raw 12-bit two's-complement values (a group with an even non-zero value)
+ *             14     eight raw 16-bit values (a group with a value outside [-2048, 2047]: only an intra DC of a damaged
+ *                    stream gets there, video.go:666-672 does not bound the predictor)
  *   payload : the groups' bytes back to back, blocks back to back; 32 blocks form a chunk,
  *             chunk_offsets[k] = byte offset of block 32k in the payload.
  * The dense blocks of BASELINE config 3 take about 49 bytes instead of 128 (96 in the 12-bit form), sparse blocks of a
  * real stream 4 bytes plus a few.  mpegb200_pack_coeffs_vlen converts the int16 form (multi-threaded; returns
- * MPEGB200_ERECORD if a value lies outside [-2048, 2047], MPEGB200_EINVAL if payload_cap is too small;
+ * MPEGB200_EINVAL if payload_cap is too small;
  * mpegb200_vlen_payload_bound(n_blocks) always suffices; *payload_bytes includes 16 bytes of padding that must be
  * transferred with it).  The _vlen entry point copies headers, chunk offsets and payload to the device, expands them
  * there (expand_vlen_kernel) and continues like mpegb200_video_decode_pictures.
- * mpegb200_vlen_validate (pure host, one pass over the headers) checks what a foreign packer produced: codes 0..13, chunk offsets
+ * mpegb200_vlen_validate (pure host, one pass over the headers) checks what a foreign packer produced: codes 0..14, chunk offsets
  * back to back and in order, payload_bytes = sum of the group sizes + 16; the device expansion clamps its reads to the payload
  * either way, so a malformed stream yields wrong coefficients, never a fault. */
 size_t mpegb200_vlen_payload_bound(size_t n_blocks);

@@ -39,6 +39,17 @@ typedef struct mpegb200_launch {
     uint32_t first_block, n_blocks;
 } mpegb200_launch;
 
+/* Where a launch's coefficients sit when the parser emits the variable-width transfer form (mpegb200.h, "vlen")
+ * instead of int16 blocks: headers at vlen_headers + first_block (n_blocks of them, as for the int16 form), its chunk
+ * offsets at vlen_chunk_offsets + first_chunk ((n_blocks + 31) / 32 of them, relative to the launch's payload), its
+ * payload at vlen_payload + payload_offset, payload_bytes long (16 bytes of padding included). */
+typedef struct mpegb200_launch_vlen {
+    uint32_t first_chunk;
+    uint32_t reserved;
+    uint64_t payload_offset;
+    uint64_t payload_bytes;
+} mpegb200_launch_vlen;
+
 /* What one Video.Decode() call amounts to (video.go:209-268). */
 typedef struct mpegb200_video_step {
     int has_frame;              /* 0: end of stream (Decode() == nil) */
@@ -47,7 +58,12 @@ typedef struct mpegb200_video_step {
     int n_launches;             /* pictures decoded on the way (0 for the end-of-stream flush, video.go:223-229) */
     const mpegb200_launch* launches;
     const mpegb200_mb* mbs;
-    const int16_t* coeffs;      /* 64 per block */
+    const int16_t* coeffs;      /* 64 per block; NULL in vlen mode */
+    /* vlen mode (mpegb200_video_parser_set_vlen), else NULL: */
+    const mpegb200_launch_vlen* vlen_launches;   /* one per launch */
+    const uint32_t* vlen_headers;
+    const uint64_t* vlen_chunk_offsets;
+    const uint8_t* vlen_payload;
 } mpegb200_video_step;
 
 mpegb200_video_parser* mpegb200_video_parser_new(const uint8_t* data, size_t len);   /* NewVideo; copies data */
@@ -57,6 +73,11 @@ int    mpegb200_video_parser_width(mpegb200_video_parser* v);
 int    mpegb200_video_parser_height(mpegb200_video_parser* v);
 double mpegb200_video_parser_framerate(mpegb200_video_parser* v);
 void   mpegb200_video_parser_set_no_delay(mpegb200_video_parser* v, int no_delay);   /* video.go:178 */
+/* Emit the coefficients in the variable-width transfer form: decodeBlock (video.go:639-746) walks a block's
+ * coefficients in zig-zag order, which is the group order of that form, so the parser writes headers and payload as it
+ * goes and no int16[64] array (128 bytes per block) is ever materialised or converted.  Byte for byte what
+ * mpegb200_pack_coeffs_vlen makes of the int16 blocks (tests/test_host_parser.py).  Takes effect at the next picture. */
+void   mpegb200_video_parser_set_vlen(mpegb200_video_parser* v, int on);
 void   mpegb200_video_parser_rewind(mpegb200_video_parser* v);                       /* video.go:195 */
 int    mpegb200_video_parser_has_ended(mpegb200_video_parser* v);
 /* Parse up to and including the picture that makes a frame due.  Pointers in *out stay valid until
@@ -75,7 +96,12 @@ typedef struct mpegb200_wave {
     size_t n_mb;
     const mpegb200_mb* mbs;        /* pic = index into pics, coeff_block = index into coeffs */
     size_t n_blocks;
-    const int16_t* coeffs;
+    const int16_t* coeffs;         /* NULL in vlen mode */
+    /* vlen mode (mpegb200_video_batch_set_vlen): arguments of mpegb200_video_decode_pictures_vlen */
+    const uint32_t* vlen_headers;
+    const uint64_t* vlen_chunk_offsets;
+    const uint8_t* vlen_payload;
+    size_t vlen_payload_bytes;
 } mpegb200_wave;
 
 typedef struct mpegb200_batch_step {
@@ -93,6 +119,8 @@ mpegb200_video_batch* mpegb200_video_batch_new(int n_streams, int threads, void*
 void mpegb200_video_batch_free(mpegb200_video_batch* b);
 int  mpegb200_video_batch_set_stream(mpegb200_video_batch* b, int index, const uint8_t* data, size_t len);
 int  mpegb200_video_batch_stream_size(mpegb200_video_batch* b, int index, int* width, int* height);
+/* Every parser of the batch emits the variable-width form; the waves carry headers / chunk offsets / payload. */
+int  mpegb200_video_batch_set_vlen(mpegb200_video_batch* b, int on);
 /* One Video.Decode() step of every stream, parsed in parallel and merged into waves. */
 int  mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out);
 

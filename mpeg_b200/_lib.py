@@ -99,6 +99,7 @@ def load():
         "mpegb200_video_parser_height": (C.c_int, [vp]),
         "mpegb200_video_parser_framerate": (C.c_double, [vp]),
         "mpegb200_video_parser_set_no_delay": (None, [vp, C.c_int]),
+        "mpegb200_video_parser_set_vlen": (None, [vp, C.c_int]),
         "mpegb200_video_parser_rewind": (None, [vp]),
         "mpegb200_video_parser_has_ended": (C.c_int, [vp]),
         "mpegb200_video_parser_next": (C.c_int, [vp, vp]),
@@ -106,6 +107,7 @@ def load():
         "mpegb200_video_batch_free": (None, [vp]),
         "mpegb200_video_batch_set_stream": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_size_t]),
         "mpegb200_video_batch_stream_size": (C.c_int, [vp, C.c_int, ip, ip]),
+        "mpegb200_video_batch_set_vlen": (C.c_int, [vp, C.c_int]),
         "mpegb200_video_batch_next": (C.c_int, [vp, vp]),
         "mpegb200_audio_parser_new": (vp, [C.c_char_p, C.c_size_t]),
         "mpegb200_audio_parser_free": (None, [vp]),

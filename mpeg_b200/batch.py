@@ -15,7 +15,8 @@ from .context import Context
 
 class Wave(C.Structure):
     _fields_ = [("n_pictures", C.c_int), ("pics", C.c_void_p), ("n_mb", C.c_size_t), ("mbs", C.c_void_p),
-                ("n_blocks", C.c_size_t), ("coeffs", C.c_void_p)]
+                ("n_blocks", C.c_size_t), ("coeffs", C.c_void_p), ("vlen_headers", C.c_void_p), ("vlen_chunk_offsets", C.c_void_p),
+                ("vlen_payload", C.c_void_p), ("vlen_payload_bytes", C.c_size_t)]
 
 
 class BatchStep(C.Structure):
@@ -24,7 +25,8 @@ class BatchStep(C.Structure):
 
 
 class VideoBatch:
-    def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True):
+    def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True,
+                 vlen: bool = True):
         self.L = _lib.load()
         ctx.set_validate(validate)   # bitstream-derived records: a malformed wave raises instead of decoding (pass False for trusted input)
         self.ctx, self.n, self.first = ctx, len(streams), first_stream
@@ -33,6 +35,7 @@ class VideoBatch:
         self.h = self.L.mpegb200_video_batch_new(self.n, threads, alloc, free)
         if not self.h:
             raise MemoryError
+        self.L.mpegb200_video_batch_set_vlen(self.h, int(vlen))   # coefficients leave the parsers in the variable-width transfer form
         self._data = [bytes(s) for s in streams]
         w, h = C.c_int(), C.c_int()
         self.sizes = []
@@ -61,6 +64,11 @@ class VideoBatch:
             if self.first:  # stream index in the batch -> stream id in the context
                 pics = np.ctypeslib.as_array(C.cast(wave.pics, C.POINTER(C.c_int32)), shape=(wave.n_pictures, 4))
                 pics[:, 0] += self.first
+            if wave.vlen_headers:
+                self.ctx._ck(self.L.mpegb200_video_decode_pictures_vlen(
+                    self.ctx.h, wave.n_pictures, C.c_void_p(wave.pics), wave.n_mb, C.c_void_p(wave.mbs), wave.n_blocks,
+                    C.c_void_p(wave.vlen_headers), C.c_void_p(wave.vlen_chunk_offsets), C.c_void_p(wave.vlen_payload), wave.vlen_payload_bytes))
+                continue
             self.ctx._ck(self.L.mpegb200_video_decode_pictures(self.ctx.h, wave.n_pictures, C.c_void_p(wave.pics), wave.n_mb,
                                                                C.c_void_p(wave.mbs), wave.n_blocks, C.c_void_p(wave.coeffs)))
         self.steps += 1

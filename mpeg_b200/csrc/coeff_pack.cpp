@@ -19,6 +19,7 @@
 #endif
 
 #include "../../include/mpegb200.h"
+#include "vlen_encode.h"
 
 namespace {
 
@@ -57,9 +58,8 @@ inline uint32_t bit_length(uint32_t a) { return a ? 32u - (uint32_t)__builtin_cl
 // scalar form of the per-block arithmetic
 inline void encode_scalar(const int16_t* blk, Packed& p) {
     uint32_t h = 0, total = 0;
-    bool ok = true;
     for (int g = 0; g < 8; g++) {
-        uint32_t mag = 0, any = 0, even = 0;
+        uint32_t mag = 0, any = 0, even = 0, wide = 0;
         int16_t x[8], c[8];
         for (int i = 0; i < 8; i++) {
             x[i] = blk[kZigZag.nat[8 * g + i]];
@@ -68,17 +68,17 @@ inline void encode_scalar(const int16_t* blk, Packed& p) {
             mag |= (uint32_t)(uint16_t)(c[i] ^ (c[i] >> 15));
             any |= (uint32_t)(uint16_t)x[i];
             even |= (uint32_t)((x[i] & 1) == 0 && x[i] != 0);
-            ok &= x[i] >= -2048 && x[i] <= 2047;
+            wide |= (uint32_t)(x[i] < -2048 || x[i] > 2047);
         }
         const uint32_t w = any ? 1u + bit_length(mag) : 0u;
-        const uint32_t code = even ? 13u : w;
+        const uint32_t code = wide ? 14u : even ? 13u : w;
         h |= code << (4 * g);
-        total += even ? 12u : w;
-        memcpy(&p.v[8 * g], even ? x : c, 16);
+        total += wide ? 16u : even ? 12u : w;
+        memcpy(&p.v[8 * g], (even | wide) ? x : c, 16);
     }
     p.header = h;
     p.bytes = total;
-    p.ok = ok;
+    p.ok = true;   // every int16 value has a representation (code 14)
 }
 
 #if defined(__x86_64__)
@@ -89,7 +89,6 @@ __attribute__((target("avx2"))) inline void encode_avx2(const int16_t* blk, Pack
     const __m256i one = _mm256_set1_epi16(1), zero = _mm256_setzero_si256();
     const __m256i lo = _mm256_set1_epi16(-2048), hi = _mm256_set1_epi16(2047);
     uint32_t h = 0, total = 0;
-    int bad = 0;
     for (int q = 0; q < 4; q++) {
         const __m256i x = _mm256_load_si256(reinterpret_cast<const __m256i*>(z + 16 * q));
         const __m256i sgn = _mm256_sign_epi16(one, x);                       // -1, 0, +1
@@ -97,7 +96,7 @@ __attribute__((target("avx2"))) inline void encode_avx2(const int16_t* blk, Pack
         const __m256i mag = _mm256_xor_si256(c, _mm256_srai_epi16(c, 15));
         const __m256i nz = _mm256_xor_si256(_mm256_cmpeq_epi16(x, zero), _mm256_set1_epi16(-1));
         const __m256i ev = _mm256_and_si256(_mm256_cmpeq_epi16(_mm256_and_si256(x, one), zero), nz);
-        bad |= _mm256_movemask_epi8(_mm256_or_si256(_mm256_cmpgt_epi16(lo, x), _mm256_cmpgt_epi16(x, hi)));
+        const uint32_t widem = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(_mm256_cmpgt_epi16(lo, x), _mm256_cmpgt_epi16(x, hi)));
         // horizontal OR inside each 128-bit half (one group each)
         __m256i m = mag;
         m = _mm256_or_si256(m, _mm256_srli_si256(m, 8));
@@ -105,19 +104,21 @@ __attribute__((target("avx2"))) inline void encode_avx2(const int16_t* blk, Pack
         m = _mm256_or_si256(m, _mm256_srli_si256(m, 2));
         const uint32_t mag0 = (uint16_t)_mm256_extract_epi16(m, 0), mag1 = (uint16_t)_mm256_extract_epi16(m, 8);
         const uint32_t nzm = (uint32_t)_mm256_movemask_epi8(nz), evm = (uint32_t)_mm256_movemask_epi8(ev);
-        const __m256i take_raw = _mm256_set_m128i(_mm_set1_epi16((evm >> 16) ? -1 : 0), _mm_set1_epi16((evm & 0xffffu) ? -1 : 0));
+        const uint32_t rawm = evm | widem;
+        const __m256i take_raw = _mm256_set_m128i(_mm_set1_epi16((rawm >> 16) ? -1 : 0), _mm_set1_epi16((rawm & 0xffffu) ? -1 : 0));
         _mm256_store_si256(reinterpret_cast<__m256i*>(p.v + 16 * q), _mm256_blendv_epi8(c, x, take_raw));
         for (int half = 0; half < 2; half++) {
             const uint32_t any = (nzm >> (16 * half)) & 0xffffu, even = (evm >> (16 * half)) & 0xffffu;
+            const uint32_t wide = (widem >> (16 * half)) & 0xffffu;
             const uint32_t w = any ? 1u + bit_length(half ? mag1 : mag0) : 0u;
-            const uint32_t code = even ? 13u : w;
+            const uint32_t code = wide ? 14u : even ? 13u : w;
             h |= code << (4 * (2 * q + half));
-            total += even ? 12u : w;
+            total += wide ? 16u : even ? 12u : w;
         }
     }
     p.header = h;
     p.bytes = total;
-    p.ok = bad == 0;
+    p.ok = true;
 }
 #endif
 
@@ -138,7 +139,7 @@ inline uint8_t* emit(const Packed& p, uint8_t* out, size_t room) {
     for (int g = 0; g < 8; g++) {
         const uint32_t code = (p.header >> (4 * g)) & 15u;
         if (code == 0) continue;
-        const uint32_t w = code == 13u ? 12u : code;
+        const uint32_t w = code == 13u ? 12u : code == 14u ? 16u : code;
         const uint32_t mask = (1u << w) - 1u;
         unsigned __int128 acc = 0;
         for (int i = 7; i >= 0; i--) acc = (acc << w) | ((uint32_t)(uint16_t)p.v[8 * g + i] & mask);
@@ -159,7 +160,7 @@ __attribute__((target("bmi2"))) inline uint8_t* emit_bmi2(const Packed& p, uint8
     for (int g = 0; g < 8; g++) {
         const uint32_t code = (p.header >> (4 * g)) & 15u;
         if (code == 0) continue;
-        const uint32_t w = code == 13u ? 12u : code;
+        const uint32_t w = code == 13u ? 12u : code == 14u ? 16u : code;
         const uint64_t lanes = 0x0001000100010001ull * ((1u << w) - 1u);
         uint64_t a, b;
         memcpy(&a, &p.v[8 * g], 8);
@@ -217,9 +218,20 @@ struct Ranges {
 
 }  // namespace
 
+namespace mpegb200 {
+VlenBlock vlen_encode_block(const int16_t* blk, uint8_t* out) {
+    static const EncodeFn encode = pick_encoder();
+    static const EmitFn emit_block = pick_emitter();
+    Packed p;
+    encode(blk, p);
+    emit_block(p, out, (size_t)1 << 30);   // the caller guarantees 16 bytes of slack behind the block: every group takes the 16-byte store
+    return VlenBlock{p.header, p.bytes, p.ok};
+}
+}  // namespace mpegb200
+
 extern "C" {
 
-size_t mpegb200_vlen_payload_bound(size_t n_blocks) { return n_blocks * 96 + 16; }
+size_t mpegb200_vlen_payload_bound(size_t n_blocks) { return n_blocks * 128 + 16; }
 
 int mpegb200_vlen_validate(const uint32_t* headers, const uint64_t* chunk_offsets, size_t n_blocks, size_t payload_bytes) {
     if (n_blocks == 0) return 0;
@@ -232,8 +244,8 @@ int mpegb200_vlen_validate(const uint32_t* headers, const uint64_t* chunk_offset
         }
         for (int g = 0; g < 8; g++) {
             const uint32_t code = (headers[b] >> (4 * g)) & 15u;
-            if (code > 13u) return MPEGB200_ERECORD;
-            run += code == 13u ? 12u : code;
+            if (code > 14u) return MPEGB200_ERECORD;
+            run += code == 13u ? 12u : code == 14u ? 16u : code;
         }
     }
     return run + 16 == payload_bytes ? 0 : MPEGB200_ERECORD;
@@ -252,7 +264,7 @@ int mpegb200_pack_coeffs_vlen(const int16_t* coeffs, size_t n_blocks, uint32_t* 
     // pass 1: every block once -- header, size, and its bytes into the range's own scratch
     ranges.run([&](unsigned r, size_t lo, size_t hi) {
         std::vector<uint8_t>& mine = scratch[r];
-        mine.resize((hi - lo) * 96 + 16);
+        mine.resize((hi - lo) * 128 + 16);
         uint8_t* out = mine.data();
         Packed p;
         bool good = true;

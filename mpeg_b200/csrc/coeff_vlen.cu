@@ -9,7 +9,7 @@
 //     code c = (x + sign(x)) / 2      (0 -> 0, +-1 -> +-1, +-3 -> +-2, ...: a bijection from {0, odd} to the integers)
 //     w      = bits of the widest c of the group in two's complement (0 when all eight are zero)
 // eight values of w bits are exactly w bytes, so groups never straddle bytes.  A group holding an even non-zero value
-// (intra DC) travels raw, 12 bits per value.  A block is a 32-bit header (eight 4-bit group codes: 0..12 = w, 13 = raw)
+// (intra DC) travels raw, 12 bits per value.  A block is a 32-bit header (eight 4-bit group codes: 0..12 = w, 13 = raw 12-bit, 14 = raw 16-bit)
 // plus sum(w) payload bytes; 32 blocks form a chunk with one 64-bit payload offset, offsets inside a chunk come from a
 // warp scan over the headers.  The dense blocks of the benchmark shrink from 128 (96 in the 12-bit form) to about 49
 // bytes, typical sparse blocks of a real stream to 4 + a few bytes.
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const uint32_t code = (my_header >> (4 * j)) & 15u;
-        my_bytes += code == 13u ? 12u : code;
+        my_bytes += code == 13u ? 12u : code == 14u ? 16u : code;
     }
     uint32_t incl = my_bytes;
 #pragma unroll
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
         uint32_t off = __shfl_sync(0xffffffffu, my_off, src);
         if (b0 + 4 * round >= n_blocks) break;   // warp-uniform
         const uint32_t code = (h >> (4 * g)) & 15u;
-        const uint32_t w = code - (code == 13u ? 1u : 0u);
+        const uint32_t w = code == 14u ? 16u : code - (code == 13u ? 1u : 0u);
         {   // the group's offset inside its block: exclusive scan of the widths over the block's eight lanes
             uint32_t incl_w = w;
 #pragma unroll
@@ -118,6 +118,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) expand_vlen_kernel(const ui
         if (w == 0) {
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = 0;
+        } else if (code == 14u) {   // eight raw 16-bit values (a level outside 12 bits: an intra DC of a damaged stream)
+            const uint8_t* p = base + min(off, off_max);
+            const uint32_t* p4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+            uint32_t r[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) r[k] = __ldg(p4 + k);   // 16 bytes of padding follow the payload, the device buffer has slack behind
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t word = __funnelshift_r(r[k], r[k + 1], sh);
+                v[2 * k] = (int)(int16_t)(word & 0xffffu);
+                v[2 * k + 1] = (int)(int16_t)(word >> 16);
+            }
         } else {
             const uint8_t* p = base + min(off, off_max);
             const uint32_t* p4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);

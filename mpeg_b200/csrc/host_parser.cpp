@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/mpegb200_host.h"
+#include "vlen_encode.h"
 
 namespace {
 
@@ -272,9 +273,19 @@ struct mpegb200_video_parser {
     std::vector<mpegb200_launch> launches;
     std::vector<mpegb200_mb> mbs;
     std::vector<int16_t> coeffs;
+    // the same in the variable-width transfer form (vlen mode: `coeffs` stays empty)
+    bool vlen = false, vlen_next = false;        // vlen_next: what mpegb200_video_parser_set_vlen asked for (applies per picture)
+    std::vector<mpegb200_launch_vlen> vl_launches;
+    std::vector<uint32_t> vl_headers;
+    std::vector<uint64_t> vl_chunks;
+    std::vector<uint8_t> vl_payload;
     // picture under construction
     std::vector<mpegb200_mb> pic_mbs;
     std::vector<int16_t> pic_coeffs;
+    std::vector<uint32_t> pic_headers;           // vlen mode: one header per coded block of the picture ...
+    std::vector<uint64_t> pic_block_at;          // ... where its bytes start in pic_payload (n + 1 entries) ...
+    std::vector<uint8_t> pic_payload;            // ... and the bytes (16 bytes of slack behind the last block)
+    size_t pic_blocks = 0;                       // coded blocks of the picture so far (both modes)
     std::vector<int32_t> last_writer;  // per macroblock address: index into pic_mbs, -1 = none
     bool pic_has_rewrites = false;
     int rec = -1;
@@ -349,7 +360,7 @@ mpegb200_mb& new_record(VP* v) {
     memset(&m, 0, sizeof(m));
     m.mb_row = (uint16_t)v->mb_row;
     m.mb_col = (uint16_t)v->mb_col;
-    m.coeff_block = (uint32_t)(v->pic_coeffs.size() / 64);
+    m.coeff_block = (uint32_t)v->pic_blocks;
     v->rec = (int)v->pic_mbs.size();
     v->pic_mbs.push_back(m);
     const int addr = v->mb_row * v->mb_w + v->mb_col;
@@ -460,9 +471,15 @@ void decode_block(VP* v, int block) {  // video.go:639-799, up to the hand-over 
         v->level[dz] = lv;
     }
     // hand-over: what idct + copy/add*ToDest would consume (video.go:772-798)
-    const size_t at = v->pic_coeffs.size();
-    v->pic_coeffs.resize(at + 64, 0);
-    int16_t* out = &v->pic_coeffs[at];
+    alignas(32) int16_t scratch[64];
+    int16_t* out = scratch;
+    if (!v->vlen) {
+        const size_t at = v->pic_coeffs.size();
+        v->pic_coeffs.resize(at + 64, 0);
+        out = &v->pic_coeffs[at];
+    } else {
+        memset(scratch, 0, sizeof(scratch));
+    }
     auto put = [&](int i) {
         const int32_t l = v->level[i];
         out[i] = (int16_t)(l > 32767 ? 32767 : (l < -32768 ? -32768 : l));
@@ -479,6 +496,14 @@ void decode_block(VP* v, int block) {  // video.go:639-799, up to the hand-over 
         }
         v->reset_levels();
     }
+    if (v->vlen) {  // the block goes out as variable-width groups: header + a few bytes instead of 128
+        const size_t at = (size_t)v->pic_block_at.back();
+        if (v->pic_payload.size() < at + 128 + 16) v->pic_payload.resize(std::max(v->pic_payload.size() * 2, at + 4096));
+        const mpegb200::VlenBlock b = mpegb200::vlen_encode_block(scratch, v->pic_payload.data() + at);
+        v->pic_headers.push_back(b.header);
+        v->pic_block_at.push_back(at + b.bytes);
+    }
+    v->pic_blocks++;
     v->pic_mbs[(size_t)v->rec].cbp |= (uint8_t)(0x20 >> block);
 }
 
@@ -596,24 +621,45 @@ void emit_picture(VP* v, int type, int dst, int fwd, int bwd) {
         L.picture.fwd_buf = (uint8_t)fwd;
         L.picture.bwd_buf = (uint8_t)bwd;
         L.first_mb = (uint32_t)v->mbs.size();
-        L.first_block = (uint32_t)(v->coeffs.size() / 64);
+        L.first_block = v->vlen ? (uint32_t)v->vl_headers.size() : (uint32_t)(v->coeffs.size() / 64);
+        mpegb200_launch_vlen LV;
+        memset(&LV, 0, sizeof(LV));
+        LV.first_chunk = (uint32_t)v->vl_chunks.size();
+        LV.payload_offset = v->vl_payload.size();
         uint32_t blocks = 0;
         for (size_t i = begin; i < cut; i++) {
             if (dead[i]) continue;
             mpegb200_mb m = v->pic_mbs[i];
             const int nc = __builtin_popcount(m.cbp);
-            const int16_t* src = &v->pic_coeffs[(size_t)m.coeff_block * 64];
+            if (!v->vlen) {
+                const int16_t* src = &v->pic_coeffs[(size_t)m.coeff_block * 64];
+                v->coeffs.insert(v->coeffs.end(), src, src + (size_t)nc * 64);
+            } else {
+                for (int k = 0; k < nc; k++) {  // a chunk offset at every 32nd block of the launch
+                    const size_t pb = (size_t)m.coeff_block + (size_t)k;
+                    if (((blocks + (uint32_t)k) & 31u) == 0) v->vl_chunks.push_back(v->vl_payload.size() - LV.payload_offset);
+                    v->vl_headers.push_back(v->pic_headers[pb]);
+                    v->vl_payload.insert(v->vl_payload.end(), v->pic_payload.begin() + (ptrdiff_t)v->pic_block_at[pb],
+                                         v->pic_payload.begin() + (ptrdiff_t)v->pic_block_at[pb + 1]);
+                }
+            }
             m.coeff_block = blocks;
             m.pic = 0;
             v->mbs.push_back(m);
-            v->coeffs.insert(v->coeffs.end(), src, src + (size_t)nc * 64);
             blocks += (uint32_t)nc;
         }
         L.n_mb = (uint32_t)v->mbs.size() - L.first_mb;
         L.n_blocks = blocks;
         L.picture.first_mb = 0;
         L.picture.n_mb = L.n_mb;
-        if (L.n_mb || cut == n) v->launches.push_back(L);
+        if (L.n_mb || cut == n) {
+            v->launches.push_back(L);
+            if (v->vlen) {
+                v->vl_payload.insert(v->vl_payload.end(), 16, 0);   // the padding the device expansion may read
+                LV.payload_bytes = v->vl_payload.size() - LV.payload_offset;
+                v->vl_launches.push_back(LV);
+            }
+        }
         begin = cut;
     }
 }
@@ -641,6 +687,10 @@ void decode_picture(VP* v) {  // video.go:374-434
 
     v->pic_mbs.clear();
     v->pic_coeffs.clear();
+    v->vlen = v->vlen_next;
+    v->pic_headers.clear();
+    v->pic_block_at.assign(1, 0);
+    v->pic_blocks = 0;
     v->last_writer.assign((size_t)v->mb_size, -1);
     v->pic_has_rewrites = false;
     v->rec = -1;
@@ -693,6 +743,9 @@ void mpegb200_video_parser_set_no_delay(mpegb200_video_parser* v, int no_delay) 
     if (v) v->no_delay = no_delay != 0;
 }
 int mpegb200_video_parser_has_ended(mpegb200_video_parser* v) { return v ? v->br.ended : 1; }
+void mpegb200_video_parser_set_vlen(mpegb200_video_parser* v, int on) {
+    if (v) v->vlen_next = on != 0;
+}
 
 void mpegb200_video_parser_rewind(mpegb200_video_parser* v) {  // video.go:195-201
     if (!v) return;
@@ -709,6 +762,10 @@ static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step*
     v->launches.clear();
     v->mbs.clear();
     v->coeffs.clear();
+    v->vl_launches.clear();
+    v->vl_headers.clear();
+    v->vl_chunks.clear();
+    v->vl_payload.clear();
     if (!ensure_header(v)) return 0;
     int frame = -1;
     for (;;) {
@@ -743,7 +800,17 @@ static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step*
     out->n_launches = (int)v->launches.size();
     out->launches = v->launches.data();
     out->mbs = v->mbs.data();
-    out->coeffs = v->coeffs.data();
+    // a step is in one form throughout: the mode switches between steps only (set_vlen is applied at a picture start,
+    // and the caller flips it between two parser_next calls)
+    if (!v->vl_launches.empty() && v->vl_launches.size() == v->launches.size()) {
+        out->coeffs = nullptr;
+        out->vlen_launches = v->vl_launches.data();
+        out->vlen_headers = v->vl_headers.data();
+        out->vlen_chunk_offsets = v->vl_chunks.data();
+        out->vlen_payload = v->vl_payload.data();
+    } else {
+        out->coeffs = v->coeffs.data();
+    }
     return 0;
 }
 
@@ -1198,8 +1265,12 @@ struct mpegb200_video_batch {
         mpegb200_picture* pics = nullptr;
         mpegb200_mb* mbs = nullptr;
         int16_t* coeffs = nullptr;
-        size_t cap_pics = 0, cap_mbs = 0, cap_blocks = 0;
+        uint32_t* headers = nullptr;       // vlen mode
+        uint64_t* chunks = nullptr;
+        uint8_t* payload = nullptr;
+        size_t cap_pics = 0, cap_mbs = 0, cap_blocks = 0, cap_headers = 0, cap_chunks = 0, cap_payload = 0;
     };
+    bool vlen = false;
     std::vector<WaveBuf> bufs[2];   // double-buffered: the previous step's arrays stay intact while the next is parsed
     int flip = 0;
     std::vector<mpegb200_wave> waves;
@@ -1251,6 +1322,9 @@ void mpegb200_video_batch_free(mpegb200_video_batch* b) {
             b->put(w.pics);
             b->put(w.mbs);
             b->put(w.coeffs);
+            b->put(w.headers);
+            b->put(w.chunks);
+            b->put(w.payload);
         }
     delete b;
 }
@@ -1259,7 +1333,15 @@ int mpegb200_video_batch_set_stream(mpegb200_video_batch* b, int index, const ui
     if (!b || index < 0 || index >= b->n) return MPEGB200_EINVAL;
     delete b->parsers[(size_t)index];
     b->parsers[(size_t)index] = mpegb200_video_parser_new(data, len);
+    mpegb200_video_parser_set_vlen(b->parsers[(size_t)index], b->vlen);
     return b->parsers[(size_t)index] ? 0 : MPEGB200_ENOMEM;
+}
+
+int mpegb200_video_batch_set_vlen(mpegb200_video_batch* b, int on) {
+    if (!b) return MPEGB200_EINVAL;
+    b->vlen = on != 0;
+    for (auto* p : b->parsers) mpegb200_video_parser_set_vlen(p, on);
+    return 0;
 }
 
 int mpegb200_video_batch_stream_size(mpegb200_video_batch* b, int index, int* width, int* height) {
@@ -1288,9 +1370,12 @@ static int video_batch_next_impl(mpegb200_video_batch* b, mpegb200_batch_step* o
     if ((int)bufs.size() < n_waves) bufs.resize((size_t)n_waves);
     b->waves.assign((size_t)n_waves, mpegb200_wave{});
     std::vector<uint32_t> pic_of((size_t)n), mb_off((size_t)n), blk_off((size_t)n);
+    std::vector<uint64_t> byte_off((size_t)n);
     for (int w = 0; w < n_waves; w++) {
         // sizes and offsets of wave w (streams that have a w-th launch with work in it)
         uint32_t np = 0, nm = 0, nb = 0;
+        uint64_t nbytes = 0;
+        bool wave_vlen = false;
         for (int i = 0; i < n; i++) {
             const mpegb200_video_step& st = b->steps[(size_t)i];
             pic_of[(size_t)i] = 0xffffffffu;
@@ -1298,13 +1383,23 @@ static int video_batch_next_impl(mpegb200_video_batch* b, mpegb200_batch_step* o
             pic_of[(size_t)i] = np++;
             mb_off[(size_t)i] = nm;
             blk_off[(size_t)i] = nb;
+            byte_off[(size_t)i] = nbytes;
             nm += st.launches[w].n_mb;
             nb += st.launches[w].n_blocks;
+            if (st.vlen_launches) {
+                wave_vlen = true;
+                nbytes += st.vlen_launches[w].payload_bytes - 16;   // the per-launch padding is dropped, the wave gets its own
+            }
         }
         auto& buf = bufs[(size_t)w];
-        if (!b->reserve(buf.pics, buf.cap_pics, np) || !b->reserve(buf.mbs, buf.cap_mbs, nm) ||
-            !b->reserve(buf.coeffs, buf.cap_blocks, (size_t)nb * 64))
+        if (!b->reserve(buf.pics, buf.cap_pics, np) || !b->reserve(buf.mbs, buf.cap_mbs, nm)) return MPEGB200_ENOMEM;
+        if (wave_vlen) {
+            if (!b->reserve(buf.headers, buf.cap_headers, (size_t)nb) || !b->reserve(buf.chunks, buf.cap_chunks, ((size_t)nb + 31) / 32) ||
+                !b->reserve(buf.payload, buf.cap_payload, (size_t)nbytes + 16))
+                return MPEGB200_ENOMEM;
+        } else if (!b->reserve(buf.coeffs, buf.cap_blocks, (size_t)nb * 64)) {
             return MPEGB200_ENOMEM;
+        }
         b->pool->run(n, [&](int i) {
             const uint32_t p = pic_of[(size_t)i];
             if (p == 0xffffffffu) return;
@@ -1322,7 +1417,22 @@ static int video_batch_next_impl(mpegb200_video_batch* b, mpegb200_batch_step* o
                 dst[k].pic = (uint16_t)p;
                 dst[k].coeff_block += blk_off[(size_t)i];
             }
-            memcpy(buf.coeffs + (size_t)blk_off[(size_t)i] * 64, st.coeffs + (size_t)L.first_block * 64, (size_t)L.n_blocks * 128);
+            if (!wave_vlen) {
+                memcpy(buf.coeffs + (size_t)blk_off[(size_t)i] * 64, st.coeffs + (size_t)L.first_block * 64, (size_t)L.n_blocks * 128);
+                return;
+            }
+            // variable-width form: headers and payload move as they are; the wave's chunk offsets (one per 32 blocks of the
+            // merged numbering) come from a running sum over this stream's headers
+            const mpegb200_launch_vlen& LV = st.vlen_launches[w];
+            const uint32_t* hs = st.vlen_headers + L.first_block;
+            memcpy(buf.headers + blk_off[(size_t)i], hs, (size_t)L.n_blocks * 4);
+            memcpy(buf.payload + byte_off[(size_t)i], st.vlen_payload + LV.payload_offset, (size_t)(LV.payload_bytes - 16));
+            uint64_t at = byte_off[(size_t)i];
+            for (uint32_t k = 0; k < L.n_blocks; k++) {
+                const uint32_t gbl = blk_off[(size_t)i] + k;
+                if ((gbl & 31u) == 0) buf.chunks[gbl >> 5] = at;
+                at += mpegb200::vlen_block_bytes(hs[k]);
+            }
         });
         mpegb200_wave& W = b->waves[(size_t)w];
         W.n_pictures = (int)np;
@@ -1330,7 +1440,16 @@ static int video_batch_next_impl(mpegb200_video_batch* b, mpegb200_batch_step* o
         W.n_mb = nm;
         W.mbs = buf.mbs;
         W.n_blocks = nb;
-        W.coeffs = buf.coeffs;
+        if (wave_vlen) {
+            memset(buf.payload + nbytes, 0, 16);
+            W.coeffs = nullptr;
+            W.vlen_headers = buf.headers;
+            W.vlen_chunk_offsets = buf.chunks;
+            W.vlen_payload = buf.payload;
+            W.vlen_payload_bytes = (size_t)nbytes + 16;
+        } else {
+            W.coeffs = buf.coeffs;
+        }
     }
     out->n_streams = n;
     out->has_frame = b->has_frame.data();

@@ -23,12 +23,18 @@ class Launch(C.Structure):
                 ("first_mb", C.c_uint32), ("n_mb", C.c_uint32), ("first_block", C.c_uint32), ("n_blocks", C.c_uint32)]
 
 
+class LaunchVlen(C.Structure):
+    _fields_ = [("first_chunk", C.c_uint32), ("reserved", C.c_uint32), ("payload_offset", C.c_uint64), ("payload_bytes", C.c_uint64)]
+
+
 class VideoStep(C.Structure):
     _fields_ = [("has_frame", C.c_int), ("frame_buf", C.c_int), ("time", C.c_double), ("n_launches", C.c_int),
-                ("launches", C.POINTER(Launch)), ("mbs", C.c_void_p), ("coeffs", C.c_void_p)]
+                ("launches", C.POINTER(Launch)), ("mbs", C.c_void_p), ("coeffs", C.c_void_p),
+                ("vlen_launches", C.POINTER(LaunchVlen)), ("vlen_headers", C.c_void_p), ("vlen_chunk_offsets", C.c_void_p),
+                ("vlen_payload", C.c_void_p)]
 
 
-assert C.sizeof(Launch) == 32
+assert C.sizeof(Launch) == 32 and C.sizeof(LaunchVlen) == 24
 
 
 class ErrInvalidMPEG(ValueError):
@@ -69,13 +75,16 @@ class Frame:
 class Video:
     """mpeg.Video (video.go:57): MPEG-1 video elementary stream -> frames."""
 
-    def __init__(self, data: bytes, ctx: Context, stream: int = 0):
+    def __init__(self, data: bytes, ctx: Context, stream: int = 0, vlen: bool = True):
+        """vlen: the parser emits the coefficients in the variable-width transfer form (a header and a few bytes per block
+        instead of int16[64]) and the launches go through mpegb200_video_decode_pictures_vlen; False: int16 blocks."""
         self.L = _lib.load()
         self.ctx, self.stream = ctx, stream
         self._data = bytes(data)
         self.h = self.L.mpegb200_video_parser_new(self._data, len(self._data))
         if not self.h:
             raise MemoryError
+        self.L.mpegb200_video_parser_set_vlen(self.h, int(vlen))
         self._opened = False
 
     def has_header(self) -> bool:
@@ -120,6 +129,13 @@ class Video:
                 continue
             ln.stream = self.stream
             mb_ptr = step.mbs + 16 * ln.first_mb
+            if step.vlen_launches:
+                lv = step.vlen_launches[i]
+                self.ctx._ck(self.L.mpegb200_video_decode_pictures_vlen(
+                    self.ctx.h, 1, C.byref(ln), ln.n_mb, C.c_void_p(mb_ptr), ln.n_blocks,
+                    C.c_void_p((step.vlen_headers or 0) + 4 * ln.first_block), C.c_void_p((step.vlen_chunk_offsets or 0) + 8 * lv.first_chunk),
+                    C.c_void_p((step.vlen_payload or 0) + lv.payload_offset), lv.payload_bytes))
+                continue
             co_ptr = step.coeffs + 128 * ln.first_block
             self.ctx._ck(self.L.mpegb200_video_decode_pictures(self.ctx.h, 1, C.byref(ln), ln.n_mb, C.c_void_p(mb_ptr),
                                                                ln.n_blocks, C.c_void_p(co_ptr)))

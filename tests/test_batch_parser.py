@@ -92,3 +92,46 @@ def test_batch_waves_equal_per_stream_launches(golden_dir):
         assert st.n_waves == 0 and not any(st.has_frame[i] for i in range(len(datas)))
     finally:
         L.mpegb200_video_batch_free(b)
+
+
+def test_batch_waves_in_vlen_form_match_the_converter(golden_dir):
+    """Lock-step batch with the parsers emitting the variable-width form: every wave's headers / chunk offsets / payload equal
+    mpegb200_pack_coeffs_vlen of the int16 wave the same batch produces without the switch (streams of different lengths and
+    phases, so waves merge launches whose blocks do not start on chunk boundaries)."""
+    import ctypes as C
+    from mpeg_b200 import _lib
+    from mpeg_b200.batch import BatchStep
+    from test_vlen_format import pack
+    L = _lib.load()
+    es = (golden_dir / "test.mpeg1video").read_bytes()
+    streams = [es, es[:50000], es[:20000], es]
+    hs = []
+    for vlen in (0, 1):
+        h = L.mpegb200_video_batch_new(len(streams), 3, None, None)
+        assert L.mpegb200_video_batch_set_vlen(h, vlen) == 0
+        for i, d in enumerate(streams):
+            assert L.mpegb200_video_batch_set_stream(h, i, d, len(d)) == 0
+        hs.append(h)
+    waves = blocks = 0
+    for step in range(60):
+        a, b = BatchStep(), BatchStep()
+        assert L.mpegb200_video_batch_next(hs[0], C.byref(a)) == 0 and L.mpegb200_video_batch_next(hs[1], C.byref(b)) == 0
+        assert a.n_waves == b.n_waves
+        for w in range(a.n_waves):
+            wa, wb = a.waves[w], b.waves[w]
+            assert (wa.n_pictures, wa.n_mb, wa.n_blocks) == (wb.n_pictures, wb.n_mb, wb.n_blocks)
+            assert C.string_at(wa.mbs, 16 * wa.n_mb) == C.string_at(wb.mbs, 16 * wb.n_mb)
+            if wa.n_blocks == 0:
+                continue
+            assert wa.coeffs and not wb.coeffs and wb.vlen_headers
+            co = np.frombuffer(C.string_at(wa.coeffs, 128 * wa.n_blocks), dtype=np.int16).reshape(-1, 64)
+            rc, hd, ch, pl = pack(co)
+            assert rc == 0 and wb.vlen_payload_bytes == len(pl)
+            assert C.string_at(wb.vlen_headers, 4 * wb.n_blocks) == hd.tobytes()
+            assert C.string_at(wb.vlen_chunk_offsets, 8 * len(ch)) == ch.tobytes()
+            assert C.string_at(wb.vlen_payload, len(pl)) == pl.tobytes()
+            waves += 1
+            blocks += wa.n_blocks
+    assert waves > 50 and blocks > 10000
+    for h in hs:
+        L.mpegb200_video_batch_free(h)

@@ -34,17 +34,17 @@ def unpack_reference(headers, chunks, payload):
         h = int(headers[b])
         for g in range(8):
             code = (h >> (4 * g)) & 15
-            assert code <= 13
+            assert code <= 14
             if code == 0:
                 continue
-            w = 12 if code == 13 else code
+            w = 12 if code == 13 else 16 if code == 14 else code
             bits = int.from_bytes(payload[off:off + w].tobytes(), "little")
             off += w
             for i in range(8):
                 c = (bits >> (i * w)) & ((1 << w) - 1)
                 if c >= 1 << (w - 1):
                     c -= 1 << w
-                x = c if code == 13 else 2 * c - (c > 0) + (c < 0)
+                x = c if code >= 13 else 2 * c - (c > 0) + (c < 0)
                 out[b, wl.ZIGZAG[8 * g + i]] = x
     return out
 
@@ -98,10 +98,14 @@ def test_sizes():
 
 def test_out_of_range_and_capacity():
     L = _lib.load()
-    bad = np.zeros((1, 64), np.int16)
-    bad[0, 10] = 2048
-    rc, *_ = pack(bad)
-    assert rc != 0
+    wide = np.zeros((3, 64), np.int16)                         # values outside 12 bits travel as raw 16-bit groups (code 14)
+    wide[0, 10] = 2048
+    wide[1, 0] = 32760                                         # an intra DC of a damaged stream (dc * 8, |dc| <= 4095)
+    wide[1, 63] = -32768
+    wide[2, :] = np.arange(-32, 32) * 1000
+    rc, h, c, p = pack(wide)
+    assert rc == 0 and ((h[0] >> (4 * (int(np.flatnonzero(wl.ZIGZAG == 10)[0]) // 8))) & 15) == 14
+    assert np.array_equal(unpack_reference(h, c, p), wide)
     coeffs = dense_blocks(64, 1)
     headers = np.zeros(64, np.uint32)
     chunks = np.zeros(2, np.uint64)
@@ -113,11 +117,11 @@ def test_out_of_range_and_capacity():
 
 
 def test_round_trip_property():
-    """Any int16 block content in [-2048, 2047] survives, whatever mixture of zeros, odd and even values the groups hold."""
+    """Any int16 block content survives, whatever mixture of zeros, odd and even values the groups hold."""
     from hypothesis import given, settings, strategies as st
     import hypothesis.extra.numpy as hnp
 
-    value = st.one_of(st.just(0), st.integers(-2048, 2047), st.sampled_from([-2047, -1, 1, 2047, -2048, 2046]),
+    value = st.one_of(st.just(0), st.integers(-2048, 2047), st.integers(-32768, 32767), st.sampled_from([-2047, -1, 1, 2047, -2048, 2046]),
                       st.integers(-40, 40).map(lambda t: 2 * t + 1))
 
     @settings(max_examples=25, deadline=None)
@@ -127,14 +131,15 @@ def test_round_trip_property():
         assert rc == 0
         assert np.array_equal(unpack_reference(h, c, p), coeffs)
         # the size the header promises: 4-bit codes -> bytes
-        want = sum(12 if (int(x) >> (4 * g)) & 15 == 13 else (int(x) >> (4 * g)) & 15 for x in h for g in range(8))
+        size = lambda code: 12 if code == 13 else 16 if code == 14 else code
+        want = sum(size((int(x) >> (4 * g)) & 15) for x in h for g in range(8))
         assert len(p) == want + 16
 
     check()
 
 
 def test_validate_foreign_streams():
-    """mpegb200_vlen_validate: accepts what the packer produces, rejects codes above 13, chunk offsets that are not back to
+    """mpegb200_vlen_validate: accepts what the packer produces, rejects codes above 14, chunk offsets that are not back to
     back, and a payload size that does not match the headers."""
     L = _lib.load()
     vp = lambda a: C.c_void_p(a.ctypes.data)
@@ -169,7 +174,7 @@ def test_portable_packer_agrees_with_the_simd_one():
         "rng = np.random.default_rng(11)\n"
         "a = t.dense_blocks(700, 2)\n"
         "b = wl._draw_blocks(rng, 700, rng.random(700) < 0.3, dense=False)\n"
-        "b[5, :] = -2048; b[6, :] = 2047; b[7, :] = 0\n"
+        "b[5, :] = -2048; b[6, :] = 2047; b[7, :] = 0; b[8, :] = 30000; b[9, 3] = -32768; b[10, 60] = 2048\n"
         "h = hashlib.sha256()\n"
         "for c in (a, b):\n"
         "    rc, hd, ch, p = t.pack(c)\n"
