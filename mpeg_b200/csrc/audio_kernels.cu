@@ -10,10 +10,12 @@
 //     (mpeg_test.go:195).
 // The matrixing and the output scaling are the same in both (explicit .rn operations, never contracted).
 //
-// Layout.  The two channels of a stream sit side by side: a V slice is 64 float2 (channel 0, channel 1), so a window tap
-// is one LDS.64 and -- with the packed FP32 pipe of sm_100 -- one FFMA2 (fused mode: the window coefficient is a scalar
-// broadcast operand) or two FMUL + one FADD2 (default mode; ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
-// whatever --fmad says, so the products stay scalar mul.rn.f32, whose no-contraction guarantee PTX documents).
+// Where the time goes (profiles/r2_audio_summary.md): the first versions of this kernel read every window tap from shared
+// memory -- 16 loads per output sample -- and ran into the LSU pipe (74 % of its wavefront peak) long before the FP32
+// pipes.  Now a warp owns one channel and a run of consecutive time slots and keeps the 16-slice V ring in registers:
+// consecutive slots share 15 of their 16 slices, so a slot costs two shared-memory loads (its own slice) and 16 register
+// taps.  (Packed FP32 was tried for the two channels: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever
+// --fmad says, so the default mode cannot use it; scalar mul.rn.f32 / add.rn.f32 carry PTX's no-contraction guarantee.)
 #include "common.cuh"
 
 namespace mpegb200 {
@@ -56,85 +58,122 @@ __device__ __forceinline__ void lee_dct(float (&x)[N]) {
     }
 }
 
-constexpr int kSlicePitch = 65;  // float2 per V slice in shared memory (64 + 1): 130 words = 2 mod 32, so the 32 (slot, channel)
-                                 // threads of a warp write one element of their slices to 32 different banks
+constexpr int kSlicePitch = 65;  // floats per V slice in shared memory (64 + 1: conflict-free column writes)
 constexpr int kHist = 15;        // slices of history a window reaches back over (taps of age 1..15)
-constexpr int kLin = kHist + 36; // a frame's slices lie linearly behind their history: tap address = slice - age * pitch
-constexpr int kAudioThreads = 128;
+constexpr int kLin = kHist + 36; // a frame's slices lie linearly behind their history: slice of age a = slot's slice - a
+constexpr int kAudioThreads = 96;  // three warps: 72 of 96 threads hold a DCT in phase (a); 80 registers each with eight CTAs per SM
+constexpr int kRunLen = 24;        // window phase: the 72 (channel, time slot) windows of a frame in three runs of 24
 
 struct AudioSmem {
-    float2 v[kLin * kSlicePitch];         // 26,520 B: 8 CTAs per SM, so 1024 streams are resident in one wave
+    float v[2][kLin * kSlicePitch];       // 26,520 B: eight CTAs per SM, so 1024 streams are resident in one wave
 };
-
-__device__ __forceinline__ float2 fma2_bcast(float d, float2 v, float2 acc) {   // (d * v.x + acc.x, d * v.y + acc.y), fused
-    uint64_t r;
-    asm("{\n\t.reg .b64 dd;\n\tmov.b64 dd, {%1, %1};\n\tfma.rn.f32x2 %0, dd, %2, %3;\n\t}"
-        : "=l"(r)
-        : "r"(__float_as_uint(d)), "l"(*reinterpret_cast<const uint64_t*>(&v)), "l"(*reinterpret_cast<const uint64_t*>(&acc)));
-    return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
-    return *reinterpret_cast<float2*>(&r);
-}
-
-// synthWindow (audio_noasm.go:8-38) for one time slot whose vPos/64 is the compile-time P.  `s` points at
-// lane's element of the slot's own slice (both channels); D[t] = window[32 t + lane].
-// With P fixed every tap's age (= which slice), half (= which 32 elements of it) and window index are constants:
-// a tap is one LDS.64 with an immediate offset plus its arithmetic, accumulated in the reference's order
-// (first loop: V positions 128 m + base, second loop: 64 + 128 m + (32 - base)).
-template <int P, bool FMA>
-__device__ __forceinline__ float2 window_taps(const float2* __restrict__ s, const float (&D)[32]) {
-    float2 u = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int pass = 0; pass < 2; pass++) {
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int q = 2 * m + pass;                                  // V position / 64
-            const int age = (q - P) & 15;
-            const int half = pass == 0 ? (P & 1) : 1 - (P & 1);
-            const int t = ((pass == 0 ? 512 : 544) - 32 * P + 64 * m) / 32;  // window index / 32 (audio_noasm.go:9,24)
-            const float2 vv = s[half * 32 - age * kSlicePitch];
-            if constexpr (FMA) {
-                u = fma2_bcast(D[t], vv, u);                             // audio_amd64.s:123-131
-            } else {
-                const float2 p = make_float2(__fmul_rn(D[t], vv.x), __fmul_rn(D[t], vv.y));
-                u = add2_rn(u, p);
-            }
-        }
-    }
-    return u;
-}
 
 // u / -1090519040.0 (audio.go:390), correctly rounded.  Fast path: q = u * y, r = fma(-q, c, u) (exact), q' = fma(r, y, q)
 // with y = RN(1 / c) equals the IEEE quotient for every float32 u with 2^-102 <= |u| < inf and for +-0 (checked over all
-// 2^32 bit patterns on the host, tools/check_fast_div.c); anything else takes the generic division.
+// 2^32 bit patterns on the host, tools/check_fast_div.c); anything else takes the generic division.  The test is made
+// once per warp (vote): the slow path is taken by all lanes or none.
 __device__ __forceinline__ float scale_out(float u) {
     constexpr float c = -1090519040.0f;
     constexpr float y = -0x1.f81f82p-31f;   // RN(1 / c)
     const uint32_t mag = __float_as_uint(u) & 0x7fffffffu;
-    if (((mag - 1u) < 0x0d7fffffu) | (mag >= 0x7f800000u)) return __fdiv_rn(u, c);   // 0 < |u| < 2^-100, inf, nan
+    const bool odd = ((mag - 1u) < 0x0d7fffffu) | (mag >= 0x7f800000u);   // 0 < |u| < 2^-100, inf, nan
+    if (__any_sync(0xffffffffu, odd)) return __fdiv_rn(u, c);
     const float q = __fmul_rn(u, y);
     const float r = __fmaf_rn(-q, c, u);
     return __fmaf_rn(r, y, q);
 }
 
+template <int FORMAT>
+__device__ __forceinline__ void emit_sample(void* __restrict__ out, size_t fidx, int pos, int ch, float s) {
+    constexpr size_t kVals = 2 * MPEGB200_SAMPLES_PER_FRAME;
+    if constexpr (FORMAT == MPEGB200_AUDIO_F32N) {
+        reinterpret_cast<float*>(out)[fidx * kVals + 2 * pos + ch] = s;
+    } else if constexpr (FORMAT == MPEGB200_AUDIO_F32NLR) {
+        reinterpret_cast<float*>(out)[fidx * kVals + ch * MPEGB200_SAMPLES_PER_FRAME + pos] = s;
+    } else if constexpr (FORMAT == MPEGB200_AUDIO_S16) {  // audio.go:400-408
+        const int a = __float2int_rz(s < 0 ? __fmul_rn(s, 32768.0f) : __fmul_rn(s, 32767.0f));
+        reinterpret_cast<int16_t*>(out)[fidx * kVals + 2 * pos + ch] = (int16_t)a;
+    } else {  // MPEGB200_AUDIO_F32, audio.go:409-417 (both constants are 2^31 as float32)
+        reinterpret_cast<float*>(out)[fidx * kVals + 2 * pos + ch] = __fmul_rn(s, 2147483648.0f);
+    }
+}
+
+// synthWindow (audio_noasm.go:8-38) for one time slot whose vPos/64 is the compile-time P, one channel, lane = output
+// sample.  The V ring lives in REGISTERS: R[q][h] = this lane's element of half h (32 floats) of the slice at ring
+// position q (v[64 q ...]).  The slot's own slice (ring position P) comes in from shared memory -- two loads -- and
+// every tap then is register arithmetic with compile-time indices: window index t and half follow from P like in the
+// reference's two loops (first: V positions 128 m + 32 (P & 1), second: 64 + 128 m + 32 (1 - (P & 1))).
+template <int P, bool FMA>
+__device__ __forceinline__ float window_slot(const float* __restrict__ own, float (&R)[16][2], const float (&D)[32]) {
+    R[P][0] = own[0];
+    R[P][1] = own[32];
+    float u = 0.0f;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            constexpr int kOdd = P & 1;
+            const int q = 2 * m + pass;                                      // ring position = V position / 64
+            const int half = pass == 0 ? kOdd : 1 - kOdd;
+            const int t = ((pass == 0 ? 512 : 544) - 32 * P + 64 * m) / 32;  // window index / 32 (audio_noasm.go:9,24)
+            if constexpr (FMA)
+                u = __fmaf_rn(D[t], R[q][half], u);                          // audio_amd64.s:123-131
+            else
+                u = __fadd_rn(u, __fmul_rn(D[t], R[q][half]));
+        }
+    }
+    return u;
+}
+
+// A run of `count` consecutive time slots of one channel, starting at slot `first` whose vPos/64 is p0: the 15 slices of
+// history before the first slot come into registers once, then the slots go through an unrolled ring of the 16 values of
+// vPos/64, entered at p0 (Duff's device; vPos decreases by 64 per slot, audio.go:380).
+template <bool FMA, int FORMAT>
+__device__ __forceinline__ void window_run(const float* __restrict__ vch, const float (&D)[32], int ch, int first, int count, int p0,
+                                           size_t fidx, void* __restrict__ out, int lane) {
+    const float* own = vch + (kHist + first) * kSlicePitch + lane;
+    float R[16][2];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {   // ring position q was written (q - p0) & 15 slots before the first slot (its own: in window_slot)
+        const int age = (q - p0) & 15;
+        const float* hs = own - age * kSlicePitch;
+        R[q][0] = age ? hs[0] : 0.0f;
+        R[q][1] = age ? hs[32] : 0.0f;
+    }
+    int left = count, pos = first * 32 + lane;
+#define MPEGB200_SLOT(PV)                                                           \
+    case PV: {                                                                      \
+        const float u = window_slot<PV, FMA>(own, R, D);                            \
+        emit_sample<FORMAT>(out, fidx, pos, ch, scale_out(u));                      \
+        own += kSlicePitch;                                                         \
+        pos += 32;                                                                  \
+        if (--left == 0) break;                                                     \
+    }
+    switch (p0) {
+        do {
+            MPEGB200_SLOT(15) MPEGB200_SLOT(14) MPEGB200_SLOT(13) MPEGB200_SLOT(12) MPEGB200_SLOT(11) MPEGB200_SLOT(10)
+            MPEGB200_SLOT(9) MPEGB200_SLOT(8) MPEGB200_SLOT(7) MPEGB200_SLOT(6) MPEGB200_SLOT(5) MPEGB200_SLOT(4)
+            MPEGB200_SLOT(3) MPEGB200_SLOT(2) MPEGB200_SLOT(1) MPEGB200_SLOT(0)
+        } while (true);
+    }
+#undef MPEGB200_SLOT
+}
+
 // One CTA per stream; frames are processed in order, each in three barriers:
-//   (a) 72 threads: one 32-point DCT each (time slot, channel) on samples read straight from global memory
-//       -> V slice (audio.go:708-771 placement)
-//   (b) 4 warps: the 36 time slots' windows, lane = output sample, both channels at once -> coalesced store
+//   (a) 72 threads: one 32-point DCT each (channel, time slot) on samples read straight from global memory
+//       -> V slice in shared memory (audio.go:708-771 placement)
+//   (b) 3 warps: the frame's 72 (channel, time slot) windows in runs of consecutive slots of one channel (window_run):
+//       two shared-memory loads per slot instead of 16
 //   (c) the last 15 slices move to the front as the next frame's history
-template <bool FMA>
-__global__ void __launch_bounds__(kAudioThreads, 7) audio_synth_kernel(AudioState* __restrict__ states, int max_streams,
+template <bool FMA, int FORMAT>
+__global__ void __launch_bounds__(kAudioThreads, 8) audio_synth_kernel(AudioState* __restrict__ states, int max_streams,
                                                                        const int32_t* __restrict__ stream_ids,
                                                                        int frames_per_stream,
-                                                                       const int32_t* __restrict__ samples, int format,
+                                                                       const int32_t* __restrict__ samples,
                                                                        void* __restrict__ out,
                                                                        const float* __restrict__ window) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     AudioSmem& sm = *reinterpret_cast<AudioSmem*>(smem_raw);
-    float* vf = reinterpret_cast<float*>(sm.v);      // word view: element e of channel ch of slice i at (i * pitch + e) * 2 + ch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sidx = blockIdx.x;
     const int stream = stream_ids[sidx];
@@ -149,22 +188,17 @@ __global__ void __launch_bounds__(kAudioThreads, 7) audio_synth_kernel(AudioStat
     for (int i = tid; i < 2 * 16 * 64; i += kAudioThreads) {
         const int ch = i >> 10, q = (i >> 6) & 15, e = i & 63;
         const int age = (q - p_init) & 15;
-        if (age < kHist) vf[((kHist - 1 - age) * kSlicePitch + e) * 2 + ch] = st.v[ch][q * 64 + e];
+        if (age < kHist) sm.v[ch][(kHist - 1 - age) * kSlicePitch + e] = st.v[ch][q * 64 + e];
     }
     // (the slice of age 15 is overwritten by the first new slot in the reference's ring and never read)
 
-    float D[32];  // the whole window table across the warp: D[t] = window[32 t + lane]
-#pragma unroll
-    for (int t = 0; t < 32; t++) D[t] = __ldg(&window[32 * t + lane]);
-
-    const size_t frame_vals = 2 * MPEGB200_SAMPLES_PER_FRAME;
     for (int f = 0; f < frames_per_stream; f++) {
         const size_t fidx = (size_t)sidx * frames_per_stream + f;
         // (a) matrixing
         if (tid < 72) {
-            const int step = tid >> 1, ch = tid & 1;
+            const int ch = tid / 36, step = tid - ch * 36;
             // the time slot's 32 subband samples: 128 contiguous bytes, read straight from global memory
-            const int4* sp = reinterpret_cast<const int4*>(samples + fidx * (2 * 36 * 32) + (ch * 36 + step) * 32);
+            const int4* sp = reinterpret_cast<const int4*>(samples + fidx * (2 * 36 * 32) + tid * 32);
             int s[32];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -185,88 +219,60 @@ __global__ void __launch_bounds__(kAudioThreads, 7) audio_synth_kernel(AudioStat
 #pragma unroll
             for (int k = 0; k < 15; k++) o[k] = __fadd_rn(o[k], o[k + 1]);  // audio.go:692-706
             // X[2k] = e[k], X[2k+1] = o[k]; placement audio.go:708-771
-            float* d = vf + (kHist + step) * kSlicePitch * 2 + ch;       // element i at d[2 i]
+            float* d = &sm.v[ch][(kHist + step) * kSlicePitch];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const float xe = e[k], xo = o[k];  // X[2k], X[2k+1]
                 // X[m], m < 16:  d[48+m] = d[48-m] = -X[m];   m >= 16: d[m-16] = X[m], d[48-m] = -X[m]
                 if (2 * k < 16) {
-                    d[2 * (48 + 2 * k)] = -xe;
-                    d[2 * (48 - 2 * k)] = -xe;
-                    d[2 * (48 + 2 * k + 1)] = -xo;
-                    d[2 * (48 - 2 * k - 1)] = -xo;
+                    d[48 + 2 * k] = -xe;
+                    d[48 - 2 * k] = -xe;
+                    d[48 + 2 * k + 1] = -xo;
+                    d[48 - 2 * k - 1] = -xo;
                 } else {
-                    d[2 * (2 * k - 16)] = xe;
-                    d[2 * (48 - 2 * k)] = -xe;
-                    d[2 * (2 * k + 1 - 16)] = xo;
-                    d[2 * (48 - 2 * k - 1)] = -xo;
+                    d[2 * k - 16] = xe;
+                    d[48 - 2 * k] = -xe;
+                    d[2 * k + 1 - 16] = xo;
+                    d[48 - 2 * k - 1] = -xo;
                 }
             }
-            d[2 * 16] = 0.0f;
+            d[16] = 0.0f;
         }
         __syncthreads();
 
-        // (b) windows: warp w takes time slots w, w+4, ...
+        // (b) windows: warp w takes the windows 24 w .. 24 w + 23 of the frame's 72 (channel-major), i.e. one or two runs of
+        // consecutive time slots of one channel
         {
-            const int p_frame = p_init - f * 36;
-            for (int step = warp; step < 36; step += 4) {
-                const int p = (p_frame - step - 1) & 15;            // vPos / 64 for this slot (audio.go:380)
-                const float2* s = &sm.v[(kHist + step) * kSlicePitch + lane];
-                float2 u;
-                switch (p) {
-                    case 0: u = window_taps<0, FMA>(s, D); break;
-                    case 1: u = window_taps<1, FMA>(s, D); break;
-                    case 2: u = window_taps<2, FMA>(s, D); break;
-                    case 3: u = window_taps<3, FMA>(s, D); break;
-                    case 4: u = window_taps<4, FMA>(s, D); break;
-                    case 5: u = window_taps<5, FMA>(s, D); break;
-                    case 6: u = window_taps<6, FMA>(s, D); break;
-                    case 7: u = window_taps<7, FMA>(s, D); break;
-                    case 8: u = window_taps<8, FMA>(s, D); break;
-                    case 9: u = window_taps<9, FMA>(s, D); break;
-                    case 10: u = window_taps<10, FMA>(s, D); break;
-                    case 11: u = window_taps<11, FMA>(s, D); break;
-                    case 12: u = window_taps<12, FMA>(s, D); break;
-                    case 13: u = window_taps<13, FMA>(s, D); break;
-                    case 14: u = window_taps<14, FMA>(s, D); break;
-                    default: u = window_taps<15, FMA>(s, D); break;
-                }
-                const float s0 = scale_out(u.x), s1 = scale_out(u.y);  // audio.go:390
-                const int pos = step * 32 + lane;
-                if (format == MPEGB200_AUDIO_F32N) {
-                    reinterpret_cast<float2*>(out)[fidx * MPEGB200_SAMPLES_PER_FRAME + pos] = make_float2(s0, s1);
-                } else if (format == MPEGB200_AUDIO_F32NLR) {
-                    float* o = reinterpret_cast<float*>(out) + fidx * frame_vals;
-                    o[pos] = s0;
-                    o[MPEGB200_SAMPLES_PER_FRAME + pos] = s1;
-                } else if (format == MPEGB200_AUDIO_S16) {  // audio.go:400-408
-                    const int a = __float2int_rz(s0 < 0 ? __fmul_rn(s0, 32768.0f) : __fmul_rn(s0, 32767.0f));
-                    const int b = __float2int_rz(s1 < 0 ? __fmul_rn(s1, 32768.0f) : __fmul_rn(s1, 32767.0f));
-                    reinterpret_cast<uint32_t*>(out)[fidx * MPEGB200_SAMPLES_PER_FRAME + pos] =
-                        ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
-                } else {  // MPEGB200_AUDIO_F32, audio.go:409-417 (both constants are 2^31 as float32)
-                    reinterpret_cast<float2*>(out)[fidx * MPEGB200_SAMPLES_PER_FRAME + pos] =
-                        make_float2(__fmul_rn(s0, 2147483648.0f), __fmul_rn(s1, 2147483648.0f));
-                }
+            float D[32];  // the whole window table across the warp: D[t] = window[32 t + lane] (4 KiB, L1 resident; loaded per
+                          // frame so that it does not occupy 32 registers during the matrixing)
+#pragma unroll
+            for (int t = 0; t < 32; t++) D[t] = __ldg(&window[32 * t + lane]);
+            int wdx = warp * kRunLen;
+            const int wend = wdx + kRunLen;
+            while (wdx < wend) {
+                const int ch = wdx >= 36 ? 1 : 0, first = wdx - 36 * ch;
+                const int count = min(wend - wdx, 36 - first);
+                window_run<FMA, FORMAT>(sm.v[ch], D, ch, first, count, (p_init - f * 36 - first - 1) & 15, fidx, out, lane);
+                wdx += count;
             }
         }
         __syncthreads();
 
         // (c) the frame's last 15 slices (36..50) become the next frame's history (0..14)
         if (f + 1 < frames_per_stream) {
-            constexpr int kMove = kHist * 64;             // float2 elements to move (the padding element stays)
+            constexpr int kMove = 2 * kHist * 64;             // floats to move (the padding elements stay)
             constexpr int kPer = (kMove + kAudioThreads - 1) / kAudioThreads;
-            float2 keep[kPer];
+            float keep[kPer];
 #pragma unroll
             for (int i = 0; i < kPer; i++) {
-                const int x = tid + i * kAudioThreads;
-                if (x < kMove) keep[i] = sm.v[(36 + (x >> 6)) * kSlicePitch + (x & 63)];
+                const int x = tid + i * kAudioThreads;        // [channel][slice][element]
+                if (x < kMove) keep[i] = sm.v[x / (kHist * 64)][(36 + (x % (kHist * 64)) / 64) * kSlicePitch + (x & 63)];
             }
             __syncthreads();   // every read of 36..50 is done before the stores below and the next frame's DCTs overwrite 15..50
 #pragma unroll
             for (int i = 0; i < kPer; i++) {
                 const int x = tid + i * kAudioThreads;
-                if (x < kMove) sm.v[(x >> 6) * kSlicePitch + (x & 63)] = keep[i];
+                if (x < kMove) sm.v[x / (kHist * 64)][((x % (kHist * 64)) / 64) * kSlicePitch + (x & 63)] = keep[i];
             }
             // the barrier after (a) orders these stores before the windows read them
         }
@@ -278,29 +284,46 @@ __global__ void __launch_bounds__(kAudioThreads, 7) audio_synth_kernel(AudioStat
     for (int i = tid; i < 2 * 16 * 64; i += kAudioThreads) {
         const int ch = i >> 10, q = (i >> 6) & 15, e = i & 63;
         const int age = (q - p_final) & 15;
-        st.v[ch][q * 64 + e] = vf[((kLin - 1 - age) * kSlicePitch + e) * 2 + ch];
+        st.v[ch][q * 64 + e] = sm.v[ch][(kLin - 1 - age) * kSlicePitch + e];
     }
     if (tid == 0) st.v_pos = p_final * 64;
+}
+
+template <bool FMA, int FORMAT>
+static cudaError_t launch_one(AudioState* d_states, int max_streams, const int32_t* d_stream_ids, int n_streams, int frames_per_stream,
+                              const int32_t* d_samples, void* d_out, const float* d_window, cudaStream_t stream) {
+    audio_synth_kernel<FMA, FORMAT><<<n_streams, kAudioThreads, sizeof(AudioSmem), stream>>>(
+        d_states, max_streams, d_stream_ids, frames_per_stream, d_samples, d_out, d_window);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_audio_synth(AudioState* d_states, int max_streams, const int32_t* d_stream_ids, int n_streams,
                                int frames_per_stream, const int32_t* d_samples, int format, void* d_out,
                                const float* d_window, cudaStream_t stream) {
     if (n_streams <= 0 || frames_per_stream <= 0) return cudaSuccess;
-    const int fmt = format & MPEGB200_AUDIO_FORMAT_MASK;
-    if (format & MPEGB200_AUDIO_WINDOW_FMA)
-        audio_synth_kernel<true><<<n_streams, kAudioThreads, sizeof(AudioSmem), stream>>>(
-            d_states, max_streams, d_stream_ids, frames_per_stream, d_samples, fmt, d_out, d_window);
-    else
-        audio_synth_kernel<false><<<n_streams, kAudioThreads, sizeof(AudioSmem), stream>>>(
-            d_states, max_streams, d_stream_ids, frames_per_stream, d_samples, fmt, d_out, d_window);
-    return cudaGetLastError();
+    const bool fma = (format & MPEGB200_AUDIO_WINDOW_FMA) != 0;
+#define MPEGB200_GO(F, FMT) return launch_one<F, FMT>(d_states, max_streams, d_stream_ids, n_streams, frames_per_stream, d_samples, d_out, d_window, stream)
+    switch (format & MPEGB200_AUDIO_FORMAT_MASK) {
+        case MPEGB200_AUDIO_F32N: if (fma) MPEGB200_GO(true, MPEGB200_AUDIO_F32N); else MPEGB200_GO(false, MPEGB200_AUDIO_F32N);
+        case MPEGB200_AUDIO_F32NLR: if (fma) MPEGB200_GO(true, MPEGB200_AUDIO_F32NLR); else MPEGB200_GO(false, MPEGB200_AUDIO_F32NLR);
+        case MPEGB200_AUDIO_F32: if (fma) MPEGB200_GO(true, MPEGB200_AUDIO_F32); else MPEGB200_GO(false, MPEGB200_AUDIO_F32);
+        case MPEGB200_AUDIO_S16: if (fma) MPEGB200_GO(true, MPEGB200_AUDIO_S16); else MPEGB200_GO(false, MPEGB200_AUDIO_S16);
+        default: return cudaErrorInvalidValue;
+    }
+#undef MPEGB200_GO
 }
 
 cudaError_t configure_audio_kernel() {
-    cudaError_t e = cudaFuncSetAttribute(audio_synth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AudioSmem));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(audio_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AudioSmem));
+    cudaError_t e = cudaSuccess;
+#define MPEGB200_CFG(F, FMT)                                                                                                         \
+    if (e == cudaSuccess)                                                                                                            \
+        e = cudaFuncSetAttribute(audio_synth_kernel<F, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AudioSmem))
+    MPEGB200_CFG(false, MPEGB200_AUDIO_F32N); MPEGB200_CFG(true, MPEGB200_AUDIO_F32N);
+    MPEGB200_CFG(false, MPEGB200_AUDIO_F32NLR); MPEGB200_CFG(true, MPEGB200_AUDIO_F32NLR);
+    MPEGB200_CFG(false, MPEGB200_AUDIO_F32); MPEGB200_CFG(true, MPEGB200_AUDIO_F32);
+    MPEGB200_CFG(false, MPEGB200_AUDIO_S16); MPEGB200_CFG(true, MPEGB200_AUDIO_S16);
+#undef MPEGB200_CFG
+    return e;
 }
 
 }  // namespace mpegb200

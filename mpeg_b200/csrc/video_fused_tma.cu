@@ -90,6 +90,18 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+// 16 bytes of a plan, straight from global memory.  The plans are written by the pre-pass grid that this kernel follows under
+// programmatic dependent launch: they may be read only after griddepcontrol.wait.  A volatile asm load keeps its place behind that
+// (volatile asm) instruction; an ordinary load of `const __restrict__` memory, or __ldg, is an invariant load (LDG.E.CONSTANT) that
+// the compiler is free to hoist to the top of the kernel -- above the wait -- where it reads whatever the previous launch left in the
+// plan buffer (a wrong byte count for the mbarrier: the CTA never wakes up).  That happened once the measurement branches that used
+// to sit between the wait and these loads were compiled out.
+__device__ __forceinline__ uint4 ld_plan16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // the same boxes, fetched into L2 only (for a group that a later CTA will decode)
 __device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -818,7 +830,8 @@ __device__ __forceinline__ void issue_group(const PlanHead& P, const PlanBox* bo
                 tma_load_4d(s_win + kStripLBytes, maps->chroma_strip, bar, P.scx >> 3, P.scy, 0, P.z);
         }
     } else if (lane < kG) {
-        const PlanBox t = boxes[lane];   // shared memory (one-shot kernel) or the plan in global memory (streaming kernel)
+        PlanBox t;                       // from the plan in global memory: like the head, not before griddepcontrol.wait
+        *reinterpret_cast<uint4*>(&t) = ld_plan16(boxes + lane);
         if (t.pred) {
             const SlabMaps* maps = slab_maps + t.slab;
             uint8_t* w = s_win + lane * kWinBytes;
@@ -842,9 +855,9 @@ __device__ __forceinline__ PlanHead load_head(const GroupPlan* gp) {
     PlanHead h;
     const uint4* src = reinterpret_cast<const uint4*>(&gp->h);
     uint4* dst = reinterpret_cast<uint4*>(&h);
-    dst[0] = __ldg(src);
-    dst[1] = __ldg(src + 1);
-    dst[2] = __ldg(src + 2);
+    dst[0] = ld_plan16(src);
+    dst[1] = ld_plan16(src + 1);
+    dst[2] = ld_plan16(src + 2);
     return h;
 }
 
@@ -853,7 +866,7 @@ static_assert(sizeof(PlanHead) + sizeof(PlanBody) <= kPlanSmemBytes, "plan copy 
 
 __global__ void __launch_bounds__(kNT, kMinCtas) fused_tma_kernel(const __grid_constant__ CUtensorMap coef_map,
                                                           const SlabMaps* __restrict__ slab_maps,
-                                                          const GroupPlan* __restrict__ plans, uint32_t n_groups,
+                                                          const GroupPlan* plans, uint32_t n_groups,
                                                           uint32_t prefetch_dist, int dbg) {
 #ifndef MPEGB200_EXPERIMENTS
     (void)dbg;   // the fetch-only / arithmetic-only timing modes exist in experiment builds only
