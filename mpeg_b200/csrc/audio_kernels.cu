@@ -69,32 +69,41 @@ struct AudioSmem {
 };
 
 // u / -1090519040.0 (audio.go:390), correctly rounded.  Fast path: q = u * y, r = fma(-q, c, u) (exact), q' = fma(r, y, q)
-// with y = RN(1 / c) equals the IEEE quotient for every float32 u with 2^-102 <= |u| < inf and for +-0 (checked over all
-// 2^32 bit patterns on the host, tools/check_fast_div.c); anything else takes the generic division.  The test is made
-// once per warp (vote): the slow path is taken by all lanes or none.
+// with y = RN(1 / c) equals the IEEE quotient for every float32 u with 2^-102 <= |u| < inf (checked over all 2^32 bit
+// patterns on the host, tools/check_fast_div.c); anything else -- tiny values, inf, nan and, to keep the test at one
+// compare, zero -- takes the generic division.  The test is made once per warp (vote): all lanes take the same path.
 __device__ __forceinline__ float scale_out(float u) {
     constexpr float c = -1090519040.0f;
     constexpr float y = -0x1.f81f82p-31f;   // RN(1 / c)
     const uint32_t mag = __float_as_uint(u) & 0x7fffffffu;
-    const bool odd = ((mag - 1u) < 0x0d7fffffu) | (mag >= 0x7f800000u);   // 0 < |u| < 2^-100, inf, nan
+    const bool odd = (mag - 0x0d800000u) >= (0x7f800000u - 0x0d800000u);   // |u| < 2^-100 (zero included), inf, nan
     if (__any_sync(0xffffffffu, odd)) return __fdiv_rn(u, c);
     const float q = __fmul_rn(u, y);
     const float r = __fmaf_rn(-q, c, u);
     return __fmaf_rn(r, y, q);
 }
 
+// Output formats (audio.go:386-418): element type, distance between a channel's consecutive samples, and the store.
+template <int FORMAT> struct OutFmt { using T = float; static constexpr int kStride = 2; };
+template <> struct OutFmt<MPEGB200_AUDIO_F32NLR> { using T = float; static constexpr int kStride = 1; };
+template <> struct OutFmt<MPEGB200_AUDIO_S16> { using T = int16_t; static constexpr int kStride = 2; };
+
 template <int FORMAT>
-__device__ __forceinline__ void emit_sample(void* __restrict__ out, size_t fidx, int pos, int ch, float s) {
-    constexpr size_t kVals = 2 * MPEGB200_SAMPLES_PER_FRAME;
-    if constexpr (FORMAT == MPEGB200_AUDIO_F32N) {
-        reinterpret_cast<float*>(out)[fidx * kVals + 2 * pos + ch] = s;
-    } else if constexpr (FORMAT == MPEGB200_AUDIO_F32NLR) {
-        reinterpret_cast<float*>(out)[fidx * kVals + ch * MPEGB200_SAMPLES_PER_FRAME + pos] = s;
-    } else if constexpr (FORMAT == MPEGB200_AUDIO_S16) {  // audio.go:400-408
-        const int a = __float2int_rz(s < 0 ? __fmul_rn(s, 32768.0f) : __fmul_rn(s, 32767.0f));
-        reinterpret_cast<int16_t*>(out)[fidx * kVals + 2 * pos + ch] = (int16_t)a;
-    } else {  // MPEGB200_AUDIO_F32, audio.go:409-417 (both constants are 2^31 as float32)
-        reinterpret_cast<float*>(out)[fidx * kVals + 2 * pos + ch] = __fmul_rn(s, 2147483648.0f);
+__device__ __forceinline__ typename OutFmt<FORMAT>::T* out_pointer(void* out, size_t fidx, int ch, int first, int lane) {
+    using T = typename OutFmt<FORMAT>::T;
+    T* base = reinterpret_cast<T*>(out) + fidx * (2 * MPEGB200_SAMPLES_PER_FRAME);
+    if constexpr (FORMAT == MPEGB200_AUDIO_F32NLR) return base + ch * MPEGB200_SAMPLES_PER_FRAME + first * 32 + lane;
+    return base + 2 * (first * 32 + lane) + ch;
+}
+
+template <int FORMAT>
+__device__ __forceinline__ void emit_sample(typename OutFmt<FORMAT>::T* o, float s) {
+    if constexpr (FORMAT == MPEGB200_AUDIO_S16) {  // audio.go:400-408
+        *o = (int16_t)__float2int_rz(s < 0 ? __fmul_rn(s, 32768.0f) : __fmul_rn(s, 32767.0f));
+    } else if constexpr (FORMAT == MPEGB200_AUDIO_F32) {  // audio.go:409-417 (both constants are 2^31 as float32)
+        *o = __fmul_rn(s, 2147483648.0f);
+    } else {
+        *o = s;
     }
 }
 
@@ -125,29 +134,40 @@ __device__ __forceinline__ float window_slot(const float* __restrict__ own, floa
     return u;
 }
 
-// A run of `count` consecutive time slots of one channel, starting at slot `first` whose vPos/64 is p0: the 15 slices of
-// history before the first slot come into registers once, then the slots go through an unrolled ring of the 16 values of
-// vPos/64, entered at p0 (Duff's device; vPos decreases by 64 per slot, audio.go:380).
+// The 15 slices of history before a run's first slot (vPos/64 = P0) into the register ring: the slice written `age`
+// slots earlier sits at ring position (P0 + age) & 15 -- a compile-time index once P0 is a template parameter.
+template <int P0>
+__device__ __forceinline__ void preload_ring(const float* __restrict__ own, float (&R)[16][2]) {
+#pragma unroll
+    for (int age = 1; age < 16; age++) {
+        R[(P0 + age) & 15][0] = own[-age * kSlicePitch];
+        R[(P0 + age) & 15][1] = own[-age * kSlicePitch + 32];
+    }
+}
+
+// A run of `count` consecutive time slots of one channel, starting at slot `first` whose vPos/64 is p0: the history comes
+// into registers once, then the slots go through an unrolled ring of the 16 values of vPos/64, entered at p0 (Duff's
+// device; vPos decreases by 64 per slot, audio.go:380).
 template <bool FMA, int FORMAT>
 __device__ __forceinline__ void window_run(const float* __restrict__ vch, const float (&D)[32], int ch, int first, int count, int p0,
                                            size_t fidx, void* __restrict__ out, int lane) {
     const float* own = vch + (kHist + first) * kSlicePitch + lane;
     float R[16][2];
-#pragma unroll
-    for (int q = 0; q < 16; q++) {   // ring position q was written (q - p0) & 15 slots before the first slot (its own: in window_slot)
-        const int age = (q - p0) & 15;
-        const float* hs = own - age * kSlicePitch;
-        R[q][0] = age ? hs[0] : 0.0f;
-        R[q][1] = age ? hs[32] : 0.0f;
+    switch (p0) {
+#define MPEGB200_PRE(PV) case PV: preload_ring<PV>(own, R); break;
+        MPEGB200_PRE(0) MPEGB200_PRE(1) MPEGB200_PRE(2) MPEGB200_PRE(3) MPEGB200_PRE(4) MPEGB200_PRE(5) MPEGB200_PRE(6) MPEGB200_PRE(7)
+        MPEGB200_PRE(8) MPEGB200_PRE(9) MPEGB200_PRE(10) MPEGB200_PRE(11) MPEGB200_PRE(12) MPEGB200_PRE(13) MPEGB200_PRE(14)
+        default: preload_ring<15>(own, R); break;
+#undef MPEGB200_PRE
     }
-    int left = count, pos = first * 32 + lane;
+    typename OutFmt<FORMAT>::T* o = out_pointer<FORMAT>(out, fidx, ch, first, lane);
+    int left = count;
 #define MPEGB200_SLOT(PV)                                                           \
     case PV: {                                                                      \
-        const float u = window_slot<PV, FMA>(own, R, D);                            \
-        emit_sample<FORMAT>(out, fidx, pos, ch, scale_out(u));                      \
-        own += kSlicePitch;                                                         \
-        pos += 32;                                                                  \
+        emit_sample<FORMAT>(o, scale_out(window_slot<PV, FMA>(own, R, D)));         \
         if (--left == 0) break;                                                     \
+        own += kSlicePitch;                                                         \
+        o += 32 * OutFmt<FORMAT>::kStride;                                          \
     }
     switch (p0) {
         do {

@@ -159,6 +159,10 @@ def test_batch_fused_window_matches_oracle(ctx, fmt):
     n_streams, frames = 20, 4
     ids = np.arange(40, 40 + n_streams)
     for s in ids:
+        try:
+            ctx.audio_close(int(s))   # left open by an earlier failing case
+        except Exception:
+            pass
         ctx.audio_open(int(s))
     states = ol.synth_states(n_streams)
     rng = wl.stream_rng(4, 100 + fmt)
@@ -167,10 +171,9 @@ def test_batch_fused_window_matches_oracle(ctx, fmt):
         got = ctx.audio_synth(ids, frames, samples, fmt | FMA)
         want = ol.synth_batch(states, n_streams, frames, samples, fmt, fma=True)
         assert np.array_equal(got.view(np.uint16 if fmt == 3 else np.uint32), want.view(np.uint16 if fmt == 3 else np.uint32))
-        if fmt != 3:   # and the fused result stays within the reference's own 1e-5 rule of the unfused one (audio_test.go:59)
-            unfused = ol.synth_batch(ol.synth_states(n_streams), n_streams, frames, samples, fmt) if launch == 0 else None
-            if unfused is not None:
-                assert within_reference_tolerance(got, unfused)
+        if fmt in (0, 1) and launch == 0:   # the fused result stays within the reference's own 1e-5 rule (on normalised samples, audio_test.go:59) of the unfused one
+            unfused = ol.synth_batch(ol.synth_states(n_streams), n_streams, frames, samples, fmt)
+            assert within_reference_tolerance(got, unfused)
     for s in ids:
         ctx.audio_close(int(s))
 
