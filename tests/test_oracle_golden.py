@@ -281,3 +281,29 @@ def test_synth_frame_equals_decoder(golden_dir):
     v, v_pos = a.state()
     assert v_pos == st[0].v_pos
     assert np.array_equal(np.ctypeslib.as_array(st[0].v).reshape(2, 1024), v)
+
+
+def test_rgba_against_go_fixture(golden_dir):
+    """Frame.RGBA() is Go standard-library arithmetic (image/draw of a 4:2:0 image.YCbCr) and the one function of the
+    path the oracle restates without a reference vector ("parity unpinned").  go/rgba_fixture.go
+    writes that vector on any machine with Go; when the file exists the oracle must reproduce it byte for byte."""
+    import struct
+    path = golden_dir / "go_rgba_fixture.bin"
+    if not path.exists():
+        pytest.skip("tests/golden/go_rgba_fixture.bin absent (no Go toolchain in the build image): run `go run go/rgba_fixture.go`")
+    data = path.read_bytes()
+    assert data[:8] == b"RGBAFIX1"
+    (n,) = struct.unpack_from("<I", data, 8)
+    off = 12
+    for _ in range(n):
+        w, h, lw, lh = struct.unpack_from("<4I", data, off)
+        off += 16
+        ny, nc = lw * lh, (lw // 2) * (lh // 2)
+        fs = ol.FrameSet(1, w, h)
+        assert (fs.luma_w, fs.luma_h) == (lw, lh)
+        buf = fs.whole(0, 0)
+        buf[:ny + 2 * nc] = np.frombuffer(data, np.uint8, ny + 2 * nc, off)
+        off += ny + 2 * nc
+        want = np.frombuffer(data, np.uint8, w * h * 4, off).reshape(h, w, 4)
+        off += w * h * 4
+        assert np.array_equal(fs.rgba(0, 0), want), f"{w}x{h}"

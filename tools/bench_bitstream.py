@@ -1,0 +1,126 @@
+#!/usr/bin/env python3
+"""Bitstream -> frames at 720p: does the host parser starve the GPU?
+
+Writes a few synthetic 720p MPEG-1 elementary streams with tests/mpeg1_writer.py (shaped like BASELINE configs[2]: dense P
+pictures -- every macroblock predicted, six coded blocks of 64 coefficients -- or "natural" ones), replicates them to N streams,
+and runs the lock-step batch decoder (mpegb200_video_batch_*, parsers emitting the variable-width coefficient form):
+
+  host     the parse + wave merge alone (no GPU needed): pictures/s, MB/s of bitstream, per host thread
+  gpu      the same with every wave going through mpegb200_video_decode_pictures_vlen (needs a B200): frames/s from
+           compressed bitstream to decoded frames in HBM
+
+usage: bench_bitstream.py [--streams 256] [--threads T] [--mode dense|natural] [--pictures 4] [--distinct 4] [--gpu]
+Prints one JSON line."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def make_streams(distinct, pictures, mode, log):
+    import mpeg1_writer as mw
+    out = []
+    for d in range(distinct):
+        t0 = time.time()
+        rng = np.random.default_rng(720 + d)
+        w = mw.StreamWriter(1280, 720, quantizer_scale=8, f_code=2)
+        w.picture(mw.PIC_I, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_I, mode, 32, 1280, 720))
+        for _ in range(pictures - 1):
+            w.picture(mw.PIC_P, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_P, mode, 32, 1280, 720))
+        out.append(w.tobytes())
+        log(f"stream {d}: {pictures} pictures, {len(out[-1]) / 1e6:.2f} MB, written in {time.time() - t0:.1f} s")
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--streams", type=int, default=256)
+    ap.add_argument("--threads", type=int, default=0, help="host threads of the batch parser (default: all)")
+    ap.add_argument("--mode", default="dense", choices=["dense", "natural"])
+    ap.add_argument("--pictures", type=int, default=5)
+    ap.add_argument("--distinct", type=int, default=2)
+    ap.add_argument("--gpu", action="store_true")
+    args = ap.parse_args()
+    threads = args.threads or len(os.sched_getaffinity(0))
+
+    def log(m):
+        print(f"[bitstream] {m}", file=sys.stderr, flush=True)
+
+    distinct = make_streams(args.distinct, args.pictures, args.mode, log)
+    streams = [distinct[i % len(distinct)] for i in range(args.streams)]
+    total_bytes = sum(len(s) for s in streams)
+    from mpeg_b200 import _lib
+    from mpeg_b200.batch import BatchStep
+    L = _lib.load()
+
+    # ---- host side alone
+    def host_run(n_threads):
+        h = L.mpegb200_video_batch_new(len(streams), n_threads, None, None)
+        L.mpegb200_video_batch_set_vlen(h, 1)
+        for i, d in enumerate(streams):
+            assert L.mpegb200_video_batch_set_stream(h, i, d, len(d)) == 0
+        st = BatchStep()
+        pics = blocks = payload = 0
+        dt, k = 0.0, 0
+        while True:
+            t0 = time.perf_counter()
+            assert L.mpegb200_video_batch_next(h, C.byref(st)) == 0
+            t1 = time.perf_counter()
+            got = int(np.ctypeslib.as_array(st.has_frame, shape=(len(streams),)).sum())
+            if got == 0:
+                break
+            k += 1
+            if k == 1:
+                continue   # the first step grows every parser's arrays (allocation, page faults): steady state starts behind it
+            dt += t1 - t0
+            for w in range(st.n_waves):
+                pics += st.waves[w].n_pictures
+                blocks += st.waves[w].n_blocks
+                payload += st.waves[w].vlen_payload_bytes + 4 * st.waves[w].n_blocks
+        L.mpegb200_video_batch_free(h)
+        return dt, pics, blocks, payload
+
+    dt1, pics1, _, _ = host_run(1) if args.streams <= 32 else (None, 0, 0, 0)
+    dtn, pics, blocks, payload = host_run(threads)
+    res = {"what": "bitstream -> records (host parser, vlen form) and -> frames (GPU)", "mode": args.mode, "streams": args.streams,
+           "pictures_per_stream": args.pictures, "bitstream_bytes_per_picture": total_bytes / (args.streams * args.pictures),
+           "coded_blocks_per_picture": blocks / max(pics, 1), "record_bytes_per_picture_vlen": (payload + 16 * 3600 * pics) / max(pics, 1),
+           "host": {"threads": threads, "pictures_per_sec": pics / dtn, "bitstream_MB_per_sec": pics * total_bytes / (args.streams * args.pictures) / dtn / 1e6,
+                    "timed": "all steps but the first (which allocates)",
+                    "pictures_per_sec_per_thread": pics / dtn / threads,
+                    "single_thread_pictures_per_sec": (pics1 / dt1) if dt1 else None}}
+    fused_fps = 814000.0   # fused MC+IDCT+add kernel alone, frames/s per GPU (bench.py, BENCH line)
+    res["host"]["threads_to_feed_one_gpu_decode_kernel"] = fused_fps / (pics / dtn / threads)
+
+    if args.gpu:
+        import mpeg_b200
+        ctx = mpeg_b200.Context(0, args.streams)
+        vb = mpeg_b200.VideoBatch(ctx, streams, threads=threads, validate=False)
+        frames = 0
+        ctx.sync()
+        t0 = time.perf_counter()
+        while True:
+            has, buf, _ = vb.step()
+            if not has.any():
+                break
+            frames += int(has.sum())
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        res["gpu"] = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "launches": ctx.launch_count,
+                      "note": "lock-step batch: parse (host threads) -> pinned waves -> H2D -> expand_vlen + plan + fused kernels; frames stay in HBM"}
+        vb.close()
+        ctx.close()
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
