@@ -245,6 +245,22 @@ int mpegb200_video_read_pictures_dev(mpegb200_ctx* ctx, int n, const int32_t* st
 /* Device address of a frame buffer (Y at +0, Cb at +luma_w*luma_h, Cr after it). */
 void* mpegb200_video_frame_dev(mpegb200_ctx* ctx, int stream, int buf);
 
+/* Display ring: the frames Video.Decode() returns, kept in device memory in display order for `depth` steps, so that
+ * consumers (RGBA conversion of an older frame, read-back, the NCCL gather) may lag behind the decoder instead of
+ * having to finish before the next Decode() re-uses the frame buffer ("valid until the next call", mpeg.go:413-415).
+ * A ring covers n streams; a slot holds their n pictures (Y|Cb|Cr without the pad) `stride` bytes apart.
+ * mpegb200_video_ring_push copies, on the context's stream, the display frame of every stream (bufs[i] = the physical
+ * buffer the host parser named as frame_buf; 255 = this stream returned no frame in this step, its place in the slot is
+ * left as it was) into the next slot and returns that slot's index (or a negative error code). */
+typedef struct mpegb200_ring mpegb200_ring;
+mpegb200_ring* mpegb200_video_ring_new(mpegb200_ctx* ctx, int n, const int32_t* streams, int depth);
+void  mpegb200_video_ring_free(mpegb200_ring* ring);
+int   mpegb200_video_ring_push(mpegb200_ring* ring, const uint8_t* bufs);
+/* Device address of slot `slot` (picture i at + i * *stride); valid until the slot is overwritten depth pushes later. */
+void* mpegb200_video_ring_slot_dev(mpegb200_ring* ring, int slot, size_t* stride);
+/* Asynchronous copy of a slot to (pinned) host memory on the read-back stream, ordered behind the pushes so far. */
+int   mpegb200_video_ring_read_host(mpegb200_ring* ring, int slot, uint8_t* dst, size_t dst_stride);
+
 /* Frame.RGBA(): YCbCr 4:2:0 -> RGBA8 over the display rectangle width x height,
  * destination stride 4*width (video.go:31-36, 367-371).  Host form copies the result
  * into `rgba` (width*height*4 bytes). */
@@ -271,6 +287,19 @@ int mpegb200_audio_synth(mpegb200_ctx* ctx, int n_streams, const int32_t* stream
                          int frames_per_stream, const int32_t* samples, int format, void* out);
 int mpegb200_audio_synth_dev(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids,
                              int frames_per_stream, const int32_t* d_samples, int format, void* d_out);
+/* Coded form: requantisation (audio.go:440-490, second half) on the device.  Per frame the host passes
+ *   info : for every (channel, subband) the quantiser number 1..17 of audio.go:955-973 (0 = no bits allocated) and the
+ *          scale-factor index 0..63 of each of the three parts (audio.go:322-342); 256 bytes;
+ *   codes: uint16[2][36][32], the sample codes as read from the bitstream (degrouped, audio.go:462-475), laid out like
+ *          `samples` above; 4608 bytes.
+ * The device computes sample = ((adj - code) * scale) x scalefactor exactly as audio.go:476-489 (int32 suffices: |val| <=
+ * 2^15, scalefactor <= 2^25 split at 12 bits) and continues like mpegb200_audio_synth. */
+typedef struct mpegb200_audio_frame_info {
+    uint8_t quant[2][32];
+    uint8_t scf[2][32][3];
+} mpegb200_audio_frame_info;
+int mpegb200_audio_synth_coded(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,
+                               const mpegb200_audio_frame_info* info, const uint16_t* codes, int format, void* out);
 /* State read-back in the reference's own form: v = float[2][1024], *v_pos (audio.go:63,78). */
 int mpegb200_audio_read_state(mpegb200_ctx* ctx, int stream, float* v, int* v_pos);
 int mpegb200_audio_write_state(mpegb200_ctx* ctx, int stream, const float* v, int v_pos);

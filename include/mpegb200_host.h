@@ -137,6 +137,39 @@ void   mpegb200_audio_parser_rewind(mpegb200_audio_parser* a);                  
 /* Parse one frame: fills samples[2][36][32] (layout of mpegb200_audio_synth) and *time.
  * Returns 1 if a frame was parsed, 0 at the end (Decode() == nil). */
 int    mpegb200_audio_parser_next(mpegb200_audio_parser* a, int32_t* samples, double* time);
+/* The same frame without the requantisation of audio.go:476-489: per (channel, subband) the quantiser and the three
+ * scale-factor indices, and the sample codes as the bitstream has them (degrouped) -- the input of
+ * mpegb200_audio_synth_coded, which requantises on the device (4.9 KB per frame over PCIe instead of 9.2 KB). */
+int    mpegb200_audio_parser_next_coded(mpegb200_audio_parser* a, mpegb200_audio_frame_info* info, uint16_t* codes, double* time);
+
+/* ---- many MP2 streams in lock-step -------------------------------------------------------------- */
+
+typedef struct mpegb200_audio_batch mpegb200_audio_batch;
+
+/* One step: every stream that still has data contributes up to frames_per_stream frames.  Streams that delivered all
+ * frames_per_stream frames form the rectangular batch of mpegb200_audio_synth (n_full of them, batch indices in
+ * full_index, samples [n_full][frames_per_stream][2][36][32]); a stream that ran dry on the way delivers its last
+ * k < frames_per_stream frames separately (tail_*; one mpegb200_audio_synth call each with frames_per_stream = k). */
+typedef struct mpegb200_audio_batch_step {
+    int n_streams;
+    const int* n_frames;           /* per stream: frames parsed in this step (0 = ended) */
+    const double* time;            /* per stream: Samples.Time of its first frame of the step (audio.go:176) */
+    int frames_per_stream;
+    int n_full;
+    const int32_t* full_index;     /* batch indices of the streams in the rectangular part */
+    const int32_t* full_samples;
+    int n_tail;
+    const int32_t* tail_index;     /* batch index of each tail stream */
+    const int32_t* tail_frames;    /* its number of frames */
+    const int32_t* tail_samples;   /* the tails' frames back to back: [sum of tail_frames][2][36][32] */
+} mpegb200_audio_batch_step;
+
+mpegb200_audio_batch* mpegb200_audio_batch_new(int n_streams, int threads, void* (*alloc)(size_t), void (*free_fn)(void*));
+void mpegb200_audio_batch_free(mpegb200_audio_batch* b);
+int  mpegb200_audio_batch_set_stream(mpegb200_audio_batch* b, int index, const uint8_t* data, size_t len);
+int  mpegb200_audio_batch_stream_info(mpegb200_audio_batch* b, int index, int* samplerate, int* channels);
+/* Parse up to frames_per_stream frames of every stream on the batch's threads (Audio.Decode's parse half, audio.go:163-375). */
+int  mpegb200_audio_batch_next(mpegb200_audio_batch* b, int frames_per_stream, mpegb200_audio_batch_step* out);
 
 /* ---- MPEG program stream ----------------------------------------------------------------------- */
 

@@ -8,7 +8,7 @@ from ._lib import MpegB200Error, build, load  # noqa: F401
 from .context import (AUDIO_F32, AUDIO_F32N, AUDIO_F32NLR, AUDIO_S16, AUDIO_WINDOW_FMA, MB_DTYPE, MB_INTRA, MB_PREDICT,  # noqa: F401
                       MB_REF_BWD, PIC_B, PIC_I, PIC_P, PICTURE_DTYPE, SAMPLES_PER_FRAME, Context)
 
-from .batch import VideoBatch  # noqa: F401
+from .batch import AudioBatch, DisplayRing, MPEGBatch, VideoBatch  # noqa: F401
 from .mpeg import MPEG, Audio, ErrInvalidMPEG, Frame, Samples, Video, demux_split  # noqa: F401
 
 __all__ = ["Context", "MpegB200Error", "build", "load", "MPEG", "Video", "Audio", "Frame", "Samples"]

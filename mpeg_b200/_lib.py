@@ -81,12 +81,18 @@ def load():
         "mpegb200_video_frame_dev": (vp, [vp, C.c_int, C.c_int]),
         "mpegb200_video_read_pictures_host": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t]),
         "mpegb200_video_read_pictures_dev": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t]),
+        "mpegb200_video_ring_new": (vp, [vp, C.c_int, vp, C.c_int]),
+        "mpegb200_video_ring_free": (None, [vp]),
+        "mpegb200_video_ring_push": (C.c_int, [vp, vp]),
+        "mpegb200_video_ring_slot_dev": (vp, [vp, C.c_int, szp]),
+        "mpegb200_video_ring_read_host": (C.c_int, [vp, C.c_int, vp, C.c_size_t]),
         "mpegb200_video_rgba": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "mpegb200_video_rgba_batch_dev": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t]),
         "mpegb200_audio_open": (C.c_int, [vp, C.c_int]),
         "mpegb200_audio_close": (C.c_int, [vp, C.c_int]),
         "mpegb200_audio_synth": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
         "mpegb200_audio_synth_dev": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
+        "mpegb200_audio_synth_coded": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp]),
         "mpegb200_audio_read_state": (C.c_int, [vp, C.c_int, vp, ip]),
         "mpegb200_audio_write_state": (C.c_int, [vp, C.c_int, vp, C.c_int]),
         "mpegb200_host_alloc": (vp, [C.c_size_t]),
@@ -116,6 +122,12 @@ def load():
         "mpegb200_audio_parser_channels": (C.c_int, [vp]),
         "mpegb200_audio_parser_rewind": (None, [vp]),
         "mpegb200_audio_parser_next": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
+        "mpegb200_audio_parser_next_coded": (C.c_int, [vp, vp, vp, C.POINTER(C.c_double)]),
+        "mpegb200_audio_batch_new": (vp, [C.c_int, C.c_int, vp, vp]),
+        "mpegb200_audio_batch_free": (None, [vp]),
+        "mpegb200_audio_batch_set_stream": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_size_t]),
+        "mpegb200_audio_batch_stream_info": (C.c_int, [vp, C.c_int, ip, ip]),
+        "mpegb200_audio_batch_next": (C.c_int, [vp, C.c_int, vp]),
         "mpegb200_demux_split": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(vp), szp, C.POINTER(vp), szp, ip, ip]),
         "mpegb200_buffer_free": (None, [vp]),
     }

@@ -227,6 +227,18 @@ class Context:
         self._ck(self.L.mpegb200_audio_synth(self.h, len(ids), _ptr(ids), frames_per_stream, _ptr(samples), fmt, _ptr(out)))
         return out
 
+    def audio_synth_coded(self, stream_ids, frames_per_stream: int, info, codes, fmt: int = AUDIO_F32N) -> np.ndarray:
+        """Like audio_synth with the requantisation on the device: info uint8 [frames, 256] (quantiser + scale-factor indices),
+        codes uint16 [frames, 2, 36, 32] (mpegb200_audio_parser_next_coded)."""
+        ids = np.ascontiguousarray(stream_ids, np.int32)
+        info = np.ascontiguousarray(info, np.uint8)
+        codes = np.ascontiguousarray(codes, np.uint16)
+        n = len(ids) * frames_per_stream
+        assert info.size == n * 256 and codes.size == n * 2304
+        out = np.empty((len(ids), frames_per_stream, 2 * SAMPLES_PER_FRAME), np.int16 if (fmt & 0xff) == AUDIO_S16 else np.float32)
+        self._ck(self.L.mpegb200_audio_synth_coded(self.h, len(ids), _ptr(ids), frames_per_stream, _ptr(info), _ptr(codes), fmt, _ptr(out)))
+        return out
+
     def audio_synth_dev(self, stream_ids, frames_per_stream: int, d_samples: int, fmt: int, d_out: int):
         ids = np.ascontiguousarray(stream_ids, np.int32)
         self._ck(self.L.mpegb200_audio_synth_dev(self.h, len(ids), _ptr(ids), frames_per_stream, C.c_void_p(d_samples), fmt, C.c_void_p(d_out)))

@@ -88,6 +88,9 @@ cudaError_t launch_unpack12(const uint8_t* d_packed, int16_t* d_coeffs, size_t n
 // variable-width transfer form (coeff_vlen.cu) -> int16 blocks
 cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chunk_offsets, const uint8_t* d_payload,
                                int16_t* d_coeffs, size_t n_blocks, size_t payload_bytes, cudaStream_t stream);
+// MP2 requantisation on the device (audio_requant.cu): info + codes -> int32 samples in the layout of mpegb200_audio_synth
+cudaError_t launch_audio_requant(const mpegb200_audio_frame_info* d_info, const uint16_t* d_codes, int32_t* d_samples,
+                                 size_t n_frames, cudaStream_t stream);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

@@ -56,7 +56,7 @@ struct mpegb200_ctx {
     std::vector<uint8_t> audio_open;
     AudioState* d_audio = nullptr;
     float* d_window = nullptr;
-    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_packed[2], s_headers[2], s_chunks[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans;
+    DevBuf s_pics[2], s_mbs[2], s_coeffs[2], s_packed[2], s_headers[2], s_chunks[2], s_ids, s_bufs, s_rgba, s_samples, s_out, s_plans, s_ainfo, s_acodes;
     // host-pointer pipeline: uploads and read-backs run on their own streams so that the H2D copy of the
     // next step overlaps the kernels and the D2H copy of the current one (double-buffered staging)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
@@ -247,7 +247,7 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     if (ctx->down_stream) cudaStreamSynchronize(ctx->down_stream);
     for (DevBuf* b : {&ctx->s_pics[0], &ctx->s_pics[1], &ctx->s_mbs[0], &ctx->s_mbs[1], &ctx->s_coeffs[0],
                       &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out,
-                      &ctx->s_plans, &ctx->s_packed[0], &ctx->s_packed[1], &ctx->s_headers[0], &ctx->s_headers[1],
+                      &ctx->s_plans, &ctx->s_ainfo, &ctx->s_acodes, &ctx->s_packed[0], &ctx->s_packed[1], &ctx->s_headers[0], &ctx->s_headers[1],
                       &ctx->s_chunks[0], &ctx->s_chunks[1]})
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) {
@@ -944,6 +944,110 @@ int mpegb200_video_rgba(mpegb200_ctx* ctx, int stream, int buf, uint8_t* rgba) {
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------------- display ring */
+
+}  // extern "C"
+
+struct mpegb200_ring {
+    mpegb200_ctx* ctx = nullptr;
+    int n = 0, depth = 0;
+    uint64_t head = 0;
+    size_t stride = 0;
+    std::vector<int32_t> streams;
+    uint8_t* dev = nullptr;
+    cudaEvent_t pushed = nullptr;
+};
+
+extern "C" {
+
+mpegb200_ring* mpegb200_video_ring_new(mpegb200_ctx* ctx, int n, const int32_t* streams, int depth) try {
+    if (!ctx || n <= 0 || !streams || depth <= 0 || depth > 4096) return nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    size_t stride = 0;
+    for (int i = 0; i < n; i++) {
+        HostStream* s = vstream(ctx, streams[i]);
+        if (!s || !s->open) {
+            fail(ctx, MPEGB200_ESTATE, "ring: video stream %d not open", streams[i]);
+            return nullptr;
+        }
+        const size_t bytes = s->luma_bytes + 2 * s->chroma_bytes;
+        if (bytes > stride) stride = bytes;
+    }
+    stride = (stride + 255) / 256 * 256;
+    mpegb200_ring* r = new mpegb200_ring();
+    r->ctx = ctx;
+    r->n = n;
+    r->depth = depth;
+    r->stride = stride;
+    r->streams.assign(streams, streams + n);
+    if (cudaMalloc(&r->dev, stride * (size_t)n * (size_t)depth) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->pushed, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (r->dev) cudaFree(r->dev);
+        delete r;
+        fail(ctx, MPEGB200_ENOMEM, "ring of %d x %d pictures (%zu bytes each)", depth, n, stride);
+        return nullptr;
+    }
+    cudaMemsetAsync(r->dev, 0, stride * (size_t)n * (size_t)depth, ctx->stream);
+    return r;
+} catch (...) {
+    return nullptr;
+}
+
+void mpegb200_video_ring_free(mpegb200_ring* r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    if (r->ctx->down_stream) cudaStreamSynchronize(r->ctx->down_stream);
+    if (r->pushed) cudaEventDestroy(r->pushed);
+    if (r->dev) cudaFree(r->dev);
+    delete r;
+}
+
+int mpegb200_video_ring_push(mpegb200_ring* r, const uint8_t* bufs) {
+    if (!r || !bufs) return MPEGB200_EINVAL;
+    mpegb200_ctx* ctx = r->ctx;
+    const int slot = (int)(r->head % (uint64_t)r->depth);
+    uint8_t* base = r->dev + (size_t)slot * r->stride * (size_t)r->n;
+    // a read-back of this slot that is still in flight must finish before the slot is overwritten
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->down_stream) {
+        CU(cudaEventRecord(ctx->ev_kernel, ctx->down_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_kernel, 0));
+    }
+    for (int i = 0; i < r->n;) {   // runs of streams that return a frame: one batched device-to-device copy each
+        if (bufs[i] == 255) {
+            i++;
+            continue;
+        }
+        int j = i;
+        while (j < r->n && bufs[j] != 255) j++;
+        if (int rc = mpegb200_video_read_pictures_dev(ctx, j - i, r->streams.data() + i, bufs + i, base + (size_t)i * r->stride, r->stride))
+            return rc;
+        i = j;
+    }
+    CU(cudaEventRecord(r->pushed, ctx->stream));
+    r->head++;
+    return slot;
+}
+
+void* mpegb200_video_ring_slot_dev(mpegb200_ring* r, int slot, size_t* stride) {
+    if (!r || slot < 0 || slot >= r->depth) return nullptr;
+    if (stride) *stride = r->stride;
+    return r->dev + (size_t)slot * r->stride * (size_t)r->n;
+}
+
+int mpegb200_video_ring_read_host(mpegb200_ring* r, int slot, uint8_t* dst, size_t dst_stride) {
+    if (!r || !dst || slot < 0 || slot >= r->depth || dst_stride < 1) return MPEGB200_EINVAL;
+    mpegb200_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamWaitEvent(ctx->down_stream, r->pushed, 0));
+    const uint8_t* src = r->dev + (size_t)slot * r->stride * (size_t)r->n;
+    const size_t width = dst_stride < r->stride ? dst_stride : r->stride;
+    CU(cudaMemcpy2DAsync(dst, dst_stride, src, r->stride, width, (size_t)r->n, cudaMemcpyDeviceToHost, ctx->down_stream));
+    return 0;
+}
+
 /* ---------------------------------------------------------------------------------------- audio */
 
 static int audio_alloc(mpegb200_ctx* ctx) {
@@ -1029,6 +1133,31 @@ int mpegb200_audio_synth(mpegb200_ctx* ctx, int n_streams, const int32_t* stream
     CU(cudaMemcpyAsync(ctx->s_samples.p, samples, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (int rc = mpegb200_audio_synth_dev(ctx, n_streams, stream_ids, frames_per_stream, (const int32_t*)ctx->s_samples.p,
                                           format, ctx->s_out.p))
+        return rc;
+    CU(cudaMemcpyAsync(out, ctx->s_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mpegb200_audio_synth_coded(mpegb200_ctx* ctx, int n_streams, const int32_t* stream_ids, int frames_per_stream,
+                               const mpegb200_audio_frame_info* info, const uint16_t* codes, int format, void* out) {
+    if (!ctx || n_streams < 0 || frames_per_stream < 0 || (n_streams && (!stream_ids || !info || !codes || !out)))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (!audio_format_ok(format)) return fail(ctx, MPEGB200_EINVAL, "unknown audio format %d", format);
+    if (n_streams == 0 || frames_per_stream == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n_frames = (size_t)n_streams * frames_per_stream;
+    const size_t out_bytes = n_frames * audio_out_bytes(format);
+    if (int rc = ensure(ctx, ctx->s_ainfo, n_frames * sizeof(mpegb200_audio_frame_info))) return rc;
+    if (int rc = ensure(ctx, ctx->s_acodes, n_frames * 2304 * sizeof(uint16_t))) return rc;
+    if (int rc = ensure(ctx, ctx->s_samples, n_frames * 2304 * sizeof(int32_t))) return rc;
+    if (int rc = ensure(ctx, ctx->s_out, out_bytes)) return rc;
+    CU(cudaMemcpyAsync(ctx->s_ainfo.p, info, n_frames * sizeof(mpegb200_audio_frame_info), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_acodes.p, codes, n_frames * 2304 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_audio_requant((const mpegb200_audio_frame_info*)ctx->s_ainfo.p, (const uint16_t*)ctx->s_acodes.p, (int32_t*)ctx->s_samples.p,
+                            n_frames, ctx->stream));
+    ctx->launches++;
+    if (int rc = mpegb200_audio_synth_dev(ctx, n_streams, stream_ids, frames_per_stream, (const int32_t*)ctx->s_samples.p, format, ctx->s_out.p))
         return rc;
     CU(cudaMemcpyAsync(out, ctx->s_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -932,21 +932,14 @@ const Quantizer* read_allocation(AP* a, int sb, int tab3) {  // audio.go:429-438
     return qtab ? &kQuant[qtab - 1] : nullptr;
 }
 
-// readSamples (audio.go:440-490): three requantised samples of one subband
-void read_samples(AP* a, int ch, int sb, int part, int64_t out[3]) {
+// readSamples (audio.go:440-490), first half: the three sample codes of one subband as the bitstream has them (degrouped)
+bool read_codes(AP* a, int ch, int sb, int64_t out[3]) {
     const Quantizer* q = a->alloc[ch][sb];
     if (!q) {
         out[0] = out[1] = out[2] = 0;
-        return;
+        return false;
     }
-    int64_t sf = a->scale[ch][sb][part];
-    if (sf == 63) {
-        sf = 0;
-    } else {
-        const int shift = (int)(sf / 3);
-        sf = (kScaleBase[sf % 3] + (((int64_t)1 << shift) >> 1)) >> shift;
-    }
-    int64_t adj = q->levels;
+    const int64_t adj = q->levels;
     if (q->group) {
         int64_t val = a->br.read(q->bits);
         out[0] = val % adj;
@@ -958,6 +951,20 @@ void read_samples(AP* a, int ch, int sb, int part, int64_t out[3]) {
         out[1] = a->br.read(q->bits);
         out[2] = a->br.read(q->bits);
     }
+    return true;
+}
+
+// ... second half: requantisation (audio.go:476-489)
+void requantise(const AP* a, int ch, int sb, int part, int64_t out[3]) {
+    const Quantizer* q = a->alloc[ch][sb];
+    int64_t sf = a->scale[ch][sb][part];
+    if (sf == 63) {
+        sf = 0;
+    } else {
+        const int shift = (int)(sf / 3);
+        sf = (kScaleBase[sf % 3] + (((int64_t)1 << shift) >> 1)) >> shift;
+    }
+    int64_t adj = q->levels;
     const int64_t scale = 65536 / (adj + 1);
     adj = ((adj + 1) >> 1) - 1;
     for (int i = 0; i < 3; i++) {
@@ -966,7 +973,12 @@ void read_samples(AP* a, int ch, int sb, int part, int64_t out[3]) {
     }
 }
 
-void decode_frame(AP* a, int32_t* samples) {  // audio.go:274-375 + the sample layout of mpegb200_audio_synth
+void read_samples(AP* a, int ch, int sb, int part, int64_t out[3]) {
+    if (read_codes(a, ch, sb, out)) requantise(a, ch, sb, part, out);
+}
+
+// samples != nullptr: requantised samples (the layout of mpegb200_audio_synth); else info + codes (mpegb200_audio_synth_coded)
+void decode_frame(AP* a, int32_t* samples, mpegb200_audio_frame_info* info = nullptr, uint16_t* codes = nullptr) {  // audio.go:274-375
     BitReader& br = a->br;
     const int tab2 = kRateClass[a->mode == kModeMono ? 0 : 1][a->bitrate_index];
     int tab3 = kTablePick[tab2][a->samplerate_index];
@@ -998,20 +1010,46 @@ void decode_frame(AP* a, int32_t* samples) {  // audio.go:274-375 + the sample l
         if (a->mode == kModeMono)
             for (int i = 0; i < 3; i++) a->scale[1][sb][i] = a->scale[0][sb][i];
     }
-    memset(samples, 0, sizeof(int32_t) * 2 * 36 * 32);  // subbands >= sblimit stay zero (audio.go:368-375)
+    if (samples) {
+        memset(samples, 0, sizeof(int32_t) * 2 * 36 * 32);  // subbands >= sblimit stay zero (audio.go:368-375)
+    } else {
+        memset(codes, 0, sizeof(uint16_t) * 2 * 36 * 32);
+        memset(info, 0, sizeof(*info));
+        for (int sb = 0; sb < sblimit; sb++)
+            for (int ch = 0; ch < 2; ch++) {
+                // above the joint-stereo bound (and for mono) channel 1 mirrors channel 0's requantised samples
+                // (audio.go:362-367): it gets channel 0's quantiser AND scale factors, so the device computes the same values
+                const int src = sb < a->bound ? ch : 0;
+                const Quantizer* q = a->alloc[src][sb];
+                info->quant[ch][sb] = q ? (uint8_t)(q - kQuant + 1) : 0;
+                for (int part = 0; part < 3; part++) info->scf[ch][sb][part] = (uint8_t)a->scale[src][sb][part];
+            }
+    }
     for (int part = 0; part < 3; part++)
         for (int granule = 0; granule < 4; granule++) {
             const int step0 = 3 * (4 * part + granule);
             int64_t s0[3], s1[3];
             for (int sb = 0; sb < sblimit; sb++) {
-                read_samples(a, 0, sb, part, s0);
-                if (sb < a->bound)
-                    read_samples(a, 1, sb, part, s1);
-                else
-                    memcpy(s1, s0, sizeof(s0));  // joint/mono: channel 1 mirrors channel 0 (audio.go:362-367)
-                for (int p = 0; p < 3; p++) {
-                    samples[(0 * 36 + step0 + p) * 32 + sb] = (int32_t)s0[p];
-                    samples[(1 * 36 + step0 + p) * 32 + sb] = (int32_t)s1[p];
+                if (samples) {
+                    read_samples(a, 0, sb, part, s0);
+                    if (sb < a->bound)
+                        read_samples(a, 1, sb, part, s1);
+                    else
+                        memcpy(s1, s0, sizeof(s0));  // joint/mono: channel 1 mirrors channel 0 (audio.go:362-367)
+                    for (int p = 0; p < 3; p++) {
+                        samples[(0 * 36 + step0 + p) * 32 + sb] = (int32_t)s0[p];
+                        samples[(1 * 36 + step0 + p) * 32 + sb] = (int32_t)s1[p];
+                    }
+                } else {
+                    read_codes(a, 0, sb, s0);
+                    if (sb < a->bound)
+                        read_codes(a, 1, sb, s1);
+                    else
+                        memcpy(s1, s0, sizeof(s0));
+                    for (int p = 0; p < 3; p++) {
+                        codes[(0 * 36 + step0 + p) * 32 + sb] = (uint16_t)s0[p];
+                        codes[(1 * 36 + step0 + p) * 32 + sb] = (uint16_t)s1[p];
+                    }
                 }
             }
         }
@@ -1057,16 +1095,23 @@ void mpegb200_audio_parser_rewind(mpegb200_audio_parser* a) {  // audio.go:149-1
     a->samples_decoded = 0;
     a->next_frame_data_size = 0;
 }
-int mpegb200_audio_parser_next(mpegb200_audio_parser* a, int32_t* samples, double* time) {  // audio.go:163-182
-    if (!a || !samples) return 0;
+static int audio_next(mpegb200_audio_parser* a, int32_t* samples, mpegb200_audio_frame_info* info, uint16_t* codes, double* time) {
     if (a->next_frame_data_size == 0) a->next_frame_data_size = decode_header(a);
     if (a->next_frame_data_size == 0 || !a->br.has((int64_t)a->next_frame_data_size << 3)) return 0;
-    decode_frame(a, samples);
+    decode_frame(a, samples, info, codes);
     a->next_frame_data_size = 0;
     if (time) *time = a->time;
     a->samples_decoded += MPEGB200_SAMPLES_PER_FRAME;
     a->time = (double)a->samples_decoded / (double)kSampleRate[a->samplerate_index];
     return 1;
+}
+int mpegb200_audio_parser_next(mpegb200_audio_parser* a, int32_t* samples, double* time) {  // audio.go:163-182
+    if (!a || !samples) return 0;
+    return audio_next(a, samples, nullptr, nullptr, time);
+}
+int mpegb200_audio_parser_next_coded(mpegb200_audio_parser* a, mpegb200_audio_frame_info* info, uint16_t* codes, double* time) {
+    if (!a || !info || !codes) return 0;
+    return audio_next(a, nullptr, info, codes, time);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1471,3 +1516,147 @@ int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out)
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Many MP2 streams in lock-step: parse the next frames of every stream on the pool, hand them over as one rectangular
+// batch (one mpegb200_audio_synth launch for all streams) plus the tails of the streams that end inside the step.
+// ------------------------------------------------------------------------------------------------
+struct mpegb200_audio_batch {
+    std::unique_ptr<WorkerPool> pool;
+    int n = 0;
+    void* (*alloc)(size_t) = nullptr;
+    void (*free_fn)(void*) = nullptr;
+    std::vector<mpegb200_audio_parser*> parsers;
+    std::vector<int> n_frames;
+    std::vector<double> time;
+    std::vector<int32_t> full_index, tail_index, tail_frames;
+    int32_t* stage = nullptr;        // [n][frames][2][36][32], every stream parses into its own rows
+    int32_t* full = nullptr;         // compacted rectangular part (pinned when alloc is given)
+    int32_t* tail = nullptr;
+    size_t cap_stage = 0, cap_full = 0, cap_tail = 0;
+
+    void* get(size_t bytes) { return alloc ? alloc(bytes ? bytes : 1) : malloc(bytes ? bytes : 1); }
+    void put(void* p) {
+        if (!p) return;
+        if (free_fn) free_fn(p); else free(p);
+    }
+    bool reserve(int32_t*& p, size_t& cap, size_t need) {
+        if (need <= cap) return true;
+        put(p);
+        cap = need + need / 4 + 64;
+        p = (int32_t*)get(cap * sizeof(int32_t));
+        return p != nullptr;
+    }
+};
+
+extern "C" {
+
+mpegb200_audio_batch* mpegb200_audio_batch_new(int n_streams, int threads, void* (*alloc)(size_t), void (*free_fn)(void*)) {
+    if (n_streams <= 0 || n_streams > (1 << 20)) return nullptr;
+    auto* b = new (std::nothrow) mpegb200_audio_batch();
+    if (!b) return nullptr;
+    try {
+        b->n = n_streams;
+        b->pool.reset(new WorkerPool(threads > 0 ? threads : 1));
+        b->alloc = alloc;
+        b->free_fn = free_fn;
+        b->parsers.assign((size_t)n_streams, nullptr);
+        b->n_frames.assign((size_t)n_streams, 0);
+        b->time.assign((size_t)n_streams, 0.0);
+    } catch (...) {
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+
+void mpegb200_audio_batch_free(mpegb200_audio_batch* b) {
+    if (!b) return;
+    for (auto* p : b->parsers) mpegb200_audio_parser_free(p);
+    b->put(b->stage);
+    b->put(b->full);
+    b->put(b->tail);
+    delete b;
+}
+
+int mpegb200_audio_batch_set_stream(mpegb200_audio_batch* b, int index, const uint8_t* data, size_t len) {
+    if (!b || index < 0 || index >= b->n) return MPEGB200_EINVAL;
+    mpegb200_audio_parser_free(b->parsers[(size_t)index]);
+    b->parsers[(size_t)index] = mpegb200_audio_parser_new(data, len);
+    return b->parsers[(size_t)index] ? 0 : MPEGB200_ENOMEM;
+}
+
+int mpegb200_audio_batch_stream_info(mpegb200_audio_batch* b, int index, int* samplerate, int* channels) {
+    if (!b || index < 0 || index >= b->n || !b->parsers[(size_t)index]) return MPEGB200_EINVAL;
+    if (samplerate) *samplerate = mpegb200_audio_parser_samplerate(b->parsers[(size_t)index]);
+    if (channels) *channels = mpegb200_audio_parser_channels(b->parsers[(size_t)index]);
+    return 0;
+}
+
+static int audio_batch_next_impl(mpegb200_audio_batch* b, int F, mpegb200_audio_batch_step* out) {
+    const size_t frame = 2 * 36 * 32;
+    const int n = b->n;
+    if (!b->reserve(b->stage, b->cap_stage, (size_t)n * F * frame)) return MPEGB200_ENOMEM;
+    b->pool->run(n, [&](int i) {
+        int k = 0;
+        double t0 = 0, t = 0;
+        mpegb200_audio_parser* p = b->parsers[(size_t)i];
+        while (p && k < F && mpegb200_audio_parser_next(p, b->stage + ((size_t)i * F + k) * frame, &t)) {
+            if (k == 0) t0 = t;
+            k++;
+        }
+        b->n_frames[(size_t)i] = k;
+        b->time[(size_t)i] = t0;
+    });
+    b->full_index.clear();
+    b->tail_index.clear();
+    b->tail_frames.clear();
+    size_t tail_total = 0;
+    for (int i = 0; i < n; i++) {
+        const int k = b->n_frames[(size_t)i];
+        if (k == F) {
+            b->full_index.push_back(i);
+        } else if (k > 0) {
+            b->tail_index.push_back(i);
+            b->tail_frames.push_back(k);
+            tail_total += (size_t)k;
+        }
+    }
+    const size_t n_full = b->full_index.size();
+    if (!b->reserve(b->full, b->cap_full, n_full * F * frame) || !b->reserve(b->tail, b->cap_tail, tail_total * frame))
+        return MPEGB200_ENOMEM;
+    b->pool->run((int)n_full, [&](int j) {
+        memcpy(b->full + (size_t)j * F * frame, b->stage + (size_t)b->full_index[(size_t)j] * F * frame, (size_t)F * frame * sizeof(int32_t));
+    });
+    size_t at = 0;
+    for (size_t j = 0; j < b->tail_index.size(); j++) {
+        memcpy(b->tail + at * frame, b->stage + (size_t)b->tail_index[j] * F * frame, (size_t)b->tail_frames[j] * frame * sizeof(int32_t));
+        at += (size_t)b->tail_frames[j];
+    }
+    out->n_streams = n;
+    out->n_frames = b->n_frames.data();
+    out->time = b->time.data();
+    out->frames_per_stream = F;
+    out->n_full = (int)n_full;
+    out->full_index = b->full_index.data();
+    out->full_samples = b->full;
+    out->n_tail = (int)b->tail_index.size();
+    out->tail_index = b->tail_index.data();
+    out->tail_frames = b->tail_frames.data();
+    out->tail_samples = b->tail;
+    return 0;
+}
+
+int mpegb200_audio_batch_next(mpegb200_audio_batch* b, int frames_per_stream, mpegb200_audio_batch_step* out) {
+    if (!b || !out || frames_per_stream <= 0 || frames_per_stream > 4096) return MPEGB200_EINVAL;
+    memset(out, 0, sizeof(*out));
+    try {
+        return audio_batch_next_impl(b, frames_per_stream, out);
+    } catch (...) {
+        memset(out, 0, sizeof(*out));
+        return MPEGB200_ENOMEM;
+    }
+}
+
+}  // extern "C"
+

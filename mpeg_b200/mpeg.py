@@ -176,9 +176,12 @@ class Samples:
 class Audio:
     """mpeg.Audio (audio.go:53): MP2 elementary stream -> 1152-sample frames."""
 
-    def __init__(self, data: bytes, ctx: Context, stream: int = 0, fmt: int = 0):
+    def __init__(self, data: bytes, ctx: Context, stream: int = 0, fmt: int = 0, coded: bool = True):
+        """coded: the host parser stops before the requantisation (audio.go:476-489) and the device does it
+        (mpegb200_audio_synth_coded: half the bytes over PCIe); False: requantised int32 samples from the host."""
         self.L = _lib.load()
-        self.ctx, self.stream, self.fmt = ctx, stream, fmt
+        self.ctx, self.stream, self.fmt, self.coded = ctx, stream, fmt, coded
+        self._info, self._codes = np.zeros(256, np.uint8), np.zeros((2, 36, 32), np.uint16)
         self._data = bytes(data)
         self.h = self.L.mpegb200_audio_parser_new(self._data, len(self._data))
         if not self.h:
@@ -202,9 +205,14 @@ class Audio:
 
     def decode(self):
         t = C.c_double()
-        if not self.L.mpegb200_audio_parser_next(self.h, C.c_void_p(self._samples.ctypes.data), C.byref(t)):
-            return None
-        out = self.ctx.audio_synth([self.stream], 1, self._samples, self.fmt)
+        if self.coded:
+            if not self.L.mpegb200_audio_parser_next_coded(self.h, C.c_void_p(self._info.ctypes.data), C.c_void_p(self._codes.ctypes.data), C.byref(t)):
+                return None
+            out = self.ctx.audio_synth_coded([self.stream], 1, self._info, self._codes, self.fmt)
+        else:
+            if not self.L.mpegb200_audio_parser_next(self.h, C.c_void_p(self._samples.ctypes.data), C.byref(t)):
+                return None
+            out = self.ctx.audio_synth([self.stream], 1, self._samples, self.fmt)
         return Samples(out[0, 0], t.value) if self.fmt != 3 else out[0, 0]
 
     def close(self):

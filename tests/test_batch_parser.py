@@ -135,3 +135,53 @@ def test_batch_waves_in_vlen_form_match_the_converter(golden_dir):
     assert waves > 50 and blocks > 10000
     for h in hs:
         L.mpegb200_video_batch_free(h)
+
+
+def test_audio_batch_matches_the_single_stream_parser(golden_dir):
+    """mpegb200_audio_batch_*: streams of different lengths, five frames per step; the rectangular part and the tails together
+    hold exactly the frames the single-stream parser yields, in order."""
+    import ctypes as C
+    from mpeg_b200 import _lib
+    from mpeg_b200.batch import AudioBatchStep
+    L = _lib.load()
+    mp2 = (golden_dir / "test.mp2").read_bytes()
+    datas = [mp2, mp2[: len(mp2) // 2], mp2[: len(mp2) // 3], mp2, b"junk" * 100]
+    want = []
+    for d in datas:
+        h = L.mpegb200_audio_parser_new(d, len(d))
+        frames, s, t = [], np.zeros((2, 36, 32), np.int32), C.c_double()
+        while L.mpegb200_audio_parser_next(h, C.c_void_p(s.ctypes.data), C.byref(t)):
+            frames.append((s.copy(), t.value))
+        L.mpegb200_audio_parser_free(h)
+        want.append(frames)
+    assert len(want[0]) > len(want[1]) > len(want[2]) > 5 and len(want[4]) == 0
+    b = L.mpegb200_audio_batch_new(len(datas), 3, None, None)
+    for i, d in enumerate(datas):
+        assert L.mpegb200_audio_batch_set_stream(b, i, d, len(d)) == 0
+    F, got = 5, [[] for _ in datas]
+    saw_tail = False
+    while True:
+        st = AudioBatchStep()
+        assert L.mpegb200_audio_batch_next(b, F, C.byref(st)) == 0
+        if st.n_full == 0 and st.n_tail == 0:
+            break
+        full = np.frombuffer(C.string_at(st.full_samples, st.n_full * F * 2304 * 4), np.int32).reshape(st.n_full, F, 2, 36, 32) if st.n_full else None
+        for j in range(st.n_full):
+            i = st.full_index[j]
+            assert st.n_frames[i] == F
+            assert st.time[i] == want[i][len(got[i])][1]
+            got[i].extend(full[j])
+        at = 0
+        for j in range(st.n_tail):
+            i, k = st.tail_index[j], st.tail_frames[j]
+            assert 0 < k < F and st.n_frames[i] == k
+            tail = np.frombuffer(C.string_at(st.tail_samples + at * 2304 * 4, k * 2304 * 4), np.int32).reshape(k, 2, 36, 32)
+            got[i].extend(tail)
+            at += k
+            saw_tail = True
+    assert saw_tail
+    for i in range(len(datas)):
+        assert len(got[i]) == len(want[i])
+        for a, (w, _) in zip(got[i], want[i]):
+            assert np.array_equal(a, w)
+    L.mpegb200_audio_batch_free(b)

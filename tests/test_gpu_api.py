@@ -147,3 +147,66 @@ def test_video_batch_lockstep_golden(golden_dir):
         assert hashes[i] == want[i % len(kinds)], f"stream {i}: {hashes[i]:#018x}"
     # the oracle's hash of the elementary stream is the reference's golden value
     assert want[0] == VIDEO_GOLDEN
+
+
+def test_program_stream_batch_with_display_ring_and_audio_batch(golden_dir):
+    """the batched front end.  Program streams are demultiplexed, their video decodes in lock-step with the
+    returned frames kept in a device display ring (read back LATE, two steps behind the decoder), their audio goes through the
+    lock-step audio batch (eight frames per stream and launch, streams of different lengths).  Every stream must reproduce
+    the oracle's hashes for its own bitstream."""
+    import mpeg_b200
+    full = (golden_dir / "test.mpg").read_bytes()
+    es_v, es_a, _, _ = ol.demux_split(full)
+
+    def oracle_hashes(video, audio):
+        o, hv = ol.VideoOracle(video), ol.FNV_OFFSET
+        while (f := o.decode()) is not None:
+            for which in ("y", "cb", "cr"):
+                hv = ol.fnv(hv, f.plane(which))
+        a, ha, k = ol.AudioOracle(audio), ol.FNV_OFFSET, 0
+        while (s := a.decode()) is not None:
+            ha = ol.fnv(ha, s)
+            k += 1
+        return hv, ha, k
+
+    # program streams cut at different packet boundaries: different lengths in both elementary streams
+    cuts = [len(full), full.rfind(b"\x00\x00\x01\xe0", 0, 300000), full.rfind(b"\x00\x00\x01\xc0", 0, 200000)]
+    datas = [full[:c] for c in cuts]
+    want = []
+    for d in datas:
+        v, a, _, _ = ol.demux_split(d)
+        want.append(oracle_hashes(v, a))
+    n = 9
+    streams = [datas[i % 3] for i in range(n)]
+    with mpeg_b200.Context(device=0, max_streams=16) as c:
+        mb = mpeg_b200.MPEGBatch(c, streams, threads=4, ring_depth=4, frames_per_step=8)
+        assert mb.packets[0] == (143, 37)
+        geo = c.video_geometry(0)
+        pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
+        hv = [ol.FNV_OFFSET] * n
+        pending = []                       # (slot, has) of the steps not yet read back
+        while True:
+            has, t, slot = mb.decode_video()
+            if has.any():
+                pending.append((slot, has.copy()))
+            while pending and (len(pending) > 2 or not has.any()):   # consume two steps behind the decoder
+                s, h = pending.pop(0)
+                pics = mb.ring.read(s, pic_bytes)
+                for i in np.nonzero(h)[0]:
+                    hv[i] = ol.fnv(hv[i], pics[i])
+            if not has.any():
+                break
+        ha, frames = [ol.FNV_OFFSET] * n, [0] * n
+        while True:
+            nf, t, out = mb.decode_audio()
+            if not nf.any():
+                break
+            for i in range(n):
+                for k in range(int(nf[i])):
+                    ha[i] = ol.fnv(ha[i], out[i][k])
+                frames[i] += int(nf[i])
+        mb.close()
+    for i in range(n):
+        assert hv[i] == want[i % 3][0], f"video of stream {i}"
+        assert ha[i] == want[i % 3][1] and frames[i] == want[i % 3][2], f"audio of stream {i}: {frames[i]} frames"
+    assert want[0][2] > want[2][2] > 8    # different lengths: the shorter streams end inside a step (tail launches)

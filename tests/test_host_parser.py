@@ -342,3 +342,52 @@ def test_parser_vlen_on_corrupted_streams(golden_dir):
             d[pos] ^= 1 << int(rng.integers(0, 8))
         launches += assert_vlen_equals_packed_int16(bytes(d), f"trial {trial}")[0]
     assert launches > 100
+
+
+def requantise_reference(info, codes):
+    """audio.go:476-489 in numpy int64, from the coded form of include/mpegb200.h (quantiser number, scale-factor indices, codes)."""
+    levels = np.array([3, 5, 7, 9, 15, 31, 63, 127, 255, 511, 1023, 2047, 4095, 8191, 16383, 32767, 65535], np.int64)
+    base = np.array([0x02000000, 0x01965FEA, 0x01428A30], np.int64)
+    quant = info[:64].reshape(2, 32).astype(np.int64)
+    scf = info[64:].reshape(2, 32, 3).astype(np.int64)
+    out = np.zeros((2, 36, 32), np.int64)
+    for ch in range(2):
+        for sb in range(32):
+            if quant[ch, sb] == 0:
+                continue
+            lv = levels[quant[ch, sb] - 1]
+            scale, adj = 65536 // (lv + 1), ((lv + 1) >> 1) - 1
+            for part in range(3):
+                i = scf[ch, sb, part]
+                sf = 0 if i == 63 else (base[i % 3] + ((1 << (i // 3)) >> 1)) >> (i // 3)
+                val = (adj - codes[ch, 12 * part:12 * part + 12, sb].astype(np.int64)) * scale
+                out[ch, 12 * part:12 * part + 12, sb] = (val * (sf >> 12) + ((val * (sf & 4095) + 2048) >> 12)) >> 12
+    return out
+
+
+@pytest.mark.parametrize("which", ["test.mp2", "test.mpg audio"])
+def test_coded_audio_frames_requantise_to_the_parsers_samples(golden_dir, which):
+    """mpegb200_audio_parser_next_coded stops before the requantisation; applying audio.go:476-489 to what it
+    emits gives exactly the samples of mpegb200_audio_parser_next (which equal the oracle's, see above).  Also bounds the
+    arithmetic: every intermediate of the formula fits int32, which is what the device kernel computes in."""
+    data = (golden_dir / "test.mp2").read_bytes() if which == "test.mp2" else ol.demux_split((golden_dir / "test.mpg").read_bytes())[1]
+    L = _lib.load()
+    a, b = L.mpegb200_audio_parser_new(data, len(data)), L.mpegb200_audio_parser_new(data, len(data))
+    s = np.zeros((2, 36, 32), np.int32)
+    info, codes = np.zeros(256, np.uint8), np.zeros((2, 36, 32), np.uint16)
+    t1, t2 = C.c_double(), C.c_double()
+    frames = 0
+    while True:
+        g1 = L.mpegb200_audio_parser_next(a, C.c_void_p(s.ctypes.data), C.byref(t1))
+        g2 = L.mpegb200_audio_parser_next_coded(b, C.c_void_p(info.ctypes.data), C.c_void_p(codes.ctypes.data), C.byref(t2))
+        assert g1 == g2
+        if not g1:
+            break
+        assert t1.value == t2.value
+        want = requantise_reference(info, codes)
+        assert np.array_equal(want, s.astype(np.int64)), f"frame {frames}"
+        assert np.abs(want).max() < 2 ** 31
+        frames += 1
+    assert frames > 30
+    L.mpegb200_audio_parser_free(a)
+    L.mpegb200_audio_parser_free(b)
