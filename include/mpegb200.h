@@ -223,6 +223,75 @@ int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const
                                         size_t n_mb, const mpegb200_mb* mbs, size_t n_blocks, const uint32_t* headers,
                                         const uint64_t* chunk_offsets, const uint8_t* payload, size_t payload_bytes);
 
+/* ---- slice-parallel VLC stage on the device -------------------------------------------------------------
+ * The serial walk of decodeSlice / decodeMacroblock / decodeBlock (video.go:436-746) is what bounds bitstream -> frames
+ * (tens of 720p pictures per second and host thread against 8 x 10^5 in the decode kernel).  MPEG-1 slices start
+ * byte-aligned at start codes and reset every predictor (video.go:436-446), so they parse independently: here the host
+ * keeps only the headers and the start-code scan (mpegb200_video_parser_next_scan / mpegb200_video_batch_next_scan in
+ * mpegb200_host.h), the compressed bytes go to the device as they are, and one GPU thread per slice walks the macroblocks
+ * (vlc_parse_kernel: bit reader, table-driven codes, motion vectors, dequantisation -- video.go:462-746) and writes the SAME
+ * packed records the host parser would write (mpegb200_mb + int16[64] blocks) into device memory, which the decode
+ * kernels then consume -- no coefficient ever crosses PCIe.
+ *
+ * A wave = at most one picture per stream.  Record slots: slice s owns mb_cap(s) record slots (a multiple of 16, so a
+ * group of 16 records never straddles two slices) and 6 * mb_cap(s) block slots starting at block 6 * mb_slot(s); unused
+ * slots hold null records (pic == 0xffff) that the kernels skip.
+ *
+ * What the serial reference resolves by order of arrival is not reproduced on the device but DETECTED there: a picture one
+ * of whose slices runs past the next start code (or into a start code the scan took for a slice), overflows its slots,
+ * hits an invalid run (video.go:712-714), drops a macroblock (address outside the picture), reads outside its frame buffer
+ * (the reference panics, video_noasm.go:49-50), whose slices overlap, come out of order or end the picture early
+ * (video.go:424-426) is FLAGGED: none of its records is executed (its destination buffer stays untouched) and the caller
+ * decodes it through the host parser (mpegb200_video_parser_redo / mpegb200_video_batch_redo), which has the reference's
+ * serial semantics.  Streams a conforming encoder wrote never flag. */
+typedef struct mpegb200_vlc_picture {
+    int32_t  stream;                 /* stream id given to mpegb200_video_open */
+    uint8_t  type, dst_buf, fwd_buf, bwd_buf;
+    uint8_t  fwd_full_px, fwd_r_size, bwd_full_px, bwd_r_size;   /* picture header, video.go:393-404 */
+    uint32_t first_slice, n_slices;  /* its slices in the wave's slice array, in bitstream order */
+    uint32_t mb_slot, n_mb_slots;    /* record slots of the picture: [mb_slot, mb_slot + n_mb_slots) */
+    uint32_t quant;                  /* index of its 128-byte quantiser pair (intra then non-intra, natural order) */
+} mpegb200_vlc_picture;              /* 32 bytes */
+
+typedef struct mpegb200_vlc_slice {
+    uint64_t data_offset;            /* byte offset, in the wave's bitstream buffer, of the first byte behind the slice start code */
+    uint32_t next_code;              /* bytes from there to the next start code of the stream (to its end if there is none):
+                                        a slice that consumes more is flagged */
+    uint32_t stream_left;            /* bytes from there to the END of the elementary stream, saturated at 2^32 - 1 (the
+                                        reader delivers zero bits beyond, buffer.go:203-255) */
+    uint32_t pic;                    /* index into the wave's pictures */
+    uint32_t vpos;                   /* slice vertical position 1..175 (the start code's last byte) */
+    uint32_t mb_slot, mb_cap;        /* record slots of the slice: [mb_slot, mb_slot + mb_cap), both multiples of 16 */
+} mpegb200_vlc_slice;                /* 32 bytes */
+
+/* per-picture flags (0 = decoded on the device) */
+#define MPEGB200_VLC_INVALID_RUN  0x01   /* a run left the block (video.go:712-714) */
+#define MPEGB200_VLC_OVERFLOW     0x02   /* more macroblocks than the slice's record slots */
+#define MPEGB200_VLC_OVERRUN      0x04   /* the slice consumed bits beyond next_code */
+#define MPEGB200_VLC_DROPPED      0x08   /* a macroblock address outside the picture */
+#define MPEGB200_VLC_WINDOW       0x10   /* a motion vector reads outside the frame buffer / reference == destination */
+#define MPEGB200_VLC_ORDER        0x20   /* slices overlap or are out of order */
+#define MPEGB200_VLC_EARLY_END    0x40   /* a slice other than the last reaches the end of the picture */
+#define MPEGB200_VLC_BAD_ARG      0x80   /* the slice or picture table itself is inconsistent */
+
+/* Parse + decode one wave: uploads the tables and the bytes, runs vlc_parse_kernel and vlc_check_kernel, then the decode
+ * kernels on the records they left in device memory.  All arrays are host memory (pinned for asynchronous uploads);
+ * `bitstream` holds the pictures' bytes, bitstream_bytes < 2^32.  quant: n_quant x 128 bytes.  n_mb_slots: total record
+ * slots of the wave (a multiple of 16, < 2^32 / 6).  Asynchronous like the other decode entry points; returns 0 or a negative code. */
+int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpegb200_vlc_picture* pics,
+                                    size_t n_slices, const mpegb200_vlc_slice* slices,
+                                    const uint8_t* bitstream, size_t bitstream_bytes,
+                                    const uint8_t* quant, size_t n_quant, size_t n_mb_slots);
+/* Waits for the last mpegb200_video_decode_bitstream call and writes its per-picture flags (n ints, n = that call's
+ * n_pictures).  Returns the number of flagged pictures or a negative code. */
+int mpegb200_video_bitstream_flags(mpegb200_ctx* ctx, int* flags_out, int n);
+/* Test / debug aid: the records the last mpegb200_video_decode_bitstream call produced, copied to host memory
+ * (n_mb_slots records, 6 * n_mb_slots blocks of 64 int16; null records have pic == 0xffff; the blocks behind a slice's
+ * last coded block are undefined). */
+int mpegb200_video_bitstream_records(mpegb200_ctx* ctx, mpegb200_mb* mbs, int16_t* coeffs);
+/* Measurement aid: duration of the parse + check kernels of the last call in milliseconds (needs mpegb200_set_kernel_timing). */
+int mpegb200_video_bitstream_parse_ms(mpegb200_ctx* ctx, float* ms);
+
 /* Plane read-back for *Frame (Plane.Data, video.go:50-54): copies the macroblock-padded
  * planes of physical buffer `buf` to host memory.  Any of y/cb/cr may be NULL. */
 int mpegb200_video_read_planes(mpegb200_ctx* ctx, int stream, int buf,

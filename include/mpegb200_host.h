@@ -84,6 +84,49 @@ int    mpegb200_video_parser_has_ended(mpegb200_video_parser* v);
  * the next call on the same parser.  Returns 0, or MPEGB200_EINVAL. */
 int    mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* out);
 
+/* ---- scan mode: headers and start codes on the host, slices to the device (mpegb200_video_decode_bitstream) ---- */
+
+typedef struct mpegb200_scan_slice {
+    uint64_t offset;            /* byte offset, in the elementary stream, of the first byte behind the slice start code */
+    uint64_t next_code;         /* byte offset of the next start code (its 00 00 01), or the stream's length if there is none */
+    uint32_t vpos;              /* vertical position 1..175 */
+    uint32_t reserved;
+} mpegb200_scan_slice;
+
+typedef struct mpegb200_scan_picture {
+    uint8_t  type, dst_buf, fwd_buf, bwd_buf;
+    uint8_t  fwd_full_px, fwd_r_size, bwd_full_px, bwd_r_size;
+    uint32_t first_slice, n_slices;    /* into the step's slice array */
+    uint64_t begin, end;               /* byte range of the picture in the elementary stream: its start code .. behind the start code that ended its slices */
+} mpegb200_scan_picture;
+
+/* What one Video.Decode() call amounts to when the slices are left unparsed. */
+typedef struct mpegb200_video_scan_step {
+    int has_frame;
+    int frame_buf;
+    double time;
+    int n_pictures;
+    const mpegb200_scan_picture* pictures;
+    const mpegb200_scan_slice* slices;
+    const uint8_t* stream;             /* the parser's copy of the elementary stream, stream_len bytes (+ 16 readable zero bytes) */
+    size_t stream_len;
+    const uint8_t* quant;              /* 128 bytes: intra then non-intra quantiser matrix, natural order (video.go:299-309) */
+    int mb_w, mb_h;
+    /* Not NULL: the host parsed this step itself (n_pictures == 0) and these are its launches.  Happens while coefficients of a
+     * dropped block (video.go:712-714) are pending: the serial reference leaks them into the next block it decodes, and only
+     * the host parser carries that state. */
+    const mpegb200_video_step* host_step;
+} mpegb200_video_scan_step;
+
+/* Like mpegb200_video_parser_next, stopping at the slice start codes.  The two calls may alternate between steps. */
+int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_scan_step* out);
+/* The device stage flagged picture k of the last scan step: the parser goes back in front of that picture and parses the
+ * REST OF THE STEP (picture k and whatever Video.Decode() would decode behind it) in full, with the serial semantics of
+ * the reference; it stands where the reference would stand afterwards, which may differ from where the scan stood (a
+ * damaged slice may swallow the start codes behind it).  *out is the step's tail: its launches replace picture k and every
+ * later picture of the scan step, its has_frame / frame_buf / time replace the scan step's. */
+int mpegb200_video_parser_redo(mpegb200_video_parser* v, int k, mpegb200_video_step* out);
+
 /* ---- many video streams in lock-step (the batched deployment of INTEGRATION.md section 6) ------- */
 
 typedef struct mpegb200_video_batch mpegb200_video_batch;
@@ -123,6 +166,40 @@ int  mpegb200_video_batch_stream_size(mpegb200_video_batch* b, int index, int* w
 int  mpegb200_video_batch_set_vlen(mpegb200_video_batch* b, int on);
 /* One Video.Decode() step of every stream, parsed in parallel and merged into waves. */
 int  mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out);
+
+/* The same in scan mode: the waves carry slice tables and the pictures' compressed bytes for mpegb200_video_decode_bitstream. */
+typedef struct mpegb200_vlc_wave {
+    int n_pictures;
+    const mpegb200_vlc_picture* pics;   /* pics[i].stream is the stream's index in the batch */
+    const int32_t* step_picture;        /* per picture: its index in its stream's scan step (argument of mpegb200_video_batch_redo) */
+    size_t n_slices;
+    const mpegb200_vlc_slice* slices;
+    const uint8_t* bitstream;
+    size_t bitstream_bytes;
+    const uint8_t* quant;               /* n_pictures x 128 bytes */
+    size_t n_quant;                     /* = n_pictures */
+    size_t n_mb_slots;
+} mpegb200_vlc_wave;
+
+typedef struct mpegb200_batch_scan_step {
+    int n_streams;
+    const int* has_frame;
+    const int* frame_buf;
+    const double* time;
+    int n_waves;
+    const mpegb200_vlc_wave* waves;
+    /* streams whose step the host parsed itself (mpegb200_video_scan_step.host_step): run their launches like those of
+     * mpegb200_video_parser_next; they take no part in the waves */
+    int n_host;
+    const int* host_index;
+    const mpegb200_video_step* host_steps;
+} mpegb200_batch_scan_step;
+
+int  mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_step* out);
+/* mpegb200_video_parser_redo for stream `index` of the batch: the rest of its step from picture `step_picture` on, parsed on
+ * the host.  The stream's pictures in the later waves of this step are void (set their type to 0 before the wave is decoded:
+ * the device then skips them); has_frame / frame_buf / time of the stream are those of *out. */
+int  mpegb200_video_batch_redo(mpegb200_video_batch* b, int index, int step_picture, mpegb200_video_step* out);
 
 /* ---- MP2 elementary stream --------------------------------------------------------------------- */
 

@@ -74,6 +74,10 @@ def load():
         "mpegb200_vlen_validate": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
         "mpegb200_pack_coeffs_vlen": (C.c_int, [vp, C.c_size_t, vp, vp, vp, C.c_size_t, szp]),
         "mpegb200_video_decode_pictures_vlen": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp, vp, C.c_size_t]),
+        "mpegb200_video_decode_bitstream": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t]),
+        "mpegb200_video_bitstream_flags": (C.c_int, [vp, vp, C.c_int]),
+        "mpegb200_video_bitstream_records": (C.c_int, [vp, vp, vp]),
+        "mpegb200_video_bitstream_parse_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "mpegb200_video_read_planes": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
         "mpegb200_video_write_planes": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
         "mpegb200_video_read_frame": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
@@ -109,6 +113,10 @@ def load():
         "mpegb200_video_parser_rewind": (None, [vp]),
         "mpegb200_video_parser_has_ended": (C.c_int, [vp]),
         "mpegb200_video_parser_next": (C.c_int, [vp, vp]),
+        "mpegb200_video_parser_next_scan": (C.c_int, [vp, vp]),
+        "mpegb200_video_parser_redo": (C.c_int, [vp, C.c_int, vp]),
+        "mpegb200_video_batch_next_scan": (C.c_int, [vp, vp]),
+        "mpegb200_video_batch_redo": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "mpegb200_video_batch_new": (vp, [C.c_int, C.c_int, vp, vp]),
         "mpegb200_video_batch_free": (None, [vp]),
         "mpegb200_video_batch_set_stream": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_size_t]),

@@ -25,10 +25,42 @@ class BatchStep(C.Structure):
                 ("time", C.POINTER(C.c_double)), ("n_waves", C.c_int), ("waves", C.POINTER(Wave))]
 
 
+class VlcPicture(C.Structure):      # mpegb200_vlc_picture
+    _fields_ = [("stream", C.c_int32), ("type", C.c_uint8), ("dst_buf", C.c_uint8), ("fwd_buf", C.c_uint8), ("bwd_buf", C.c_uint8),
+                ("fwd_full_px", C.c_uint8), ("fwd_r_size", C.c_uint8), ("bwd_full_px", C.c_uint8), ("bwd_r_size", C.c_uint8),
+                ("first_slice", C.c_uint32), ("n_slices", C.c_uint32), ("mb_slot", C.c_uint32), ("n_mb_slots", C.c_uint32),
+                ("quant", C.c_uint32)]
+
+
+class VlcSlice(C.Structure):        # mpegb200_vlc_slice
+    _fields_ = [("data_offset", C.c_uint64), ("next_code", C.c_uint32), ("stream_left", C.c_uint32), ("pic", C.c_uint32),
+                ("vpos", C.c_uint32), ("mb_slot", C.c_uint32), ("mb_cap", C.c_uint32)]
+
+
+class VlcWave(C.Structure):         # mpegb200_vlc_wave
+    _fields_ = [("n_pictures", C.c_int), ("pics", C.POINTER(VlcPicture)), ("step_picture", C.POINTER(C.c_int32)),
+                ("n_slices", C.c_size_t), ("slices", C.POINTER(VlcSlice)), ("bitstream", C.c_void_p), ("bitstream_bytes", C.c_size_t),
+                ("quant", C.c_void_p), ("n_quant", C.c_size_t), ("n_mb_slots", C.c_size_t)]
+
+
+class BatchScanStep(C.Structure):   # mpegb200_batch_scan_step
+    _fields_ = [("n_streams", C.c_int), ("has_frame", C.POINTER(C.c_int)), ("frame_buf", C.POINTER(C.c_int)),
+                ("time", C.POINTER(C.c_double)), ("n_waves", C.c_int), ("waves", C.POINTER(VlcWave)),
+                ("n_host", C.c_int), ("host_index", C.POINTER(C.c_int)), ("host_steps", C.c_void_p)]
+
+
+assert C.sizeof(VlcPicture) == 32 and C.sizeof(VlcSlice) == 32
+
+
 class VideoBatch:
     def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True,
-                 vlen: bool = True):
+                 vlen: bool = True, device_vlc: bool = False):
+        """device_vlc: the host only scans headers and start codes; the slices are parsed on the GPU, one thread per slice
+        (mpegb200_video_decode_bitstream), and pictures the device flags are re-parsed by the host parser."""
         self.L = _lib.load()
+        self.device_vlc = device_vlc
+        self.flagged = 0    # pictures the device flagged so far: their step's tail took the host path (device_vlc)
+        self.host_steps = 0  # steps the host parsed itself because stale coefficients were pending (device_vlc)
         ctx.set_validate(validate)   # bitstream-derived records: a malformed wave raises instead of decoding (pass False for trusted input)
         self.ctx, self.n, self.first = ctx, len(streams), first_stream
         alloc = C.cast(self.L.mpegb200_host_alloc, C.c_void_p) if pinned else None
@@ -54,6 +86,8 @@ class VideoBatch:
     def step(self):
         """One Video.Decode() of every stream.  Returns (has_frame[n] bool, frame_buf[n] uint8, time[n]).
         The kernels run asynchronously; call ctx.sync() (or read frames back) before touching results."""
+        if self.device_vlc:
+            return self._step_device_vlc()
         if self.steps >= 2:
             self.ctx._ck(self.L.mpegb200_sync_uploads(self.ctx.h))  # the arrays about to be re-used were uploaded
         st = BatchStep()
@@ -77,6 +111,67 @@ class VideoBatch:
         buf = np.ctypeslib.as_array(st.frame_buf, shape=(self.n,)).astype(np.uint8)
         t = np.ctypeslib.as_array(st.time, shape=(self.n,)).copy()
         return has, buf, t
+
+    def _step_device_vlc(self):
+        from .mpeg import VideoStep
+        st = BatchScanStep()
+        self.ctx._ck(self.L.mpegb200_video_batch_next_scan(self.h, C.byref(st)))
+        # streams whose step the host parsed itself (stale coefficients pending): plain launches, no part in the waves
+        host_steps = C.cast(st.host_steps, C.POINTER(VideoStep))
+        for j in range(st.n_host):
+            self._run_launches(host_steps[j], st.host_index[j] + self.first)
+            self.host_steps += 1
+        done = set()    # streams whose step was finished by the host parser after a flag: their later pictures are void
+        for w in range(st.n_waves):
+            wave = st.waves[w]
+            if wave.n_pictures == 0:
+                continue
+            for k in range(wave.n_pictures):
+                if wave.pics[k].stream in done:
+                    wave.pics[k].type = 0
+                wave.pics[k].stream += self.first
+            self.ctx._ck(self.L.mpegb200_video_decode_bitstream(
+                self.ctx.h, wave.n_pictures, wave.pics, wave.n_slices, wave.slices, C.c_void_p(wave.bitstream), wave.bitstream_bytes,
+                C.c_void_p(wave.quant), wave.n_quant, wave.n_mb_slots))
+            # the flags come back with the wave (one synchronisation per wave): what the serial reference resolves by order of
+            # arrival goes through the host parser, before the next wave builds on this one
+            flags = np.zeros(wave.n_pictures, np.int32)
+            bad = self.L.mpegb200_video_bitstream_flags(self.ctx.h, C.c_void_p(flags.ctypes.data), wave.n_pictures)
+            if bad < 0:
+                self.ctx._ck(bad)
+            for k in np.nonzero(flags)[0] if bad else ():
+                index = wave.pics[k].stream - self.first
+                if index in done:
+                    continue
+                redo = VideoStep()
+                self.ctx._ck(self.L.mpegb200_video_batch_redo(self.h, index, wave.step_picture[k], C.byref(redo)))
+                self._run_launches(redo, index + self.first)
+                done.add(index)
+                self.flagged += 1
+        self.steps += 1
+        has = np.ctypeslib.as_array(st.has_frame, shape=(self.n,)).astype(bool)
+        buf = np.ctypeslib.as_array(st.frame_buf, shape=(self.n,)).astype(np.uint8)
+        t = np.ctypeslib.as_array(st.time, shape=(self.n,)).copy()
+        return has, buf, t
+
+    def _run_launches(self, step, stream_id: int):
+        """The launches of one host-parsed picture (mpegb200_video_step) for context stream `stream_id`."""
+        for i in range(step.n_launches):
+            ln = step.launches[i]
+            if ln.n_mb == 0:
+                continue
+            ln.stream = stream_id
+            mb_ptr = step.mbs + 16 * ln.first_mb
+            if step.vlen_launches:
+                lv = step.vlen_launches[i]
+                self.ctx._ck(self.L.mpegb200_video_decode_pictures_vlen(
+                    self.ctx.h, 1, C.byref(ln), ln.n_mb, C.c_void_p(mb_ptr), ln.n_blocks,
+                    C.c_void_p((step.vlen_headers or 0) + 4 * ln.first_block), C.c_void_p((step.vlen_chunk_offsets or 0) + 8 * lv.first_chunk),
+                    C.c_void_p((step.vlen_payload or 0) + lv.payload_offset), lv.payload_bytes))
+            else:
+                self.ctx._ck(self.L.mpegb200_video_decode_pictures(self.ctx.h, 1, C.byref(ln), ln.n_mb, C.c_void_p(mb_ptr), ln.n_blocks,
+                                                                   C.c_void_p(step.coeffs + 128 * ln.first_block)))
+        self.ctx._ck(self.L.mpegb200_sync_uploads(self.ctx.h))   # the parser re-uses these arrays on its next call
 
     def close(self):
         if getattr(self, "h", None):

@@ -91,6 +91,14 @@ cudaError_t launch_expand_vlen(const uint32_t* d_headers, const uint64_t* d_chun
 // MP2 requantisation on the device (audio_requant.cu): info + codes -> int32 samples in the layout of mpegb200_audio_synth
 cudaError_t launch_audio_requant(const mpegb200_audio_frame_info* d_info, const uint16_t* d_codes, int32_t* d_samples,
                                  size_t n_frames, cudaStream_t stream);
+// slice-parallel VLC stage (vlc_slices.cu): bitstream -> records + int16 blocks in device memory, flagged pictures disabled
+struct VlcDeviceTables;
+size_t vlc_summary_bytes(size_t n_slices);
+cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc_picture* d_vpics, mpegb200_picture* d_pics,
+                             int n_pics, const mpegb200_vlc_slice* d_slices, uint32_t n_slices, const uint8_t* d_bitstream,
+                             uint32_t n_words, const uint8_t* d_quant, uint32_t n_quant, const StreamInfo* d_streams,
+                             int max_streams, mpegb200_mb* d_mbs, uint32_t n_mb_slots, int16_t* d_coeffs, void* d_summary,
+                             int32_t* d_flags, cudaStream_t stream);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

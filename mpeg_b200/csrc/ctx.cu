@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "mp2_window.inc"
+#include "vlc_device_tables.h"
 
 namespace mpegb200 {
 cudaError_t configure_audio_kernel();
@@ -75,6 +76,15 @@ struct mpegb200_ctx {
     bool validate = false;                   // mpegb200_set_validate / MPEGB200_VALIDATE=1
     bool kernel_timing = false;              // mpegb200_set_kernel_timing
     std::vector<cudaEvent_t> timing_events;  // three per timed decode call
+    // slice-parallel VLC stage (mpegb200_video_decode_bitstream): tables, double-buffered uploads, the records it leaves on the device
+    VlcDeviceTables* d_vlc_tables = nullptr;
+    DevBuf s_vpics[2], s_slices[2], s_bits[2], s_quant[2], s_vlc_pics, s_vlc_mbs, s_vlc_coeffs, s_vlc_summary, s_vlc_flags;
+    int32_t* h_vlc_flags = nullptr;          // pinned
+    size_t h_vlc_flags_cap = 0;
+    int vlc_n_pictures = 0;
+    size_t vlc_n_mb_slots = 0;
+    cudaEvent_t ev_vlc_flags = nullptr, ev_vlc_t0 = nullptr, ev_vlc_t1 = nullptr;
+    bool vlc_timed = false;
     int max_w = 0, max_h = 0;
     char err[512] = {0};
 };
@@ -248,8 +258,14 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
     for (DevBuf* b : {&ctx->s_pics[0], &ctx->s_pics[1], &ctx->s_mbs[0], &ctx->s_mbs[1], &ctx->s_coeffs[0],
                       &ctx->s_coeffs[1], &ctx->s_ids, &ctx->s_bufs, &ctx->s_rgba, &ctx->s_samples, &ctx->s_out,
                       &ctx->s_plans, &ctx->s_ainfo, &ctx->s_acodes, &ctx->s_packed[0], &ctx->s_packed[1], &ctx->s_headers[0], &ctx->s_headers[1],
-                      &ctx->s_chunks[0], &ctx->s_chunks[1]})
+                      &ctx->s_chunks[0], &ctx->s_chunks[1], &ctx->s_vpics[0], &ctx->s_vpics[1], &ctx->s_slices[0], &ctx->s_slices[1],
+                      &ctx->s_bits[0], &ctx->s_bits[1], &ctx->s_quant[0], &ctx->s_quant[1], &ctx->s_vlc_pics, &ctx->s_vlc_mbs,
+                      &ctx->s_vlc_coeffs, &ctx->s_vlc_summary, &ctx->s_vlc_flags})
         if (b->p) cudaFree(b->p);
+    if (ctx->d_vlc_tables) cudaFree(ctx->d_vlc_tables);
+    if (ctx->h_vlc_flags) cudaFreeHost(ctx->h_vlc_flags);
+    for (cudaEvent_t e : {ctx->ev_vlc_flags, ctx->ev_vlc_t0, ctx->ev_vlc_t1})
+        if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
@@ -773,6 +789,138 @@ int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const
                                  dst_buffers(pics, n_pictures));
     CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
     return rc;
+}
+
+// ---- slice-parallel VLC stage: compressed slices in, records parsed and executed on the device ----
+
+int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpegb200_vlc_picture* pics, size_t n_slices,
+                                    const mpegb200_vlc_slice* slices, const uint8_t* bitstream, size_t bitstream_bytes,
+                                    const uint8_t* quant, size_t n_quant, size_t n_mb_slots) try {
+    if (!ctx || n_pictures < 0 || (n_pictures && !pics) || (n_slices && (!slices || !bitstream || !quant)))
+        return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n_pictures >= 65535 || n_slices > 0x7fffffffull || bitstream_bytes >= 0xffffff00ull || n_mb_slots > 0xffffffffull / 6 ||
+        (n_mb_slots & 15) || n_quant > 0xffffffffull)
+        return fail(ctx, MPEGB200_EINVAL, "wave too large (or record slots not a multiple of 16)");
+    // the slot tables must tile the wave's record slots in order: a hole would be executed as records
+    size_t expect = 0;
+    for (size_t i = 0; i < n_slices; i++) {
+        const mpegb200_vlc_slice& sl = slices[i];
+        if (sl.mb_slot != expect || (sl.mb_cap & 15u) || sl.pic >= (uint32_t)n_pictures || sl.data_offset >= bitstream_bytes)
+            return fail(ctx, MPEGB200_EINVAL, "slice %zu: record slots must follow each other in multiples of 16, picture and offset must be in range", i);
+        expect += sl.mb_cap;
+    }
+    if (expect != n_mb_slots) return fail(ctx, MPEGB200_EINVAL, "the slices' record slots add up to %zu, not %zu", expect, n_mb_slots);
+    unsigned dst_mask = 0;
+    for (int i = 0; i < n_pictures; i++) {
+        const mpegb200_vlc_picture& P = pics[i];
+        if (P.quant >= n_quant || P.first_slice > n_slices || P.n_slices > n_slices - P.first_slice)
+            return fail(ctx, MPEGB200_EINVAL, "picture %d: quantiser or slice range out of range", i);
+        dst_mask |= P.dst_buf < 3 ? 1u << P.dst_buf : 7u;
+    }
+    ctx->vlc_n_pictures = n_pictures;
+    ctx->vlc_n_mb_slots = n_mb_slots;
+    if (n_pictures == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_vlc_tables) {   // once per context
+        VlcDeviceTables* h = new VlcDeviceTables;
+        const bool ok = fill_vlc_device_tables(h);
+        cudaError_t e = ok ? cudaMalloc(&ctx->d_vlc_tables, sizeof(VlcDeviceTables)) : cudaErrorUnknown;
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_vlc_tables, h, sizeof(VlcDeviceTables), cudaMemcpyHostToDevice);
+        delete h;
+        if (e != cudaSuccess) {
+            if (ctx->d_vlc_tables) cudaFree(ctx->d_vlc_tables);
+            ctx->d_vlc_tables = nullptr;
+            return fail(ctx, ok ? MPEGB200_ECUDA : MPEGB200_ESTATE, "variable-length-code tables: %s", ok ? cudaGetErrorString(e) : "host tables have an unexpected shape");
+        }
+        CU(cudaEventCreateWithFlags(&ctx->ev_vlc_flags, cudaEventDisableTiming));
+        CU(cudaEventCreate(&ctx->ev_vlc_t0));
+        CU(cudaEventCreate(&ctx->ev_vlc_t1));
+    }
+    if ((size_t)n_pictures > ctx->h_vlc_flags_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_vlc_flags) cudaFreeHost(ctx->h_vlc_flags);
+        ctx->h_vlc_flags = nullptr;
+        ctx->h_vlc_flags_cap = 0;
+        const size_t cap = (size_t)n_pictures + (size_t)n_pictures / 4 + 64;
+        if (cudaMallocHost(&ctx->h_vlc_flags, cap * sizeof(int32_t)) != cudaSuccess) {
+            ctx->h_vlc_flags = nullptr;
+            cudaGetLastError();
+            return fail(ctx, MPEGB200_ENOMEM, "pinned allocation failed");
+        }
+        ctx->h_vlc_flags_cap = cap;
+    }
+    const int slot = (int)(ctx->upload_seq++ & 1);
+    const size_t n_blocks = 6 * n_mb_slots;
+    if (int rc = ensure(ctx, ctx->s_vpics[slot], sizeof(mpegb200_vlc_picture) * (size_t)n_pictures)) return rc;
+    if (int rc = ensure(ctx, ctx->s_slices[slot], sizeof(mpegb200_vlc_slice) * (n_slices ? n_slices : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_bits[slot], bitstream_bytes + 32)) return rc;
+    if (int rc = ensure(ctx, ctx->s_quant[slot], 128 * (n_quant ? n_quant : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_vlc_pics, sizeof(mpegb200_picture) * (size_t)n_pictures)) return rc;
+    if (int rc = ensure(ctx, ctx->s_vlc_mbs, sizeof(mpegb200_mb) * (n_mb_slots ? n_mb_slots : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_vlc_coeffs, 128 * (n_blocks ? n_blocks : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->s_vlc_summary, vlc_summary_bytes(n_slices))) return rc;
+    if (int rc = ensure(ctx, ctx->s_vlc_flags, sizeof(int32_t) * (size_t)n_pictures)) return rc;
+    CU(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_free[slot], 0));
+    CU(cudaMemcpyAsync(ctx->s_vpics[slot].p, pics, sizeof(mpegb200_vlc_picture) * (size_t)n_pictures, cudaMemcpyHostToDevice, ctx->up_stream));
+    if (n_slices) {
+        CU(cudaMemcpyAsync(ctx->s_slices[slot].p, slices, sizeof(mpegb200_vlc_slice) * n_slices, cudaMemcpyHostToDevice, ctx->up_stream));
+        CU(cudaMemcpyAsync(ctx->s_quant[slot].p, quant, 128 * n_quant, cudaMemcpyHostToDevice, ctx->up_stream));
+        // the bit reader loads whole 32-bit words: zero what lies behind the last byte, then the bytes
+        CU(cudaMemsetAsync((uint8_t*)ctx->s_bits[slot].p + (bitstream_bytes & ~(size_t)3), 0, 16, ctx->up_stream));
+        CU(cudaMemcpyAsync(ctx->s_bits[slot].p, bitstream, bitstream_bytes, cudaMemcpyHostToDevice, ctx->up_stream));
+    }
+    CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
+    if (int rc = flush_info(ctx)) return rc;
+    ctx->vlc_timed = ctx->kernel_timing;
+    if (ctx->vlc_timed) CU(cudaEventRecord(ctx->ev_vlc_t0, ctx->stream));
+    CU(launch_vlc_parse(ctx->d_vlc_tables, (const mpegb200_vlc_picture*)ctx->s_vpics[slot].p, (mpegb200_picture*)ctx->s_vlc_pics.p,
+                        n_pictures, (const mpegb200_vlc_slice*)ctx->s_slices[slot].p, (uint32_t)n_slices,
+                        (const uint8_t*)ctx->s_bits[slot].p, (uint32_t)(bitstream_bytes / 4 + 2), (const uint8_t*)ctx->s_quant[slot].p,
+                        (uint32_t)n_quant, ctx->d_info, ctx->max_streams, (mpegb200_mb*)ctx->s_vlc_mbs.p, (uint32_t)n_mb_slots,
+                        (int16_t*)ctx->s_vlc_coeffs.p, ctx->s_vlc_summary.p, (int32_t*)ctx->s_vlc_flags.p, ctx->stream));
+    ctx->launches += n_slices ? 2 : 1;
+    if (ctx->vlc_timed) CU(cudaEventRecord(ctx->ev_vlc_t1, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));   // the uploads are consumed: the staging slot may be refilled
+    CU(cudaMemcpyAsync(ctx->h_vlc_flags, ctx->s_vlc_flags.p, sizeof(int32_t) * (size_t)n_pictures, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_vlc_flags, ctx->stream));
+    return decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_vlc_pics.p, n_mb_slots,
+                               (const mpegb200_mb*)ctx->s_vlc_mbs.p, n_blocks, (const int16_t*)ctx->s_vlc_coeffs.p, dst_mask);
+} catch (...) {
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
+}
+
+int mpegb200_video_bitstream_flags(mpegb200_ctx* ctx, int* flags_out, int n) {
+    if (!ctx || n < 0 || (n && !flags_out)) return fail(ctx, MPEGB200_EINVAL, "null argument");
+    if (n != ctx->vlc_n_pictures) return fail(ctx, MPEGB200_ESTATE, "the last wave had %d pictures, not %d", ctx->vlc_n_pictures, n);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_vlc_flags));
+    int flagged = 0;
+    for (int i = 0; i < n; i++) {
+        flags_out[i] = ctx->h_vlc_flags[i];
+        flagged += flags_out[i] != 0;
+    }
+    return flagged;
+}
+
+int mpegb200_video_bitstream_records(mpegb200_ctx* ctx, mpegb200_mb* mbs, int16_t* coeffs) {
+    if (!ctx) return MPEGB200_EINVAL;
+    if (ctx->vlc_n_pictures == 0 || ctx->vlc_n_mb_slots == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (mbs) CU(cudaMemcpy(mbs, ctx->s_vlc_mbs.p, sizeof(mpegb200_mb) * ctx->vlc_n_mb_slots, cudaMemcpyDeviceToHost));
+    if (coeffs) CU(cudaMemcpy(coeffs, ctx->s_vlc_coeffs.p, 128 * 6 * ctx->vlc_n_mb_slots, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mpegb200_video_bitstream_parse_ms(mpegb200_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return MPEGB200_EINVAL;
+    if (!ctx->vlc_timed || ctx->vlc_n_pictures == 0) return fail(ctx, MPEGB200_ESTATE, "the last wave was not timed (mpegb200_set_kernel_timing)");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_vlc_t1));
+    CU(cudaEventElapsedTime(ms, ctx->ev_vlc_t0, ctx->ev_vlc_t1));
+    return 0;
 }
 
 static int check_buf(mpegb200_ctx* ctx, int stream, int buf, HostStream** out) {

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/mpegb200_host.h"
+#include "vlc_device_tables.h"
 #include "vlen_encode.h"
 
 namespace {
@@ -234,6 +235,17 @@ const Tables& tables() {
     return t;
 }
 
+// A single-level table as the device reads it: value | length << 16 per index.
+bool flatten(const VlcTable& t, int bits, uint32_t* out) {
+    if (t.max_bits != bits || t.first_bits != bits || !t.second.empty()) return false;
+    for (size_t i = 0; i < ((size_t)1 << bits); i++) {
+        const VlcTable::Entry e = t.first[i];
+        if (e.len == 0 || e.len == 0xff || e.value < -32768 || e.value > 32767) return false;
+        out[i] = ((uint32_t)e.value & 0xffffu) | ((uint32_t)e.len << 16);
+    }
+    return true;
+}
+
 const uint8_t kIntraQuant[64] = {  // ISO 11172-2 default intra matrix (video.go:1055-1064)
     8,  16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37, 19, 22, 26, 27, 29, 34, 34, 38, 22, 22, 26, 27, 29, 34, 37, 40,
     22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32, 35, 40, 48, 58, 26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
@@ -249,6 +261,37 @@ struct Motion {
 };
 
 }  // namespace
+
+// The tables above in the flat form of the device-side slice parser (vlc_device_tables.h).
+bool mpegb200::fill_vlc_device_tables(mpegb200::VlcDeviceTables* out) {
+    using namespace mpegb200;
+    const Tables& t = tables();
+    memset(out, 0, sizeof(*out));
+    static_assert(kVlcCoefFastBits == kCoefBits && sizeof(CoefEntry) == 4, "fast coefficient table layout");
+    for (size_t i = 0; i < ((size_t)1 << kCoefBits); i++) {
+        const CoefEntry e = t.coef_fast[i];
+        out->coef_fast[i] = ((uint32_t)(uint16_t)e.level) | ((uint32_t)e.run << 16) | ((uint32_t)e.len << 24);
+    }
+    const VlcTable& c = t.coeff;
+    if (c.first_bits != kVlcCoefFirstBits || c.max_bits != kVlcCoefFirstBits + kVlcCoefSecondBits ||
+        c.second.size() > (size_t)kVlcCoefSecondTables)
+        return false;
+    auto entry = [](const VlcTable::Entry& e, uint32_t* o) {
+        if (e.len == 0xff || e.value < 0 || e.value > 0xffff) return false;
+        *o = e.len == 0 ? ((uint32_t)e.value | kVlcLink) : ((uint32_t)e.value | ((uint32_t)e.len << 16));
+        return true;
+    };
+    for (size_t i = 0; i < c.first.size(); i++)
+        if (!entry(c.first[i], &out->coeff_first[i])) return false;
+    for (size_t k = 0; k < c.second.size(); k++)
+        for (size_t i = 0; i < c.second[k].size(); i++)
+            if (c.second[k][i].len == 0 || !entry(c.second[k][i], &out->coeff_second[k][i])) return false;
+    memcpy(out->zigzag, t.zigzag, 64);
+    return flatten(t.addr_inc, kVlcAddrIncBits, out->addr_inc) && flatten(t.motion, kVlcMotionBits, out->motion) &&
+           flatten(t.cbp, kVlcCbpBits, out->cbp) && flatten(t.type_i, kVlcTypeIBits, out->type_i) &&
+           flatten(t.type_p, kVlcTypePBits, out->type_p) && flatten(t.type_b, kVlcTypeBBits, out->type_b) &&
+           flatten(t.dc_luma, kVlcDcLumaBits, out->dc_luma) && flatten(t.dc_chroma, kVlcDcChromaBits, out->dc_chroma);
+}
 
 // ------------------------------------------------------------------------------------------------
 // video
@@ -286,6 +329,21 @@ struct mpegb200_video_parser {
     std::vector<uint64_t> pic_block_at;          // ... where its bytes start in pic_payload (n + 1 entries) ...
     std::vector<uint8_t> pic_payload;            // ... and the bytes (16 bytes of slack behind the last block)
     size_t pic_blocks = 0;                       // coded blocks of the picture so far (both modes)
+    // scan mode (mpegb200_video_parser_next_scan): pictures and slice start codes of the step, and where to resume a host re-parse
+    // everything the serial walk carries from picture to picture, as it is when decode_picture is entered
+    struct Saved {
+        BitReader br;
+        int start_code, picture_type, cur, fwd_buf, bwd_buf;
+        bool has_reference;
+        Motion fwd, bwd;
+    };
+    int step_frames_decoded = 0;       // the step counters in front of the current scan step (a re-parse restarts the step's tail)
+    double step_time = 0;
+    mpegb200_video_step host_step;     // scan mode: a step the host had to parse itself (stale coefficients pending, see next_scan)
+    std::vector<mpegb200_scan_picture> scan_pics;
+    std::vector<mpegb200_scan_slice> scan_slices;
+    std::vector<Saved> scan_saved;
+    uint8_t quant128[128];
     std::vector<int32_t> last_writer;  // per macroblock address: index into pic_mbs, -1 = none
     bool pic_has_rewrites = false;
     int rec = -1;
@@ -664,8 +722,10 @@ void emit_picture(VP* v, int type, int dst, int fwd, int bwd) {
     }
 }
 
-void decode_picture(VP* v) {  // video.go:374-434
+void decode_picture(VP* v, bool scan = false) {  // video.go:374-434
     BitReader& br = v->br;
+    const VP::Saved at_entry{br, v->start_code, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf, v->has_reference, v->fwd, v->bwd};
+    const uint64_t begin_byte = (br.pos >> 3) - 4;   // the picture start code
     br.skip(10);
     v->picture_type = (int)br.read(3);
     br.skip(16);
@@ -684,6 +744,45 @@ void decode_picture(VP* v) {  // video.go:374-434
     }
     const int temp = v->fwd_buf;  // rotation by index instead of by struct copy (video.go:406-409)
     if (v->picture_type == kPicI || v->picture_type == kPicP) v->fwd_buf = v->bwd_buf;
+
+    if (scan) {
+        // Headers and start codes only: the slices stay unparsed (the device walks them, one thread per slice).  For a stream
+        // whose slices are what the reference expects this consumes exactly the bytes the full parse consumes.
+        mpegb200_scan_picture P;
+        memset(&P, 0, sizeof(P));
+        P.type = (uint8_t)v->picture_type;
+        P.dst_buf = (uint8_t)v->cur;
+        P.fwd_buf = (uint8_t)v->fwd_buf;
+        P.bwd_buf = (uint8_t)v->bwd_buf;
+        P.fwd_full_px = (uint8_t)v->fwd.full_px;
+        P.fwd_r_size = (uint8_t)v->fwd.r_size;
+        P.bwd_full_px = (uint8_t)v->bwd.full_px;
+        P.bwd_r_size = (uint8_t)v->bwd.r_size;
+        P.first_slice = (uint32_t)v->scan_slices.size();
+        P.begin = begin_byte;
+        do {
+            v->start_code = br.next_start_code();
+        } while (v->start_code == kExtension || v->start_code == kUserData);
+        while (v->start_code >= kSliceFirst && v->start_code <= kSliceLast) {
+            mpegb200_scan_slice S;
+            memset(&S, 0, sizeof(S));
+            S.offset = br.pos >> 3;
+            S.vpos = (uint32_t)(v->start_code & 0xff);
+            v->start_code = br.next_start_code();
+            S.next_code = v->start_code == -1 ? (uint64_t)br.len : (br.pos >> 3) - 4;
+            v->scan_slices.push_back(S);
+        }
+        P.n_slices = (uint32_t)v->scan_slices.size() - P.first_slice;
+        const uint64_t end = br.pos >> 3;            // behind the start code that ended the slices (or the end of the stream)
+        P.end = end < br.len ? end : br.len;
+        v->scan_pics.push_back(P);
+        v->scan_saved.push_back(at_entry);
+        if (v->picture_type == kPicI || v->picture_type == kPicP) {  // video.go:430-433
+            v->bwd_buf = v->cur;
+            v->cur = temp;
+        }
+        return;
+    }
 
     v->pic_mbs.clear();
     v->pic_coeffs.clear();
@@ -757,8 +856,30 @@ void mpegb200_video_parser_rewind(mpegb200_video_parser* v) {  // video.go:195-2
     v->start_code = -1;
 }
 
-static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step* out) {  // Video.Decode, video.go:209-268
+// resume >= 0: the tail of the last scan step, from its picture `resume` on, parsed in full (mpegb200_video_parser_redo)
+static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step* out, bool scan = false, int resume = -1) {  // Video.Decode, video.go:209-268
     memset(out, 0, sizeof(*out));
+    bool resuming = resume >= 0;
+    if (resuming) {
+        const VP::Saved sv = v->scan_saved[(size_t)resume];
+        v->br = sv.br;
+        v->start_code = sv.start_code;
+        v->picture_type = sv.picture_type;
+        v->cur = sv.cur;
+        v->fwd_buf = sv.fwd_buf;
+        v->bwd_buf = sv.bwd_buf;
+        v->has_reference = sv.has_reference;
+        v->fwd = sv.fwd;
+        v->bwd = sv.bwd;
+        v->frames_decoded = v->step_frames_decoded;
+        v->time = v->step_time;
+    } else {
+        v->step_frames_decoded = v->frames_decoded;
+        v->step_time = v->time;
+    }
+    v->scan_pics.clear();
+    v->scan_slices.clear();
+    v->scan_saved.clear();
     v->launches.clear();
     v->mbs.clear();
     v->coeffs.clear();
@@ -769,19 +890,22 @@ static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step*
     if (!ensure_header(v)) return 0;
     int frame = -1;
     for (;;) {
-        if (v->start_code != kStartPicture) {
-            v->start_code = v->br.find_start_code(kStartPicture);
-            if (v->start_code == -1) {
-                if (v->has_reference && !v->no_delay && v->br.ended && (v->picture_type == kPicI || v->picture_type == kPicP)) {
-                    v->has_reference = false;  // flush the last reference frame (video.go:223-229)
-                    frame = v->bwd_buf;
-                    break;
+        if (!resuming) {
+            if (v->start_code != kStartPicture) {
+                v->start_code = v->br.find_start_code(kStartPicture);
+                if (v->start_code == -1) {
+                    if (v->has_reference && !v->no_delay && v->br.ended && (v->picture_type == kPicI || v->picture_type == kPicP)) {
+                        v->has_reference = false;  // flush the last reference frame (video.go:223-229)
+                        frame = v->bwd_buf;
+                        break;
+                    }
+                    return 0;
                 }
-                return 0;
             }
+            if (v->br.has_start_code(kStartPicture) == -1 && !v->br.ended) return 0;
         }
-        if (v->br.has_start_code(kStartPicture) == -1 && !v->br.ended) return 0;
-        decode_picture(v);
+        resuming = false;
+        decode_picture(v, scan);
         if (v->no_delay)
             frame = v->bwd_buf;
         else if (v->picture_type == kPicB)
@@ -820,6 +944,49 @@ int mpegb200_video_parser_next(mpegb200_video_parser* v, mpegb200_video_step* ou
     if (!v || !out) return MPEGB200_EINVAL;
     try {
         return video_parser_next_impl(v, out);
+    } catch (...) {
+        memset(out, 0, sizeof(*out));
+        return MPEGB200_ENOMEM;
+    }
+}
+
+int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_scan_step* out) {
+    if (!v || !out) return MPEGB200_EINVAL;
+    memset(out, 0, sizeof(*out));
+    try {
+        // Coefficients a dropped block left behind (video.go:712-714) leak into the next block the serial reference decodes,
+        // possibly a picture later.  Only the host parser carries that state: while it is pending the host parses the step itself.
+        bool stale = false;
+        for (int i = 0; i < 64 && !stale; i++) stale = v->level[i] != 0;
+        mpegb200_video_step st;
+        const int rc = video_parser_next_impl(v, stale ? &v->host_step : &st, !stale);
+        if (stale) st = v->host_step;
+        if (rc != 0 || !st.has_frame) return rc;
+        memcpy(v->quant128, v->intra_q, 64);
+        memcpy(v->quant128 + 64, v->non_intra_q, 64);
+        out->has_frame = 1;
+        out->frame_buf = st.frame_buf;
+        out->time = st.time;
+        out->n_pictures = (int)v->scan_pics.size();
+        out->pictures = v->scan_pics.data();
+        out->slices = v->scan_slices.data();
+        out->stream = v->data.data();
+        out->stream_len = v->br.len;
+        out->quant = v->quant128;
+        out->mb_w = v->mb_w;
+        out->mb_h = v->mb_h;
+        out->host_step = stale ? &v->host_step : nullptr;
+        return 0;
+    } catch (...) {
+        memset(out, 0, sizeof(*out));
+        return MPEGB200_ENOMEM;
+    }
+}
+
+int mpegb200_video_parser_redo(mpegb200_video_parser* v, int k, mpegb200_video_step* out) {
+    if (!v || !out || k < 0 || k >= (int)v->scan_saved.size()) return MPEGB200_EINVAL;
+    try {
+        return video_parser_next_impl(v, out, false, k);
     } catch (...) {
         memset(out, 0, sizeof(*out));
         return MPEGB200_ENOMEM;
@@ -1319,6 +1486,20 @@ struct mpegb200_video_batch {
     std::vector<WaveBuf> bufs[2];   // double-buffered: the previous step's arrays stay intact while the next is parsed
     int flip = 0;
     std::vector<mpegb200_wave> waves;
+    // scan mode (mpegb200_video_batch_next_scan): slice tables and compressed bytes instead of records
+    struct ScanBuf {
+        mpegb200_vlc_picture* pics = nullptr;
+        mpegb200_vlc_slice* slices = nullptr;
+        uint8_t* bits = nullptr;
+        uint8_t* quant = nullptr;
+        int32_t* step_picture = nullptr;
+        size_t cap_pics = 0, cap_slices = 0, cap_bits = 0, cap_quant = 0, cap_step = 0;
+    };
+    std::vector<mpegb200_video_scan_step> scan_steps;
+    std::vector<ScanBuf> scan_bufs[2];
+    std::vector<mpegb200_vlc_wave> scan_waves;
+    std::vector<int> host_index;
+    std::vector<mpegb200_video_step> host_steps;
 
     void* get(size_t bytes) { return alloc ? alloc(bytes ? bytes : 1) : malloc(bytes ? bytes : 1); }
     void put(void* p) {
@@ -1370,6 +1551,14 @@ void mpegb200_video_batch_free(mpegb200_video_batch* b) {
             b->put(w.headers);
             b->put(w.chunks);
             b->put(w.payload);
+        }
+    for (auto& set : b->scan_bufs)
+        for (auto& w : set) {
+            b->put(w.pics);
+            b->put(w.slices);
+            b->put(w.bits);
+            b->put(w.quant);
+            b->put(w.step_picture);
         }
     delete b;
 }
@@ -1513,6 +1702,179 @@ int mpegb200_video_batch_next(mpegb200_video_batch* b, mpegb200_batch_step* out)
         memset(out, 0, sizeof(*out));
         return MPEGB200_ENOMEM;
     }
+}
+
+// Scan mode: every stream's parser stops at the slice start codes; wave w holds the w-th picture of every stream's step as
+// slice tables over one buffer of compressed bytes (the argument list of mpegb200_video_decode_bitstream).
+static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_scan_step* out) {
+    memset(out, 0, sizeof(*out));
+    const int n = b->n;
+    b->scan_steps.resize((size_t)n);
+    b->pool->run(n, [&](int i) {
+        mpegb200_video_scan_step& st = b->scan_steps[(size_t)i];
+        memset(&st, 0, sizeof(st));
+        if (b->parsers[(size_t)i] && mpegb200_video_parser_next_scan(b->parsers[(size_t)i], &st) != 0) throw std::bad_alloc();
+        b->has_frame[(size_t)i] = st.has_frame;
+        b->frame_buf[(size_t)i] = st.frame_buf;
+        b->time[(size_t)i] = st.time;
+    });
+    if (b->pool->failed()) return MPEGB200_ENOMEM;
+    int n_waves = 0;
+    b->host_index.clear();
+    b->host_steps.clear();
+    for (int i = 0; i < n; i++) {
+        const mpegb200_video_scan_step& st = b->scan_steps[(size_t)i];
+        n_waves = std::max(n_waves, st.has_frame ? st.n_pictures : 0);
+        if (st.has_frame && st.host_step) {
+            b->host_index.push_back(i);
+            b->host_steps.push_back(*st.host_step);
+        }
+    }
+    b->flip ^= 1;
+    auto& bufs = b->scan_bufs[b->flip];
+    if ((int)bufs.size() < n_waves) bufs.resize((size_t)n_waves);
+    b->scan_waves.assign((size_t)n_waves, mpegb200_vlc_wave{});
+    std::vector<uint32_t> pic_of((size_t)n), slice_off((size_t)n), slot_off((size_t)n);
+    std::vector<uint64_t> byte_off((size_t)n), first_byte((size_t)n), n_bytes((size_t)n);
+    for (int w = 0; w < n_waves; w++) {
+        uint32_t np = 0, ns = 0;
+        uint64_t nbytes = 0, nslots = 0;
+        for (int i = 0; i < n; i++) {
+            const mpegb200_video_scan_step& st = b->scan_steps[(size_t)i];
+            pic_of[(size_t)i] = 0xffffffffu;
+            if (!st.has_frame || w >= st.n_pictures) continue;
+            const mpegb200_scan_picture& P = st.pictures[w];
+            pic_of[(size_t)i] = np++;
+            slice_off[(size_t)i] = ns;
+            slot_off[(size_t)i] = (uint32_t)nslots;
+            byte_off[(size_t)i] = nbytes;
+            ns += P.n_slices;
+            // record slots: a slice may write the addresses from its own row to the next slice's (or to the picture's end)
+            const mpegb200_scan_slice* S = st.slices + P.first_slice;
+            const int64_t mb_size = (int64_t)st.mb_w * st.mb_h;
+            for (uint32_t k = 0; k < P.n_slices; k++) {
+                const int64_t from = ((int64_t)S[k].vpos - 1) * st.mb_w;
+                const int64_t to = k + 1 < P.n_slices ? ((int64_t)S[k + 1].vpos - 1) * st.mb_w : mb_size;
+                const int64_t cap = std::max<int64_t>(0, std::min(to, mb_size) - from);
+                nslots += (uint64_t)((cap + 15) & ~(int64_t)15);
+            }
+            // bytes: from the first slice to eight bytes behind the start code that ends the last one (what a reader that
+            // stops in front of that code may still look at)
+            if (P.n_slices) {
+                first_byte[(size_t)i] = S[0].offset;
+                const uint64_t last = std::min<uint64_t>(S[P.n_slices - 1].next_code + 8, st.stream_len);
+                n_bytes[(size_t)i] = last - S[0].offset;
+            } else {
+                first_byte[(size_t)i] = 0;
+                n_bytes[(size_t)i] = 0;
+            }
+            nbytes += (n_bytes[(size_t)i] + 15) & ~(uint64_t)15;
+        }
+        if (nslots > 0xffffffffull / 6 || nbytes >= 0xffffff00ull) return MPEGB200_EINVAL;
+        auto& buf = bufs[(size_t)w];
+        if (!b->reserve(buf.pics, buf.cap_pics, np) || !b->reserve(buf.slices, buf.cap_slices, ns) ||
+            !b->reserve(buf.bits, buf.cap_bits, (size_t)nbytes + 16) || !b->reserve(buf.quant, buf.cap_quant, (size_t)np * 128) ||
+            !b->reserve(buf.step_picture, buf.cap_step, np))
+            return MPEGB200_ENOMEM;
+        b->pool->run(n, [&](int i) {
+            const uint32_t p = pic_of[(size_t)i];
+            if (p == 0xffffffffu) return;
+            const mpegb200_video_scan_step& st = b->scan_steps[(size_t)i];
+            const mpegb200_scan_picture& P = st.pictures[w];
+            const mpegb200_scan_slice* S = st.slices + P.first_slice;
+            mpegb200_vlc_picture V;
+            memset(&V, 0, sizeof(V));
+            V.stream = i;
+            V.type = P.type;
+            V.dst_buf = P.dst_buf;
+            V.fwd_buf = P.fwd_buf;
+            V.bwd_buf = P.bwd_buf;
+            V.fwd_full_px = P.fwd_full_px;
+            V.fwd_r_size = P.fwd_r_size;
+            V.bwd_full_px = P.bwd_full_px;
+            V.bwd_r_size = P.bwd_r_size;
+            V.first_slice = slice_off[(size_t)i];
+            V.n_slices = P.n_slices;
+            V.mb_slot = slot_off[(size_t)i];
+            V.quant = p;
+            memcpy(buf.quant + (size_t)p * 128, st.quant, 128);
+            buf.step_picture[p] = w;
+            const int64_t mb_size = (int64_t)st.mb_w * st.mb_h;
+            uint32_t slot = slot_off[(size_t)i];
+            for (uint32_t k = 0; k < P.n_slices; k++) {
+                const int64_t from = ((int64_t)S[k].vpos - 1) * st.mb_w;
+                const int64_t to = k + 1 < P.n_slices ? ((int64_t)S[k + 1].vpos - 1) * st.mb_w : mb_size;
+                const int64_t cap = std::max<int64_t>(0, std::min(to, mb_size) - from);
+                mpegb200_vlc_slice L;
+                memset(&L, 0, sizeof(L));
+                L.data_offset = byte_off[(size_t)i] + (S[k].offset - first_byte[(size_t)i]);
+                L.next_code = (uint32_t)std::min<uint64_t>(S[k].next_code - S[k].offset, 0xffffffffull);
+                L.stream_left = (uint32_t)std::min<uint64_t>(st.stream_len - S[k].offset, 0xffffffffull);
+                L.pic = p;
+                L.vpos = S[k].vpos;
+                L.mb_slot = slot;
+                L.mb_cap = (uint32_t)((cap + 15) & ~(int64_t)15);
+                slot += L.mb_cap;
+                buf.slices[slice_off[(size_t)i] + k] = L;
+            }
+            V.n_mb_slots = slot - slot_off[(size_t)i];
+            buf.pics[p] = V;
+            uint8_t* dst = buf.bits + byte_off[(size_t)i];
+            memcpy(dst, st.stream + first_byte[(size_t)i], (size_t)n_bytes[(size_t)i]);
+            memset(dst + n_bytes[(size_t)i], 0, (size_t)(((n_bytes[(size_t)i] + 15) & ~(uint64_t)15) - n_bytes[(size_t)i]));
+        });
+        if (b->pool->failed()) return MPEGB200_ENOMEM;
+        memset(buf.bits + nbytes, 0, 16);
+        mpegb200_vlc_wave& W = b->scan_waves[(size_t)w];
+        W.n_pictures = (int)np;
+        W.pics = buf.pics;
+        W.step_picture = buf.step_picture;
+        W.n_slices = ns;
+        W.slices = buf.slices;
+        W.bitstream = buf.bits;
+        W.bitstream_bytes = (size_t)nbytes;
+        W.quant = buf.quant;
+        W.n_quant = np;
+        W.n_mb_slots = (size_t)nslots;
+    }
+    out->n_streams = n;
+    out->has_frame = b->has_frame.data();
+    out->frame_buf = b->frame_buf.data();
+    out->time = b->time.data();
+    out->n_waves = n_waves;
+    out->waves = b->scan_waves.data();
+    out->n_host = (int)b->host_index.size();
+    out->host_index = b->host_index.data();
+    out->host_steps = b->host_steps.data();
+    return 0;
+}
+
+int mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_step* out) {
+    if (!b || !out) return MPEGB200_EINVAL;
+    try {
+        return video_batch_next_scan_impl(b, out);
+    } catch (...) {
+        memset(out, 0, sizeof(*out));
+        return MPEGB200_ENOMEM;
+    }
+}
+
+// Not part of the C-ABI (no declaration in include/): the device tables as bytes, for the test that runs the device-side
+// slice walker on the CPU (tests/vlc_emu).  Returns their size, or 0 if `cap` is too small or the tables have an unexpected shape.
+size_t mpegb200_internal_vlc_tables(void* out, size_t cap) {
+    if (!out || cap < sizeof(mpegb200::VlcDeviceTables)) return 0;
+    return mpegb200::fill_vlc_device_tables(static_cast<mpegb200::VlcDeviceTables*>(out)) ? sizeof(mpegb200::VlcDeviceTables) : 0;
+}
+
+int mpegb200_video_batch_redo(mpegb200_video_batch* b, int index, int step_picture, mpegb200_video_step* out) {
+    if (!b || !out || index < 0 || index >= b->n || !b->parsers[(size_t)index]) return MPEGB200_EINVAL;
+    const int rc = mpegb200_video_parser_redo(b->parsers[(size_t)index], step_picture, out);
+    if (rc == 0) {   // the step's result for this stream is the re-parsed tail's
+        b->has_frame[(size_t)index] = out->has_frame;
+        b->frame_buf[(size_t)index] = out->frame_buf;
+        b->time[(size_t)index] = out->time;
+    }
+    return rc;
 }
 
 }  // extern "C"

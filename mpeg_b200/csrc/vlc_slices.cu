@@ -1,0 +1,117 @@
+// vlc_slices.cu -- slice-parallel MPEG-1 VLC stage on the device (include/mpegb200.h "slice-parallel VLC stage").
+//
+// One thread walks one slice (vlc_slice_walk.h: the reference's decodeSlice .. decodeBlock, video.go:436-746, table-driven
+// like the host parser) and writes packed records -- mpegb200_mb + int16[64] per coded block -- into the slots the slice
+// owns.  Slices are independent in MPEG-1 (byte-aligned start code, every predictor reset, video.go:436-446); what is NOT
+// independent (overlapping or over-running slices, a picture ended early) is detected, never emulated: vlc_check_kernel
+// flags such pictures, disables their records and the caller re-parses them on the host.
+//
+// Memory: the bitstream is read through L1 with one aligned 32-bit load per 32 bits consumed (a 64-bit window lives in
+// registers); a block is assembled in shared memory (128 bytes per thread, 16-byte chunks swizzled by lane so that lanes at
+// the same zig-zag position do not share a bank) and leaves as eight 16-byte stores; the hot table (16 KB) sits in shared
+// memory, the others are read through the read-only cache.
+#include "common.cuh"
+#include "vlc_slice_walk.h"
+
+namespace mpegb200 {
+
+namespace {
+constexpr int kVlcThreads = 64;
+}
+
+__global__ void __launch_bounds__(kVlcThreads) vlc_parse_kernel(
+    const VlcDeviceTables* __restrict__ T, const mpegb200_vlc_picture* __restrict__ pics, int n_pics,
+    const mpegb200_vlc_slice* __restrict__ slices, uint32_t n_slices, const uint32_t* __restrict__ words, uint32_t n_words,
+    const uint8_t* __restrict__ quant, uint32_t n_quant, const StreamInfo* __restrict__ streams, int max_streams,
+    mpegb200_mb* __restrict__ mbs, uint32_t n_mb_slots, int16_t* __restrict__ coeffs, SliceSummary* __restrict__ summary) {
+    __shared__ uint32_t s_fast[1 << kVlcCoefFastBits];
+    __shared__ __align__(16) uint8_t s_block[kVlcThreads * 128];
+    __shared__ uint8_t s_zigzag[64];
+    for (int i = threadIdx.x; i < (1 << kVlcCoefFastBits); i += kVlcThreads) s_fast[i] = T->coef_fast[i];
+    if (threadIdx.x < 64) s_zigzag[threadIdx.x] = T->zigzag[threadIdx.x];
+    for (int i = threadIdx.x; i < kVlcThreads * 8; i += kVlcThreads) reinterpret_cast<uint4*>(s_block)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t s = blockIdx.x * kVlcThreads + threadIdx.x;
+    if (s >= n_slices) return;
+
+    const mpegb200_vlc_slice sl = slices[s];
+    // the entry point has checked the slot tables on the host; a slice whose slots are off anyway writes nothing
+    const bool slots_ok = sl.pic < (uint32_t)n_pics && (sl.mb_slot & 15u) == 0 && (sl.mb_cap & 15u) == 0 && sl.mb_slot <= n_mb_slots &&
+                          sl.mb_cap <= n_mb_slots - sl.mb_slot;
+    bool ok = slots_ok && sl.data_offset < (uint64_t)n_words * 4u;
+    mpegb200_vlc_picture P;
+    VlcGeometry g;
+    if (ok) {
+        P = pics[sl.pic];
+        ok = P.stream >= 0 && P.stream < max_streams && P.quant < n_quant && P.dst_buf < 3 && P.fwd_buf < 3 && P.bwd_buf < 3 &&
+             P.type >= MPEGB200_PIC_I && P.type <= MPEGB200_PIC_B && P.fwd_r_size < 7 && P.bwd_r_size < 7;
+        if (ok) {
+            const StreamInfo si = streams[P.stream];
+            ok = si.open != 0;
+            g.mb_w = si.mb_w;
+            g.mb_h = si.mb_h;
+            g.luma_w = si.luma_w;
+            g.luma_h = si.luma_h;
+            g.buf_bytes = si.buf_bytes;
+        }
+    }
+    SliceSummary sum;
+    if (ok) {
+        sum = walk_slice(T, s_fast, s_zigzag, s_block + threadIdx.x * 128, threadIdx.x & 7u, sl, P, g, words, n_words, quant, mbs, coeffs);
+    } else {
+        // a picture that is void (type 0: the caller withdrew it) or inconsistent: its slots hold null records, its picture is flagged
+        sum.flags = MPEGB200_VLC_BAD_ARG;
+        sum.first_addr = sum.last_addr = -1;
+        sum.end_addr = 0;
+        if (slots_ok)
+            for (uint32_t slot = sl.mb_slot; slot < sl.mb_slot + sl.mb_cap; slot++) vlc_store16(mbs + slot, 0u, 0u, 0xffffu << 16, 6u * sl.mb_slot);
+    }
+    reinterpret_cast<uint4*>(summary)[s] = make_uint4(sum.flags, (uint32_t)sum.first_addr, (uint32_t)sum.last_addr, (uint32_t)sum.end_addr);
+}
+
+// One thread per picture.  A flagged picture loses its stream id, which makes the decode kernels drop every record of it
+// (their own validity check), and reports its flags.
+__global__ void vlc_check_kernel(const mpegb200_vlc_picture* __restrict__ vpics, mpegb200_picture* __restrict__ pics, int n_pics,
+                                 const SliceSummary* __restrict__ summary, uint32_t n_slices,
+                                 const StreamInfo* __restrict__ streams, int max_streams, int32_t* __restrict__ flags_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pics) return;
+    const mpegb200_vlc_picture P = vpics[p];
+    uint32_t flags;
+    if (P.stream < 0 || P.stream >= max_streams || P.first_slice > n_slices || P.n_slices > n_slices - P.first_slice) {
+        flags = MPEGB200_VLC_BAD_ARG;
+    } else {
+        const StreamInfo si = streams[P.stream];
+        flags = vlc_check_picture(P, summary, (int)si.mb_w * (int)si.mb_h);
+    }
+    mpegb200_picture out;
+    out.stream = flags ? -1 : P.stream;
+    out.type = P.type;
+    out.dst_buf = P.dst_buf;
+    out.fwd_buf = P.fwd_buf;
+    out.bwd_buf = P.bwd_buf;
+    out.first_mb = P.mb_slot;
+    out.n_mb = P.n_mb_slots;
+    pics[p] = out;
+    flags_out[p] = (int32_t)flags;
+}
+
+size_t vlc_summary_bytes(size_t n_slices) { return sizeof(SliceSummary) * (n_slices ? n_slices : 1); }
+
+cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc_picture* d_vpics, mpegb200_picture* d_pics,
+                             int n_pics, const mpegb200_vlc_slice* d_slices, uint32_t n_slices, const uint8_t* d_bitstream,
+                             uint32_t n_words, const uint8_t* d_quant, uint32_t n_quant, const StreamInfo* d_streams,
+                             int max_streams, mpegb200_mb* d_mbs, uint32_t n_mb_slots, int16_t* d_coeffs, void* d_summary,
+                             int32_t* d_flags, cudaStream_t stream) {
+    if (n_slices)
+        vlc_parse_kernel<<<(n_slices + kVlcThreads - 1) / kVlcThreads, kVlcThreads, 0, stream>>>(
+            d_tables, d_vpics, n_pics, d_slices, n_slices, reinterpret_cast<const uint32_t*>(d_bitstream), n_words, d_quant,
+            n_quant, d_streams, max_streams, d_mbs, n_mb_slots, d_coeffs, reinterpret_cast<SliceSummary*>(d_summary));
+    if (n_pics)
+        vlc_check_kernel<<<(n_pics + 127) / 128, 128, 0, stream>>>(d_vpics, d_pics, n_pics,
+                                                                  reinterpret_cast<const SliceSummary*>(d_summary), n_slices,
+                                                                  d_streams, max_streams, d_flags);
+    return cudaGetLastError();
+}
+
+}  // namespace mpegb200

@@ -1,0 +1,175 @@
+"""The slice-parallel VLC stage on the GPU: compressed slices go to the device as they are, vlc_parse_kernel writes
+the records, the decode kernels execute them.  Checked against the CPU run of the same walker (tests/vlc_emu), against the host
+parser path, and against the reference's golden hash.  Needs a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mpeg1_writer as mw
+import oracle_lib as ol
+import vlc_emu_lib as ve
+from test_mpeg1_writer import write_stream
+
+pytestmark = pytest.mark.gpu
+
+VIDEO_GOLDEN = 0xEA6D7FCB1340BA3F          # mpeg_test.go:227
+
+
+def oracle_hash(data):
+    o, h, n = ol.VideoOracle(data), ol.FNV_OFFSET, 0
+    while (f := o.decode()) is not None:
+        for which in ("y", "cb", "cr"):
+            h = ol.fnv(h, f.plane(which))
+        n += 1
+    return h, n
+
+
+def batch_hashes(c, datas, first=0, **kw):
+    import mpeg_b200
+    n = len(datas)
+    batch = mpeg_b200.VideoBatch(c, datas, threads=4, first_stream=first, **kw)
+    hashes, frames = [ol.FNV_OFFSET] * n, [0] * n
+    hosts = {}
+    while True:
+        has, buf, t = batch.step()
+        if not has.any():
+            break
+        for i in np.nonzero(has)[0]:
+            geo = c.video_geometry(first + int(i))
+            pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
+            host = hosts.setdefault(pic_bytes, np.empty((1, pic_bytes), np.uint8))
+            c.video_read_pictures(np.array([first + int(i)]), buf[i:i + 1], host.ctypes.data, pic_bytes)
+            c.sync()
+            hashes[i] = ol.fnv(hashes[i], host[0])
+            frames[i] += 1
+    stats = (batch.flagged, batch.host_steps)
+    batch.close()
+    return hashes, frames, stats
+
+
+def test_device_vlc_reproduces_the_golden_hash(golden_dir):
+    """TestVideoGolden (mpeg_test.go:203-231) with the slices parsed on the GPU.  testdata/test.mpeg1video is damaged: about a
+    quarter of its pictures flag and finish on the host parser -- the hash must come out all the same; the video of test.mpg is
+    clean and must not flag at all."""
+    import mpeg_b200
+    from test_batch_parser import cut_at_picture
+    es = (golden_dir / "test.mpeg1video").read_bytes()
+    ps_video = ol.demux_split((golden_dir / "test.mpg").read_bytes())[0]
+    with mpeg_b200.Context(device=0, max_streams=16) as c:
+        hashes, frames, (flagged, _) = batch_hashes(c, [es], device_vlc=True)
+        assert hashes[0] == VIDEO_GOLDEN, f"{hashes[0]:#018x} after {frames[0]} frames"
+        assert 0 < flagged < frames[0] // 2
+    with mpeg_b200.Context(device=0, max_streams=16) as c:
+        kinds = [ps_video, cut_at_picture(ps_video, 33), es, cut_at_picture(es, 7)]
+        want = [oracle_hash(d) for d in kinds]
+        datas = [kinds[i % 4] for i in range(12)]
+        hashes, frames, _ = batch_hashes(c, datas, first=2, device_vlc=True)
+        for i in range(12):
+            assert (hashes[i], frames[i]) == want[i % 4], f"stream {i}"
+    with mpeg_b200.Context(device=0, max_streams=4) as c:
+        hashes, frames, (flagged, host_steps) = batch_hashes(c, [ps_video], device_vlc=True)
+        assert (hashes[0], frames[0]) == oracle_hash(ps_video) and flagged == 0 and host_steps == 0
+
+
+@pytest.mark.parametrize("size,pictures,mode", [
+    ((352, 288), [mw.PIC_I, mw.PIC_P, mw.PIC_B, mw.PIC_B, mw.PIC_P], "natural"),
+    ((1280, 720), [mw.PIC_I, mw.PIC_P, mw.PIC_B], "natural"),
+    ((1280, 720), [mw.PIC_I, mw.PIC_P], "dense"),
+    ((720, 576), [mw.PIC_I, mw.PIC_P, mw.PIC_B], "natural"),      # odd macroblock width: the generic decode kernel executes the records
+])
+def test_device_records_equal_the_cpu_run_of_the_walker(size, pictures, mode):
+    """vlc_parse_kernel against the same walker compiled for the CPU (which the no-GPU suite holds against the host parser):
+    every record slot, every coefficient block the records name, every flag; and the frames the decode kernels make of the
+    device records against the host-parser path."""
+    import mpeg_b200
+    w, _ = write_stream(size[0], size[1], pictures, seed=size[0] + len(pictures), mode=mode)
+    data = w.tobytes()
+    L = mpeg_b200._lib.load()
+    tab = ve.tables()
+    with mpeg_b200.Context(device=0, max_streams=4) as c:
+        c.video_open(0, *size)
+        sb = ve.ScanBatch([data])
+        ref = mpeg_b200.Video(data, c, stream=1)            # the host-parser path decodes the same stream next to it
+        mb_w, mb_h = sb.sizes[0]
+        n = 0
+        try:
+            while True:
+                st = sb.next()
+                if not st.has_frame[0]:
+                    break
+                for wv in range(st.n_waves):
+                    wave = st.waves[wv]
+                    c._ck(L.mpegb200_video_decode_bitstream(c.h, wave.n_pictures, wave.pics, wave.n_slices, wave.slices, C.c_void_p(wave.bitstream),
+                                                            wave.bitstream_bytes, C.c_void_p(wave.quant), wave.n_quant, wave.n_mb_slots))
+                    flags = np.zeros(wave.n_pictures, np.int32)
+                    assert L.mpegb200_video_bitstream_flags(c.h, C.c_void_p(flags.ctypes.data), wave.n_pictures) == 0
+                    gm = np.zeros(wave.n_mb_slots, ol.MB_DTYPE)
+                    gc = np.zeros((6 * wave.n_mb_slots, 64), np.int16)
+                    c._ck(L.mpegb200_video_bitstream_records(c.h, C.c_void_p(gm.ctypes.data), C.c_void_p(gc.ctypes.data)))
+                    em, ec, ef = ve.emulate_wave(wave, mb_w, mb_h, tab)
+                    assert not ef.any()
+                    assert np.array_equal(gm, em), "record slots differ from the CPU run of the walker"
+                    for m in em[em["pic"] != 0xffff]:
+                        b0, nc = int(m["coeff_block"]), bin(int(m["cbp"])).count("1")
+                        assert np.array_equal(gc[b0:b0 + nc], ec[b0:b0 + nc])
+                    n += 1
+                f = ref.decode()
+                assert f is not None and f._buf == st.frame_buf[0]
+                for b in range(3):
+                    assert np.array_equal(c.video_read_frame(0, b), c.video_read_frame(1, b)), f"frame buffer {b} after step {n}"
+        finally:
+            sb.close()
+            ref.close()
+        assert n == len(pictures)
+
+
+def test_device_vlc_batch_720p_equals_host_parser_batch():
+    """48 streams of 720p (three distinct ones, I P B P) through both front ends of the lock-step batch: the frames every step
+    returns must be identical, and the device path must not have flagged anything."""
+    import mpeg_b200
+    distinct = []
+    for d in range(3):
+        w, _ = write_stream(1280, 720, [mw.PIC_I, mw.PIC_P, mw.PIC_B, mw.PIC_P], seed=40 + d, mode="natural")
+        distinct.append(w.tobytes())
+    datas = [distinct[i % 3] for i in range(48)]
+    with mpeg_b200.Context(device=0, max_streams=48) as c:
+        h_host, f_host, _ = batch_hashes(c, datas)
+    with mpeg_b200.Context(device=0, max_streams=48) as c:
+        h_dev, f_dev, (flagged, host_steps) = batch_hashes(c, datas, device_vlc=True)
+    assert f_host == f_dev and f_host[0] == 4
+    assert h_host == h_dev
+    assert flagged == 0 and host_steps == 0
+    want = [oracle_hash(d)[0] for d in distinct]
+    assert all(h_dev[i] == want[i % 3] for i in range(48))
+
+
+def test_void_and_foreign_tables_are_refused_or_skipped(golden_dir):
+    """The slot tables are checked on the host before anything is enqueued; a picture withdrawn by the caller (type 0) leaves
+    null records and its flag, and touches no frame buffer."""
+    import mpeg_b200
+    w, _ = write_stream(64, 48, [mw.PIC_I, mw.PIC_P], seed=3, mode="natural")
+    L = mpeg_b200._lib.load()
+    with mpeg_b200.Context(device=0, max_streams=2) as c:
+        c.video_open(0, 64, 48)
+        sb = ve.ScanBatch([w.tobytes()])
+        try:
+            st = sb.next()
+            wave = st.waves[0]
+            args = lambda: (c.h, wave.n_pictures, wave.pics, wave.n_slices, wave.slices, C.c_void_p(wave.bitstream), wave.bitstream_bytes,
+                            C.c_void_p(wave.quant), wave.n_quant, wave.n_mb_slots)
+            wave.slices[1].mb_slot += 16
+            assert L.mpegb200_video_decode_bitstream(*args()) == -1      # MPEGB200_EINVAL: a hole in the record slots
+            wave.slices[1].mb_slot -= 16
+            before = [c.video_read_frame(0, b) for b in range(3)]
+            wave.pics[0].type = 0
+            c._ck(L.mpegb200_video_decode_bitstream(*args()))
+            flags = np.zeros(1, np.int32)
+            assert L.mpegb200_video_bitstream_flags(c.h, C.c_void_p(flags.ctypes.data), 1) == 1 and flags[0] == 0x80
+            gm = np.zeros(wave.n_mb_slots, ol.MB_DTYPE)
+            c._ck(L.mpegb200_video_bitstream_records(c.h, C.c_void_p(gm.ctypes.data), None))
+            assert (gm["pic"] == 0xffff).all()
+            for b in range(3):
+                assert np.array_equal(c.video_read_frame(0, b), before[b])
+        finally:
+            sb.close()

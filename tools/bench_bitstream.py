@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--pictures", type=int, default=5)
     ap.add_argument("--distinct", type=int, default=2)
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--device-vlc", action="store_true", help="with --gpu: also run the slice-parallel VLC stage on the device")
     args = ap.parse_args()
     threads = args.threads or len(os.sched_getaffinity(0))
 
@@ -119,6 +120,54 @@ def main():
                       "note": "lock-step batch: parse (host threads) -> pinned waves -> H2D -> expand_vlen + plan + fused kernels; frames stay in HBM"}
         vb.close()
         ctx.close()
+        if args.device_vlc:
+            # the same streams with the slices parsed on the GPU: the host scans start codes and copies compressed bytes
+            from mpeg_b200.batch import BatchScanStep
+            h = L.mpegb200_video_batch_new(len(streams), threads, None, None)
+            for i, d in enumerate(streams):
+                assert L.mpegb200_video_batch_set_stream(h, i, d, len(d)) == 0
+            st = BatchScanStep()
+            dt_scan, k, scanned = 0.0, 0, 0
+            while True:
+                t0 = time.perf_counter()
+                assert L.mpegb200_video_batch_next_scan(h, C.byref(st)) == 0
+                t1 = time.perf_counter()
+                got = int(np.ctypeslib.as_array(st.has_frame, shape=(len(streams),)).sum())
+                if got == 0:
+                    break
+                k += 1
+                if k > 1:
+                    dt_scan += t1 - t0
+                    scanned += sum(st.waves[w].n_pictures for w in range(st.n_waves))
+            L.mpegb200_video_batch_free(h)
+            ctx = mpeg_b200.Context(0, args.streams)
+            ctx.set_kernel_timing(True)
+            vb = mpeg_b200.VideoBatch(ctx, streams, threads=threads, validate=False, device_vlc=True)
+            frames, parse_ms, steps = 0, [], 0
+            ms = C.c_float()
+            ctx.sync()
+            t0 = time.perf_counter()
+            while True:
+                has, buf, _ = vb.step()
+                if not has.any():
+                    break
+                frames += int(has.sum())
+                steps += 1
+                if L.mpegb200_video_bitstream_parse_ms(ctx.h, C.byref(ms)) == 0:
+                    parse_ms.append(ms.value)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+            plan, fused = ctx.kernel_times()
+            res["device_vlc"] = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "launches": ctx.launch_count,
+                                 "flagged_pictures": vb.flagged, "host_steps": vb.host_steps,
+                                 "host_scan_pictures_per_sec": scanned / dt_scan if dt_scan else None,
+                                 "parse_kernel_ms_per_wave": parse_ms, "decode_ms_per_wave": [float(a + b) for a, b in zip(plan, fused)],
+                                 "parse_kernel_pictures_per_sec": (args.streams / (min(parse_ms[1:] or parse_ms) / 1e3)) if parse_ms else None,
+                                 "speedup_vs_host_parser_path": (frames / dt) / res["gpu"]["frames_per_sec"],
+                                 "note": "host: start-code scan + copy of compressed bytes; device: vlc_parse_kernel (one thread per slice) + "
+                                         "vlc_check_kernel + plan + fused kernels; one flag read-back (synchronisation) per wave"}
+            vb.close()
+            ctx.close()
     print(json.dumps(res))
 
 
