@@ -120,6 +120,11 @@ typedef struct mpegb200_video_scan_step {
 
 /* Like mpegb200_video_parser_next, stopping at the slice start codes.  The two calls may alternate between steps. */
 int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_scan_step* out);
+/* Withdraw the last scan step: the parser stands where it stood before that mpegb200_video_parser_next_scan call and the
+ * step before it is the "last scan step" again (for mpegb200_video_parser_redo).  One step back only.  This is what lets a
+ * caller scan step k + 1 while the device still works on step k: if step k then flags a picture, step k + 1 is withdrawn,
+ * step k's tail re-parsed, and step k + 1 scanned again from where the serial reference really stands. */
+int mpegb200_video_parser_unscan(mpegb200_video_parser* v);
 /* The device stage flagged picture k of the last scan step: the parser goes back in front of that picture and parses the
  * REST OF THE STEP (picture k and whatever Video.Decode() would decode behind it) in full, with the serial semantics of
  * the reference; it stands where the reference would stand afterwards, which may differ from where the scan stood (a
@@ -196,6 +201,8 @@ typedef struct mpegb200_batch_scan_step {
 } mpegb200_batch_scan_step;
 
 int  mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_step* out);
+/* mpegb200_video_parser_unscan for every stream of the batch (the wave arrays of the step before stay valid). */
+int  mpegb200_video_batch_unscan(mpegb200_video_batch* b);
 /* mpegb200_video_parser_redo for stream `index` of the batch: the rest of its step from picture `step_picture` on, parsed on
  * the host.  The stream's pictures in the later waves of this step are void (set their type to 0 before the wave is decoded:
  * the device then skips them); has_frame / frame_buf / time of the stream are those of *out. */

@@ -115,6 +115,8 @@ def load():
         "mpegb200_video_parser_next": (C.c_int, [vp, vp]),
         "mpegb200_video_parser_next_scan": (C.c_int, [vp, vp]),
         "mpegb200_video_parser_redo": (C.c_int, [vp, C.c_int, vp]),
+        "mpegb200_video_parser_unscan": (C.c_int, [vp]),
+        "mpegb200_video_batch_unscan": (C.c_int, [vp]),
         "mpegb200_video_batch_next_scan": (C.c_int, [vp, vp]),
         "mpegb200_video_batch_redo": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "mpegb200_video_batch_new": (vp, [C.c_int, C.c_int, vp, vp]),

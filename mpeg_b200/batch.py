@@ -54,13 +54,16 @@ assert C.sizeof(VlcPicture) == 32 and C.sizeof(VlcSlice) == 32
 
 class VideoBatch:
     def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True,
-                 vlen: bool = True, device_vlc: bool = False):
+                 vlen: bool = True, device_vlc: bool = False, scan_ahead: bool = True):
         """device_vlc: the host only scans headers and start codes; the slices are parsed on the GPU, one thread per slice
         (mpegb200_video_decode_bitstream), and pictures the device flags are re-parsed by the host parser."""
         self.L = _lib.load()
         self.device_vlc = device_vlc
         self.flagged = 0    # pictures the device flagged so far: their step's tail took the host path (device_vlc)
         self.host_steps = 0  # steps the host parsed itself because stale coefficients were pending (device_vlc)
+        self.t_scan = self.t_submit = self.t_wait = 0.0   # device_vlc: seconds in the host scan, in the submission, waiting for the flags
+        self.scan_ahead = scan_ahead   # device_vlc: scan step k + 1 on the host while the device works on step k
+        self._ahead = None
         ctx.set_validate(validate)   # bitstream-derived records: a malformed wave raises instead of decoding (pass False for trusted input)
         self.ctx, self.n, self.first = ctx, len(streams), first_stream
         alloc = C.cast(self.L.mpegb200_host_alloc, C.c_void_p) if pinned else None
@@ -112,10 +115,23 @@ class VideoBatch:
         t = np.ctypeslib.as_array(st.time, shape=(self.n,)).copy()
         return has, buf, t
 
-    def _step_device_vlc(self):
-        from .mpeg import VideoStep
+    def _scan(self):
+        """One scan step of every stream (host): the step structure plus copies of its per-stream results."""
+        import time
         st = BatchScanStep()
+        t0 = time.perf_counter()
         self.ctx._ck(self.L.mpegb200_video_batch_next_scan(self.h, C.byref(st)))
+        self.t_scan += time.perf_counter() - t0
+        has = np.ctypeslib.as_array(st.has_frame, shape=(self.n,)).astype(bool)
+        buf = np.ctypeslib.as_array(st.frame_buf, shape=(self.n,)).astype(np.uint8)
+        t = np.ctypeslib.as_array(st.time, shape=(self.n,)).copy()
+        return st, has, buf, t
+
+    def _step_device_vlc(self):
+        import time
+        from .mpeg import VideoStep
+        st, has, buf, t = self._ahead if self._ahead is not None else self._scan()
+        self._ahead = None
         # streams whose step the host parsed itself (stale coefficients pending): plain launches, no part in the waves
         host_steps = C.cast(st.host_steps, C.POINTER(VideoStep))
         for j in range(st.n_host):
@@ -126,32 +142,42 @@ class VideoBatch:
             wave = st.waves[w]
             if wave.n_pictures == 0:
                 continue
-            for k in range(wave.n_pictures):
-                if wave.pics[k].stream in done:
-                    wave.pics[k].type = 0
-                wave.pics[k].stream += self.first
+            if done or self.first:
+                for k in range(wave.n_pictures):
+                    if wave.pics[k].stream in done:
+                        wave.pics[k].type = 0
+                    wave.pics[k].stream += self.first
+            t0 = time.perf_counter()
             self.ctx._ck(self.L.mpegb200_video_decode_bitstream(
                 self.ctx.h, wave.n_pictures, wave.pics, wave.n_slices, wave.slices, C.c_void_p(wave.bitstream), wave.bitstream_bytes,
                 C.c_void_p(wave.quant), wave.n_quant, wave.n_mb_slots))
-            # the flags come back with the wave (one synchronisation per wave): what the serial reference resolves by order of
-            # arrival goes through the host parser, before the next wave builds on this one
+            self.t_submit += time.perf_counter() - t0
+            # While the device parses the step's last wave the host scans the next step.  That is a guess -- it assumes no
+            # picture of this wave flags; if one does the guess is withdrawn below (mpegb200_video_batch_unscan).
+            if self.scan_ahead and w == st.n_waves - 1:
+                self._ahead = self._scan()
+            # The flags come back with the wave: what the serial reference resolves by order of arrival goes through the host
+            # parser, before anything builds on this wave.
+            t1 = time.perf_counter()
             flags = np.zeros(wave.n_pictures, np.int32)
             bad = self.L.mpegb200_video_bitstream_flags(self.ctx.h, C.c_void_p(flags.ctypes.data), wave.n_pictures)
+            self.t_wait += time.perf_counter() - t1
             if bad < 0:
                 self.ctx._ck(bad)
             for k in np.nonzero(flags)[0] if bad else ():
                 index = wave.pics[k].stream - self.first
                 if index in done:
                     continue
+                if self._ahead is not None:    # the parsers go back to where they stood after this step's scan
+                    self.ctx._ck(self.L.mpegb200_video_batch_unscan(self.h))
+                    self._ahead = None
                 redo = VideoStep()
                 self.ctx._ck(self.L.mpegb200_video_batch_redo(self.h, index, wave.step_picture[k], C.byref(redo)))
                 self._run_launches(redo, index + self.first)
+                has[index], buf[index], t[index] = bool(redo.has_frame), redo.frame_buf, redo.time
                 done.add(index)
                 self.flagged += 1
         self.steps += 1
-        has = np.ctypeslib.as_array(st.has_frame, shape=(self.n,)).astype(bool)
-        buf = np.ctypeslib.as_array(st.frame_buf, shape=(self.n,)).astype(np.uint8)
-        t = np.ctypeslib.as_array(st.time, shape=(self.n,)).copy()
         return has, buf, t
 
     def _run_launches(self, step, stream_id: int):

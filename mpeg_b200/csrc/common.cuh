@@ -98,7 +98,8 @@ cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc
                              int n_pics, const mpegb200_vlc_slice* d_slices, uint32_t n_slices, const uint8_t* d_bitstream,
                              uint32_t n_words, const uint8_t* d_quant, uint32_t n_quant, const StreamInfo* d_streams,
                              int max_streams, mpegb200_mb* d_mbs, uint32_t n_mb_slots, int16_t* d_coeffs, void* d_summary,
-                             int32_t* d_flags, cudaStream_t stream);
+                             int32_t* d_flags, int sm_count, cudaStream_t stream);
+cudaError_t configure_vlc_kernel();
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 
 }  // namespace mpegb200

@@ -81,7 +81,7 @@ struct mpegb200_ctx {
     DevBuf s_vpics[2], s_slices[2], s_bits[2], s_quant[2], s_vlc_pics, s_vlc_mbs, s_vlc_coeffs, s_vlc_summary, s_vlc_flags;
     int32_t* h_vlc_flags = nullptr;          // pinned
     size_t h_vlc_flags_cap = 0;
-    int vlc_n_pictures = 0;
+    int vlc_n_pictures = 0, sm_count = 148;
     size_t vlc_n_mb_slots = 0;
     cudaEvent_t ev_vlc_flags = nullptr, ev_vlc_t0 = nullptr, ev_vlc_t1 = nullptr;
     bool vlc_timed = false;
@@ -832,6 +832,8 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
             ctx->d_vlc_tables = nullptr;
             return fail(ctx, ok ? MPEGB200_ECUDA : MPEGB200_ESTATE, "variable-length-code tables: %s", ok ? cudaGetErrorString(e) : "host tables have an unexpected shape");
         }
+        CU(configure_vlc_kernel());
+        CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
         CU(cudaEventCreateWithFlags(&ctx->ev_vlc_flags, cudaEventDisableTiming));
         CU(cudaEventCreate(&ctx->ev_vlc_t0));
         CU(cudaEventCreate(&ctx->ev_vlc_t1));
@@ -878,7 +880,7 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
                         n_pictures, (const mpegb200_vlc_slice*)ctx->s_slices[slot].p, (uint32_t)n_slices,
                         (const uint8_t*)ctx->s_bits[slot].p, (uint32_t)(bitstream_bytes / 4 + 2), (const uint8_t*)ctx->s_quant[slot].p,
                         (uint32_t)n_quant, ctx->d_info, ctx->max_streams, (mpegb200_mb*)ctx->s_vlc_mbs.p, (uint32_t)n_mb_slots,
-                        (int16_t*)ctx->s_vlc_coeffs.p, ctx->s_vlc_summary.p, (int32_t*)ctx->s_vlc_flags.p, ctx->stream));
+                        (int16_t*)ctx->s_vlc_coeffs.p, ctx->s_vlc_summary.p, (int32_t*)ctx->s_vlc_flags.p, ctx->sm_count, ctx->stream));
     ctx->launches += n_slices ? 2 : 1;
     if (ctx->vlc_timed) CU(cudaEventRecord(ctx->ev_vlc_t1, ctx->stream));
     CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));   // the uploads are consumed: the staging slot may be refilled

@@ -6,6 +6,9 @@
 // machinery is its own: a 64-bit window bit reader and table-driven multi-bit VLC decoding instead of
 // the reference's one-bit-per-step tree walk (buffer.go:352-376), records instead of pixels.
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -68,17 +71,63 @@ struct BitReader {
         }
         return n;
     }
+    // Start codes found so far: every 00 00 01 xx whose first byte lies in [sc_from, sc_to) is in sc_at, in order.  Video.Decode
+    // looks for the next picture start code before it decodes a picture (hasStartCode, video.go:239) and the scan mode walks the
+    // slice start codes of the same bytes again: with the memo every byte of the stream is searched once.
+    std::vector<uint64_t> sc_at;
+    uint64_t sc_from = 0, sc_to = 0;
+
+    // first index f >= i with p[f..f+2] == 00 00 01 and f + 5 <= len, or len if there is none (16 bytes at a time: SSE2 is baseline x86-64)
+    size_t raw_find(size_t i) const {
+        if (len < 5) return len;
+        const size_t last = len - 5;
+#if defined(__SSE2__)
+        const __m128i zero = _mm_setzero_si128(), one = _mm_set1_epi8(1);
+        while (i + 18 <= len) {   // three loads of 16 bytes at i, i + 1, i + 2
+            const __m128i a = _mm_loadu_si128((const __m128i*)(p + i)), b = _mm_loadu_si128((const __m128i*)(p + i + 1)),
+                          c = _mm_loadu_si128((const __m128i*)(p + i + 2));
+            const unsigned m = (unsigned)_mm_movemask_epi8(_mm_and_si128(_mm_and_si128(_mm_cmpeq_epi8(a, zero), _mm_cmpeq_epi8(b, zero)), _mm_cmpeq_epi8(c, one)));
+            if (m) {
+                const size_t f = i + (size_t)__builtin_ctz(m);
+                return f <= last ? f : len;
+            }
+            i += 16;
+        }
+#endif
+        for (; i <= last; i++)
+            if (p[i] == 0 && p[i + 1] == 0 && p[i + 2] == 1) return i;
+        return len;
+    }
     int next_start_code() {  // buffer.go:279-302
         align();
-        size_t i = (size_t)(pos >> 3);
-        while (i + 5 <= len) {
-            if (p[i] == 0 && p[i + 1] == 0 && p[i + 2] == 1) {
-                pos = (uint64_t)(i + 4) << 3;
-                return p[i + 3];
-            }
-            i++;
+        const uint64_t i = pos >> 3;
+        if (i < sc_from || i > sc_to + 65536 || sc_at.size() > 4096) {   // outside what the memo covers (or time to forget): start over here
+            sc_at.clear();
+            sc_from = sc_to = i;
         }
-        pos = (uint64_t)i << 3;
+        const auto it = std::lower_bound(sc_at.begin(), sc_at.end(), i);
+        uint64_t f = len;
+        if (it != sc_at.end()) {
+            f = *it;
+        } else {
+            for (;;) {   // extend the memo until it holds a start code at or behind i (the bytes between sc_to and i are searched too)
+                f = raw_find((size_t)sc_to);
+                if (f >= len) {
+                    sc_to = len;
+                    break;
+                }
+                sc_at.push_back(f);
+                sc_to = f + 3;   // no 00 00 01 can begin at f + 1 or f + 2
+                if (f >= i) break;
+            }
+        }
+        if (f < len) {
+            pos = (f + 4) << 3;
+            return p[f + 3];
+        }
+        // where the reference's byte-by-byte walk stops: the first position that has no room for a start code
+        const uint64_t stop = len >= 4 ? (uint64_t)len - 4 : 0;
+        pos = (i > stop ? i : stop) << 3;
         ended = true;
         return -1;
     }
@@ -339,6 +388,18 @@ struct mpegb200_video_parser {
     };
     int step_frames_decoded = 0;       // the step counters in front of the current scan step (a re-parse restarts the step's tail)
     double step_time = 0;
+    // One step back (mpegb200_video_parser_unscan): the caller scans step k + 1 while the device still works on step k; if step k
+    // then flags a picture, step k + 1 is withdrawn and step k's saved states are current again.
+    struct StepBegin {
+        bool valid = false;
+        Saved at;
+        int frames_decoded = 0;
+        double time = 0;
+        int32_t level[64];
+        std::vector<Saved> prev_saved;
+        int prev_step_frames_decoded = 0;
+        double prev_step_time = 0;
+    } step_begin;
     mpegb200_video_step host_step;     // scan mode: a step the host had to parse itself (stale coefficients pending, see next_scan)
     std::vector<mpegb200_scan_picture> scan_pics;
     std::vector<mpegb200_scan_slice> scan_slices;
@@ -958,6 +1019,17 @@ int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_sca
         // possibly a picture later.  Only the host parser carries that state: while it is pending the host parses the step itself.
         bool stale = false;
         for (int i = 0; i < 64 && !stale; i++) stale = v->level[i] != 0;
+        {   // what mpegb200_video_parser_unscan goes back to
+            auto& sb = v->step_begin;
+            sb.valid = true;
+            sb.at = VP::Saved{v->br, v->start_code, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf, v->has_reference, v->fwd, v->bwd};
+            sb.frames_decoded = v->frames_decoded;
+            sb.time = v->time;
+            memcpy(sb.level, v->level, sizeof(sb.level));
+            sb.prev_saved.swap(v->scan_saved);          // next_impl clears scan_saved: the previous step's states move here first
+            sb.prev_step_frames_decoded = v->step_frames_decoded;
+            sb.prev_step_time = v->step_time;
+        }
         mpegb200_video_step st;
         const int rc = video_parser_next_impl(v, stale ? &v->host_step : &st, !stale);
         if (stale) st = v->host_step;
@@ -981,6 +1053,30 @@ int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_sca
         memset(out, 0, sizeof(*out));
         return MPEGB200_ENOMEM;
     }
+}
+
+int mpegb200_video_parser_unscan(mpegb200_video_parser* v) {
+    if (!v || !v->step_begin.valid) return MPEGB200_EINVAL;
+    auto& sb = v->step_begin;
+    v->br = sb.at.br;
+    v->start_code = sb.at.start_code;
+    v->picture_type = sb.at.picture_type;
+    v->cur = sb.at.cur;
+    v->fwd_buf = sb.at.fwd_buf;
+    v->bwd_buf = sb.at.bwd_buf;
+    v->has_reference = sb.at.has_reference;
+    v->fwd = sb.at.fwd;
+    v->bwd = sb.at.bwd;
+    v->frames_decoded = sb.frames_decoded;
+    v->time = sb.time;
+    memcpy(v->level, sb.level, sizeof(sb.level));
+    v->scan_saved.swap(sb.prev_saved);
+    v->step_frames_decoded = sb.prev_step_frames_decoded;
+    v->step_time = sb.prev_step_time;
+    v->scan_pics.clear();
+    v->scan_slices.clear();
+    sb.valid = false;   // one step back, not two
+    return 0;
 }
 
 int mpegb200_video_parser_redo(mpegb200_video_parser* v, int k, mpegb200_video_step* out) {
@@ -1497,7 +1593,7 @@ struct mpegb200_video_batch {
     };
     std::vector<mpegb200_video_scan_step> scan_steps;
     std::vector<ScanBuf> scan_bufs[2];
-    std::vector<mpegb200_vlc_wave> scan_waves;
+    std::vector<mpegb200_vlc_wave> scan_waves[2];   // the descriptors are double-buffered like the arrays they point to
     std::vector<int> host_index;
     std::vector<mpegb200_video_step> host_steps;
 
@@ -1733,7 +1829,8 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
     b->flip ^= 1;
     auto& bufs = b->scan_bufs[b->flip];
     if ((int)bufs.size() < n_waves) bufs.resize((size_t)n_waves);
-    b->scan_waves.assign((size_t)n_waves, mpegb200_vlc_wave{});
+    auto& scan_waves = b->scan_waves[b->flip];
+    scan_waves.assign((size_t)n_waves, mpegb200_vlc_wave{});
     std::vector<uint32_t> pic_of((size_t)n), slice_off((size_t)n), slot_off((size_t)n);
     std::vector<uint64_t> byte_off((size_t)n), first_byte((size_t)n), n_bytes((size_t)n);
     for (int w = 0; w < n_waves; w++) {
@@ -1825,7 +1922,7 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
         });
         if (b->pool->failed()) return MPEGB200_ENOMEM;
         memset(buf.bits + nbytes, 0, 16);
-        mpegb200_vlc_wave& W = b->scan_waves[(size_t)w];
+        mpegb200_vlc_wave& W = scan_waves[(size_t)w];
         W.n_pictures = (int)np;
         W.pics = buf.pics;
         W.step_picture = buf.step_picture;
@@ -1842,7 +1939,7 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
     out->frame_buf = b->frame_buf.data();
     out->time = b->time.data();
     out->n_waves = n_waves;
-    out->waves = b->scan_waves.data();
+    out->waves = scan_waves.data();
     out->n_host = (int)b->host_index.size();
     out->host_index = b->host_index.data();
     out->host_steps = b->host_steps.data();
@@ -1864,6 +1961,14 @@ int mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_
 size_t mpegb200_internal_vlc_tables(void* out, size_t cap) {
     if (!out || cap < sizeof(mpegb200::VlcDeviceTables)) return 0;
     return mpegb200::fill_vlc_device_tables(static_cast<mpegb200::VlcDeviceTables*>(out)) ? sizeof(mpegb200::VlcDeviceTables) : 0;
+}
+
+int mpegb200_video_batch_unscan(mpegb200_video_batch* b) {
+    if (!b) return MPEGB200_EINVAL;
+    int rc = 0;
+    for (auto* p : b->parsers)
+        if (p && mpegb200_video_parser_unscan(p) != 0) rc = MPEGB200_ESTATE;
+    return rc;
 }
 
 int mpegb200_video_batch_redo(mpegb200_video_batch* b, int index, int step_picture, mpegb200_video_step* out) {

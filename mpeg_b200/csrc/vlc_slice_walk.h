@@ -38,13 +38,16 @@ struct SliceSummary {        // 16 bytes per slice, read by vlc_check_picture
     int32_t end_addr;        // the reference's mbAddress when the slice ended
 };
 
-VLC_HD uint32_t vlc_ld32(const uint32_t* p) {
+// bitstream words and quantiser bytes come from global memory through the read-only path; the code tables are read with plain
+// loads (they sit in shared memory on the device: the walker is inlined into the kernel and the compiler sees the address space)
+VLC_HD uint32_t vlc_ldg32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
 #else
     return *p;
 #endif
 }
+VLC_HD uint32_t vlc_ld32(const uint32_t* p) { return *p; }
 VLC_HD uint32_t vlc_ld8(const uint8_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
@@ -90,28 +93,31 @@ struct Bits {                // most significant bit first (buffer.go:223-255)
     const uint32_t* w;
     uint32_t n_words, next, end_byte;   // end_byte: where the elementary stream ends in the buffer (zero bits beyond)
     uint32_t origin;                    // word index and byte phase of the slice's first bit: pos() counts from there
+    uint32_t ahead;                     // word `next`, already loaded: its latency hides behind the bits in front of it
     uint64_t buf;
     int cnt;                            // valid bits at the top of buf; >= 32 between two operations
 
     VLC_HD uint32_t load(uint32_t i) const {
         if (i >= n_words) return 0;
-        uint32_t v = vlc_bswap(vlc_ld32(w + i));
+        uint32_t v = vlc_bswap(vlc_ldg32(w + i));
         const uint32_t o = i * 4u;
         if (o + 4u > end_byte) v = o >= end_byte ? 0u : (v & (0xffffffffu << (8u * (o + 4u - end_byte))));
         return v;
     }
     VLC_HD void refill() {
         if (cnt < 32) {
-            buf |= (uint64_t)load(next++) << (32 - cnt);
+            buf |= (uint64_t)ahead << (32 - cnt);
             cnt += 32;
+            ahead = load(++next);
         }
     }
     VLC_HD void init(uint32_t byte_offset) {
         next = byte_offset >> 2;
         const int mis = (int)(byte_offset & 3u);
         origin = next * 32u + 8u * (uint32_t)mis;   // modulo 2^32, like pos(): a slice is shorter than 2^32 bits
-        buf = (uint64_t)load(next++) << (32 + 8 * mis);
+        buf = (uint64_t)load(next) << (32 + 8 * mis);
         cnt = 32 - 8 * mis;
+        ahead = load(++next);
         refill();
     }
     VLC_HD uint32_t pos() const { return next * 32u - (uint32_t)cnt - origin; }   // bits consumed since init
@@ -361,10 +367,16 @@ VLC_HD SliceSummary walk_slice(const VlcDeviceTables* T, const uint32_t* fast, c
                             lv = (int)(int16_t)(fe & 0xffffu);
                         } else {
                             const uint32_t bits16 = (uint32_t)(w >> 48);
-                            uint32_t e = vlc_ld32(&T->coeff_first[bits16 >> kVlcCoefSecondBits]);
-                            if (e & kVlcLink) e = vlc_ld32(&T->coeff_second[e & 0xffu][bits16 & ((1u << kVlcCoefSecondBits) - 1u)]);
-                            const uint32_t c = e & 0xffffu;
-                            used = vlc_entry_len(e);
+                            uint32_t c;
+                            if ((bits16 >> 10) == 1u) {   // "000001": escape, no look-up needed
+                                c = 0xffffu;
+                                used = 6;
+                            } else {
+                                uint32_t e = vlc_ld32(&T->coeff_first[bits16 >> kVlcCoefSecondBits]);
+                                if (e & kVlcLink) e = vlc_ld32(&T->coeff_second[e & 0xffu][bits16 & ((1u << kVlcCoefSecondBits) - 1u)]);
+                                c = e & 0xffffu;
+                                used = vlc_entry_len(e);
+                            }
                             w <<= used;
                             if (c == 0x0001u && n > 0) {   // "1" behind the first coefficient: a 0 bit ends the block (video.go:686) ...
                                 if ((w >> 63) == 0) {

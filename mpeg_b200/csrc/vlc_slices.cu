@@ -6,32 +6,42 @@
 // independent (overlapping or over-running slices, a picture ended early) is detected, never emulated: vlc_check_kernel
 // flags such pictures, disables their records and the caller re-parses them on the host.
 //
-// Memory: the bitstream is read through L1 with one aligned 32-bit load per 32 bits consumed (a 64-bit window lives in
-// registers); a block is assembled in shared memory (128 bytes per thread, 16-byte chunks swizzled by lane so that lanes at
-// the same zig-zag position do not share a bank) and leaves as eight 16-byte stores; the hot table (16 KB) sits in shared
-// memory, the others are read through the read-only cache.
+// Shape of the kernel.  The walk is a chain of dependent look-ups (window -> table -> shift -> next window): latency bound,
+// and the slices of a warp diverge.  So a warp carries only a FEW slices (`lanes` of its 32 lanes, chosen by the launcher so
+// that the wave fills the SMs with sixteen warps each) and the idle lanes only help to load the tables: more warps hide
+// the latency, fewer slices per warp serialise less.  All code tables (47 KB) live in shared memory; the bitstream is read
+// through L1 with one aligned 32-bit load per 32 bits consumed, issued one word ahead; a block is assembled in shared memory
+// (128 bytes per slice, 16-byte chunks swizzled by lane) and leaves as eight 16-byte stores.
 #include "common.cuh"
 #include "vlc_slice_walk.h"
 
 namespace mpegb200 {
 
 namespace {
-constexpr int kVlcThreads = 64;
+constexpr int kVlcWarps = 4, kVlcCtasPerSm = 4;               // warps per CTA; CTAs per SM (51 KB of shared memory, <= 128 registers)
+constexpr int kVlcMaxLanes = 8;                               // slices per warp, at most
+constexpr size_t kVlcSmem = sizeof(VlcDeviceTables) + (size_t)kVlcWarps * kVlcMaxLanes * 128;
+static_assert(sizeof(VlcDeviceTables) % 16 == 0, "the block scratch behind the tables must be 16-byte aligned");
 }
 
-__global__ void __launch_bounds__(kVlcThreads) vlc_parse_kernel(
-    const VlcDeviceTables* __restrict__ T, const mpegb200_vlc_picture* __restrict__ pics, int n_pics,
+__global__ void __launch_bounds__(kVlcWarps * 32, kVlcCtasPerSm) vlc_parse_kernel(
+    const VlcDeviceTables* __restrict__ tables, int lanes, const mpegb200_vlc_picture* __restrict__ pics, int n_pics,
     const mpegb200_vlc_slice* __restrict__ slices, uint32_t n_slices, const uint32_t* __restrict__ words, uint32_t n_words,
     const uint8_t* __restrict__ quant, uint32_t n_quant, const StreamInfo* __restrict__ streams, int max_streams,
     mpegb200_mb* __restrict__ mbs, uint32_t n_mb_slots, int16_t* __restrict__ coeffs, SliceSummary* __restrict__ summary) {
-    __shared__ uint32_t s_fast[1 << kVlcCoefFastBits];
-    __shared__ __align__(16) uint8_t s_block[kVlcThreads * 128];
-    __shared__ uint8_t s_zigzag[64];
-    for (int i = threadIdx.x; i < (1 << kVlcCoefFastBits); i += kVlcThreads) s_fast[i] = T->coef_fast[i];
-    if (threadIdx.x < 64) s_zigzag[threadIdx.x] = T->zigzag[threadIdx.x];
-    for (int i = threadIdx.x; i < kVlcThreads * 8; i += kVlcThreads) reinterpret_cast<uint4*>(s_block)[i] = make_uint4(0, 0, 0, 0);
+    extern __shared__ __align__(16) uint8_t smem[];
+    VlcDeviceTables* const T = reinterpret_cast<VlcDeviceTables*>(smem);
+    uint8_t* const s_block = smem + sizeof(VlcDeviceTables);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(tables);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(VlcDeviceTables) / 16); i += kVlcWarps * 32) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < kVlcWarps * kVlcMaxLanes * 8; i += kVlcWarps * 32) reinterpret_cast<uint4*>(s_block)[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
-    const uint32_t s = blockIdx.x * kVlcThreads + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane >= lanes) return;
+    const uint32_t s = (blockIdx.x * kVlcWarps + warp) * (uint32_t)lanes + (uint32_t)lane;
     if (s >= n_slices) return;
 
     const mpegb200_vlc_slice sl = slices[s];
@@ -57,7 +67,8 @@ __global__ void __launch_bounds__(kVlcThreads) vlc_parse_kernel(
     }
     SliceSummary sum;
     if (ok) {
-        sum = walk_slice(T, s_fast, s_zigzag, s_block + threadIdx.x * 128, threadIdx.x & 7u, sl, P, g, words, n_words, quant, mbs, coeffs);
+        sum = walk_slice(T, T->coef_fast, T->zigzag, s_block + (warp * kVlcMaxLanes + lane) * 128, (uint32_t)lane & 7u, sl, P, g, words,
+                         n_words, quant, mbs, coeffs);
     } else {
         // a picture that is void (type 0: the caller withdrew it) or inconsistent: its slots hold null records, its picture is flagged
         sum.flags = MPEGB200_VLC_BAD_ARG;
@@ -98,15 +109,28 @@ __global__ void vlc_check_kernel(const mpegb200_vlc_picture* __restrict__ vpics,
 
 size_t vlc_summary_bytes(size_t n_slices) { return sizeof(SliceSummary) * (n_slices ? n_slices : 1); }
 
+cudaError_t configure_vlc_kernel() {
+    return cudaFuncSetAttribute(vlc_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVlcSmem);
+}
+
 cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc_picture* d_vpics, mpegb200_picture* d_pics,
                              int n_pics, const mpegb200_vlc_slice* d_slices, uint32_t n_slices, const uint8_t* d_bitstream,
                              uint32_t n_words, const uint8_t* d_quant, uint32_t n_quant, const StreamInfo* d_streams,
                              int max_streams, mpegb200_mb* d_mbs, uint32_t n_mb_slots, int16_t* d_coeffs, void* d_summary,
-                             int32_t* d_flags, cudaStream_t stream) {
-    if (n_slices)
-        vlc_parse_kernel<<<(n_slices + kVlcThreads - 1) / kVlcThreads, kVlcThreads, 0, stream>>>(
-            d_tables, d_vpics, n_pics, d_slices, n_slices, reinterpret_cast<const uint32_t*>(d_bitstream), n_words, d_quant,
+                             int32_t* d_flags, int sm_count, cudaStream_t stream) {
+    if (n_slices) {
+        // slices per warp: as few as put the whole wave on the SMs at once (sixteen resident warps each)
+        const uint32_t resident = (uint32_t)sm_count * kVlcCtasPerSm * kVlcWarps;
+        int lanes = (int)((n_slices + resident - 1) / resident);
+        lanes = lanes < 1 ? 1 : (lanes > kVlcMaxLanes ? kVlcMaxLanes : lanes);
+#ifdef MPEGB200_EXPERIMENTS
+        if (const char* e = getenv("MPEGB200_VLC_LANES")) lanes = atoi(e) < 1 ? 1 : (atoi(e) > kVlcMaxLanes ? kVlcMaxLanes : atoi(e));
+#endif
+        const uint32_t per_cta = (uint32_t)(kVlcWarps * lanes);
+        vlc_parse_kernel<<<(n_slices + per_cta - 1) / per_cta, kVlcWarps * 32, kVlcSmem, stream>>>(
+            d_tables, lanes, d_vpics, n_pics, d_slices, n_slices, reinterpret_cast<const uint32_t*>(d_bitstream), n_words, d_quant,
             n_quant, d_streams, max_streams, d_mbs, n_mb_slots, d_coeffs, reinterpret_cast<SliceSummary*>(d_summary));
+    }
     if (n_pics)
         vlc_check_kernel<<<(n_pics + 127) / 128, 128, 0, stream>>>(d_vpics, d_pics, n_pics,
                                                                   reinterpret_cast<const SliceSummary*>(d_summary), n_slices,

@@ -188,3 +188,65 @@ def test_batch_scan_waves_hold_each_streams_picture(golden_dir):
         assert stats["steps"] >= 4 and stats["pictures"] > 20
     finally:
         sb.close()
+
+
+def run_stream_scanning_ahead(data, label=""):
+    """The product's pipelined flow (mpeg_b200.VideoBatch, scan_ahead): step k + 1 is scanned BEFORE step k's flags are known; a
+    flag withdraws that scan (mpegb200_video_batch_unscan), the host finishes step k, and step k + 1 is scanned again.  Every step
+    must still equal the full host parser's, and the wave arrays of step k must survive the scan of step k + 1."""
+    full = parser_steps(data)
+    sb = ve.ScanBatch([data])
+    tab = ve.tables()
+    mb_w, mb_h = sb.sizes[0]
+    ahead, steps, withdrawn = None, 0, 0
+    try:
+        while True:
+            st = ahead if ahead is not None else sb.next()
+            ahead = None
+            has, buf, t = st.has_frame[0], st.frame_buf[0], st.time[0]
+            hosted = ve.ScanBatch.host_steps(st)
+            launches = hosted.get(0, [])
+            for w in range(st.n_waves if 0 not in hosted else 0):
+                wave = st.waves[w]
+                if w == st.n_waves - 1:
+                    ahead = sb.next()                      # the guess, made while "the device" still holds wave w
+                mbs, coeffs, flags = ve.emulate_wave(wave, mb_w, mb_h, tab)
+                P = wave.pics[0]
+                if flags[0]:
+                    if ahead is not None:
+                        sb.unscan()
+                        ahead = None
+                        withdrawn += 1
+                    has, buf, t, tail = sb.redo(0, w)
+                    launches = launches + tail
+                    break
+                gm, gc = ve.picture_records(mbs, coeffs, P)
+                launches.append(((P.type, P.dst_buf, P.fwd_buf, P.bwd_buf, len(gm)), gm, gc))
+            want = next(full, None)
+            if not has:
+                assert want is None, f"{label}: ends early at step {steps}"
+                break
+            assert want is not None and (buf, t) == (want[0], want[1]), f"{label}: step {steps}"
+            got = [l for l in launches if l[0][4]]
+            ref = [l for l in want[2] if l[0][4]]
+            assert len(got) == len(ref), f"{label}: step {steps}"
+            for (h1, m1, c1), (h2, m2, c2) in zip(got, ref):
+                assert h1 == h2 and same_records((m1, c1), (m2, c2)), f"{label}: step {steps} differs from the host parser"
+            steps += 1
+    finally:
+        sb.close()
+    return steps, withdrawn
+
+
+def test_scanning_ahead_and_withdrawing(golden_dir):
+    steps, withdrawn = run_stream_scanning_ahead(video_streams(golden_dir)["test.mpeg1video"], "test.mpeg1video")
+    assert steps > 250 and withdrawn > 20
+    steps, withdrawn = run_stream_scanning_ahead(video_streams(golden_dir)["test.mpg video"], "test.mpg video")
+    assert steps > 250 and withdrawn == 0
+    data = (golden_dir / "test.mpeg1video").read_bytes()[:80000]
+    rng = np.random.default_rng(21)
+    for trial in range(6):
+        d = bytearray(data)
+        for pos in rng.integers(200, len(d), 30):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        run_stream_scanning_ahead(bytes(d), f"damaged {trial}")

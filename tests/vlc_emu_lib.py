@@ -102,6 +102,9 @@ class ScanBatch:
         assert self.L.mpegb200_video_batch_next_scan(self.h, C.byref(st)) == 0
         return st
 
+    def unscan(self):
+        assert self.L.mpegb200_video_batch_unscan(self.h) == 0
+
     def redo(self, index, step_picture):
         """The tail of stream `index`'s step from `step_picture` on, parsed by the host: (has_frame, frame_buf, time, launches)."""
         st = VideoStep()

@@ -27,9 +27,18 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 
 def make_streams(distinct, pictures, mode, log):
+    """Synthetic 720p streams (I then P pictures); cached under tools/_build/streams/ (git-ignored, travels to the GPU box) because
+    the Python writer needs seconds per picture."""
     import mpeg1_writer as mw
+    cache = ROOT / "tools" / "_build" / "streams"
+    cache.mkdir(parents=True, exist_ok=True)
     out = []
     for d in range(distinct):
+        f = cache / f"{mode}_720p_seed{720 + d}_{pictures}pictures.m1v"
+        if f.exists():
+            out.append(f.read_bytes())
+            log(f"stream {d}: {f.name} from the cache, {len(out[-1]) / 1e6:.2f} MB")
+            continue
         t0 = time.time()
         rng = np.random.default_rng(720 + d)
         w = mw.StreamWriter(1280, 720, quantizer_scale=8, f_code=2)
@@ -37,6 +46,7 @@ def make_streams(distinct, pictures, mode, log):
         for _ in range(pictures - 1):
             w.picture(mw.PIC_P, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_P, mode, 32, 1280, 720))
         out.append(w.tobytes())
+        f.write_bytes(out[-1])
         log(f"stream {d}: {pictures} pictures, {len(out[-1]) / 1e6:.2f} MB, written in {time.time() - t0:.1f} s")
     return out
 
@@ -57,6 +67,8 @@ def main():
         print(f"[bitstream] {m}", file=sys.stderr, flush=True)
 
     distinct = make_streams(args.distinct, args.pictures, args.mode, log)
+    if args.streams == 0:
+        return
     streams = [distinct[i % len(distinct)] for i in range(args.streams)]
     total_bytes = sum(len(s) for s in streams)
     from mpeg_b200 import _lib
@@ -159,7 +171,8 @@ def main():
             dt = time.perf_counter() - t0
             plan, fused = ctx.kernel_times()
             res["device_vlc"] = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "launches": ctx.launch_count,
-                                 "flagged_pictures": vb.flagged, "host_steps": vb.host_steps,
+                                 "flagged_pictures": vb.flagged, "host_steps": vb.host_steps, "steps": steps,
+                                 "seconds_in": {"host_scan": vb.t_scan, "submit": vb.t_submit, "waiting_for_flags": vb.t_wait},
                                  "host_scan_pictures_per_sec": scanned / dt_scan if dt_scan else None,
                                  "parse_kernel_ms_per_wave": parse_ms, "decode_ms_per_wave": [float(a + b) for a, b in zip(plan, fused)],
                                  "parse_kernel_pictures_per_sec": (args.streams / (min(parse_ms[1:] or parse_ms) / 1e3)) if parse_ms else None,
