@@ -23,6 +23,9 @@ holds its own 256 streams (configs[4] layout: stream-parallel, no data-path coll
             the other picture steps of the configuration (natural P, natural B, I-only, dense P with +-64 pixel vectors),
             each parity-checked against the oracle and timed like the headline step, fraction of the roofline on ITS bytes
   audio     BASELINE configs[3]: 1024 MP2 streams x 8 frames per launch, both window modes, parity-checked
+  bitstream compressed 720p elementary streams in, frames in HBM out: the lock-step batch with the host parser
+            against the same batch with the slices parsed on the device (vlc_parse_kernel), every stream's frames hashed
+            against the CPU oracle's decode of its bitstream
   sustained the headline step looped for --sustain-seconds with clocks sampled (burst vs sustained)
   transfers H2D / D2H bandwidth of this rank's PCIe link and the host's memcpy bandwidth (explains e2e at N > 1)
   gathered  (N > 1) the frames of every step gathered to rank 0 over NVLink inside the timed region, double-buffered
@@ -570,6 +573,7 @@ def main():
         extras["sustained"] = sustained_leg(args, torch, stream, step_dev, local_rank, S, alg_total, peak)
         extras["picture_steps"] = picture_steps(torch, ctx, stream, g, S, peak, log)
         extras["audio"] = audio_leg(torch, local_rank, peak, log)
+        extras["bitstream"] = bitstream_leg(args, local_rank, log)
 
     # ---- frames gathered to rank 0 over NVLink (the only collective of the path)
     gather = gathered = None
@@ -825,6 +829,81 @@ def audio_leg(torch, device_index, peak, log):
                 actx.audio_close(s)
             if not ok:
                 fail_parity({"metric": METRIC, "error": f"audio ({mode}): GPU samples differ from the CPU oracle"})
+    return out
+
+
+def bitstream_leg(args, device_index, log):
+    """Bitstream in, frames out: S natural 720p streams (two distinct ones written by tests/mpeg1_writer.py, I + P pictures)
+    through mpeg_b200.VideoBatch with the host parser and with the device-side slice parser.  Frames stay in HBM; every step's
+    returned frames are hashed on the host for the first streams and held against the oracle's decode of the same bitstream."""
+    import ctypes as C
+    import mpeg_b200
+    import oracle_lib as ol
+    sys.path.insert(0, str(ROOT / "tools"))
+    import bench_bitstream as bb
+    S = args.streams
+    cached = sorted((ROOT / "tools" / "_build" / "streams").glob("natural_720p_seed72[01]_40pictures.m1v"))
+    if len(cached) == 2:
+        distinct = [f.read_bytes() for f in cached]
+    else:
+        distinct = bb.make_streams(2, 6, "natural", log)
+    n_pictures = sum(1 for i in range(len(distinct[0]) - 3) if distinct[0][i:i + 4] == b"\x00\x00\x01\x00")
+    streams = [distinct[i % 2] for i in range(S)]
+    want = []
+    for d in distinct:   # the oracle's full decoder on the bitstream (parse + reconstruct), hash over all returned frames
+        o, h = ol.VideoOracle(d), ol.FNV_OFFSET
+        while (f := o.decode()) is not None:
+            for which in ("y", "cb", "cr"):
+                h = ol.fnv(h, f.plane(which))
+        want.append(h)
+    threads = host_threads()
+    L = mpeg_b200._lib.load()
+    out = {"config": f"{S} natural 720p streams of {n_pictures} pictures ({len(distinct[0]) / n_pictures / 1e3:.1f} KB per picture), frames stay in HBM",
+           "host_threads": threads, "paths": {}}
+    check = [0, 1, S - 2, S - 1] if S >= 4 else list(range(S))
+    for name, kw in (("host_parser", {}), ("device_vlc", {"device_vlc": True})):
+        with mpeg_b200.Context(device=device_index, max_streams=S) as c:
+            c.set_kernel_timing(name == "device_vlc")
+            vb = mpeg_b200.VideoBatch(c, streams, threads=threads, validate=False, **kw)
+            geo = c.video_geometry(0)
+            pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
+            host = np.empty((len(check), pic_bytes), np.uint8)
+            hashes = [ol.FNV_OFFSET] * len(check)
+            frames, parse_ms, ms = 0, [], C.c_float()
+            t_hash = 0.0
+            c.sync()
+            t0 = time.perf_counter()
+            while True:
+                has, buf, _ = vb.step()
+                if not has.any():
+                    break
+                frames += int(has.sum())
+                if name == "device_vlc" and L.mpegb200_video_bitstream_parse_ms(c.h, C.byref(ms)) == 0:
+                    parse_ms.append(ms.value)
+                th = time.perf_counter()   # parity read-back of a few streams: outside the rate
+                live = [k for k, i in enumerate(check) if has[i]]
+                if live:
+                    c.video_read_pictures(np.array([check[k] for k in live]), buf[[check[k] for k in live]], host.ctypes.data, pic_bytes)
+                    c.sync()
+                    for j, k in enumerate(live):
+                        hashes[k] = ol.fnv(hashes[k], host[j])
+                t_hash += time.perf_counter() - th
+            c.sync()
+            dt = time.perf_counter() - t0 - t_hash
+            ok = all(hashes[k] == want[check[k] % 2] for k in range(len(check)))
+            rec = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "parity_ok": bool(ok), "checked_streams": check}
+            if name == "device_vlc":
+                steady = sorted(parse_ms[1:] or parse_ms)
+                rec.update({"flagged_pictures": vb.flagged, "host_steps": vb.host_steps,
+                            "parse_kernel_ms_per_wave": steady[len(steady) // 2] if steady else None,
+                            "parse_kernel_pictures_per_sec": S / (steady[len(steady) // 2] * 1e-3) if steady else None,
+                            "seconds_in": {"host_scan": vb.t_scan, "submit": vb.t_submit, "waiting_for_flags": vb.t_wait}})
+            out["paths"][name] = rec
+            log(f"bitstream {name}: {frames / dt:.0f} frames/s, parity {'ok' if ok else 'MISMATCH'}")
+            vb.close()
+            if not ok:
+                fail_parity({"metric": METRIC, "error": f"bitstream ({name}): frames differ from the oracle's decode of the bitstream"})
+    out["device_vlc_speedup"] = out["paths"]["device_vlc"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
     return out
 
 

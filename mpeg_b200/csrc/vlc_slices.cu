@@ -18,7 +18,13 @@
 namespace mpegb200 {
 
 namespace {
-constexpr int kVlcWarps = 4, kVlcCtasPerSm = 4;               // warps per CTA; CTAs per SM (51 KB of shared memory, <= 128 registers)
+#ifndef MPEGB200_VLC_WARPS
+#define MPEGB200_VLC_WARPS 4
+#endif
+#ifndef MPEGB200_VLC_CTAS
+#define MPEGB200_VLC_CTAS 4
+#endif
+constexpr int kVlcWarps = MPEGB200_VLC_WARPS, kVlcCtasPerSm = MPEGB200_VLC_CTAS;   // warps per CTA; CTAs per SM (51 KB of shared memory each, <= 128 registers)
 constexpr int kVlcMaxLanes = 8;                               // slices per warp, at most
 constexpr size_t kVlcSmem = sizeof(VlcDeviceTables) + (size_t)kVlcWarps * kVlcMaxLanes * 128;
 static_assert(sizeof(VlcDeviceTables) % 16 == 0, "the block scratch behind the tables must be 16-byte aligned");
