@@ -104,13 +104,15 @@ struct Bits {                // most significant bit first (buffer.go:223-255)
     uint64_t buf;
     int cnt;                            // valid bits at the top of buf; >= 32 between two operations
 
-    // (a fast path for words that need no masking, with this tail in a function of its own, measured slower: 1.37 against 1.19 ms)
+    // Word i of the buffer, most significant bit first, zero behind the end of the stream and of the buffer -- without a branch:
+    // the index is clamped, the bytes that count are kept by a mask (1.154 against 1.195 ms per wave for the branching form; a
+    // fast path for words that need no masking with the rest in a function of its own: 1.37 ms).
+    uint32_t end_eff, last_word;        // min(end_byte, 4 * n_words); n_words - 1
     VLC_HD uint32_t load(uint32_t i) const {
-        if (i >= n_words) return 0;
-        uint32_t v = vlc_bswap(vlc_ldg32(w + i));
-        const uint32_t o = i * 4u;
-        if (o + 4u > end_byte) v = o >= end_byte ? 0u : (v & (0xffffffffu << (8u * (o + 4u - end_byte))));
-        return v;
+        const uint32_t v = vlc_bswap(vlc_ldg32(w + (i < last_word ? i : last_word)));
+        long long vb = (long long)end_eff - 4ll * (long long)i;          // bytes of word i in front of the end
+        vb = vb < 0 ? 0 : (vb > 4 ? 4 : vb);
+        return v & (uint32_t)(0xffffffff00000000ull >> (8 * (int)vb));
     }
     VLC_HD void refill() {
         if (cnt < 32) {
@@ -120,6 +122,8 @@ struct Bits {                // most significant bit first (buffer.go:223-255)
         }
     }
     VLC_HD void init(uint32_t byte_offset) {
+        end_eff = end_byte < n_words * 4u ? end_byte : n_words * 4u;   // n_words < 2^30 (the entry point bounds the buffer)
+        last_word = n_words - 1u;
         next = byte_offset >> 2;
         const int mis = (int)(byte_offset & 3u);
         origin = next * 32u + 8u * (uint32_t)mis;   // modulo 2^32, like pos(): a slice is shorter than 2^32 bits
