@@ -274,9 +274,20 @@ typedef struct mpegb200_vlc_slice {
 #define MPEGB200_VLC_EARLY_END    0x40   /* a slice other than the last reaches the end of the picture */
 #define MPEGB200_VLC_BAD_ARG      0x80   /* the slice or picture table itself is inconsistent */
 
+/* Elementary streams resident in device memory.  mpegb200_video_stream_upload copies a stream's bytes to the device once (any
+ * stream id below max_streams, opened or not; a second upload replaces the first; len 0 frees it); a wave whose `bitstream`
+ * argument is NULL then reads its slices from there: data_offset counts from the first byte of the stream of the slice's
+ * picture.  No compressed byte crosses PCIe per step, only the tables.  mpegb200_video_stream_index finds every start code
+ * prefix 00 00 01 xx of the resident stream on the device (the search of buffer.go:279-302, all at once) and writes the byte
+ * offsets of the prefixes in ascending order: *n = how many there are; at most `cap` are written (MPEGB200_EINVAL if cap is too
+ * small, *n still valid).  mpegb200_video_parser_set_start_codes (mpegb200_host.h) hands them to the host parser, which then
+ * never searches a byte. */
+int mpegb200_video_stream_upload(mpegb200_ctx* ctx, int stream, const uint8_t* data, size_t len);
+int mpegb200_video_stream_index(mpegb200_ctx* ctx, int stream, uint64_t* positions, size_t cap, size_t* n);
+
 /* Parse + decode one wave: uploads the tables and the bytes, runs vlc_parse_kernel and vlc_check_kernel, then the decode
  * kernels on the records they left in device memory.  All arrays are host memory (pinned for asynchronous uploads);
- * `bitstream` holds the pictures' bytes, bitstream_bytes < 2^32.  quant: n_quant x 128 bytes.  n_mb_slots: total record
+ * `bitstream` holds the pictures' bytes, bitstream_bytes < 2^32 (NULL: the streams are resident, see above).  quant: n_quant x 128 bytes.  n_mb_slots: total record
  * slots of the wave (a multiple of 16, < 2^32 / 6).  Asynchronous like the other decode entry points; returns 0 or a negative code. */
 int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpegb200_vlc_picture* pics,
                                     size_t n_slices, const mpegb200_vlc_slice* slices,

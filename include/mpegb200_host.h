@@ -120,6 +120,10 @@ typedef struct mpegb200_video_scan_step {
 
 /* Like mpegb200_video_parser_next, stopping at the slice start codes.  The two calls may alternate between steps. */
 int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_scan_step* out);
+/* Every start code prefix (00 00 01) of the stream, byte offsets ascending -- e.g. from mpegb200_video_stream_index, which finds
+ * them on the device: the parser then never searches a byte of the stream (it checks that the positions are start codes of its
+ * stream; MPEGB200_EINVAL otherwise). */
+int mpegb200_video_parser_set_start_codes(mpegb200_video_parser* v, const uint64_t* positions, size_t n);
 /* Withdraw the last scan step: the parser stands where it stood before that mpegb200_video_parser_next_scan call and the
  * step before it is the "last scan step" again (for mpegb200_video_parser_redo).  One step back only.  This is what lets a
  * caller scan step k + 1 while the device still works on step k: if step k then flags a picture, step k + 1 is withdrawn,
@@ -201,6 +205,10 @@ typedef struct mpegb200_batch_scan_step {
 } mpegb200_batch_scan_step;
 
 int  mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_step* out);
+/* Resident mode: the streams were uploaded with mpegb200_video_stream_upload (stream id = index + the caller's offset); the waves
+ * then carry no bytes (bitstream = NULL) and the slices' data_offset counts from the first byte of their stream. */
+int  mpegb200_video_batch_set_resident(mpegb200_video_batch* b, int on);
+int  mpegb200_video_batch_set_start_codes(mpegb200_video_batch* b, int index, const uint64_t* positions, size_t n);
 /* mpegb200_video_parser_unscan for every stream of the batch (the wave arrays of the step before stay valid). */
 int  mpegb200_video_batch_unscan(mpegb200_video_batch* b);
 /* mpegb200_video_parser_redo for stream `index` of the batch: the rest of its step from picture `step_picture` on, parsed on

@@ -75,6 +75,8 @@ def load():
         "mpegb200_pack_coeffs_vlen": (C.c_int, [vp, C.c_size_t, vp, vp, vp, C.c_size_t, szp]),
         "mpegb200_video_decode_pictures_vlen": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp, vp, C.c_size_t]),
         "mpegb200_video_decode_bitstream": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t]),
+        "mpegb200_video_stream_upload": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_size_t]),
+        "mpegb200_video_stream_index": (C.c_int, [vp, C.c_int, vp, C.c_size_t, szp]),
         "mpegb200_video_bitstream_flags": (C.c_int, [vp, vp, C.c_int]),
         "mpegb200_video_bitstream_records": (C.c_int, [vp, vp, vp]),
         "mpegb200_video_bitstream_parse_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
@@ -116,6 +118,9 @@ def load():
         "mpegb200_video_parser_next_scan": (C.c_int, [vp, vp]),
         "mpegb200_video_parser_redo": (C.c_int, [vp, C.c_int, vp]),
         "mpegb200_video_parser_unscan": (C.c_int, [vp]),
+        "mpegb200_video_parser_set_start_codes": (C.c_int, [vp, vp, C.c_size_t]),
+        "mpegb200_video_batch_set_resident": (C.c_int, [vp, C.c_int]),
+        "mpegb200_video_batch_set_start_codes": (C.c_int, [vp, C.c_int, vp, C.c_size_t]),
         "mpegb200_video_batch_unscan": (C.c_int, [vp]),
         "mpegb200_video_batch_next_scan": (C.c_int, [vp, vp]),
         "mpegb200_video_batch_redo": (C.c_int, [vp, C.c_int, C.c_int, vp]),

@@ -54,9 +54,11 @@ assert C.sizeof(VlcPicture) == 32 and C.sizeof(VlcSlice) == 32
 
 class VideoBatch:
     def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True,
-                 vlen: bool = True, device_vlc: bool = False, scan_ahead: bool = True):
+                 vlen: bool = True, device_vlc: bool = False, scan_ahead: bool = True, resident: bool = False):
         """device_vlc: the host only scans headers and start codes; the slices are parsed on the GPU, one thread per slice
-        (mpegb200_video_decode_bitstream), and pictures the device flags are re-parsed by the host parser."""
+        (mpegb200_video_decode_bitstream), and pictures the device flags are re-parsed by the host parser.
+        resident (with device_vlc): every stream is uploaded to device memory once and its start codes are indexed there
+        (mpegb200_video_stream_upload / _index): per step the host touches headers only and the waves carry tables only."""
         self.L = _lib.load()
         self.device_vlc = device_vlc
         self.flagged = 0    # pictures the device flagged so far: their step's tail took the host path (device_vlc)
@@ -83,6 +85,20 @@ class VideoBatch:
                 raise ValueError(f"stream {i}: no MPEG-1 sequence header")
             self.sizes.append((w.value, h.value))
             ctx.video_open(first_stream + i, w.value, h.value)
+        self.resident = bool(resident and device_vlc)
+        if self.resident:
+            self.L.mpegb200_video_batch_set_resident(self.h, 1)
+            n_codes = C.c_size_t()
+            for i, d in enumerate(self._data):
+                ctx._ck(self.L.mpegb200_video_stream_upload(ctx.h, first_stream + i, d, len(d)))
+                pos = np.empty(len(d) // 64 + 4096, np.uint64)
+                rc = self.L.mpegb200_video_stream_index(ctx.h, first_stream + i, C.c_void_p(pos.ctypes.data), len(pos), C.byref(n_codes))
+                if rc != 0 and n_codes.value > len(pos):   # a stream of (almost) nothing but start codes
+                    pos = np.empty(n_codes.value, np.uint64)
+                    rc = self.L.mpegb200_video_stream_index(ctx.h, first_stream + i, C.c_void_p(pos.ctypes.data), len(pos), C.byref(n_codes))
+                ctx._ck(rc)
+                if self.L.mpegb200_video_batch_set_start_codes(self.h, i, C.c_void_p(pos.ctypes.data), n_codes.value) != 0:
+                    raise RuntimeError(f"stream {i}: the device's start-code index does not fit the stream")
         self._pic_dtype = np.dtype([("stream", "<i4"), ("rest", "V12")])
         self.steps = 0
 
@@ -205,6 +221,8 @@ class VideoBatch:
             for i in range(self.n):
                 try:
                     self.ctx.video_close(self.first + i)
+                    if self.resident:
+                        self.L.mpegb200_video_stream_upload(self.ctx.h, self.first + i, None, 0)
                 except Exception:
                     pass
             self.L.mpegb200_video_batch_free(self.h)

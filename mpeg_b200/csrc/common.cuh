@@ -93,12 +93,19 @@ cudaError_t launch_audio_requant(const mpegb200_audio_frame_info* d_info, const 
                                  size_t n_frames, cudaStream_t stream);
 // slice-parallel VLC stage (vlc_slices.cu): bitstream -> records + int16 blocks in device memory, flagged pictures disabled
 struct VlcDeviceTables;
+struct ResidentStream {      // an elementary stream kept in device memory (mpegb200_video_stream_upload)
+    const uint8_t* bytes;    // 16-byte aligned, 32 zero bytes behind the last
+    uint32_t n_words;        // readable 32-bit words
+    uint32_t pad;
+};
 size_t vlc_summary_bytes(size_t n_slices);
+cudaError_t launch_startcode_index(const uint8_t* d_bytes, uint64_t len, uint64_t* d_out, uint32_t cap, uint32_t* d_count,
+                                   cudaStream_t stream);
 cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc_picture* d_vpics, mpegb200_picture* d_pics,
                              int n_pics, const mpegb200_vlc_slice* d_slices, uint32_t n_slices, const uint8_t* d_bitstream,
                              uint32_t n_words, const uint8_t* d_quant, uint32_t n_quant, const StreamInfo* d_streams,
                              int max_streams, mpegb200_mb* d_mbs, uint32_t n_mb_slots, int16_t* d_coeffs, void* d_summary,
-                             int32_t* d_flags, int sm_count, cudaStream_t stream);
+                             int32_t* d_flags, int sm_count, cudaStream_t stream, const ResidentStream* d_resident = nullptr);
 cudaError_t configure_vlc_kernel();
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory; call once per device
 

@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: if CUDA is unavailable every entry point reports MPEGB200_ECUDA.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -85,6 +86,13 @@ struct mpegb200_ctx {
     size_t vlc_n_mb_slots = 0;
     cudaEvent_t ev_vlc_flags = nullptr, ev_vlc_t0 = nullptr, ev_vlc_t1 = nullptr;
     bool vlc_timed = false;
+    // elementary streams resident in device memory (mpegb200_video_stream_upload): per stream id its bytes and length
+    std::vector<void*> resident_dev;
+    std::vector<size_t> resident_len;
+    std::vector<ResidentStream> h_resident;
+    ResidentStream* d_resident = nullptr;
+    bool resident_dirty = false;
+    DevBuf s_index;
     int max_w = 0, max_h = 0;
     char err[512] = {0};
 };
@@ -263,6 +271,10 @@ void mpegb200_destroy(mpegb200_ctx* ctx) {
                       &ctx->s_vlc_coeffs, &ctx->s_vlc_summary, &ctx->s_vlc_flags})
         if (b->p) cudaFree(b->p);
     if (ctx->d_vlc_tables) cudaFree(ctx->d_vlc_tables);
+    for (void* r : ctx->resident_dev)
+        if (r) cudaFree(r);
+    if (ctx->d_resident) cudaFree(ctx->d_resident);
+    if (ctx->s_index.p) cudaFree(ctx->s_index.p);
     if (ctx->h_vlc_flags) cudaFreeHost(ctx->h_vlc_flags);
     for (cudaEvent_t e : {ctx->ev_vlc_flags, ctx->ev_vlc_t0, ctx->ev_vlc_t1})
         if (e) cudaEventDestroy(e);
@@ -793,11 +805,89 @@ int mpegb200_video_decode_pictures_vlen(mpegb200_ctx* ctx, int n_pictures, const
 
 // ---- slice-parallel VLC stage: compressed slices in, records parsed and executed on the device ----
 
+int mpegb200_video_stream_upload(mpegb200_ctx* ctx, int stream, const uint8_t* data, size_t len) try {
+    if (!ctx || stream < 0 || stream >= ctx->max_streams || (len && !data)) return fail(ctx, MPEGB200_EINVAL, "bad argument");
+    if (len >= 0xffffff00ull) return fail(ctx, MPEGB200_EINVAL, "stream too long for one resident buffer (2^32 bytes)");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->resident_dev.empty()) {
+        ctx->resident_dev.assign((size_t)ctx->max_streams, nullptr);
+        ctx->resident_len.assign((size_t)ctx->max_streams, 0);
+        ctx->h_resident.assign((size_t)ctx->max_streams, ResidentStream{nullptr, 0, 0});
+        if (cudaMalloc(&ctx->d_resident, sizeof(ResidentStream) * (size_t)ctx->max_streams) != cudaSuccess) {
+            ctx->d_resident = nullptr;
+            cudaGetLastError();
+            ctx->resident_dev.clear();
+            return fail(ctx, MPEGB200_ENOMEM, "device allocation failed");
+        }
+        ctx->resident_dirty = true;
+    }
+    if (ctx->resident_dev[(size_t)stream]) {   // a wave in flight may still read the old bytes
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(ctx->resident_dev[(size_t)stream]));
+        ctx->resident_dev[(size_t)stream] = nullptr;
+        ctx->resident_len[(size_t)stream] = 0;
+        ctx->h_resident[(size_t)stream] = ResidentStream{nullptr, 0, 0};
+        ctx->resident_dirty = true;
+    }
+    if (len == 0) return 0;
+    void* d = nullptr;
+    const size_t padded = ((len + 3) & ~(size_t)3) + 64;
+    if (cudaMalloc(&d, padded) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MPEGB200_ENOMEM, "device allocation of %zu bytes failed", padded);
+    }
+    cudaError_t e = cudaMemsetAsync((uint8_t*)d + (len & ~(size_t)3), 0, padded - (len & ~(size_t)3), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, data, len, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // `data` may go away when this returns
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(ctx, MPEGB200_ECUDA, "upload of the stream failed: %s", cudaGetErrorString(e));
+    }
+    ctx->resident_dev[(size_t)stream] = d;
+    ctx->resident_len[(size_t)stream] = len;
+    ctx->h_resident[(size_t)stream] = ResidentStream{(const uint8_t*)d, (uint32_t)(len / 4 + 2), 0};
+    ctx->resident_dirty = true;
+    return 0;
+} catch (...) {
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
+}
+
+int mpegb200_video_stream_index(mpegb200_ctx* ctx, int stream, uint64_t* positions, size_t cap, size_t* n) try {
+    if (!ctx || !n || stream < 0 || stream >= ctx->max_streams || (cap && !positions)) return fail(ctx, MPEGB200_EINVAL, "bad argument");
+    *n = 0;
+    if (ctx->resident_dev.empty() || !ctx->resident_dev[(size_t)stream]) return fail(ctx, MPEGB200_ESTATE, "stream %d is not resident", stream);
+    if (cap > 0x7fffffffull) cap = 0x7fffffffull;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure(ctx, ctx->s_index, 8 * cap + 16)) return rc;
+    uint32_t* d_count = (uint32_t*)ctx->s_index.p;
+    uint64_t* d_out = (uint64_t*)((uint8_t*)ctx->s_index.p + 16);
+    CU(cudaMemsetAsync(d_count, 0, 16, ctx->stream));
+    CU(launch_startcode_index((const uint8_t*)ctx->resident_dev[(size_t)stream], ctx->resident_len[(size_t)stream], d_out, (uint32_t)cap,
+                              d_count, ctx->stream));
+    ctx->launches++;
+    uint32_t count = 0;
+    CU(cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n = count;
+    const size_t got = count < cap ? count : cap;
+    if (got) CU(cudaMemcpy(positions, d_out, 8 * got, cudaMemcpyDeviceToHost));
+    std::sort(positions, positions + got);
+    if (count > cap) return fail(ctx, MPEGB200_EINVAL, "%u start codes, room for %zu", count, cap);
+    return 0;
+} catch (...) {
+    return fail(ctx, MPEGB200_ENOMEM, "host allocation failed");
+}
+
 int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpegb200_vlc_picture* pics, size_t n_slices,
                                     const mpegb200_vlc_slice* slices, const uint8_t* bitstream, size_t bitstream_bytes,
                                     const uint8_t* quant, size_t n_quant, size_t n_mb_slots) try {
-    if (!ctx || n_pictures < 0 || (n_pictures && !pics) || (n_slices && (!slices || !bitstream || !quant)))
+    if (!ctx || n_pictures < 0 || (n_pictures && !pics) || (n_slices && (!slices || !quant)))
         return fail(ctx, MPEGB200_EINVAL, "null argument");
+    const bool resident = bitstream == nullptr;   // the slices read their streams' resident copies
+    if (resident) {
+        bitstream_bytes = 0;
+        if (n_slices && ctx->resident_dev.empty()) return fail(ctx, MPEGB200_ESTATE, "no resident stream (mpegb200_video_stream_upload) and no bitstream given");
+    }
     if (n_pictures >= 65535 || n_slices > 0x7fffffffull || bitstream_bytes >= 0xffffff00ull || n_mb_slots > 0xffffffffull / 6 ||
         (n_mb_slots & 15) || n_quant > 0xffffffffull)
         return fail(ctx, MPEGB200_EINVAL, "wave too large (or record slots not a multiple of 16)");
@@ -805,7 +895,7 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
     size_t expect = 0;
     for (size_t i = 0; i < n_slices; i++) {
         const mpegb200_vlc_slice& sl = slices[i];
-        if (sl.mb_slot != expect || (sl.mb_cap & 15u) || sl.pic >= (uint32_t)n_pictures || sl.data_offset >= bitstream_bytes)
+        if (sl.mb_slot != expect || (sl.mb_cap & 15u) || sl.pic >= (uint32_t)n_pictures || (!resident && sl.data_offset >= bitstream_bytes))
             return fail(ctx, MPEGB200_EINVAL, "slice %zu: record slots must follow each other in multiples of 16, picture and offset must be in range", i);
         expect += sl.mb_cap;
     }
@@ -816,6 +906,8 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
         if (P.quant >= n_quant || P.first_slice > n_slices || P.n_slices > n_slices - P.first_slice)
             return fail(ctx, MPEGB200_EINVAL, "picture %d: quantiser or slice range out of range", i);
         dst_mask |= P.dst_buf < 3 ? 1u << P.dst_buf : 7u;
+        if (resident && P.n_slices && (P.stream < 0 || P.stream >= ctx->max_streams || !ctx->resident_dev[(size_t)P.stream]))
+            return fail(ctx, MPEGB200_ESTATE, "picture %d: stream %d is not resident", i, P.stream);
     }
     ctx->vlc_n_pictures = n_pictures;
     ctx->vlc_n_mb_slots = n_mb_slots;
@@ -829,6 +921,10 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
         delete h;
         if (e != cudaSuccess) {
             if (ctx->d_vlc_tables) cudaFree(ctx->d_vlc_tables);
+    for (void* r : ctx->resident_dev)
+        if (r) cudaFree(r);
+    if (ctx->d_resident) cudaFree(ctx->d_resident);
+    if (ctx->s_index.p) cudaFree(ctx->s_index.p);
             ctx->d_vlc_tables = nullptr;
             return fail(ctx, ok ? MPEGB200_ECUDA : MPEGB200_ESTATE, "variable-length-code tables: %s", ok ? cudaGetErrorString(e) : "host tables have an unexpected shape");
         }
@@ -867,9 +963,17 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
     if (n_slices) {
         CU(cudaMemcpyAsync(ctx->s_slices[slot].p, slices, sizeof(mpegb200_vlc_slice) * n_slices, cudaMemcpyHostToDevice, ctx->up_stream));
         CU(cudaMemcpyAsync(ctx->s_quant[slot].p, quant, 128 * n_quant, cudaMemcpyHostToDevice, ctx->up_stream));
-        // the bit reader loads whole 32-bit words: zero what lies behind the last byte, then the bytes
-        CU(cudaMemsetAsync((uint8_t*)ctx->s_bits[slot].p + (bitstream_bytes & ~(size_t)3), 0, 16, ctx->up_stream));
-        CU(cudaMemcpyAsync(ctx->s_bits[slot].p, bitstream, bitstream_bytes, cudaMemcpyHostToDevice, ctx->up_stream));
+        if (!resident) {
+            // the bit reader loads whole 32-bit words: zero what lies behind the last byte, then the bytes
+            CU(cudaMemsetAsync((uint8_t*)ctx->s_bits[slot].p + (bitstream_bytes & ~(size_t)3), 0, 16, ctx->up_stream));
+            CU(cudaMemcpyAsync(ctx->s_bits[slot].p, bitstream, bitstream_bytes, cudaMemcpyHostToDevice, ctx->up_stream));
+        }
+    }
+    if (resident && ctx->resident_dirty) {
+        CU(cudaMemcpyAsync(ctx->d_resident, ctx->h_resident.data(), sizeof(ResidentStream) * (size_t)ctx->max_streams, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->resident_dirty = false;
     }
     CU(cudaEventRecord(ctx->ev_up[slot], ctx->up_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
@@ -880,7 +984,8 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
                         n_pictures, (const mpegb200_vlc_slice*)ctx->s_slices[slot].p, (uint32_t)n_slices,
                         (const uint8_t*)ctx->s_bits[slot].p, (uint32_t)(bitstream_bytes / 4 + 2), (const uint8_t*)ctx->s_quant[slot].p,
                         (uint32_t)n_quant, ctx->d_info, ctx->max_streams, (mpegb200_mb*)ctx->s_vlc_mbs.p, (uint32_t)n_mb_slots,
-                        (int16_t*)ctx->s_vlc_coeffs.p, ctx->s_vlc_summary.p, (int32_t*)ctx->s_vlc_flags.p, ctx->sm_count, ctx->stream));
+                        (int16_t*)ctx->s_vlc_coeffs.p, ctx->s_vlc_summary.p, (int32_t*)ctx->s_vlc_flags.p, ctx->sm_count, ctx->stream,
+                        resident ? ctx->d_resident : nullptr));
     ctx->launches += n_slices ? 2 : 1;
     if (ctx->vlc_timed) CU(cudaEventRecord(ctx->ev_vlc_t1, ctx->stream));
     CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));   // the uploads are consumed: the staging slot may be refilled

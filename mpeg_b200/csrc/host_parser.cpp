@@ -76,6 +76,7 @@ struct BitReader {
     // slice start codes of the same bytes again: with the memo every byte of the stream is searched once.
     std::vector<uint64_t> sc_at;
     uint64_t sc_from = 0, sc_to = 0;
+    bool sc_complete = false;   // sc_at holds every start code of the stream (indexed elsewhere, e.g. on the device): never searched, never forgotten
 
     // first index f >= i with p[f..f+2] == 00 00 01 and f + 5 <= len, or len if there is none (16 bytes at a time: SSE2 is baseline x86-64)
     size_t raw_find(size_t i) const {
@@ -101,7 +102,7 @@ struct BitReader {
     int next_start_code() {  // buffer.go:279-302
         align();
         const uint64_t i = pos >> 3;
-        if (i < sc_from || i > sc_to + 65536 || sc_at.size() > 4096) {   // outside what the memo covers (or time to forget): start over here
+        if (!sc_complete && (i < sc_from || i > sc_to + 65536 || sc_at.size() > 4096)) {   // outside what the memo covers (or time to forget): start over here
             sc_at.clear();
             sc_from = sc_to = i;
         }
@@ -381,7 +382,8 @@ struct mpegb200_video_parser {
     // scan mode (mpegb200_video_parser_next_scan): pictures and slice start codes of the step, and where to resume a host re-parse
     // everything the serial walk carries from picture to picture, as it is when decode_picture is entered
     struct Saved {
-        BitReader br;
+        uint64_t br_pos;       // the reader's position and end flag (its start-code memo stays: it describes the bytes, not the walk)
+        bool br_ended;
         int start_code, picture_type, cur, fwd_buf, bwd_buf;
         bool has_reference;
         Motion fwd, bwd;
@@ -785,7 +787,7 @@ void emit_picture(VP* v, int type, int dst, int fwd, int bwd) {
 
 void decode_picture(VP* v, bool scan = false) {  // video.go:374-434
     BitReader& br = v->br;
-    const VP::Saved at_entry{br, v->start_code, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf, v->has_reference, v->fwd, v->bwd};
+    const VP::Saved at_entry{br.pos, br.ended, v->start_code, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf, v->has_reference, v->fwd, v->bwd};
     const uint64_t begin_byte = (br.pos >> 3) - 4;   // the picture start code
     br.skip(10);
     v->picture_type = (int)br.read(3);
@@ -923,7 +925,8 @@ static int video_parser_next_impl(mpegb200_video_parser* v, mpegb200_video_step*
     bool resuming = resume >= 0;
     if (resuming) {
         const VP::Saved sv = v->scan_saved[(size_t)resume];
-        v->br = sv.br;
+        v->br.pos = sv.br_pos;
+        v->br.ended = sv.br_ended;
         v->start_code = sv.start_code;
         v->picture_type = sv.picture_type;
         v->cur = sv.cur;
@@ -1022,7 +1025,7 @@ int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_sca
         {   // what mpegb200_video_parser_unscan goes back to
             auto& sb = v->step_begin;
             sb.valid = true;
-            sb.at = VP::Saved{v->br, v->start_code, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf, v->has_reference, v->fwd, v->bwd};
+            sb.at = VP::Saved{v->br.pos, v->br.ended, v->start_code, v->picture_type, v->cur, v->fwd_buf, v->bwd_buf, v->has_reference, v->fwd, v->bwd};
             sb.frames_decoded = v->frames_decoded;
             sb.time = v->time;
             memcpy(sb.level, v->level, sizeof(sb.level));
@@ -1055,10 +1058,35 @@ int mpegb200_video_parser_next_scan(mpegb200_video_parser* v, mpegb200_video_sca
     }
 }
 
+int mpegb200_video_parser_set_start_codes(mpegb200_video_parser* v, const uint64_t* positions, size_t n) {
+    if (!v || (n && !positions)) return MPEGB200_EINVAL;
+    try {
+        BitReader& br = v->br;
+        br.sc_at.clear();
+        br.sc_at.reserve(n);
+        uint64_t prev = 0;
+        for (size_t k = 0; k < n; k++) {
+            const uint64_t f = positions[k];
+            if (k && f <= prev) return MPEGB200_EINVAL;                      // ascending, please
+            prev = f;
+            if (br.len < 5 || f > (uint64_t)br.len - 5) continue;             // no room for the code byte and one more (buffer.go:284)
+            if (br.p[f] != 0 || br.p[f + 1] != 0 || br.p[f + 2] != 1) return MPEGB200_EINVAL;   // not a start code of THIS stream
+            br.sc_at.push_back(f);
+        }
+        br.sc_from = 0;
+        br.sc_to = br.len;
+        br.sc_complete = true;
+        return 0;
+    } catch (...) {
+        return MPEGB200_ENOMEM;
+    }
+}
+
 int mpegb200_video_parser_unscan(mpegb200_video_parser* v) {
     if (!v || !v->step_begin.valid) return MPEGB200_EINVAL;
     auto& sb = v->step_begin;
-    v->br = sb.at.br;
+    v->br.pos = sb.at.br_pos;
+    v->br.ended = sb.at.br_ended;
     v->start_code = sb.at.start_code;
     v->picture_type = sb.at.picture_type;
     v->cur = sb.at.cur;
@@ -1596,6 +1624,7 @@ struct mpegb200_video_batch {
     std::vector<mpegb200_vlc_wave> scan_waves[2];   // the descriptors are double-buffered like the arrays they point to
     std::vector<int> host_index;
     std::vector<mpegb200_video_step> host_steps;
+    bool resident = false;          // the streams live in device memory: the waves carry tables only
 
     void* get(size_t bytes) { return alloc ? alloc(bytes ? bytes : 1) : malloc(bytes ? bytes : 1); }
     void put(void* p) {
@@ -1857,7 +1886,7 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
             }
             // bytes: from the first slice to eight bytes behind the start code that ends the last one (what a reader that
             // stops in front of that code may still look at)
-            if (P.n_slices) {
+            if (P.n_slices && !b->resident) {
                 first_byte[(size_t)i] = S[0].offset;
                 const uint64_t last = std::min<uint64_t>(S[P.n_slices - 1].next_code + 8, st.stream_len);
                 n_bytes[(size_t)i] = last - S[0].offset;
@@ -1904,7 +1933,7 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
                 const int64_t cap = std::max<int64_t>(0, std::min(to, mb_size) - from);
                 mpegb200_vlc_slice L;
                 memset(&L, 0, sizeof(L));
-                L.data_offset = byte_off[(size_t)i] + (S[k].offset - first_byte[(size_t)i]);
+                L.data_offset = b->resident ? S[k].offset : byte_off[(size_t)i] + (S[k].offset - first_byte[(size_t)i]);
                 L.next_code = (uint32_t)std::min<uint64_t>(S[k].next_code - S[k].offset, 0xffffffffull);
                 L.stream_left = (uint32_t)std::min<uint64_t>(st.stream_len - S[k].offset, 0xffffffffull);
                 L.pic = p;
@@ -1916,9 +1945,11 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
             }
             V.n_mb_slots = slot - slot_off[(size_t)i];
             buf.pics[p] = V;
-            uint8_t* dst = buf.bits + byte_off[(size_t)i];
-            memcpy(dst, st.stream + first_byte[(size_t)i], (size_t)n_bytes[(size_t)i]);
-            memset(dst + n_bytes[(size_t)i], 0, (size_t)(((n_bytes[(size_t)i] + 15) & ~(uint64_t)15) - n_bytes[(size_t)i]));
+            if (!b->resident) {
+                uint8_t* dst = buf.bits + byte_off[(size_t)i];
+                memcpy(dst, st.stream + first_byte[(size_t)i], (size_t)n_bytes[(size_t)i]);
+                memset(dst + n_bytes[(size_t)i], 0, (size_t)(((n_bytes[(size_t)i] + 15) & ~(uint64_t)15) - n_bytes[(size_t)i]));
+            }
         });
         if (b->pool->failed()) return MPEGB200_ENOMEM;
         memset(buf.bits + nbytes, 0, 16);
@@ -1928,7 +1959,7 @@ static int video_batch_next_scan_impl(mpegb200_video_batch* b, mpegb200_batch_sc
         W.step_picture = buf.step_picture;
         W.n_slices = ns;
         W.slices = buf.slices;
-        W.bitstream = buf.bits;
+        W.bitstream = b->resident ? nullptr : buf.bits;
         W.bitstream_bytes = (size_t)nbytes;
         W.quant = buf.quant;
         W.n_quant = np;
@@ -1961,6 +1992,17 @@ int mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_
 size_t mpegb200_internal_vlc_tables(void* out, size_t cap) {
     if (!out || cap < sizeof(mpegb200::VlcDeviceTables)) return 0;
     return mpegb200::fill_vlc_device_tables(static_cast<mpegb200::VlcDeviceTables*>(out)) ? sizeof(mpegb200::VlcDeviceTables) : 0;
+}
+
+int mpegb200_video_batch_set_resident(mpegb200_video_batch* b, int on) {
+    if (!b) return MPEGB200_EINVAL;
+    b->resident = on != 0;
+    return 0;
+}
+
+int mpegb200_video_batch_set_start_codes(mpegb200_video_batch* b, int index, const uint64_t* positions, size_t n) {
+    if (!b || index < 0 || index >= b->n || !b->parsers[(size_t)index]) return MPEGB200_EINVAL;
+    return mpegb200_video_parser_set_start_codes(b->parsers[(size_t)index], positions, n);
 }
 
 int mpegb200_video_batch_unscan(mpegb200_video_batch* b) {

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(kVlcWarps * 32, kVlcCtasPerSm) vlc_parse_kerne
     const VlcDeviceTables* __restrict__ tables, int lanes, const mpegb200_vlc_picture* __restrict__ pics, int n_pics,
     const mpegb200_vlc_slice* __restrict__ slices, uint32_t n_slices, const uint32_t* __restrict__ words, uint32_t n_words,
     const uint8_t* __restrict__ quant, uint32_t n_quant, const StreamInfo* __restrict__ streams, int max_streams,
-    mpegb200_mb* __restrict__ mbs, uint32_t n_mb_slots, int16_t* __restrict__ coeffs, SliceSummary* __restrict__ summary) {
+    mpegb200_mb* __restrict__ mbs, uint32_t n_mb_slots, int16_t* __restrict__ coeffs, SliceSummary* __restrict__ summary,
+    const ResidentStream* __restrict__ resident) {
     extern __shared__ __align__(16) uint8_t smem[];
     VlcDeviceTables* const T = reinterpret_cast<VlcDeviceTables*>(smem);
     uint8_t* const s_block = smem + sizeof(VlcDeviceTables);
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kVlcWarps * 32, kVlcCtasPerSm) vlc_parse_kerne
     // the entry point has checked the slot tables on the host; a slice whose slots are off anyway writes nothing
     const bool slots_ok = sl.pic < (uint32_t)n_pics && (sl.mb_slot & 15u) == 0 && (sl.mb_cap & 15u) == 0 && sl.mb_slot <= n_mb_slots &&
                           sl.mb_cap <= n_mb_slots - sl.mb_slot;
-    bool ok = slots_ok && sl.data_offset < (uint64_t)n_words * 4u;
+    bool ok = slots_ok && (resident != nullptr || sl.data_offset < (uint64_t)n_words * 4u);
     mpegb200_vlc_picture P;
     VlcGeometry g;
     if (ok) {
@@ -69,6 +70,12 @@ __global__ void __launch_bounds__(kVlcWarps * 32, kVlcCtasPerSm) vlc_parse_kerne
             g.luma_w = si.luma_w;
             g.luma_h = si.luma_h;
             g.buf_bytes = si.buf_bytes;
+            if (resident) {   // the slice's bytes come from its stream's own copy in device memory
+                const ResidentStream rs = resident[P.stream];
+                words = reinterpret_cast<const uint32_t*>(rs.bytes);
+                n_words = rs.n_words;
+                ok = ok && rs.bytes != nullptr && sl.data_offset < (uint64_t)n_words * 4u;
+            }
         }
     }
     SliceSummary sum;
@@ -113,6 +120,37 @@ __global__ void vlc_check_kernel(const mpegb200_vlc_picture* __restrict__ vpics,
     flags_out[p] = (int32_t)flags;
 }
 
+// Every start code prefix 00 00 01 xx of a resident stream (buffer.go:279-302 for all positions at once): one thread per 16
+// bytes, positions appended through an atomic counter (the host sorts them: a few thousand per stream).
+__global__ void startcode_index_kernel(const uint8_t* __restrict__ p, uint64_t len, uint64_t* __restrict__ out, uint32_t cap,
+                                       uint32_t* __restrict__ count) {
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16u;
+    if (i0 >= len) return;
+    // bytes i0 .. i0 + 17 (the buffer is padded with zeros: 32 readable bytes behind len)
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p + i0));
+    const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(p + i0 + 16));
+    const uint32_t w[5] = {a.x, a.y, a.z, a.w, b};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        // three consecutive bytes, little-endian words
+        const uint32_t lo = w[k >> 2], hi = w[(k >> 2) + 1];
+        const uint32_t three = (uint32_t)((((uint64_t)hi << 32) | lo) >> (8 * (k & 3))) & 0xffffffu;
+        if (three == 0x010000u && i0 + (uint64_t)k + 5u <= len) {
+            const uint32_t at = atomicAdd(count, 1u);
+            if (at < cap) out[at] = i0 + (uint64_t)k;
+        }
+    }
+}
+
+cudaError_t launch_startcode_index(const uint8_t* d_bytes, uint64_t len, uint64_t* d_out, uint32_t cap, uint32_t* d_count,
+                                   cudaStream_t stream) {
+    if (len) {
+        const uint64_t threads = (len + 15) / 16;
+        startcode_index_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_bytes, len, d_out, cap, d_count);
+    }
+    return cudaGetLastError();
+}
+
 size_t vlc_summary_bytes(size_t n_slices) { return sizeof(SliceSummary) * (n_slices ? n_slices : 1); }
 
 cudaError_t configure_vlc_kernel() {
@@ -123,7 +161,7 @@ cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc
                              int n_pics, const mpegb200_vlc_slice* d_slices, uint32_t n_slices, const uint8_t* d_bitstream,
                              uint32_t n_words, const uint8_t* d_quant, uint32_t n_quant, const StreamInfo* d_streams,
                              int max_streams, mpegb200_mb* d_mbs, uint32_t n_mb_slots, int16_t* d_coeffs, void* d_summary,
-                             int32_t* d_flags, int sm_count, cudaStream_t stream) {
+                             int32_t* d_flags, int sm_count, cudaStream_t stream, const ResidentStream* d_resident) {
     if (n_slices) {
         // slices per warp: as few as put the whole wave on the SMs at once (sixteen resident warps each)
         const uint32_t resident = (uint32_t)sm_count * kVlcCtasPerSm * kVlcWarps;
@@ -135,7 +173,7 @@ cudaError_t launch_vlc_parse(const VlcDeviceTables* d_tables, const mpegb200_vlc
         const uint32_t per_cta = (uint32_t)(kVlcWarps * lanes);
         vlc_parse_kernel<<<(n_slices + per_cta - 1) / per_cta, kVlcWarps * 32, kVlcSmem, stream>>>(
             d_tables, lanes, d_vpics, n_pics, d_slices, n_slices, reinterpret_cast<const uint32_t*>(d_bitstream), n_words, d_quant,
-            n_quant, d_streams, max_streams, d_mbs, n_mb_slots, d_coeffs, reinterpret_cast<SliceSummary*>(d_summary));
+            n_quant, d_streams, max_streams, d_mbs, n_mb_slots, d_coeffs, reinterpret_cast<SliceSummary*>(d_summary), d_resident);
     }
     if (n_pics)
         vlc_check_kernel<<<(n_pics + 127) / 128, 128, 0, stream>>>(d_vpics, d_pics, n_pics,

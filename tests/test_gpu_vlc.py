@@ -173,3 +173,43 @@ def test_void_and_foreign_tables_are_refused_or_skipped(golden_dir):
                 assert np.array_equal(c.video_read_frame(0, b), before[b])
         finally:
             sb.close()
+
+
+def test_resident_streams_and_the_device_start_code_index(golden_dir):
+    """Streams uploaded to HBM once, start codes indexed by startcode_index_kernel: the index must equal a plain search of the
+    bytes, and the batch that runs from it (waves without bytes) must return the same frames as every other path -- the damaged
+    reference clip with its flagged pictures included."""
+    import mpeg_b200
+    from test_batch_parser import cut_at_picture
+    es = (golden_dir / "test.mpeg1video").read_bytes()
+    ps_video = ol.demux_split((golden_dir / "test.mpg").read_bytes())[0]
+    L = mpeg_b200._lib.load()
+    with mpeg_b200.Context(device=0, max_streams=16) as c:
+        for sid, d in ((5, es), (6, ps_video), (7, b"\x00\x00\x01" * 40 + b"\x00"), (8, b"\x00\x00\x01\xb3"), (9, b"\x00\x00\x01\xb3\x00")):
+            c._ck(L.mpegb200_video_stream_upload(c.h, sid, d, len(d)))
+            want = ve.start_code_positions(d)
+            want = want[want + 5 <= len(d)]          # buffer.go:284: a start code needs its code byte and one more
+            got = np.zeros(len(want) + 8, np.uint64)
+            n = C.c_size_t()
+            c._ck(L.mpegb200_video_stream_index(c.h, sid, C.c_void_p(got.ctypes.data), len(got), C.byref(n)))
+            assert n.value == len(want) and np.array_equal(got[:n.value], want), f"stream {sid}"
+            if len(want) > 2:                        # too little room: the count still comes back
+                assert L.mpegb200_video_stream_index(c.h, sid, C.c_void_p(got.ctypes.data), 2, C.byref(n)) == -1 and n.value == len(want)
+            c._ck(L.mpegb200_video_stream_upload(c.h, sid, None, 0))
+    with mpeg_b200.Context(device=0, max_streams=16) as c:
+        kinds = [ps_video, cut_at_picture(ps_video, 33), es, cut_at_picture(es, 7)]
+        want = [oracle_hash(d) for d in kinds]
+        datas = [kinds[i % 4] for i in range(12)]
+        hashes, frames, (flagged, _) = batch_hashes(c, datas, first=2, device_vlc=True, resident=True)
+        for i in range(12):
+            assert (hashes[i], frames[i]) == want[i % 4], f"stream {i}"
+        assert flagged > 0 and want[2][0] == VIDEO_GOLDEN
+    distinct = []
+    for d in range(2):
+        w, _ = write_stream(1280, 720, [mw.PIC_I, mw.PIC_P, mw.PIC_B, mw.PIC_P], seed=60 + d, mode="natural")
+        distinct.append(w.tobytes())
+    datas = [distinct[i % 2] for i in range(32)]
+    with mpeg_b200.Context(device=0, max_streams=32) as c:
+        h_dev, f_dev, (flagged, host_steps) = batch_hashes(c, datas, device_vlc=True, resident=True)
+    want = [oracle_hash(d)[0] for d in distinct]
+    assert all(h_dev[i] == want[i % 2] for i in range(32)) and f_dev[0] == 4 and flagged == 0 and host_steps == 0

@@ -27,7 +27,7 @@ def same_records(a, b):
     return np.array_equal(ac, bc)
 
 
-def step_through_the_walker(sb, st, i, tab, stats):
+def step_through_the_walker(sb, st, i, tab, stats, resident=False):
     """Stream i of scan step `st` the way the product drives it (mpeg_b200.VideoBatch): device pictures wave by wave; at the first
     flagged picture the host parses the rest of the step.  Returns (has_frame, frame_buf, time, launches)."""
     hosted = ve.ScanBatch.host_steps(st)
@@ -44,7 +44,8 @@ def step_through_the_walker(sb, st, i, tab, stats):
         k = ks[0]
         assert wave.step_picture[k] == w
         members = [wave.pics[j].stream for j in range(wave.n_pictures)]
-        mbs, coeffs, flags = ve.emulate_wave(wave, [sb.sizes[j][0] for j in members], [sb.sizes[j][1] for j in members], tab)
+        mbs, coeffs, flags = ve.emulate_wave(wave, [sb.sizes[j][0] for j in members], [sb.sizes[j][1] for j in members], tab,
+                                             resident_bytes=sb.datas[i] if resident else None)
         P = wave.pics[k]
         stats["pictures"] += 1
         if flags[k]:
@@ -56,17 +57,18 @@ def step_through_the_walker(sb, st, i, tab, stats):
     return st.has_frame[i], st.frame_buf[i], st.time[i], launches
 
 
-def run_stream(data, expect_clean, label=""):
-    """Walk `data` in scan mode next to the full host parser: every step must come out the same.  Returns the statistics."""
+def run_stream(data, expect_clean, label="", resident=False):
+    """Walk `data` in scan mode next to the full host parser: every step must come out the same.  Returns the statistics.
+    resident: the batch works like with streams resident in device memory (start codes handed in, waves without bytes)."""
     full = parser_steps(data)
-    sb = ve.ScanBatch([data])
+    sb = ve.ScanBatch([data], resident=resident)
     tab = ve.tables()
     stats = {"pictures": 0, "flagged": 0, "host_steps": 0, "steps": 0}
     try:
         while True:
             st = sb.next()
             want = next(full, None)
-            has, buf, t, launches = step_through_the_walker(sb, st, 0, tab, stats)
+            has, buf, t, launches = step_through_the_walker(sb, st, 0, tab, stats, resident)
             if not has:
                 assert want is None, f"{label}: the scan parser ends before the full parser (step {stats['steps']})"
                 break
@@ -250,3 +252,30 @@ def test_scanning_ahead_and_withdrawing(golden_dir):
         for pos in rng.integers(200, len(d), 30):
             d[pos] ^= 1 << int(rng.integers(0, 8))
         run_stream_scanning_ahead(bytes(d), f"damaged {trial}")
+
+
+def test_resident_mode_with_handed_in_start_codes(golden_dir):
+    """Streams resident in device memory: the parser takes the start codes from an index (found on the device in the product,
+    by bytes.find here) instead of searching, the waves carry no bytes and the slices' offsets count from the first byte of
+    their stream.  Every step must still equal the full host parser's -- clean, damaged and truncated streams."""
+    for which in ("test.mpg video", "test.mpeg1video"):
+        a = run_stream(video_streams(golden_dir)[which], expect_clean=which == "test.mpg video", label=which)
+        b = run_stream(video_streams(golden_dir)[which], expect_clean=which == "test.mpg video", label=which + " resident", resident=True)
+        assert a == b
+    w, _ = write_stream(352, 288, [mw.PIC_I, mw.PIC_P, mw.PIC_B], seed=8, mode="natural")
+    run_stream(w.tobytes(), expect_clean=True, label="written resident", resident=True)
+    data = (golden_dir / "test.mpeg1video").read_bytes()[:60000]
+    rng = np.random.default_rng(31)
+    for trial in range(6):
+        d = bytearray(data)
+        for pos in rng.integers(200, len(d), 30):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        d = bytes(d[: len(d) - int(rng.integers(0, 3000))])
+        assert run_stream(d, False, f"damaged {trial}") == run_stream(d, False, f"damaged {trial} resident", resident=True)
+    # an index that does not belong to the stream is refused
+    from mpeg_b200 import _lib
+    L = _lib.load()
+    h = L.mpegb200_video_parser_new(data, len(data))
+    bad = np.array([5, 17], np.uint64)
+    assert L.mpegb200_video_parser_set_start_codes(h, C.c_void_p(bad.ctypes.data), 2) == -1
+    L.mpegb200_video_parser_free(h)

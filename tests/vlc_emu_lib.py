@@ -40,17 +40,32 @@ def tables():
     return buf
 
 
-def emulate_wave(wave, mb_w, mb_h, tab=None):
-    """Run the walker over one mpegb200_vlc_wave.  Returns (mbs [n_mb_slots], coeffs [6 * n_mb_slots, 64], flags [n_pictures])."""
+def start_code_positions(data: bytes) -> np.ndarray:
+    """Byte offsets of every 00 00 01 of `data`, ascending (what mpegb200_video_stream_index finds on the device)."""
+    out, at = [], data.find(b"\x00\x00\x01")
+    while at >= 0:
+        out.append(at)
+        at = data.find(b"\x00\x00\x01", at + 1)
+    return np.array(out, np.uint64)
+
+
+def emulate_wave(wave, mb_w, mb_h, tab=None, resident_bytes: bytes = None):
+    """Run the walker over one mpegb200_vlc_wave.  Returns (mbs [n_mb_slots], coeffs [6 * n_mb_slots, 64], flags [n_pictures]).
+    resident_bytes: the (single) stream a wave of a resident batch reads from (its bitstream pointer is NULL)."""
     tab = tab or tables()
     n = wave.n_pictures
+    bits, n_bits = C.c_void_p(wave.bitstream), wave.bitstream_bytes
+    if resident_bytes is not None:
+        assert not wave.bitstream
+        keep = C.create_string_buffer(resident_bytes, len(resident_bytes) + 64)
+        bits, n_bits = C.cast(keep, C.c_void_p), len(resident_bytes)
     mbs = np.zeros(max(1, wave.n_mb_slots), ol.MB_DTYPE)
     coeffs = np.full((max(1, 6 * wave.n_mb_slots), 64), 0x5555, np.int16)     # blocks the walker does not write keep the pattern
     flags = np.zeros(max(1, n), np.int32)
     w = (C.c_int * max(1, n))(*([mb_w] * n if np.isscalar(mb_w) else mb_w))
     h = (C.c_int * max(1, n))(*([mb_h] * n if np.isscalar(mb_h) else mb_h))
-    rc = emu().vlc_emu_wave(tab, C.c_int(n), wave.pics, C.c_size_t(wave.n_slices), wave.slices, C.c_void_p(wave.bitstream),
-                            C.c_size_t(wave.bitstream_bytes), C.c_void_p(wave.quant), C.c_size_t(wave.n_quant), C.c_size_t(wave.n_mb_slots),
+    rc = emu().vlc_emu_wave(tab, C.c_int(n), wave.pics, C.c_size_t(wave.n_slices), wave.slices, bits,
+                            C.c_size_t(n_bits), C.c_void_p(wave.quant), C.c_size_t(wave.n_quant), C.c_size_t(wave.n_mb_slots),
                             w, h, C.c_void_p(mbs.ctypes.data), C.c_void_p(coeffs.ctypes.data), C.c_void_p(flags.ctypes.data))
     assert rc == 0, f"emulator refused the wave: {rc}"
     return mbs[:wave.n_mb_slots], coeffs[:6 * wave.n_mb_slots], flags[:n]
@@ -85,17 +100,23 @@ def host_records(step: VideoStep):
 class ScanBatch:
     """mpegb200_video_batch_* in scan mode over a list of elementary streams (host side only)."""
 
-    def __init__(self, datas, threads=2):
+    def __init__(self, datas, threads=2, resident=False):
         self.L = _lib.load()
         self.datas = [bytes(d) for d in datas]
         self.h = self.L.mpegb200_video_batch_new(len(self.datas), threads, None, None)
         assert self.h
+        self.resident = resident
         self.sizes = []
         w, h = C.c_int(), C.c_int()
         for i, d in enumerate(self.datas):
             assert self.L.mpegb200_video_batch_set_stream(self.h, i, d, len(d)) == 0
             self.L.mpegb200_video_batch_stream_size(self.h, i, C.byref(w), C.byref(h))
             self.sizes.append(((w.value + 15) >> 4, (h.value + 15) >> 4))
+        if resident:   # as if the streams sat in device memory with their start codes indexed there
+            assert self.L.mpegb200_video_batch_set_resident(self.h, 1) == 0
+            for i, d in enumerate(self.datas):
+                pos = start_code_positions(d)
+                assert self.L.mpegb200_video_batch_set_start_codes(self.h, i, C.c_void_p(pos.ctypes.data), len(pos)) == 0
 
     def next(self):
         st = BatchScanStep()

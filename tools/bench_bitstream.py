@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=2)
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--device-vlc", action="store_true", help="with --gpu: also run the slice-parallel VLC stage on the device")
+    ap.add_argument("--resident", action="store_true", help="with --device-vlc: also with the streams resident in HBM and indexed there")
     args = ap.parse_args()
     threads = args.threads or len(os.sched_getaffinity(0))
 
@@ -181,6 +182,33 @@ def main():
                                          "vlc_check_kernel + plan + fused kernels; one flag read-back (synchronisation) per wave"}
             vb.close()
             ctx.close()
+            if args.resident:
+                ctx = mpeg_b200.Context(0, args.streams)
+                ctx.set_kernel_timing(True)
+                t0 = time.perf_counter()
+                vb = mpeg_b200.VideoBatch(ctx, streams, threads=threads, validate=False, device_vlc=True, resident=True)
+                ctx.sync()
+                t_setup = time.perf_counter() - t0
+                frames, parse_ms, steps = 0, [], 0
+                t0 = time.perf_counter()
+                while True:
+                    has, buf, _ = vb.step()
+                    if not has.any():
+                        break
+                    frames += int(has.sum())
+                    steps += 1
+                    if L.mpegb200_video_bitstream_parse_ms(ctx.h, C.byref(ms)) == 0:
+                        parse_ms.append(ms.value)
+                ctx.sync()
+                dt = time.perf_counter() - t0
+                res["device_vlc_resident"] = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "steps": steps,
+                                              "setup_seconds": t_setup, "setup": "batch creation incl. upload of every stream to HBM and its start-code index (device)",
+                                              "flagged_pictures": vb.flagged, "host_steps": vb.host_steps,
+                                              "seconds_in": {"host_scan": vb.t_scan, "submit": vb.t_submit, "waiting_for_flags": vb.t_wait},
+                                              "parse_kernel_ms_per_wave_median": sorted(parse_ms)[len(parse_ms) // 2] if parse_ms else None,
+                                              "speedup_vs_host_parser_path": (frames / dt) / res["gpu"]["frames_per_sec"]}
+                vb.close()
+                ctx.close()
     print(json.dumps(res))
 
 
