@@ -190,6 +190,7 @@ type Video struct {
 	parser *C.mpegb200_video_parser
 	data   unsafe.Pointer // C copy of the elementary stream (the parser keeps its own copy; freed at once)
 	opened bool
+	deviceVLC bool // SetDeviceVLC: slices parsed on the GPU from the stream's resident copy
 	frames [3]Frame // one per physical buffer, like frameCurrent / frameForward / frameBackward (video.go:97-99)
 	time   float64
 }
@@ -296,11 +297,130 @@ func (v *Video) open() bool {
 	return true
 }
 
+// SetDeviceVLC switches the stream to the slice-parallel VLC stage (SURVEY 8f1): the elementary stream is uploaded to device
+// memory once, its start codes are indexed there, and from then on Decode only reads headers on the host; the slices are
+// parsed by one GPU thread each (mpegb200_video_decode_bitstream) and pictures whose slices are not independent (damaged
+// streams) finish on the host parser with the serial semantics of the reference.  Call before the first Decode.
+func (v *Video) SetDeviceVLC(es []byte) error {
+	if len(es) == 0 {
+		return errors.New("mpegb200: empty stream")
+	}
+	ctx := v.gpu.ctx
+	if C.mpegb200_video_stream_upload(ctx, C.int(v.stream), (*C.uint8_t)(unsafe.Pointer(&es[0])), C.size_t(len(es))) != 0 {
+		return errors.New("mpegb200: " + v.gpu.lastError())
+	}
+	at := make([]C.uint64_t, len(es)/64+4096)
+	var n C.size_t
+	rc := C.mpegb200_video_stream_index(ctx, C.int(v.stream), &at[0], C.size_t(len(at)), &n)
+	if rc != 0 && int(n) > len(at) { // a stream of (almost) nothing but start codes
+		at = make([]C.uint64_t, int(n))
+		rc = C.mpegb200_video_stream_index(ctx, C.int(v.stream), &at[0], C.size_t(len(at)), &n)
+	}
+	if rc != 0 || C.mpegb200_video_parser_set_start_codes(v.parser, &at[0], n) != 0 {
+		return errors.New("mpegb200: start-code index: " + v.gpu.lastError())
+	}
+	v.deviceVLC = true
+	return nil
+}
+
+// runLaunches executes the launches of a host-parsed step (variable-width coefficient form).
+func (v *Video) runLaunches(step *C.mpegb200_video_step) bool {
+	launches := unsafe.Slice(step.launches, int(step.n_launches))
+	vlen := unsafe.Slice(step.vlen_launches, int(step.n_launches))
+	for i := range launches {
+		ln := &launches[i]
+		if ln.n_mb == 0 {
+			continue
+		}
+		pic := ln.picture
+		pic.stream = C.int32_t(v.stream)
+		mbs := (*C.mpegb200_mb)(unsafe.Add(unsafe.Pointer(step.mbs), uintptr(ln.first_mb)*C.sizeof_mpegb200_mb))
+		lv := &vlen[i]
+		if C.mpegb200_video_decode_pictures_vlen(v.gpu.ctx, 1, &pic, C.size_t(ln.n_mb), mbs, C.size_t(ln.n_blocks),
+			(*C.uint32_t)(unsafe.Add(unsafe.Pointer(step.vlen_headers), uintptr(ln.first_block)*4)),
+			(*C.uint64_t)(unsafe.Add(unsafe.Pointer(step.vlen_chunk_offsets), uintptr(lv.first_chunk)*8)),
+			(*C.uint8_t)(unsafe.Add(unsafe.Pointer(step.vlen_payload), uintptr(lv.payload_offset))), C.size_t(lv.payload_bytes)) != 0 {
+			return false
+		}
+	}
+	return true
+}
+
+// decodeOnDevice is Decode with the slices parsed on the GPU: one wave per picture of the step (a step decodes more than one
+// picture only at the start of a stream), the tables built like mpegb200_video_batch_next_scan builds them for many streams.
+func (v *Video) decodeOnDevice() (frameBuf int, time float64, ok bool) {
+	ctx := v.gpu.ctx
+	var ss C.mpegb200_video_scan_step
+	if C.mpegb200_video_parser_next_scan(v.parser, &ss) != 0 || ss.has_frame == 0 {
+		return 0, 0, false
+	}
+	frameBuf, time = int(ss.frame_buf), float64(ss.time)
+	if ss.host_step != nil { // stale coefficients of a dropped block pending: the host parsed this step itself
+		return frameBuf, time, v.runLaunches(ss.host_step)
+	}
+	pictures := unsafe.Slice(ss.pictures, int(ss.n_pictures))
+	mbW, mbSize := int(ss.mb_w), int(ss.mb_w)*int(ss.mb_h)
+	for k := range pictures {
+		p := &pictures[k]
+		scan := unsafe.Slice((*C.mpegb200_scan_slice)(unsafe.Add(unsafe.Pointer(ss.slices), uintptr(p.first_slice)*C.sizeof_mpegb200_scan_slice)), int(p.n_slices))
+		slices := make([]C.mpegb200_vlc_slice, len(scan))
+		slot := 0
+		for i := range scan {
+			from := (int(scan[i].vpos) - 1) * mbW
+			to := mbSize
+			if i+1 < len(scan) {
+				to = min((int(scan[i+1].vpos)-1)*mbW, mbSize)
+			}
+			room := (max(0, to-from) + 15) &^ 15 // record slots: the addresses from this slice's row to the next slice's
+			slices[i] = C.mpegb200_vlc_slice{data_offset: scan[i].offset, // resident stream: offsets count from its first byte
+				next_code:   C.uint32_t(scan[i].next_code - scan[i].offset),
+				stream_left: C.uint32_t(min(uint64(ss.stream_len)-uint64(scan[i].offset), 1<<32-1)),
+				pic:         0, vpos: scan[i].vpos, mb_slot: C.uint32_t(slot), mb_cap: C.uint32_t(room)}
+			slot += room
+		}
+		pic := C.mpegb200_vlc_picture{stream: C.int32_t(v.stream), _type: p._type, dst_buf: p.dst_buf, fwd_buf: p.fwd_buf, bwd_buf: p.bwd_buf,
+			fwd_full_px: p.fwd_full_px, fwd_r_size: p.fwd_r_size, bwd_full_px: p.bwd_full_px, bwd_r_size: p.bwd_r_size,
+			first_slice: 0, n_slices: C.uint32_t(len(slices)), mb_slot: 0, n_mb_slots: C.uint32_t(slot), quant: 0}
+		var first *C.mpegb200_vlc_slice
+		if len(slices) > 0 {
+			first = &slices[0]
+		}
+		if C.mpegb200_video_decode_bitstream(ctx, 1, &pic, C.size_t(len(slices)), first, nil, 0, ss.quant, 1, C.size_t(slot)) != 0 {
+			return 0, 0, false
+		}
+		var flag C.int
+		if C.mpegb200_video_bitstream_flags(ctx, &flag, 1) < 0 {
+			return 0, 0, false
+		}
+		if flag != 0 { // not a set of independent slices: the host parser finishes the step from this picture on
+			var tail C.mpegb200_video_step
+			if C.mpegb200_video_parser_redo(v.parser, C.int(k), &tail) != 0 || !v.runLaunches(&tail) {
+				return 0, 0, false
+			}
+			return int(tail.frame_buf), float64(tail.time), tail.has_frame != 0
+		}
+	}
+	return frameBuf, time, true
+}
+
 // Decode mirrors Video.Decode (video.go:209-268): parse up to the picture that makes a frame due, run its
 // launches on the GPU, return the frame (nil at the end of the stream or on any failure).
 func (v *Video) Decode() *Frame {
 	if !v.HasHeader() || !v.open() {
 		return nil
+	}
+	if v.deviceVLC {
+		buf, t, ok := v.decodeOnDevice()
+		if !ok {
+			return nil
+		}
+		f := &v.frames[buf]
+		f.Time, v.time = t, t
+		if C.mpegb200_video_read_planes(v.gpu.ctx, C.int(v.stream), C.int(buf), (*C.uint8_t)(unsafe.Pointer(&f.Y.Data[0])),
+			(*C.uint8_t)(unsafe.Pointer(&f.Cb.Data[0])), (*C.uint8_t)(unsafe.Pointer(&f.Cr.Data[0]))) != 0 {
+			return nil
+		}
+		return f
 	}
 	var step C.mpegb200_video_step
 	if C.mpegb200_video_parser_next(v.parser, &step) != 0 || step.has_frame == 0 {

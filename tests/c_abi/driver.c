@@ -30,6 +30,12 @@ _Static_assert(offsetof(mpegb200_picture, first_mb) == 8 && offsetof(mpegb200_pi
 _Static_assert(sizeof(mpegb200_launch) == 32, "mpegb200_launch is 32 bytes");
 _Static_assert(sizeof(mpegb200_launch_vlen) == 24, "mpegb200_launch_vlen is 24 bytes");
 _Static_assert(MPEGB200_SAMPLES_PER_FRAME == 1152, "audio.go:9");
+/* the tables of the slice-parallel VLC stage (mpegb200_video_decode_bitstream): 32-byte entries, read by the device as they are */
+_Static_assert(sizeof(mpegb200_vlc_picture) == 32 && offsetof(mpegb200_vlc_picture, type) == 4 && offsetof(mpegb200_vlc_picture, fwd_full_px) == 8, "vlc picture head");
+_Static_assert(offsetof(mpegb200_vlc_picture, first_slice) == 12 && offsetof(mpegb200_vlc_picture, mb_slot) == 20 && offsetof(mpegb200_vlc_picture, quant) == 28, "vlc picture tail");
+_Static_assert(sizeof(mpegb200_vlc_slice) == 32 && offsetof(mpegb200_vlc_slice, next_code) == 8 && offsetof(mpegb200_vlc_slice, stream_left) == 12, "vlc slice head");
+_Static_assert(offsetof(mpegb200_vlc_slice, pic) == 16 && offsetof(mpegb200_vlc_slice, vpos) == 20 && offsetof(mpegb200_vlc_slice, mb_slot) == 24 && offsetof(mpegb200_vlc_slice, mb_cap) == 28, "vlc slice tail");
+_Static_assert(sizeof(mpegb200_scan_slice) == 24 && sizeof(mpegb200_scan_picture) == 32, "scan step entries");
 
 #define CHECK(cond)                                                                  \
     do {                                                                             \
@@ -38,6 +44,8 @@ _Static_assert(MPEGB200_SAMPLES_PER_FRAME == 1152, "audio.go:9");
             return 1;                                                                \
         }                                                                            \
     } while (0)
+
+static const uint8_t kTinyStream[178];
 
 static int run_abi(void) {
     CHECK(mpegb200_abi_version() == MPEGB200_ABI_VERSION);
@@ -65,9 +73,89 @@ static int run_abi(void) {
     CHECK(mpegb200_video_parser_next(vp, &st) == 0 && !st.has_frame);
     mpegb200_video_parser_free(vp);
     CHECK(mpegb200_video_parser_next(NULL, &st) == MPEGB200_EINVAL);
+    /* scan mode (the host half of the slice-parallel VLC stage) is host code too */
+    vp = mpegb200_video_parser_new(kTinyStream, sizeof kTinyStream);
+    mpegb200_video_scan_step ss;
+    CHECK(vp != NULL && mpegb200_video_parser_next_scan(vp, &ss) == 0 && ss.has_frame && ss.n_pictures == 1 && ss.pictures[0].n_slices == 2);
+    CHECK(mpegb200_video_parser_unscan(vp) == 0 && mpegb200_video_parser_unscan(vp) == MPEGB200_EINVAL);     /* one step back, not two */
+    CHECK(mpegb200_video_parser_next_scan(vp, &ss) == 0 && ss.has_frame && ss.slices[1].vpos == 2);
+    CHECK(mpegb200_video_parser_redo(vp, 0, &st) == 0 && st.has_frame && st.n_launches == 1 && st.launches[0].n_mb == 4);
+    const uint64_t wrong[2] = {1, 2};
+    CHECK(mpegb200_video_parser_set_start_codes(vp, wrong, 2) == MPEGB200_EINVAL);
+    mpegb200_video_parser_free(vp);
+    CHECK(mpegb200_video_decode_bitstream(NULL, 0, NULL, 0, NULL, NULL, 0, NULL, 0, 0) == MPEGB200_EINVAL);
     /* null handling of the context entry points */
     CHECK(mpegb200_sync(NULL) == MPEGB200_EINVAL && mpegb200_launch_count(NULL) == 0);
     puts("abi ok");
+    return 0;
+}
+
+/* A 32 x 32 I picture written by hand: sequence header (default matrices), picture header, two slices (one per macroblock row) of
+ * two intra macroblocks each -- address increment "1", type "1", six blocks of dct_dc_size 0 ("100" luma, "00" chroma) and end of
+ * block "10" -- so every DC equals its predictor 128 and every pixel of the frame is 128; sequence end code; zero padding (the
+ * reference wants 136 bytes behind a sequence start code before it reads the header, video.go:271). */
+static const uint8_t kTinyStream[178] = {
+    0x00, 0x00, 0x01, 0xb3, 0x02, 0x00, 0x20, 0x15, 0xff, 0xff, 0xe0, 0xa0, 0x00, 0x00, 0x01, 0x00, 0x00, 0x0f, 0xff, 0xf8,
+    0x00, 0x00, 0x01, 0x01, 0x0b, 0x94, 0xa5, 0x22, 0x2e, 0x52, 0x94, 0x88, 0x80, 0x00, 0x00, 0x01, 0x02, 0x0b, 0x94, 0xa5,
+    0x22, 0x2e, 0x52, 0x94, 0x88, 0x80, 0x00, 0x00, 0x01, 0xb7};
+
+/* Bitstream in: the host scans headers and start codes, the device parses the slices (mpegb200_video_decode_bitstream) --
+ * first with the picture's bytes travelling with the wave, then with the stream resident in device memory and its start codes
+ * indexed there.  The call sequence a cgo binding would make. */
+static int run_bitstream(mpegb200_ctx* ctx, int stream, int resident) {
+    mpegb200_video_parser* vp = mpegb200_video_parser_new(kTinyStream, sizeof kTinyStream);
+    CHECK(vp != NULL && mpegb200_video_parser_has_header(vp) && mpegb200_video_parser_width(vp) == 32);
+    if (resident) {
+        uint64_t at[8];
+        size_t n = 0;
+        CHECK(mpegb200_video_stream_upload(ctx, stream, kTinyStream, sizeof kTinyStream) == 0);
+        CHECK(mpegb200_video_stream_index(ctx, stream, at, 8, &n) == 0);
+        CHECK(n == 5 && at[0] == 0 && at[1] == 12 && at[2] == 20 && at[3] == 33 && at[4] == 46);   /* b3, picture, slice 1, slice 2, b7 */
+        CHECK(mpegb200_video_parser_set_start_codes(vp, at, n) == 0);
+    }
+    mpegb200_video_scan_step ss;
+    CHECK(mpegb200_video_parser_next_scan(vp, &ss) == 0 && ss.has_frame && ss.n_pictures == 1 && ss.host_step == NULL);
+    CHECK(ss.pictures[0].type == MPEGB200_PIC_I && ss.pictures[0].n_slices == 2 && ss.mb_w == 2 && ss.mb_h == 2);
+    CHECK(ss.slices[0].offset == 24 && ss.slices[0].next_code == 33 && ss.slices[0].vpos == 1 && ss.slices[1].offset == 37 && ss.slices[1].vpos == 2);
+    mpegb200_vlc_picture pic;
+    memset(&pic, 0, sizeof pic);
+    pic.stream = stream;
+    pic.type = ss.pictures[0].type;
+    pic.dst_buf = ss.pictures[0].dst_buf;
+    pic.fwd_buf = ss.pictures[0].fwd_buf;
+    pic.bwd_buf = ss.pictures[0].bwd_buf;
+    pic.n_slices = 2;
+    pic.n_mb_slots = 32;               /* two slices of two macroblocks: 16 record slots each */
+    mpegb200_vlc_slice sl[2];
+    memset(sl, 0, sizeof sl);
+    const uint64_t first = ss.slices[0].offset;
+    for (int k = 0; k < 2; k++) {
+        sl[k].data_offset = resident ? ss.slices[k].offset : ss.slices[k].offset - first;
+        sl[k].next_code = (uint32_t)(ss.slices[k].next_code - ss.slices[k].offset);
+        sl[k].stream_left = (uint32_t)(ss.stream_len - ss.slices[k].offset);
+        sl[k].vpos = ss.slices[k].vpos;
+        sl[k].mb_slot = 16u * (uint32_t)k;
+        sl[k].mb_cap = 16;
+    }
+    const size_t n_bytes = (size_t)(ss.slices[1].next_code + 8 - first);
+    CHECK(mpegb200_video_decode_bitstream(ctx, 1, &pic, 2, sl, resident ? NULL : ss.stream + first, resident ? 0 : n_bytes, ss.quant, 1, 32) == 0);
+    int flag = -1;
+    CHECK(mpegb200_video_bitstream_flags(ctx, &flag, 1) == 0 && flag == 0);
+    static mpegb200_mb recs[32];
+    CHECK(mpegb200_video_bitstream_records(ctx, recs, NULL) == 0);
+    CHECK(recs[0].flags == MPEGB200_MB_INTRA && recs[0].cbp == 0x3f && recs[1].mb_col == 1 && recs[2].pic == 0xffff);
+    CHECK(recs[16].mb_row == 1 && recs[17].mb_col == 1 && recs[17].coeff_block == 6 * 16 + 6 && recs[18].pic == 0xffff);
+    static uint8_t y[32 * 32], cb[16 * 16], cr[16 * 16];
+    memset(y, 0, sizeof y);
+    CHECK(mpegb200_video_read_planes(ctx, stream, ss.frame_buf, y, cb, cr) == 0);
+    for (int i = 0; i < 32 * 32; i++) CHECK(y[i] == 128);
+    for (int i = 0; i < 16 * 16; i++) CHECK(cb[i] == 128 && cr[i] == 128);
+    /* a slot table with a hole is refused before anything is enqueued */
+    sl[1].mb_slot = 32;
+    CHECK(mpegb200_video_decode_bitstream(ctx, 1, &pic, 2, sl, resident ? NULL : ss.stream + first, resident ? 0 : n_bytes, ss.quant, 1, 48) == MPEGB200_EINVAL);
+    CHECK(mpegb200_video_parser_next_scan(vp, &ss) == 0 && !ss.has_frame);   /* one picture, handed out by the flush above */
+    if (resident) CHECK(mpegb200_video_stream_upload(ctx, stream, NULL, 0) == 0);
+    mpegb200_video_parser_free(vp);
     return 0;
 }
 
@@ -159,6 +247,11 @@ static int run_gpu(void) {
     CHECK(mpegb200_audio_synth(ctx, 1, &id, 1, samples, 7, out) == MPEGB200_EINVAL);
     CHECK(mpegb200_launch_count(ctx) >= 5);
     CHECK(mpegb200_audio_close(ctx, 2) == 0 && mpegb200_video_close(ctx, 1) == 0);
+    /* bitstream in: slices parsed on the device */
+    CHECK(mpegb200_video_open(ctx, 3, 32, 32) == 0);
+    if (run_bitstream(ctx, 3, 0) != 0) return 1;
+    if (run_bitstream(ctx, 3, 1) != 0) return 1;
+    CHECK(mpegb200_video_close(ctx, 3) == 0);
     mpegb200_destroy(ctx);
     puts("gpu ok");
     return 0;
