@@ -574,6 +574,9 @@ def main():
         extras["picture_steps"] = picture_steps(torch, ctx, stream, g, S, peak, log)
         extras["audio"] = audio_leg(torch, local_rank, peak, log)
         extras["bitstream"] = bitstream_leg(args, local_rank, log)
+    elif not args.no_extras:
+        # N > 1: every rank decodes its own 256 streams from their bitstreams (resident path only), barrier + max over ranks
+        extras["bitstream"] = bitstream_leg(args, local_rank, log, paths=("device_vlc_resident",), barrier=barrier, max_over_ranks=max_over_ranks, world=world)
 
     # ---- frames gathered to rank 0 over NVLink (the only collective of the path)
     gather = gathered = None
@@ -832,7 +835,7 @@ def audio_leg(torch, device_index, peak, log):
     return out
 
 
-def bitstream_leg(args, device_index, log):
+def bitstream_leg(args, device_index, log, paths=("host_parser", "device_vlc", "device_vlc_resident"), barrier=None, max_over_ranks=None, world=1):
     """Bitstream in, frames out: S natural 720p streams (two distinct ones written by tests/mpeg1_writer.py, I + P pictures)
     through mpeg_b200.VideoBatch with the host parser and with the device-side slice parser.  Frames stay in HBM; every step's
     returned frames are hashed on the host for the first streams and held against the oracle's decode of the same bitstream."""
@@ -861,7 +864,12 @@ def bitstream_leg(args, device_index, log):
     out = {"config": f"{S} natural 720p streams of {n_pictures} pictures ({len(distinct[0]) / n_pictures / 1e3:.1f} KB per picture), frames stay in HBM",
            "host_threads": threads, "paths": {}}
     check = [0, 1, S - 2, S - 1] if S >= 4 else list(range(S))
-    for name, kw in (("host_parser", {}), ("device_vlc", {"device_vlc": True}), ("device_vlc_resident", {"device_vlc": True, "resident": True})):
+    all_paths = {"host_parser": {}, "device_vlc": {"device_vlc": True}, "device_vlc_resident": {"device_vlc": True, "resident": True}}
+    if world > 1:
+        threads = max(1, threads // world)   # the ranks share the host's cores
+        out["host_threads"] = threads
+    for name in paths:
+        kw = all_paths[name]
         with mpeg_b200.Context(device=device_index, max_streams=S) as c:
             c.set_kernel_timing(name != "host_parser")
             vb = mpeg_b200.VideoBatch(c, streams, threads=threads, validate=False, **kw)
@@ -872,6 +880,8 @@ def bitstream_leg(args, device_index, log):
             frames, parse_ms, ms = 0, [], C.c_float()
             t_hash = 0.0
             c.sync()
+            if barrier:
+                barrier()
             t0 = time.perf_counter()
             while True:
                 has, buf, _ = vb.step()
@@ -890,6 +900,9 @@ def bitstream_leg(args, device_index, log):
                 t_hash += time.perf_counter() - th
             c.sync()
             dt = time.perf_counter() - t0 - t_hash
+            if max_over_ranks:
+                dt = max_over_ranks(dt * 1e3) * 1e-3   # the slowest rank
+                frames *= world
             ok = all(hashes[k] == want[check[k] % 2] for k in range(len(check)))
             rec = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "parity_ok": bool(ok), "checked_streams": check}
             if name != "host_parser":
@@ -903,8 +916,11 @@ def bitstream_leg(args, device_index, log):
             vb.close()
             if not ok:
                 fail_parity({"metric": METRIC, "error": f"bitstream ({name}): frames differ from the oracle's decode of the bitstream"})
-    out["device_vlc_speedup"] = out["paths"]["device_vlc"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
-    out["device_vlc_resident_speedup"] = out["paths"]["device_vlc_resident"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
+    if "host_parser" in out["paths"]:
+        out["device_vlc_speedup"] = out["paths"]["device_vlc"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
+        out["device_vlc_resident_speedup"] = out["paths"]["device_vlc_resident"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
+    if world > 1:
+        out["config"] += f"; {world} ranks, whole-job frames/s over the slowest rank's time"
     out["paths"]["device_vlc_resident"]["note"] = ("streams uploaded to HBM and their start codes indexed on the device when the batch is created (outside the rate, "
                                                     "like the demux); per step the host reads headers and builds slice tables, no compressed byte crosses PCIe")
     return out

@@ -75,12 +75,16 @@ class Frame:
 class Video:
     """mpeg.Video (video.go:57): MPEG-1 video elementary stream -> frames."""
 
-    def __init__(self, data: bytes, ctx: Context, stream: int = 0, vlen: bool = True):
+    def __init__(self, data: bytes, ctx: Context, stream: int = 0, vlen: bool = True, device_vlc: bool = False):
         """vlen: the parser emits the coefficients in the variable-width transfer form (a header and a few bytes per block
-        instead of int16[64]) and the launches go through mpegb200_video_decode_pictures_vlen; False: int16 blocks."""
+        instead of int16[64]) and the launches go through mpegb200_video_decode_pictures_vlen; False: int16 blocks.
+        device_vlc: the stream is uploaded to device memory, its start codes are indexed there and the slices are parsed on the
+        GPU (mpegb200_video_decode_bitstream); the host reads headers only (a one-stream VideoBatch does the work)."""
         self.L = _lib.load()
         self.ctx, self.stream = ctx, stream
         self._data = bytes(data)
+        self._batch = None
+        self._device_vlc = device_vlc
         self.h = self.L.mpegb200_video_parser_new(self._data, len(self._data))
         if not self.h:
             raise MemoryError
@@ -115,6 +119,15 @@ class Video:
         """Video.Decode(): parse up to the picture that makes a frame due, run its launches, return the Frame."""
         if not self.has_header():
             return None
+        if self._device_vlc:
+            if self._batch is None:
+                from .batch import VideoBatch
+                self._batch = VideoBatch(self.ctx, [self._data], threads=1, first_stream=self.stream, device_vlc=True, resident=True)
+            has, buf, t = self._batch.step()
+            if not has[0]:
+                return None
+            self.ctx.sync()
+            return Frame(self, int(buf[0]), float(t[0]))
         if not self._opened:
             self.ctx.video_open(self.stream, self.width, self.height)
             self.ctx.set_validate(True)   # records parsed from a bitstream are untrusted: malformed ones raise (the reference panics)
@@ -144,6 +157,9 @@ class Video:
         return Frame(self, step.frame_buf, step.time)
 
     def close(self):
+        if getattr(self, "_batch", None) is not None:
+            self._batch.close()
+            self._batch = None
         if getattr(self, "h", None):
             if self._opened:
                 try:

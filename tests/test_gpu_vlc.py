@@ -213,3 +213,20 @@ def test_resident_streams_and_the_device_start_code_index(golden_dir):
         h_dev, f_dev, (flagged, host_steps) = batch_hashes(c, datas, device_vlc=True, resident=True)
     want = [oracle_hash(d)[0] for d in distinct]
     assert all(h_dev[i] == want[i % 2] for i in range(32)) and f_dev[0] == 4 and flagged == 0 and host_steps == 0
+
+
+def test_single_stream_video_with_device_vlc(golden_dir):
+    """mpeg_b200.Video(device_vlc=True): TestVideoGolden (mpeg_test.go:203-231) frame by frame through the public mirror."""
+    import mpeg_b200
+    with mpeg_b200.Context(device=0, max_streams=4) as c:
+        video = mpeg_b200.Video((golden_dir / "test.mpeg1video").read_bytes(), c, stream=1, device_vlc=True)
+        assert (video.width, video.height, video.framerate) == (160, 120, 30.0)
+        h, frames, last = ol.FNV_OFFSET, 0, -1.0
+        while (frame := video.decode()) is not None:
+            for plane in (frame.y, frame.cb, frame.cr):
+                h = ol.fnv(h, plane)
+            assert frame.time > last
+            last = frame.time
+            frames += 1
+        assert h == VIDEO_GOLDEN, f"{h:#018x} after {frames} frames"
+        video.close()
