@@ -181,8 +181,9 @@ VLC_HD int read_motion(Bits& br, const VlcDeviceTables* T, int r_size, int motio
     return motion;
 }
 
-VLC_HD bool vlc_window_inside(long long off, int stride, int size, int odd_h, int odd_v, long long avail) {
-    const long long hi = off + (long long)(size - 1 + odd_v) * stride + (size - 1 + odd_h);
+// 32-bit arithmetic suffices: a frame buffer of 4096 x 4096 luma is 2^24.6 bytes, a vector at most 2^11 pixels
+VLC_HD bool vlc_window_inside(int off, int stride, int size, int odd_h, int odd_v, int avail) {
+    const int hi = off + (size - 1 + odd_v) * stride + (size - 1 + odd_h);
     return off >= 0 && hi < avail;
 }
 
@@ -210,7 +211,7 @@ VLC_HD SliceSummary walk_slice(const VlcDeviceTables* T, const uint32_t* fast, c
         const int type = P.type;
         const uint32_t* const type_table = type == MPEGB200_PIC_I ? T->type_i : (type == MPEGB200_PIC_P ? T->type_p : T->type_b);
         const int type_bits = type == MPEGB200_PIC_I ? kVlcTypeIBits : (type == MPEGB200_PIC_P ? kVlcTypePBits : kVlcTypeBBits);
-        const long long total = (long long)g.buf_bytes, luma_bytes = (long long)g.luma_w * g.luma_h;
+        const int total = (int)g.buf_bytes, luma_bytes = g.luma_w * g.luma_h;
         const int chroma_w = g.luma_w >> 1;
 
         Bits br;
@@ -263,10 +264,10 @@ VLC_HD SliceSummary walk_slice(const VlcDeviceTables* T, const uint32_t* fast, c
                 v = (int)(int16_t)v;
                 // the windows copyMacroblock reads must lie inside the frame buffer (mpegb200_video_validate)
                 const int hp = h >> 1, vp = v >> 1;
-                const long long lsi = (long long)((row << 4) + vp) * g.luma_w + (col << 4) + hp;
+                const int lsi = ((row << 4) + vp) * g.luma_w + (col << 4) + hp;
                 const int cmh = h / 2, cmv = v / 2;
-                const long long csi = (long long)((row << 3) + (cmv >> 1)) * chroma_w + (col << 3) + (cmh >> 1);
-                const long long cb0 = luma_bytes, cr0 = cb0 + luma_bytes / 4;
+                const int csi = ((row << 3) + (cmv >> 1)) * chroma_w + (col << 3) + (cmh >> 1);
+                const int cb0 = luma_bytes, cr0 = cb0 + luma_bytes / 4;
                 if ((use_bwd ? P.bwd_buf : P.fwd_buf) == P.dst_buf || !vlc_window_inside(lsi, g.luma_w, 16, h & 1, v & 1, total) ||
                     !vlc_window_inside(csi, chroma_w, 8, cmh & 1, cmv & 1, total - cb0) ||
                     !vlc_window_inside(csi, chroma_w, 8, cmh & 1, cmv & 1, total - cr0))
