@@ -576,7 +576,8 @@ def main():
         extras["bitstream"] = bitstream_leg(args, local_rank, log)
     elif not args.no_extras:
         # N > 1: every rank decodes its own 256 streams from their bitstreams (resident path only), barrier + max over ranks
-        extras["bitstream"] = bitstream_leg(args, local_rank, log, paths=("device_vlc_resident",), barrier=barrier, max_over_ranks=max_over_ranks, world=world)
+        extras["bitstream"] = bitstream_leg(args, local_rank, log, paths=("device_vlc_resident", "device_vlc_resident_to_host"), barrier=barrier,
+                                            max_over_ranks=max_over_ranks, world=world)
 
     # ---- frames gathered to rank 0 over NVLink (the only collective of the path)
     gather = gathered = None
@@ -835,11 +836,15 @@ def audio_leg(torch, device_index, peak, log):
     return out
 
 
-def bitstream_leg(args, device_index, log, paths=("host_parser", "device_vlc", "device_vlc_resident"), barrier=None, max_over_ranks=None, world=1):
+def bitstream_leg(args, device_index, log, paths=("host_parser", "device_vlc", "device_vlc_resident", "device_vlc_resident_to_host"), barrier=None,
+                  max_over_ranks=None, world=1):
     """Bitstream in, frames out: S natural 720p streams (two distinct ones written by tests/mpeg1_writer.py, I + P pictures)
-    through mpeg_b200.VideoBatch with the host parser and with the device-side slice parser.  Frames stay in HBM; every step's
-    returned frames are hashed on the host for the first streams and held against the oracle's decode of the same bitstream."""
+    through mpeg_b200.VideoBatch with the host parser and with the device-side slice parser.  Frames stay in HBM (the frames of four
+    streams are read back every step, outside the rate, and hashed against the oracle's decode of the same bitstream), except in the
+    `_to_host` path, which is the end-to-end form: every returned frame of every stream travels to pinned host memory inside the
+    timed region (its parity is taken in a second, untimed pass that waits for every copy)."""
     import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
     import mpeg_b200
     import oracle_lib as ol
     sys.path.insert(0, str(ROOT / "tools"))
@@ -852,77 +857,127 @@ def bitstream_leg(args, device_index, log, paths=("host_parser", "device_vlc", "
         distinct = bb.make_streams(2, 6, "natural", log)
     n_pictures = sum(1 for i in range(len(distinct[0]) - 3) if distinct[0][i:i + 4] == b"\x00\x00\x01\x00")
     streams = [distinct[i % 2] for i in range(S)]
-    want = []
-    for d in distinct:   # the oracle's full decoder on the bitstream (parse + reconstruct), hash over all returned frames
-        o, h = ol.VideoOracle(d), ol.FNV_OFFSET
+    threads = host_threads()
+
+    def oracle_decode(d):   # the oracle's full decoder on the bitstream (parse + reconstruct), hash over all returned frames
+        o, h, n = ol.VideoOracle(d), ol.FNV_OFFSET, 0
         while (f := o.decode()) is not None:
             for which in ("y", "cb", "cr"):
                 h = ol.fnv(h, f.plane(which))
-        want.append(h)
-    threads = host_threads()
-    L = mpeg_b200._lib.load()
-    out = {"config": f"{S} natural 720p streams of {n_pictures} pictures ({len(distinct[0]) / n_pictures / 1e3:.1f} KB per picture), frames stay in HBM",
+            n += 1
+        return h, n
+
+    want = [oracle_decode(d)[0] for d in distinct]
+    out = {"config": f"{S} natural 720p streams of {n_pictures} pictures ({len(distinct[0]) / n_pictures / 1e3:.1f} KB per picture)",
            "host_threads": threads, "paths": {}}
+    if world == 1:
+        # the CPU restatement of the reference's decoder on the same bitstreams: one stream per host thread, bit-serial VLC walk like the Go code
+        def cpu_decode(d):
+            o, n = ol.VideoOracle(d), 0
+            while o.decode() is not None:
+                n += 1
+            return n
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:   # ctypes releases the GIL inside the oracle
+            n_cpu = sum(ex.map(cpu_decode, [distinct[i % 2] for i in range(threads)]))
+        cpu_s = time.perf_counter() - t0
+        out["cpu_decoder"] = {"frames_per_sec": n_cpu / cpu_s, "threads": threads, "kind": "port",
+                              "what": "oracle/ full decoder (parse + reconstruct) on the same bitstreams, one stream per thread, planes in host memory"}
+        log(f"bitstream cpu decoder: {n_cpu / cpu_s:.0f} frames/s on {threads} threads")
     check = [0, 1, S - 2, S - 1] if S >= 4 else list(range(S))
-    all_paths = {"host_parser": {}, "device_vlc": {"device_vlc": True}, "device_vlc_resident": {"device_vlc": True, "resident": True}}
+    L = mpeg_b200._lib.load()
+    all_paths = {"host_parser": {}, "device_vlc": {"device_vlc": True}, "device_vlc_resident": {"device_vlc": True, "resident": True},
+                 "device_vlc_resident_to_host": {"device_vlc": True, "resident": True}}
     if world > 1:
         threads = max(1, threads // world)   # the ranks share the host's cores
         out["host_threads"] = threads
     for name in paths:
         kw = all_paths[name]
-        with mpeg_b200.Context(device=device_index, max_streams=S) as c:
-            c.set_kernel_timing(name != "host_parser")
-            vb = mpeg_b200.VideoBatch(c, streams, threads=threads, validate=False, **kw)
-            geo = c.video_geometry(0)
-            pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
-            host = np.empty((len(check), pic_bytes), np.uint8)
-            hashes = [ol.FNV_OFFSET] * len(check)
-            frames, parse_ms, ms = 0, [], C.c_float()
-            t_hash = 0.0
-            c.sync()
-            if barrier:
-                barrier()
-            t0 = time.perf_counter()
-            while True:
-                has, buf, _ = vb.step()
-                if not has.any():
-                    break
-                frames += int(has.sum())
-                if name != "host_parser" and L.mpegb200_video_bitstream_parse_ms(c.h, C.byref(ms)) == 0:
-                    parse_ms.append(ms.value)
-                th = time.perf_counter()   # parity read-back of a few streams: outside the rate
-                live = [k for k, i in enumerate(check) if has[i]]
-                if live:
-                    c.video_read_pictures(np.array([check[k] for k in live]), buf[[check[k] for k in live]], host.ctypes.data, pic_bytes)
-                    c.sync()
-                    for j, k in enumerate(live):
-                        hashes[k] = ol.fnv(hashes[k], host[j])
-                t_hash += time.perf_counter() - th
-            c.sync()
-            dt = time.perf_counter() - t0 - t_hash
-            if max_over_ranks:
-                dt = max_over_ranks(dt * 1e3) * 1e-3   # the slowest rank
-                frames *= world
-            ok = all(hashes[k] == want[check[k] % 2] for k in range(len(check)))
-            rec = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "parity_ok": bool(ok), "checked_streams": check}
-            if name != "host_parser":
-                steady = sorted(parse_ms[1:] or parse_ms)
-                rec.update({"flagged_pictures": vb.flagged, "host_steps": vb.host_steps,
-                            "parse_kernel_ms_per_wave": steady[len(steady) // 2] if steady else None,
-                            "parse_kernel_pictures_per_sec": S / (steady[len(steady) // 2] * 1e-3) if steady else None,
-                            "seconds_in": {"host_scan": vb.t_scan, "submit": vb.t_submit, "waiting_for_flags": vb.t_wait}})
-            out["paths"][name] = rec
-            log(f"bitstream {name}: {frames / dt:.0f} frames/s, parity {'ok' if ok else 'MISMATCH'}")
-            vb.close()
-            if not ok:
-                fail_parity({"metric": METRIC, "error": f"bitstream ({name}): frames differ from the oracle's decode of the bitstream"})
+        to_host = name.endswith("_to_host")
+        for timed_pass in ((True, False) if to_host else (True,)):
+            with mpeg_b200.Context(device=device_index, max_streams=S) as c:
+                c.set_kernel_timing(name != "host_parser")
+                vb = mpeg_b200.VideoBatch(c, streams, threads=threads, validate=False, **kw)
+                geo = c.video_geometry(0)
+                pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
+                host = np.empty((len(check), pic_bytes), np.uint8)
+                if to_host:
+                    import torch
+                    h_all = [torch.empty((S, pic_bytes), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+                    all_ids = np.arange(S, dtype=np.int32)
+                hashes = [ol.FNV_OFFSET] * len(check)
+                frames, parse_ms, ms, steps = 0, [], C.c_float(), 0
+                t_hash = 0.0
+                c.sync()
+                if barrier:
+                    barrier()
+                t0 = time.perf_counter()
+                while True:
+                    has, buf, _ = vb.step()
+                    if not has.any():
+                        break
+                    frames += int(has.sum())
+                    if name != "host_parser" and L.mpegb200_video_bitstream_parse_ms(c.h, C.byref(ms)) == 0:
+                        parse_ms.append(ms.value)
+                    if to_host:
+                        live = np.nonzero(has)[0]
+                        dst = h_all[steps & 1]
+                        c.video_read_pictures(all_ids[live], buf[live], dst.data_ptr(), pic_bytes)   # asynchronous, on the read-back stream
+                        if not timed_pass:   # parity pass: wait for the copy and hash what arrived on the host
+                            c.sync()
+                            for k, i in enumerate(check):
+                                if has[i]:
+                                    hashes[k] = ol.fnv(hashes[k], dst[int(np.searchsorted(live, i))].numpy())
+                    else:
+                        th = time.perf_counter()   # parity read-back of a few streams: outside the rate
+                        live = [k for k, i in enumerate(check) if has[i]]
+                        if live:
+                            c.video_read_pictures(np.array([check[k] for k in live]), buf[[check[k] for k in live]], host.ctypes.data, pic_bytes)
+                            c.sync()
+                            for j, k in enumerate(live):
+                                hashes[k] = ol.fnv(hashes[k], host[j])
+                        t_hash += time.perf_counter() - th
+                    steps += 1
+                c.sync()   # waits for the read-back stream too
+                dt = time.perf_counter() - t0 - t_hash
+                if max_over_ranks:
+                    dt = max_over_ranks(dt * 1e3) * 1e-3   # the slowest rank
+                    frames *= world
+                if to_host and timed_pass:
+                    timed = (frames, dt, list(parse_ms), vb.flagged, vb.host_steps, (vb.t_scan, vb.t_submit, vb.t_wait))
+                    vb.close()
+                    continue
+                if to_host:
+                    frames, dt, parse_ms, flagged, host_steps, t_in = timed
+                else:
+                    flagged, host_steps, t_in = vb.flagged, vb.host_steps, (vb.t_scan, vb.t_submit, vb.t_wait)
+                ok = all(hashes[k] == want[check[k] % 2] for k in range(len(check)))
+                rec = {"frames_per_sec": frames / dt, "frames": frames, "seconds": dt, "parity_ok": bool(ok), "checked_streams": check}
+                if name != "host_parser":
+                    steady = sorted(parse_ms[1:] or parse_ms)
+                    rec.update({"flagged_pictures": flagged, "host_steps": host_steps,
+                                "parse_kernel_ms_per_wave": steady[len(steady) // 2] if steady else None,
+                                "parse_kernel_pictures_per_sec": S / (steady[len(steady) // 2] * 1e-3) if steady else None,
+                                "seconds_in": {"host_scan": t_in[0], "submit": t_in[1], "waiting_for_flags": t_in[2]}})
+                if to_host:
+                    rec["d2h_bytes_per_step"] = int(S * pic_bytes)
+                    rec["note"] = ("end to end from the bitstream: streams resident in HBM, every returned frame copied to pinned host memory inside the timed "
+                                   "region (double-buffered, asynchronous); parity from a second pass that waits for every copy")
+                out["paths"][name] = rec
+                log(f"bitstream {name}: {frames / dt:.0f} frames/s, parity {'ok' if ok else 'MISMATCH'}")
+                vb.close()
+                if not ok:
+                    fail_parity({"metric": METRIC, "error": f"bitstream ({name}): frames differ from the oracle's decode of the bitstream"})
     if "host_parser" in out["paths"]:
         out["device_vlc_speedup"] = out["paths"]["device_vlc"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
         out["device_vlc_resident_speedup"] = out["paths"]["device_vlc_resident"]["frames_per_sec"] / out["paths"]["host_parser"]["frames_per_sec"]
+    if "cpu_decoder" in out and "device_vlc_resident_to_host" in out["paths"]:
+        out["to_host_vs_cpu_decoder"] = out["paths"]["device_vlc_resident_to_host"]["frames_per_sec"] / out["cpu_decoder"]["frames_per_sec"]
     if world > 1:
         out["config"] += f"; {world} ranks, whole-job frames/s over the slowest rank's time"
-    out["paths"]["device_vlc_resident"]["note"] = ("streams uploaded to HBM and their start codes indexed on the device when the batch is created (outside the rate, "
-                                                    "like the demux); per step the host reads headers and builds slice tables, no compressed byte crosses PCIe")
+    if "device_vlc_resident" in out["paths"]:
+        out["paths"]["device_vlc_resident"]["note"] = ("streams uploaded to HBM and their start codes indexed on the device when the batch is created (outside the rate, "
+                                                        "like the demux); per step the host reads headers and builds slice tables, no compressed byte crosses PCIe")
     return out
 
 
