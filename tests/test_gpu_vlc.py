@@ -230,3 +230,34 @@ def test_single_stream_video_with_device_vlc(golden_dir):
             frames += 1
         assert h == VIDEO_GOLDEN, f"{h:#018x} after {frames} frames"
         video.close()
+
+
+def test_damaged_streams_through_the_device_parser():
+    """Forty mutations of a written stream (four flipped bits each; two of them leave stale coefficients behind a dropped block, which
+    makes the host parse the following step as a whole) in one lock-step batch, wave form and resident form: every stream's frames
+    must equal the oracle's decode of the same damaged bytes -- whatever mix of device-parsed, flagged and host-parsed pictures it
+    takes.  (Mutations whose vectors leave the frame buffer are left out: the reference panics there, this path raises.)"""
+    import mpeg_b200
+    w, _ = write_stream(176, 144, [mw.PIC_I, mw.PIC_P, mw.PIC_B, mw.PIC_P, mw.PIC_P], seed=5, mode="natural")
+    data = w.tobytes()
+    datas, want = [], []
+    for trial in list(range(100, 140)) + [368]:
+        rng = np.random.default_rng(1000 + trial)
+        d = bytearray(data)
+        for pos in rng.integers(20, len(d), 4):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        o = ol.VideoOracle(bytes(d))
+        h, n = ol.FNV_OFFSET, 0
+        while (f := o.decode()) is not None:
+            for which in ("y", "cb", "cr"):
+                h = ol.fnv(h, f.plane(which))
+            n += 1
+        if o.oob_count() == 0:
+            datas.append(bytes(d))
+            want.append((h, n))
+    assert len(datas) >= 36
+    for kw in ({"device_vlc": True}, {"device_vlc": True, "resident": True}, {"device_vlc": True, "scan_ahead": False}):
+        with mpeg_b200.Context(device=0, max_streams=64) as c:
+            hashes, frames, (flagged, host_steps) = batch_hashes(c, datas, **kw)
+        assert list(zip(hashes, frames)) == want, kw
+        assert flagged > 5 and host_steps >= 2, (flagged, host_steps)

@@ -279,3 +279,21 @@ def test_resident_mode_with_handed_in_start_codes(golden_dir):
     bad = np.array([5, 17], np.uint64)
     assert L.mpegb200_video_parser_set_start_codes(h, C.c_void_p(bad.ctypes.data), 2) == -1
     L.mpegb200_video_parser_free(h)
+
+
+def test_stale_coefficients_make_the_host_parse_the_next_step():
+    """An invalid run in the last block a picture decodes leaves coefficients behind that the serial reference leaks into the next
+    block it decodes -- a picture later (video.go:712-714, 774-777).  Only the host parser carries that state: the flagged picture's
+    step ends on the host, and the NEXT step is parsed by the host as a whole (mpegb200_video_scan_step.host_step) until the stale
+    coefficients are gone.  Two mutations of a written stream that do exactly that (found by search, seeds fixed)."""
+    w, _ = write_stream(176, 144, [mw.PIC_I, mw.PIC_P, mw.PIC_B, mw.PIC_P, mw.PIC_P], seed=5, mode="natural")
+    data = w.tobytes()
+    for trial in (106, 368):
+        rng = np.random.default_rng(1000 + trial)
+        d = bytearray(data)
+        for pos in rng.integers(20, len(d), 4):
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+        stats = run_stream(bytes(d), expect_clean=False, label=f"stale {trial}")
+        assert stats["host_steps"] >= 1 and stats["flagged"] >= 1, stats
+        assert run_stream(bytes(d), expect_clean=False, label=f"stale {trial} resident", resident=True) == stats
+        run_stream_scanning_ahead(bytes(d), f"stale {trial} ahead")
