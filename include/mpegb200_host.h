@@ -205,6 +205,9 @@ typedef struct mpegb200_batch_scan_step {
 } mpegb200_batch_scan_step;
 
 int  mpegb200_video_batch_next_scan(mpegb200_video_batch* b, mpegb200_batch_scan_step* out);
+/* The parser of stream `index` (owned by the batch), for the per-stream controls: mpegb200_video_parser_set_no_delay, _rewind,
+ * _has_ended, _framerate.  Do not call its _next functions. */
+mpegb200_video_parser* mpegb200_video_batch_parser(mpegb200_video_batch* b, int index);
 /* Resident mode: the streams were uploaded with mpegb200_video_stream_upload (stream id = index + the caller's offset); the waves
  * then carry no bytes (bitstream = NULL) and the slices' data_offset counts from the first byte of their stream. */
 int  mpegb200_video_batch_set_resident(mpegb200_video_batch* b, int on);

@@ -119,6 +119,7 @@ def load():
         "mpegb200_video_parser_redo": (C.c_int, [vp, C.c_int, vp]),
         "mpegb200_video_parser_unscan": (C.c_int, [vp]),
         "mpegb200_video_parser_set_start_codes": (C.c_int, [vp, vp, C.c_size_t]),
+        "mpegb200_video_batch_parser": (vp, [vp, C.c_int]),
         "mpegb200_video_batch_set_resident": (C.c_int, [vp, C.c_int]),
         "mpegb200_video_batch_set_start_codes": (C.c_int, [vp, C.c_int, vp, C.c_size_t]),
         "mpegb200_video_batch_unscan": (C.c_int, [vp]),

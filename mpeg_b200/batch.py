@@ -131,6 +131,16 @@ class VideoBatch:
         t = np.ctypeslib.as_array(st.time, shape=(self.n,)).copy()
         return has, buf, t
 
+    def parser(self, i: int):
+        """Handle of stream i's host parser (set_no_delay / rewind / has_ended of one stream of the batch)."""
+        return self.L.mpegb200_video_batch_parser(self.h, i)
+
+    def drop_scan_ahead(self):
+        """Withdraw a scan made ahead of time (before a control call that changes where a parser stands)."""
+        if self._ahead is not None:
+            self.ctx._ck(self.L.mpegb200_video_batch_unscan(self.h))
+            self._ahead = None
+
     def _scan(self):
         """One scan step of every stream (host): the step structure plus copies of its per-stream results."""
         import time

@@ -1994,6 +1994,10 @@ size_t mpegb200_internal_vlc_tables(void* out, size_t cap) {
     return mpegb200::fill_vlc_device_tables(static_cast<mpegb200::VlcDeviceTables*>(out)) ? sizeof(mpegb200::VlcDeviceTables) : 0;
 }
 
+mpegb200_video_parser* mpegb200_video_batch_parser(mpegb200_video_batch* b, int index) {
+    return b && index >= 0 && index < b->n ? b->parsers[(size_t)index] : nullptr;
+}
+
 int mpegb200_video_batch_set_resident(mpegb200_video_batch* b, int on) {
     if (!b) return MPEGB200_EINVAL;
     b->resident = on != 0;

@@ -106,23 +106,32 @@ class Video:
     def framerate(self):
         return self.L.mpegb200_video_parser_framerate(self.h)
 
+    def _parsers(self):
+        """The parser that answers header queries, and (device_vlc) the one inside the one-stream batch that walks the stream."""
+        if self._device_vlc and self._batch is None:
+            from .batch import VideoBatch
+            self._batch = VideoBatch(self.ctx, [self._data], threads=1, first_stream=self.stream, device_vlc=True, resident=True)
+        return [self.h] + ([self._batch.parser(0)] if self._batch is not None else [])
+
     def set_no_delay(self, on: bool):
-        self.L.mpegb200_video_parser_set_no_delay(self.h, int(on))
+        for h in self._parsers():
+            self.L.mpegb200_video_parser_set_no_delay(h, int(on))
 
     def rewind(self):
-        self.L.mpegb200_video_parser_rewind(self.h)
+        if self._batch is not None:
+            self._batch.drop_scan_ahead()
+        for h in self._parsers():
+            self.L.mpegb200_video_parser_rewind(h)
 
     def has_ended(self) -> bool:
-        return bool(self.L.mpegb200_video_parser_has_ended(self.h))
+        return bool(self.L.mpegb200_video_parser_has_ended(self._parsers()[-1]))
 
     def decode(self):
         """Video.Decode(): parse up to the picture that makes a frame due, run its launches, return the Frame."""
         if not self.has_header():
             return None
         if self._device_vlc:
-            if self._batch is None:
-                from .batch import VideoBatch
-                self._batch = VideoBatch(self.ctx, [self._data], threads=1, first_stream=self.stream, device_vlc=True, resident=True)
+            self._parsers()
             has, buf, t = self._batch.step()
             if not has[0]:
                 return None

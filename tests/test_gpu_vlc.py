@@ -261,3 +261,24 @@ def test_damaged_streams_through_the_device_parser():
             hashes, frames, (flagged, host_steps) = batch_hashes(c, datas, **kw)
         assert list(zip(hashes, frames)) == want, kw
         assert flagged > 5 and host_steps >= 2, (flagged, host_steps)
+
+
+def test_rewind_and_no_delay_in_device_mode(golden_dir):
+    """Video.Rewind (video.go:195-201: the frame buffers are NOT cleared) and SetNoDelay reach the parser that walks the stream
+    when the slices are parsed on the device; a scan made ahead of time is withdrawn first."""
+    import mpeg_b200
+    data = ol.demux_split((golden_dir / "test.mpg").read_bytes())[0]
+    for no_delay in (False, True):
+        with mpeg_b200.Context(device=0, max_streams=2) as c:
+            video, oracle = mpeg_b200.Video(data, c, stream=0, device_vlc=True), ol.VideoOracle(data)
+            video.set_no_delay(no_delay)
+            oracle.set_no_delay(no_delay)
+            for rounds in (7, 25):
+                for k in range(rounds):
+                    f, want = video.decode(), oracle.decode()
+                    assert (f is None) == (want is None) and f.time == want.time
+                    assert np.array_equal(f.y.reshape(-1), want.plane("y").reshape(-1)) and np.array_equal(f.cr.reshape(-1), want.plane("cr").reshape(-1))
+                assert not video.has_ended()
+                video.rewind()
+                oracle.rewind()
+            video.close()
