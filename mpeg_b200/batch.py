@@ -367,13 +367,15 @@ class MPEGBatch:
     .mpg is split into its video and audio elementary streams (host threads), the video streams decode in lock-step through a
     VideoBatch with a display ring behind it, the audio streams through an AudioBatch."""
 
-    def __init__(self, ctx: Context, program_streams, threads: int = 8, ring_depth: int = 4, audio_fmt: int = 0, frames_per_step: int = 8):
+    def __init__(self, ctx: Context, program_streams, threads: int = 8, ring_depth: int = 4, audio_fmt: int = 0, frames_per_step: int = 8,
+                 device_vlc: bool = False):
         from concurrent.futures import ThreadPoolExecutor
         from .mpeg import demux_split
         with ThreadPoolExecutor(max(1, threads)) as ex:   # ctypes releases the GIL inside mpegb200_demux_split
             parts = list(ex.map(demux_split, [bytes(p) for p in program_streams]))
         self.packets = [(p[2], p[3]) for p in parts]
-        self.video = VideoBatch(ctx, [p[0] for p in parts], threads=threads)
+        # device_vlc: the video elementary streams stay in HBM and their slices are parsed there (VideoBatch, resident form)
+        self.video = VideoBatch(ctx, [p[0] for p in parts], threads=threads, device_vlc=device_vlc, resident=device_vlc)
         self.audio = AudioBatch(ctx, [p[1] for p in parts], threads=threads, fmt=audio_fmt, frames_per_step=frames_per_step)
         self.ring = DisplayRing(ctx, np.arange(len(parts), dtype=np.int32), ring_depth)
 

@@ -149,7 +149,8 @@ def test_video_batch_lockstep_golden(golden_dir):
     assert want[0] == VIDEO_GOLDEN
 
 
-def test_program_stream_batch_with_display_ring_and_audio_batch(golden_dir):
+@pytest.mark.parametrize("device_vlc", [False, True])
+def test_program_stream_batch_with_display_ring_and_audio_batch(golden_dir, device_vlc):
     """the batched front end.  Program streams are demultiplexed, their video decodes in lock-step with the
     returned frames kept in a device display ring (read back LATE, two steps behind the decoder), their audio goes through the
     lock-step audio batch (eight frames per stream and launch, streams of different lengths).  Every stream must reproduce
@@ -179,7 +180,7 @@ def test_program_stream_batch_with_display_ring_and_audio_batch(golden_dir):
     n = 9
     streams = [datas[i % 3] for i in range(n)]
     with mpeg_b200.Context(device=0, max_streams=16) as c:
-        mb = mpeg_b200.MPEGBatch(c, streams, threads=4, ring_depth=4, frames_per_step=8)
+        mb = mpeg_b200.MPEGBatch(c, streams, threads=4, ring_depth=4, frames_per_step=8, device_vlc=device_vlc)   # True: video slices parsed on the device
         assert mb.packets[0] == (143, 37)
         geo = c.video_geometry(0)
         pic_bytes = geo[0] * geo[1] + 2 * geo[2] * geo[3]
