@@ -282,3 +282,22 @@ def test_rewind_and_no_delay_in_device_mode(golden_dir):
                 video.rewind()
                 oracle.rewind()
             video.close()
+
+
+def test_mixed_geometries_in_one_wave(golden_dir):
+    """Streams of different picture sizes (one of them with an odd macroblock width, which the generic decode kernel executes) and
+    different lengths in one lock-step batch with the slices parsed on the device: per-picture geometry, slot tables and quantiser
+    matrices in one wave."""
+    import mpeg_b200
+    ps_video = ol.demux_split((golden_dir / "test.mpg").read_bytes())[0]
+    w1, _ = write_stream(352, 288, [mw.PIC_I, mw.PIC_P, mw.PIC_B, mw.PIC_B, mw.PIC_P], seed=71, mode="natural")
+    w2, _ = write_stream(720, 576, [mw.PIC_I, mw.PIC_P, mw.PIC_B], seed=72, mode="natural")
+    w3, _ = write_stream(64, 48, [mw.PIC_I] + [mw.PIC_P] * 9, seed=73, mode="dense")
+    kinds = [ps_video[:60000], w1.tobytes(), w2.tobytes(), w3.tobytes()]
+    want = [oracle_hash(d) for d in kinds]
+    datas = [kinds[i % 4] for i in range(8)]
+    for kw in ({"device_vlc": True}, {"device_vlc": True, "resident": True}):
+        with mpeg_b200.Context(device=0, max_streams=16) as c:
+            hashes, frames, _ = batch_hashes(c, datas, first=1, **kw)
+        for i in range(8):
+            assert (hashes[i], frames[i]) == want[i % 4], (i, kw)
