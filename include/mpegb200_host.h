@@ -219,6 +219,30 @@ int  mpegb200_video_batch_unscan(mpegb200_video_batch* b);
  * the device then skips them); has_frame / frame_buf / time of the stream are those of *out. */
 int  mpegb200_video_batch_redo(mpegb200_video_batch* b, int index, int step_picture, mpegb200_video_step* out);
 
+/* ---- the whole lock-step step with the slices parsed on the device, as one call -------------------------------------------
+ * What a binding would otherwise write itself around mpegb200_video_batch_next_scan / mpegb200_video_decode_bitstream /
+ * mpegb200_video_bitstream_flags / mpegb200_video_batch_redo / _unscan: host-parsed steps, waves,
+ * scan-ahead, flags, re-parse of a flagged picture's step tail.  Stream i of the batch is stream id first_stream + i of the
+ * context (opened by the caller with mpegb200_video_open; resident mode: uploaded and indexed by the caller, see
+ * mpegb200_video_batch_set_resident).  One stepper per batch; do not call the batch's _next functions beside it. */
+typedef struct mpegb200_device_stepper mpegb200_device_stepper;
+typedef struct mpegb200_device_stepper_stats {
+    uint64_t steps, waves;
+    uint64_t flagged_pictures;      /* pictures the device flagged: their step's tail took the host parser */
+    uint64_t host_steps;            /* steps the host parsed itself (stale coefficients pending) */
+    uint64_t withdrawn_scans;       /* scans made ahead of time and withdrawn because the step before flagged */
+    double seconds_host_scan, seconds_submit, seconds_waiting;   /* host time in the scan, in the submission, waiting for the flags */
+} mpegb200_device_stepper_stats;
+
+mpegb200_device_stepper* mpegb200_device_stepper_new(mpegb200_ctx* ctx, mpegb200_video_batch* batch, int first_stream, int scan_ahead);
+void mpegb200_device_stepper_free(mpegb200_device_stepper* s);
+/* One Video.Decode() of every stream: has_frame / frame_buf / time receive n_streams entries each (has_frame 0: that stream has
+ * ended).  The kernels of the step's last wave may still run when it returns (mpegb200_sync, or a read-back, waits for them). */
+int  mpegb200_device_stepper_step(mpegb200_device_stepper* s, int* has_frame, int* frame_buf, double* time);
+/* Withdraw a scan made ahead of time (before a control call that moves a parser: rewind, no-delay). */
+int  mpegb200_device_stepper_drop_scan_ahead(mpegb200_device_stepper* s);
+int  mpegb200_device_stepper_get_stats(mpegb200_device_stepper* s, mpegb200_device_stepper_stats* out);
+
 /* ---- MP2 elementary stream --------------------------------------------------------------------- */
 
 typedef struct mpegb200_audio_parser mpegb200_audio_parser;

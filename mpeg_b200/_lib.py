@@ -131,6 +131,11 @@ def load():
         "mpegb200_video_batch_stream_size": (C.c_int, [vp, C.c_int, ip, ip]),
         "mpegb200_video_batch_set_vlen": (C.c_int, [vp, C.c_int]),
         "mpegb200_video_batch_next": (C.c_int, [vp, vp]),
+        "mpegb200_device_stepper_new": (vp, [vp, vp, C.c_int, C.c_int]),
+        "mpegb200_device_stepper_free": (None, [vp]),
+        "mpegb200_device_stepper_step": (C.c_int, [vp, vp, vp, vp]),
+        "mpegb200_device_stepper_drop_scan_ahead": (C.c_int, [vp]),
+        "mpegb200_device_stepper_get_stats": (C.c_int, [vp, vp]),
         "mpegb200_audio_parser_new": (vp, [C.c_char_p, C.c_size_t]),
         "mpegb200_audio_parser_free": (None, [vp]),
         "mpegb200_audio_parser_has_header": (C.c_int, [vp]),

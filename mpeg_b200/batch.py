@@ -52,13 +52,21 @@ class BatchScanStep(C.Structure):   # mpegb200_batch_scan_step
 assert C.sizeof(VlcPicture) == 32 and C.sizeof(VlcSlice) == 32
 
 
+class StepperStats(C.Structure):   # mpegb200_device_stepper_stats
+    _fields_ = [("steps", C.c_uint64), ("waves", C.c_uint64), ("flagged_pictures", C.c_uint64), ("host_steps", C.c_uint64),
+                ("withdrawn_scans", C.c_uint64), ("seconds_host_scan", C.c_double), ("seconds_submit", C.c_double), ("seconds_waiting", C.c_double)]
+
+
 class VideoBatch:
     def __init__(self, ctx: Context, streams, threads: int = 8, first_stream: int = 0, pinned: bool = True, validate: bool = True,
-                 vlen: bool = True, device_vlc: bool = False, scan_ahead: bool = True, resident: bool = False):
+                 vlen: bool = True, device_vlc: bool = False, scan_ahead: bool = True, resident: bool = False, native_step: bool = True):
         """device_vlc: the host only scans headers and start codes; the slices are parsed on the GPU, one thread per slice
         (mpegb200_video_decode_bitstream), and pictures the device flags are re-parsed by the host parser.
         resident (with device_vlc): every stream is uploaded to device memory once and its start codes are indexed there
-        (mpegb200_video_stream_upload / _index): per step the host touches headers only and the waves carry tables only."""
+        (mpegb200_video_stream_upload / _index): per step the host touches headers only and the waves carry tables only.
+        native_step (with device_vlc): the step's control flow (waves, scan-ahead, flags, re-parses) runs in the library
+        (mpegb200_device_stepper_*, C++); False: the same flow written out in Python below (_step_device_vlc), kept as the
+        readable reference of the call sequence and for A/B."""
         self.L = _lib.load()
         self.device_vlc = device_vlc
         self.flagged = 0    # pictures the device flagged so far: their step's tail took the host path (device_vlc)
@@ -99,12 +107,26 @@ class VideoBatch:
                 ctx._ck(rc)
                 if self.L.mpegb200_video_batch_set_start_codes(self.h, i, C.c_void_p(pos.ctypes.data), n_codes.value) != 0:
                     raise RuntimeError(f"stream {i}: the device's start-code index does not fit the stream")
+        self._stepper = None
+        if device_vlc and native_step:
+            self._stepper = self.L.mpegb200_device_stepper_new(ctx.h, self.h, first_stream, int(scan_ahead))
+            if not self._stepper:
+                raise MemoryError
+            self._has, self._buf, self._time = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32), np.zeros(self.n, np.float64)
         self._pic_dtype = np.dtype([("stream", "<i4"), ("rest", "V12")])
         self.steps = 0
 
     def step(self):
         """One Video.Decode() of every stream.  Returns (has_frame[n] bool, frame_buf[n] uint8, time[n]).
         The kernels run asynchronously; call ctx.sync() (or read frames back) before touching results."""
+        if self._stepper:
+            self.ctx._ck(self.L.mpegb200_device_stepper_step(self._stepper, C.c_void_p(self._has.ctypes.data), C.c_void_p(self._buf.ctypes.data),
+                                                              C.c_void_p(self._time.ctypes.data)))
+            st = StepperStats()
+            self.L.mpegb200_device_stepper_get_stats(self._stepper, C.byref(st))
+            self.flagged, self.host_steps, self.steps = int(st.flagged_pictures), int(st.host_steps), int(st.steps)
+            self.t_scan, self.t_submit, self.t_wait = st.seconds_host_scan, st.seconds_submit, st.seconds_waiting
+            return self._has.astype(bool), self._buf.astype(np.uint8), self._time.copy()
         if self.device_vlc:
             return self._step_device_vlc()
         if self.steps >= 2:
@@ -137,6 +159,8 @@ class VideoBatch:
 
     def drop_scan_ahead(self):
         """Withdraw a scan made ahead of time (before a control call that changes where a parser stands)."""
+        if self._stepper:
+            self.ctx._ck(self.L.mpegb200_device_stepper_drop_scan_ahead(self._stepper))
         if self._ahead is not None:
             self.ctx._ck(self.L.mpegb200_video_batch_unscan(self.h))
             self._ahead = None
@@ -228,6 +252,9 @@ class VideoBatch:
     def close(self):
         if getattr(self, "h", None):
             self.ctx.sync()
+            if getattr(self, "_stepper", None):
+                self.L.mpegb200_device_stepper_free(self._stepper)
+                self._stepper = None
             for i in range(self.n):
                 try:
                     self.ctx.video_close(self.first + i)

@@ -252,6 +252,28 @@ static int run_gpu(void) {
     if (run_bitstream(ctx, 3, 0) != 0) return 1;
     if (run_bitstream(ctx, 3, 1) != 0) return 1;
     CHECK(mpegb200_video_close(ctx, 3) == 0);
+    /* the same for a lock-step batch of two streams as ONE call per step (mpegb200_device_stepper_*) */
+    {
+        mpegb200_video_batch* vb = mpegb200_video_batch_new(2, 1, NULL, NULL);
+        CHECK(vb != NULL && mpegb200_video_batch_set_stream(vb, 0, kTinyStream, sizeof kTinyStream) == 0);
+        CHECK(mpegb200_video_batch_set_stream(vb, 1, kTinyStream, sizeof kTinyStream) == 0);
+        CHECK(mpegb200_video_open(ctx, 2, 32, 32) == 0 && mpegb200_video_open(ctx, 3, 32, 32) == 0);
+        mpegb200_device_stepper* ds = mpegb200_device_stepper_new(ctx, vb, 2, 1);
+        CHECK(ds != NULL);
+        int has[2], buf[2];
+        double tm[2];
+        CHECK(mpegb200_device_stepper_step(ds, has, buf, tm) == 0 && has[0] == 1 && has[1] == 1 && buf[0] == buf[1] && tm[0] == 0.0);
+        static uint8_t y[32 * 32];
+        memset(y, 0, sizeof y);
+        CHECK(mpegb200_video_read_planes(ctx, 3, buf[1], y, NULL, NULL) == 0);
+        for (int i = 0; i < 32 * 32; i++) CHECK(y[i] == 128);
+        CHECK(mpegb200_device_stepper_step(ds, has, buf, tm) == 0 && has[0] == 0 && has[1] == 0);
+        mpegb200_device_stepper_stats stats;
+        CHECK(mpegb200_device_stepper_get_stats(ds, &stats) == 0 && stats.steps == 2 && stats.waves == 1 && stats.flagged_pictures == 0);
+        mpegb200_device_stepper_free(ds);
+        mpegb200_video_batch_free(vb);
+        CHECK(mpegb200_video_close(ctx, 2) == 0 && mpegb200_video_close(ctx, 3) == 0);
+    }
     mpegb200_destroy(ctx);
     puts("gpu ok");
     return 0;

@@ -256,7 +256,8 @@ def test_damaged_streams_through_the_device_parser():
             datas.append(bytes(d))
             want.append((h, n))
     assert len(datas) >= 36
-    for kw in ({"device_vlc": True}, {"device_vlc": True, "resident": True}, {"device_vlc": True, "scan_ahead": False}):
+    for kw in ({"device_vlc": True}, {"device_vlc": True, "resident": True}, {"device_vlc": True, "scan_ahead": False},
+               {"device_vlc": True, "native_step": False}, {"device_vlc": True, "resident": True, "native_step": False, "scan_ahead": False}):
         with mpeg_b200.Context(device=0, max_streams=64) as c:
             hashes, frames, (flagged, host_steps) = batch_hashes(c, datas, **kw)
         assert list(zip(hashes, frames)) == want, kw
