@@ -173,6 +173,42 @@ def test_dense_720p_batch_bit_exact(ctx):
         ctx.video_close(10 + s)
 
 
+@pytest.mark.parametrize("mode,pic_type", [("dense", wl.PIC_P), ("natural", wl.PIC_B)])
+def test_full_size_config3_parity(mode, pic_type):
+    """BASELINE configs[2] at its full size -- 256 streams of 1280x720 in ONE launch, 921,600 macroblocks -- dense P (the benchmarked
+    step) and natural B (both references, the per-macroblock-box mode): every plane of every stream against the oracle executing
+    the same records on all host threads, plus the size-independent property that a second decode of the same records into the
+    same buffers changes nothing.  (bench.py repeats the dense-P comparison inside every run.)"""
+    import mpeg_b200
+    S, g = 256, wl.HD720
+    per, refs = [], []
+    for s in range(S):
+        rng = wl.stream_rng(3, 5000 + s)
+        refs.append((wl.random_reference_frame(rng, g), wl.random_reference_frame(rng, g)))
+        per.append(wl.make_picture(rng, g, pic_type, mode))
+    pics, mbs, coeffs = wl.batch_pictures(per, list(range(S)), pic_type, [(0, 1, 2)] * S)
+    fs = ol.FrameSet(S, g.width, g.height)
+    with mpeg_b200.Context(device=0, max_streams=S) as c:
+        for s in range(S):
+            c.video_open(s, g.width, g.height)
+            for b in (1, 2):
+                fs.whole(s, b)[:] = refs[s][b - 1]
+                c.video_write_frame(s, b, refs[s][b - 1])
+        c.video_validate(pics, mbs, len(coeffs))
+        c.video_decode_pictures(pics, mbs, coeffs)
+        assert fs.exec_pictures(pics, mbs, coeffs, threads=ol.lib().orc_max_threads()) == 0
+        first = []
+        for s in range(S):
+            got = c.video_read_frame(s, 0)
+            assert np.array_equal(got, fs.whole(s, 0)), f"{mode}: stream {s} differs from the oracle"
+            if s % 37 == 0:
+                first.append((s, got))
+        c.video_decode_pictures(pics, mbs, coeffs)
+        for s, before in first:
+            assert np.array_equal(before, c.video_read_frame(s, 0))
+    fs.close()
+
+
 def test_zero_residual_zero_vector_picture_is_a_copy(ctx):
     """A P picture whose macroblocks all have a zero vector and no coded blocks reproduces the
     reference picture byte for byte (skipped macroblocks, video.go:503-510)."""
