@@ -909,8 +909,8 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
         if (resident && P.n_slices && (P.stream < 0 || P.stream >= ctx->max_streams || !ctx->resident_dev[(size_t)P.stream]))
             return fail(ctx, MPEGB200_ESTATE, "picture %d: stream %d is not resident", i, P.stream);
     }
-    ctx->vlc_n_pictures = n_pictures;
-    ctx->vlc_n_mb_slots = n_mb_slots;
+    ctx->vlc_n_pictures = 0;   // until this wave is enqueued: a failed call leaves no flags to read
+    ctx->vlc_n_mb_slots = 0;
     if (n_pictures == 0) return 0;
     CU(cudaSetDevice(ctx->device));
     if (!ctx->d_vlc_tables) {   // once per context
@@ -991,6 +991,8 @@ int mpegb200_video_decode_bitstream(mpegb200_ctx* ctx, int n_pictures, const mpe
     CU(cudaEventRecord(ctx->ev_free[slot], ctx->stream));   // the uploads are consumed: the staging slot may be refilled
     CU(cudaMemcpyAsync(ctx->h_vlc_flags, ctx->s_vlc_flags.p, sizeof(int32_t) * (size_t)n_pictures, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev_vlc_flags, ctx->stream));
+    ctx->vlc_n_pictures = n_pictures;
+    ctx->vlc_n_mb_slots = n_mb_slots;
     return decode_pictures_dev(ctx, n_pictures, (const mpegb200_picture*)ctx->s_vlc_pics.p, n_mb_slots,
                                (const mpegb200_mb*)ctx->s_vlc_mbs.p, n_blocks, (const int16_t*)ctx->s_vlc_coeffs.p, dst_mask);
 } catch (...) {
