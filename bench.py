@@ -854,7 +854,7 @@ def bitstream_leg(args, device_index, log, paths=("host_parser", "device_vlc", "
     if len(cached) == 2:
         distinct = [f.read_bytes() for f in cached]
     else:
-        distinct = bb.make_streams(2, 6, "natural", log)
+        distinct = bb.make_streams(2, 16, "natural", log)   # no cached streams on this box: two worker processes write them (about ten seconds)
     n_pictures = sum(1 for i in range(len(distinct[0]) - 3) if distinct[0][i:i + 4] == b"\x00\x00\x01\x00")
     streams = [distinct[i % 2] for i in range(S)]
     threads = host_threads()

@@ -26,28 +26,36 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def write_one(d, pictures, mode):
+    """Stream number d: an I picture and pictures - 1 P pictures of 1280x720 (a top-level function: it also runs in worker processes)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import mpeg1_writer as mw
+    rng = np.random.default_rng(720 + d)
+    w = mw.StreamWriter(1280, 720, quantizer_scale=8, f_code=2)
+    w.picture(mw.PIC_I, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_I, mode, 32, 1280, 720))
+    for _ in range(pictures - 1):
+        w.picture(mw.PIC_P, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_P, mode, 32, 1280, 720))
+    return w.tobytes()
+
+
 def make_streams(distinct, pictures, mode, log):
     """Synthetic 720p streams (I then P pictures); cached under tools/_build/streams/ (git-ignored, travels to the GPU box) because
-    the Python writer needs seconds per picture."""
-    import mpeg1_writer as mw
+    the Python writer needs about half a second per picture.  Missing streams are written in parallel worker processes."""
     cache = ROOT / "tools" / "_build" / "streams"
     cache.mkdir(parents=True, exist_ok=True)
-    out = []
-    for d in range(distinct):
-        f = cache / f"{mode}_720p_seed{720 + d}_{pictures}pictures.m1v"
-        if f.exists():
-            out.append(f.read_bytes())
-            log(f"stream {d}: {f.name} from the cache, {len(out[-1]) / 1e6:.2f} MB")
-            continue
+    files = [cache / f"{mode}_720p_seed{720 + d}_{pictures}pictures.m1v" for d in range(distinct)]
+    missing = [d for d in range(distinct) if not files[d].exists()]
+    if missing:   # one writer process per missing stream (plain subprocesses: nothing of the caller's state, CUDA or otherwise, is inherited)
+        import subprocess
         t0 = time.time()
-        rng = np.random.default_rng(720 + d)
-        w = mw.StreamWriter(1280, 720, quantizer_scale=8, f_code=2)
-        w.picture(mw.PIC_I, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_I, mode, 32, 1280, 720))
-        for _ in range(pictures - 1):
-            w.picture(mw.PIC_P, mw.random_picture(rng, w.mb_w, w.mb_h, mw.PIC_P, mode, 32, 1280, 720))
-        out.append(w.tobytes())
-        f.write_bytes(out[-1])
-        log(f"stream {d}: {pictures} pictures, {len(out[-1]) / 1e6:.2f} MB, written in {time.time() - t0:.1f} s")
+        procs = [subprocess.Popen([sys.executable, str(Path(__file__).resolve()), "--write-one", str(d), "--pictures", str(pictures), "--mode", mode,
+                                   "--out", str(files[d])]) for d in missing]
+        if any(p.wait() != 0 for p in procs):
+            raise RuntimeError("writing the synthetic streams failed")
+        log(f"{len(missing)} stream(s) of {pictures} pictures written in {time.time() - t0:.1f} s")
+    out = [f.read_bytes() for f in files]
+    for d, data in enumerate(out):
+        log(f"stream {d}: {files[d].name}, {len(data) / 1e6:.2f} MB")
     return out
 
 
@@ -59,9 +67,14 @@ def main():
     ap.add_argument("--pictures", type=int, default=5)
     ap.add_argument("--distinct", type=int, default=2)
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--write-one", type=int, default=None, help="(internal) write stream number N to --out and exit")
+    ap.add_argument("--out", default=None)
     ap.add_argument("--device-vlc", action="store_true", help="with --gpu: also run the slice-parallel VLC stage on the device")
     ap.add_argument("--resident", action="store_true", help="with --device-vlc: also with the streams resident in HBM and indexed there")
     args = ap.parse_args()
+    if args.write_one is not None:
+        Path(args.out).write_bytes(write_one(args.write_one, args.pictures, args.mode))
+        return
     threads = args.threads or len(os.sched_getaffinity(0))
 
     def log(m):
