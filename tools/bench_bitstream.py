@@ -73,7 +73,9 @@ def main():
     ap.add_argument("--resident", action="store_true", help="with --device-vlc: also with the streams resident in HBM and indexed there")
     args = ap.parse_args()
     if args.write_one is not None:
-        Path(args.out).write_bytes(write_one(args.write_one, args.pictures, args.mode))
+        tmp = Path(f"{args.out}.{os.getpid()}.tmp")   # ranks of one job may write the same stream at the same time: rename is atomic
+        tmp.write_bytes(write_one(args.write_one, args.pictures, args.mode))
+        os.replace(tmp, args.out)
         return
     threads = args.threads or len(os.sched_getaffinity(0))
 
