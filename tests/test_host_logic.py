@@ -175,3 +175,51 @@ def test_bench_rank_binding_to_gpu_local_cpus(tmp_path, monkeypatch):
             assert os.sched_getaffinity(0) == before
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_one_interpolation_path_gives_all_four_half_pel_modes():
+    """The arithmetic of block_load's single interpolation path (video_fused_tma.cu, v5.3), lane for lane in Python: row sums
+    a[x] + a[x + hx] and their vertical sums with row y + vy in 16-bit lanes, the missing neighbour replaced by the pixel itself
+    through a mask, then (s + 2) >> 2 and the byte pack -- against the four modes of video_noasm.go:44-80 (copy, (a+b+1)>>1
+    horizontally / vertically, (a+b+c+d+2)>>2), all byte alignments, saturated inputs included."""
+    def funnel_rc(lo, hi, sh):
+        return (((hi << 32) | lo) >> min(sh, 32)) & 0xffffffff
+
+    def funnel_r(lo, hi, sh):
+        return (((hi << 32) | lo) >> (sh & 31)) & 0xffffffff
+
+    def byte_perm(a, b, sel):
+        by = [(a >> (8 * i)) & 0xff for i in range(4)] + [(b >> (8 * i)) & 0xff for i in range(4)]
+        return sum(by[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4))
+
+    def sel32(m, a, b):
+        return (a & m) | (b & ~m & 0xffffffff)
+
+    def hsum_row_sel(w0, w1, w2, sh, mh):
+        u0, u1, s1 = funnel_rc(w0, w1, sh), funnel_rc(w1, w2, sh), funnel_rc(w1, w2, sh + 8)
+        e0, o0, e1, o1 = u0 & 0x00ff00ff, byte_perm(u0, 0, 0x4341), u1 & 0x00ff00ff, byte_perm(u1, 0, 0x4341)
+        m0, m1 = funnel_r(e0, e1, 16), byte_perm(s1, 0, 0x4341)
+        return [(e0 + sel32(mh, o0, e0)) & 0xffffffff, (o0 + sel32(mh, m0, o0)) & 0xffffffff,
+                (e1 + sel32(mh, o1, e1)) & 0xffffffff, (o1 + sel32(mh, m1, o1)) & 0xffffffff]
+
+    def vsum_pack(ae, be, ao, bo):
+        return byte_perm(((ae + be + 0x00020002) & 0xffffffff) >> 2, ((ao + bo + 0x00020002) & 0xffffffff) >> 2, 0x6240)
+
+    rng = np.random.default_rng(53)
+    for trial in range(400):
+        win = rng.integers(0, 256, (9, 16), dtype=np.uint8)
+        if trial < 8:
+            win[:] = 255 if trial % 2 else 0
+        words = win.view("<u4")
+        for x0 in range(4):
+            for mode in range(4):
+                mh, mv = (0xffffffff if mode & 1 else 0), (0xffffffff if mode & 2 else 0)
+                rows = [hsum_row_sel(int(words[r, 0]), int(words[r, 1]), int(words[r, 2]), 8 * x0, mh) for r in range(9)]
+                for r in range(8):
+                    up, dn = rows[r], [sel32(mv, rows[r + 1][i], rows[r][i]) for i in range(4)]
+                    p0, p1 = vsum_pack(up[0], dn[0], up[1], dn[1]), vsum_pack(up[2], dn[2], up[3], dn[3])
+                    got = [(p0 >> (8 * i)) & 0xff for i in range(4)] + [(p1 >> (8 * i)) & 0xff for i in range(4)]
+                    a = win[r, x0:x0 + 8].astype(int)
+                    b, c, d = win[r, x0 + 1:x0 + 9].astype(int), win[r + 1, x0:x0 + 8].astype(int), win[r + 1, x0 + 1:x0 + 9].astype(int)
+                    want = [a, (a + b + 1) >> 1, (a + c + 1) >> 1, (a + b + c + d + 2) >> 2][mode]
+                    assert got == list(want), (trial, x0, mode, r)
