@@ -391,3 +391,21 @@ def test_coded_audio_frames_requantise_to_the_parsers_samples(golden_dir, which)
     assert frames > 30
     L.mpegb200_audio_parser_free(a)
     L.mpegb200_audio_parser_free(b)
+
+
+def test_start_code_memo_equals_the_byte_by_byte_walk():
+    """BitReader::next_start_code keeps a memo of the start codes it has found (so that hasStartCode's look-ahead and the slice
+    walk search every byte once) and can take a complete index from the device.  tests/startcode/memo_test.cpp includes the
+    product source and holds the memo against buffer.go:279-302 walked literally: 240,000 searches on random, zero-heavy, dense
+    and sparse start-code buffers, with backward jumps, long forward jumps and bit-granular positions, under ASan + UBSan."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    build = root / "tests" / "startcode" / "_build"
+    build.mkdir(parents=True, exist_ok=True)
+    exe = build / "memo_test"
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-pthread",
+                    str(root / "tests" / "startcode" / "memo_test.cpp"), str(root / "mpeg_b200" / "csrc" / "coeff_pack.cpp"), "-o", str(exe)],
+                   check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "memo ok" in r.stdout, r.stdout + r.stderr
